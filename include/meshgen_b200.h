@@ -1,0 +1,168 @@
+/*
+ * meshgen_b200 -- C ABI of the B200-native batched BoudaryEnv (quad-mesh generation RL env).
+ *
+ * This is the drop-in boundary of the hot path.  The reference has no
+ * native interface: its boundary is the Python class BoudaryEnv.  Each entry point below names
+ * the reference method it replaces; citations are relative to the reference tree,
+ *   E = v2/src/mesh_rl/envs/boundary_env.py   (legacy twin: rl/boundary_env.py)
+ *   M = v2/src/mesh_rl/mesh_core.py           (legacy twin: general/mesh.py)
+ *   C = v2/src/mesh_rl/components_core.py     (legacy twin: general/components.py)
+ *   V = rl/baselines/dummy_vec_env.py         (the VecEnv surface the trainers use)
+ *
+ * Conventions
+ *   - plain C types only; every call returns 0 on success, a negative mg_status otherwise, and
+ *     never throws.  mg_last_error() gives a human-readable message for the last failure.
+ *   - a handle owns all device state of `num_envs` environments on one CUDA device.
+ *   - pointers named *_dev are device pointers owned by the caller (e.g. tensor.data_ptr());
+ *     pointers named *_host are host pointers.  `stream` is a cudaStream_t passed as void*.
+ *   - calls enqueue work on `stream` and do not synchronise unless stated.
+ *   - one handle is not thread-safe; different handles are independent.
+ *   - there is no CPU fallback: without a CUDA device mg_create fails with MG_ERR_CUDA.
+ */
+#ifndef MESHGEN_B200_H
+#define MESHGEN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MG_OBS_DIM 18 /* E:91-94  2 * (neighbor_num 6 + radius_num 3) float32 */
+#define MG_ACT_DIM 3  /* E:78-80  Box([-1,-1.5,0],[1,1.5,1.5]) float32 */
+
+typedef struct mg_env_s *mg_handle;
+
+typedef enum mg_status {
+    MG_OK = 0,
+    MG_ERR_ARG = -1,    /* bad argument */
+    MG_ERR_CUDA = -2,   /* CUDA runtime failure (message has the cudaError string) */
+    MG_ERR_STATE = -3,  /* call order (e.g. step before domains were set) */
+    MG_ERR_CAPACITY = -4 /* polygon larger than max_verts */
+} mg_status;
+
+/* Random star-polygon generator configuration (ui/GenerateRandomPolygon.py:5-49, defaults :63;
+ * densifier ui/tk-ui.py:252-276).  Lengths in pixel units of the reference tools; the
+ * generated coordinates are divided by 100 like read_polygon does (geometry.py:46). */
+typedef struct mg_polygen_cfg {
+    double ctr_x, ctr_y;     /* 250, 250 */
+    double ave_radius;       /* 100 */
+    double irregularity;     /* 0.55 */
+    double spikeyness;       /* 0.7 */
+    int32_t min_coarse;      /* 8   coarse vertices K ~ U{min_coarse..max_coarse} */
+    int32_t max_coarse;      /* 24 */
+    int32_t min_verts;       /* 64  densified vertex count n, even, min_verts <= n <= max_verts */
+    int32_t max_verts;       /* 512 */
+} mg_polygen_cfg;
+
+/* Episode statistics summed over all envs of the handle since the last mg_stats(reset=1).
+ * This 10-element vector is the only thing the multi-GPU driver all-reduces. */
+typedef struct mg_episode_stats {
+    int64_t episodes;      /* finished episodes */
+    int64_t completed;     /* ... that ended with is_complete (terminated) */
+    int64_t truncated;     /* ... that ended by 100 consecutive failures (E:382-384) */
+    int64_t steps;         /* env steps executed */
+    int64_t successes;     /* steps that created an element */
+    int64_t elements;      /* elements in finished episodes */
+    int64_t sum_n;         /* sum over steps of the live boundary size (roofline accounting) */
+    int64_t sum_n_success; /* same, restricted to successful steps */
+    double sum_return;     /* sum of finished-episode returns */
+    double sum_length;     /* sum of finished-episode lengths */
+} mg_episode_stats;
+
+/* Read-back of one env's state for parity tests (host buffers sized by max_verts). */
+typedef struct mg_state_view {
+    int32_t n;              /* live boundary size, len(updated_boundary.vertices) */
+    int32_t ref_index;      /* index of the reference point in the boundary list, -1 if none */
+    int32_t n_elements;     /* len(generated_meshes) */
+    int32_t failed_num;     /* E:378-384 */
+    int32_t n0;             /* original polygon size */
+    int32_t reserved;
+    double base_length;     /* C:1089-1090 */
+    double current_area;    /* E:336 */
+    double original_area;   /* E:72 */
+    double area_min, area_crit; /* M:705-718 estimated_area_range */
+    double *xy_host;        /* out, 2*max_verts doubles (x0,y0,x1,y1,...) or NULL */
+    int32_t *vertex_id_host;/* out, max_verts: 0..n0-1 original, n0+k k-th inserted vertex */
+    double *cand_key_host;  /* out, max_verts: candidate key (degrees) or +inf when not a candidate */
+    int32_t *cand_stamp_host;/* out, max_verts: tie-break stamp (smaller = earlier in the list) */
+} mg_state_view;
+
+/* Replaces BoudaryEnv.__init__ (E:58-120) for a batch: allocates state for num_envs
+ * environments whose polygons have at most max_verts vertices, on CUDA device `device`. */
+int mg_create(mg_handle *out, int device, int num_envs, int max_verts);
+
+/* Replaces BoudaryEnv(boundary) / from_domain_file (E:45-56) + read_polygon (geometry.py:34-52):
+ * n_domains polygons given clockwise as packed (x, y) float64 pairs; polygon d spans
+ * xy_host[2*offsets_host[d] .. 2*offsets_host[d+1]).  env_domain_host[e] selects the polygon of
+ * env e.  areas_host (optional, may be NULL) carries Boundary2D.poly_area() (C:485-487) per
+ * domain as computed by the caller; when NULL the library evaluates the shoelace sum itself.
+ * Computes the per-domain reset template on the device (candidate keys M:228-287, area range
+ * M:705-718, first observation C:1192-1290) and synchronises. */
+int mg_set_domains(mg_handle h, const double *xy_host, const int32_t *offsets_host, int n_domains,
+                   const int32_t *env_domain_host, const double *areas_host);
+
+/* Workload generator for BASELINE configs 3/4: every reset draws a fresh random star polygon
+ * in-kernel (counter-based Philox stream: seed, subsequence = global env id, so results do not
+ * depend on how envs are sharded over ranks).  env_id_offset = first global env id of this handle. */
+int mg_set_random(mg_handle h, uint64_t seed, const mg_polygen_cfg *cfg, int64_t env_id_offset);
+
+/* enabled != 0 (default): VecEnv convention, a finished env is reset in place by mg_step and
+ * the pre-reset observation goes to term_obs.  enabled == 0: plain Gym env semantics
+ * (E:388-457): the env stays in its final state until mg_reset; obs_dev holds the final
+ * observation, stepping a finished env repeats the reference's behaviour (reward 10, done). */
+int mg_set_auto_reset(mg_handle h, int enabled);
+
+/* Replaces BoudaryEnv.reset (E:136-184).  mask_dev: num_envs bytes (non-zero = reset that env)
+ * or NULL for all.  obs_dev: out, num_envs * 18 float32 (all envs' current observation). */
+int mg_reset(mg_handle h, const uint8_t *mask_dev, float *obs_dev, void *stream);
+
+/* Replaces BoudaryEnv.step (E:388-457) followed by the VecEnv auto-reset (V:40-52 with the
+ * stock SB3 behaviour): one transition for every env.
+ *   act_dev      in  num_envs*3 float32
+ *   obs_dev      out num_envs*18 float32   next observation (after auto-reset when done)
+ *   rew_dev      out num_envs float64      reward (the reference returns np.float64)
+ *   term_dev     out num_envs uint8        terminated = done and is_complete
+ *   trunc_dev    out num_envs uint8        truncated  = done and not is_complete
+ *   term_obs_dev out num_envs*18 float32   observation before the auto-reset (valid where done;
+ *                                          may be NULL)
+ *   n_elem_dev   out num_envs int32        len(generated_meshes) after the step, before reset
+ *                                          (may be NULL) */
+int mg_step(mg_handle h, const float *act_dev, float *obs_dev, double *rew_dev, uint8_t *term_dev,
+            uint8_t *trunc_dev, float *term_obs_dev, int32_t *n_elem_dev, void *stream);
+
+/* Same transition through HOST buffers (what a numpy-facing caller such as SB3's VecEnv pays):
+ * H2D of the actions, the step, D2H of all outputs, one stream synchronise. */
+int mg_step_host(mg_handle h, const float *act_host, float *obs_host, double *rew_host,
+                 uint8_t *term_host, uint8_t *trunc_host, float *term_obs_host, int32_t *n_elem_host);
+
+/* Uniform actions in the action box (E:78-80) from the handle's Philox stream -- the synthetic
+ * policy used by the benchmarks.  act_dev: out num_envs*3 float32. */
+int mg_sample_actions(mg_handle h, uint64_t seed, uint64_t step_index, float *act_dev, void *stream);
+
+/* Parity/debug read-back of env `env` (synchronises). */
+int mg_get_state(mg_handle h, int env, mg_state_view *view);
+
+/* Element log of env `env` (generated_meshes, E:331,351): up to max_elements quads as 4 vertex
+ * ids each, and the coordinates of every vertex id < n_vertices.  Synchronises.  Returns the
+ * number of elements through *n_elements_out and of vertices through *n_vertices_out. */
+int mg_get_elements(mg_handle h, int env, int32_t *quads_host, int max_elements, int32_t *n_elements_out,
+                    double *vertex_xy_host, int max_vertices, int32_t *n_vertices_out);
+
+/* Sum the per-env episode counters on the device, copy them to *out (synchronises);
+ * reset != 0 zeroes the counters afterwards. */
+int mg_stats(mg_handle h, mg_episode_stats *out, int reset);
+
+int mg_num_envs(mg_handle h);
+int mg_max_verts(mg_handle h);
+/* number of kernel launches issued by this handle so far (bench.py's gpu_launches) */
+int64_t mg_launch_count(mg_handle h);
+
+int mg_destroy(mg_handle h);
+const char *mg_last_error(mg_handle h);
+const char *mg_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MESHGEN_B200_H */

@@ -888,6 +888,8 @@ void oracle_rollout(OEnv *e, const float *actions, int T, float *obs, double *re
         if (truncated) truncated[t] = (uint8_t)tr;
         if (n_elements) n_elements[t] = e->n_elements;
         if (success) success[t] = (uint8_t)e->last_success;
+        if (n_boundary) n_boundary[t] = e->n;                       /* before the auto-reset */
+        if (ref_index) ref_index[t] = oracle_ref_index(e);
         if (te || tr || e->obs_none) {
             if (terminal_obs) {
                 if (e->obs_none) memset(terminal_obs + 18 * t, 0, sizeof(float) * 18);
@@ -897,8 +899,6 @@ void oracle_rollout(OEnv *e, const float *actions, int T, float *obs, double *re
             oracle_reset(e);
         } else if (terminal_obs) memset(terminal_obs + 18 * t, 0, sizeof(float) * 18);
         if (obs) memcpy(obs + 18 * t, e->obs, sizeof(float) * 18);
-        if (n_boundary) n_boundary[t] = e->n;
-        if (ref_index) ref_index[t] = oracle_ref_index(e);
     }
 }
 

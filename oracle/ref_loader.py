@@ -195,14 +195,14 @@ class TracedEnv:
             out.append(self.ids[key])
         return out
 
-    def state(self):
+    def state(self, have_ref=True):
         env = self.env
         verts = env.updated_boundary.vertices
         ids = self.boundary_ids()
         xy = np.array([[float(v.x), float(v.y)] for v in verts], dtype=np.float64)
         rp = env.current_point_environment.reference_point
         cands = [(self.ids[id(v)], float(k)) for v, k in env.candidate_vertices]
-        return dict(ids=ids, xy=xy, ref_index=verts.index(rp), n=len(verts),
+        return dict(ids=ids, xy=xy, ref_index=verts.index(rp) if have_ref else -1, n=len(verts),
                     n_elements=len(env.generated_meshes), candidates=cands,
                     base_length=float(env.current_point_environment.base_length),
                     current_area=float(env.current_area), failed_num=env.failed_num)
@@ -216,8 +216,9 @@ class TracedEnv:
         rec = dict(reward=float(rew), terminated=bool(term), truncated=bool(trunc),
                    is_complete=bool(info["is_complete"]), n_elements=n_el,
                    success=n_el > n_el_before, terminal_obs=None)
-        st = self.state() if obs is not None else None
+        st = self.state(have_ref=obs is not None)
         rec["pre_reset_state"] = st
+        rec["obs_none"] = obs is None
         if term or trunc:
             rec["terminal_obs"] = None if obs is None else np.array(obs, dtype=np.float32)
             obs, _ = env.reset()

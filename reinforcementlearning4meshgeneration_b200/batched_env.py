@@ -1,0 +1,224 @@
+"""Native batched API: ``BatchedBoudaryEnv`` -- N reference ``BoudaryEnv`` instances stepped in
+lock-step by the sm_100a kernels, observations / rewards / flags returned as device-resident
+torch tensors (no host synchronisation on the step path).
+
+Reference behaviour: v2/src/mesh_rl/envs/boundary_env.py:34 (``BoudaryEnv``), reset :136-184,
+step :388-457; auto-reset follows the stock SB3 VecEnv convention
+(rl/baselines/dummy_vec_env.py:40-52 with the reset the vendored copy comments out).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import EpisodeStats, PolygenCfg, StateView, check
+
+OBS_DIM = 18
+ACT_DIM = 3
+# E:78-80
+ACTION_LOW = np.array([-1.0, -1.5, 0.0], dtype=np.float32)
+ACTION_HIGH = np.array([1.0, 1.5, 1.5], dtype=np.float32)
+
+
+def poly_area(xy: np.ndarray) -> float:
+    """Boundary2D.poly_area as the reference's __init__ evaluates it on the host
+    (components_core.py:485-487, envs/boundary_env.py:72)."""
+    xy = np.asarray(xy, dtype=np.float64)
+    return float(0.5 * np.abs(np.dot(xy[:, 0], np.roll(xy[:, 1], 1)) - np.dot(xy[:, 1], np.roll(xy[:, 0], 1))))
+
+
+def as_xy(boundary) -> np.ndarray:
+    """Accept an (n,2) array or any object exposing ``.vertices[i].x/.y`` (the reference's
+    Boundary2D, rl/boundary_env.py:21-24)."""
+    if hasattr(boundary, "vertices"):
+        return np.array([[float(v.x), float(v.y)] for v in boundary.vertices], dtype=np.float64)
+    xy = np.asarray(boundary, dtype=np.float64)
+    if xy.ndim != 2 or xy.shape[1] != 2:
+        raise ValueError("boundary must be (n, 2) or expose .vertices")
+    return np.ascontiguousarray(xy)
+
+
+class StepResult:
+    __slots__ = ("obs", "reward", "terminated", "truncated", "terminal_obs", "n_elements")
+
+    def __init__(self, obs, reward, terminated, truncated, terminal_obs, n_elements):
+        self.obs, self.reward, self.terminated, self.truncated = obs, reward, terminated, truncated
+        self.terminal_obs, self.n_elements = terminal_obs, n_elements
+
+    def __iter__(self):
+        info = {"terminal_obs": self.terminal_obs, "n_elements": self.n_elements,
+                "is_complete": self.truncated == 0}
+        return iter((self.obs, self.reward, self.terminated, self.truncated, info))
+
+
+class BatchedBoudaryEnv:
+    """``num_envs`` BoudaryEnv instances on one CUDA device.
+
+    domains   : a polygon or list of polygons ((n,2) arrays or Boundary2D-like objects), or None
+                when ``random_polygons`` is given.
+    env_domain: per-env index into ``domains`` (default: round-robin blocks, env e -> e*D//N).
+    random_polygons: dict of generator settings (see ``PolygenCfg``) -> every reset draws a fresh
+                random star polygon in-kernel (BASELINE configs 3/4).
+    """
+
+    def __init__(self, domains=None, num_envs: int = 1, device: Optional[int | str | torch.device] = None,
+                 env_domain: Optional[Sequence[int]] = None, max_verts: Optional[int] = None,
+                 random_polygons: Optional[dict] = None, seed: int = 0, env_id_offset: int = 0,
+                 auto_reset: bool = True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("BatchedBoudaryEnv needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self._L = _lib.load()
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.type != "cuda":
+            raise ValueError("device must be a CUDA device")
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        self.num_envs = int(num_envs)
+        self._h = C.c_void_p()
+        self.random_mode = random_polygons is not None
+        if self.random_mode:
+            cfg = dict(ctr_x=250.0, ctr_y=250.0, ave_radius=100.0, irregularity=0.55, spikeyness=0.7,
+                       min_coarse=8, max_coarse=24, min_verts=64, max_verts=512)
+            cfg.update(random_polygons)
+            self.max_verts = int(max_verts or cfg["max_verts"])
+            check(self._L.mg_create(C.byref(self._h), self.device.index, self.num_envs, self.max_verts), None, "mg_create")
+            c = PolygenCfg(**cfg)
+            check(self._L.mg_set_random(self._h, int(seed), C.byref(c), int(env_id_offset)), self._h, "mg_set_random")
+            self.domains = None
+        else:
+            if domains is None:
+                raise ValueError("give domains or random_polygons")
+            if hasattr(domains, "vertices") or (isinstance(domains, np.ndarray) and domains.ndim == 2):
+                domains = [domains]
+            self.domains = [as_xy(d) for d in domains]
+            D = len(self.domains)
+            self.max_verts = int(max_verts or max(len(d) for d in self.domains))
+            if env_domain is None:
+                env_domain = (np.arange(self.num_envs, dtype=np.int64) * D) // self.num_envs
+            self.env_domain = np.ascontiguousarray(np.asarray(env_domain, dtype=np.int32))
+            if len(self.env_domain) != self.num_envs:
+                raise ValueError("env_domain must have num_envs entries")
+            check(self._L.mg_create(C.byref(self._h), self.device.index, self.num_envs, self.max_verts), None, "mg_create")
+            offsets = np.zeros(D + 1, dtype=np.int32)
+            offsets[1:] = np.cumsum([len(d) for d in self.domains])
+            xy = np.ascontiguousarray(np.concatenate(self.domains, axis=0))
+            areas = np.array([poly_area(d) for d in self.domains], dtype=np.float64)
+            check(self._L.mg_set_domains(self._h, xy.ctypes.data, offsets.ctypes.data, D, self.env_domain.ctypes.data,
+                                         areas.ctypes.data), self._h, "mg_set_domains")
+        self.auto_reset = bool(auto_reset)
+        check(self._L.mg_set_auto_reset(self._h, int(self.auto_reset)), self._h, "mg_set_auto_reset")
+        N = self.num_envs
+        with torch.cuda.device(self.device):
+            self.obs = torch.zeros((N, OBS_DIM), dtype=torch.float32, device=self.device)
+            self.reward = torch.zeros(N, dtype=torch.float64, device=self.device)
+            self.terminated = torch.zeros(N, dtype=torch.uint8, device=self.device)
+            self.truncated = torch.zeros(N, dtype=torch.uint8, device=self.device)
+            self.terminal_obs = torch.zeros((N, OBS_DIM), dtype=torch.float32, device=self.device)
+            self.n_elements = torch.zeros(N, dtype=torch.int32, device=self.device)
+            self._act = torch.zeros((N, ACT_DIM), dtype=torch.float32, device=self.device)
+
+    # ------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.mg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------
+    def reset(self, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Reset all envs (mask None) or those with mask != 0; returns obs[N,18] (device)."""
+        mptr = None
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            mptr = C.c_void_p(mask.data_ptr())
+        check(self._L.mg_reset(self._h, mptr, C.c_void_p(self.obs.data_ptr()), self._stream()), self._h, "mg_reset")
+        return self.obs
+
+    def step(self, actions: torch.Tensor) -> StepResult:
+        """One transition for every env. ``actions``: float32 [N,3] on this device.
+        Returns device tensors (views of internal buffers, overwritten by the next step)."""
+        if actions.device != self.device or actions.dtype != torch.float32 or not actions.is_contiguous():
+            actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
+        if actions.shape != (self.num_envs, ACT_DIM):
+            raise ValueError(f"actions must have shape ({self.num_envs}, {ACT_DIM})")
+        check(self._L.mg_step(self._h, C.c_void_p(actions.data_ptr()), C.c_void_p(self.obs.data_ptr()),
+                              C.c_void_p(self.reward.data_ptr()), C.c_void_p(self.terminated.data_ptr()),
+                              C.c_void_p(self.truncated.data_ptr()), C.c_void_p(self.terminal_obs.data_ptr()),
+                              C.c_void_p(self.n_elements.data_ptr()), self._stream()), self._h, "mg_step")
+        return StepResult(self.obs, self.reward, self.terminated, self.truncated, self.terminal_obs, self.n_elements)
+
+    def step_host(self, actions: np.ndarray, out: Optional[dict] = None) -> dict:
+        """Same transition through host (numpy / pinned) buffers: H2D + step + D2H + sync inside the
+        library (mg_step_host) -- the path a numpy-facing caller such as SB3 pays."""
+        a = np.ascontiguousarray(actions, dtype=np.float32)
+        N = self.num_envs
+        if out is None:
+            out = dict(obs=np.empty((N, OBS_DIM), np.float32), reward=np.empty(N, np.float64),
+                       terminated=np.empty(N, np.uint8), truncated=np.empty(N, np.uint8),
+                       terminal_obs=np.empty((N, OBS_DIM), np.float32), n_elements=np.empty(N, np.int32))
+
+        def ptr(x):
+            return C.c_void_p(x.data_ptr()) if isinstance(x, torch.Tensor) else C.c_void_p(x.ctypes.data)
+
+        aptr = ptr(actions) if isinstance(actions, torch.Tensor) else C.c_void_p(a.ctypes.data)
+        check(self._L.mg_step_host(self._h, aptr, ptr(out["obs"]), ptr(out["reward"]), ptr(out["terminated"]),
+                                   ptr(out["truncated"]), ptr(out["terminal_obs"]), ptr(out["n_elements"])),
+              self._h, "mg_step_host")
+        return out
+
+    def sample_actions(self, seed: int, step_index: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Uniform actions in the action box from the library's Philox stream (synthetic policy)."""
+        out = self._act if out is None else out
+        check(self._L.mg_sample_actions(self._h, int(seed), int(step_index), C.c_void_p(out.data_ptr()), self._stream()),
+              self._h, "mg_sample_actions")
+        return out
+
+    # ------------------------------------------------------------------
+    def get_state(self, env: int) -> dict:
+        cap = self.max_verts + 2
+        xy = np.zeros((cap, 2), np.float64)
+        vid = np.zeros(cap, np.int32)
+        key = np.zeros(cap, np.float64)
+        stamp = np.zeros(cap, np.int32)
+        v = StateView()
+        v.xy_host, v.vertex_id_host = xy.ctypes.data, vid.ctypes.data
+        v.cand_key_host, v.cand_stamp_host = key.ctypes.data, stamp.ctypes.data
+        check(self._L.mg_get_state(self._h, int(env), C.byref(v)), self._h, "mg_get_state")
+        n = v.n
+        cand = [(int(vid[j]), float(key[j]), int(stamp[j])) for j in range(n) if np.isfinite(key[j])]
+        cand.sort(key=lambda t: (t[1], t[2]))
+        return dict(n=n, ref_index=v.ref_index, n_elements=v.n_elements, failed_num=v.failed_num, n0=v.n0,
+                    base_length=v.base_length, current_area=v.current_area, original_area=v.original_area,
+                    area_range=(v.area_min, v.area_crit), xy=xy[:n].copy(), ids=vid[:n].copy(),
+                    cand_key=key[:n].copy(), cand_stamp=stamp[:n].copy(),
+                    candidates=[(c[0], c[1]) for c in cand])
+
+    def get_elements(self, env: int):
+        """(quads[m,4] int32 vertex ids, vertex_xy[nv,2]) of env's current episode (generated_meshes)."""
+        cap = self.max_verts + 2
+        quads = np.zeros((cap, 4), np.int32)
+        vxy = np.zeros((2 * cap, 2), np.float64)
+        ne, nv = C.c_int32(), C.c_int32()
+        check(self._L.mg_get_elements(self._h, int(env), quads.ctypes.data, cap, C.byref(ne), vxy.ctypes.data, 2 * cap,
+                                      C.byref(nv)), self._h, "mg_get_elements")
+        return quads[:min(ne.value, cap)].copy(), vxy[:min(nv.value, 2 * cap)].copy(), ne.value
+
+    def stats(self, reset: bool = False) -> dict:
+        s = EpisodeStats()
+        check(self._L.mg_stats(self._h, C.byref(s), int(reset)), self._h, "mg_stats")
+        return s.as_dict()
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.mg_launch_count(self._h))

@@ -1,0 +1,337 @@
+// C ABI of libmeshgen_b200.so (include/meshgen_b200.h): handle management, device memory,
+// kernel launches.  No torch types, no exceptions across the boundary, no CPU fallback.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "mg_kernels.cu"
+
+using namespace mg;
+
+struct mg_env_s {
+    int device = 0;
+    int num_envs = 0;
+    int max_verts = 0;
+    Params P{};
+    // owned device buffers
+    double2 *t_xy = nullptr;
+    double *t_key = nullptr;
+    int32_t *t_stamp = nullptr;
+    DomainScalars *t_sc = nullptr;
+    float *t_obs = nullptr;
+    mg_episode_stats *d_stats_out = nullptr;
+    // staging buffers for mg_step_host
+    float *d_act = nullptr, *d_obs = nullptr, *d_term_obs = nullptr;
+    double *d_rew = nullptr;
+    uint8_t *d_term = nullptr, *d_trunc = nullptr;
+    int32_t *d_nel = nullptr;
+    cudaStream_t host_stream = nullptr;
+    bool ready = false;       // domains or generator configured
+    bool was_reset = false;
+    int64_t launches = 0;
+    size_t smem = 0;
+    std::string err;
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(mg_handle h, int code, const std::string &msg) {
+    if (h) h->err = msg;
+    g_err = msg;
+    return code;
+}
+
+#define MG_CUDA(h, call)                                                                              \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(h, MG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+    } while (0)
+
+template <class T>
+cudaError_t dalloc(T **p, size_t count) {
+    cudaError_t e = cudaMalloc((void **)p, count * sizeof(T));
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, count * sizeof(T));
+    return e;
+}
+
+int grid_for(int n) { return (n + WPB - 1) / WPB; }
+
+int configure_kernels(mg_handle h) {
+    h->smem = smem_bytes(h->P.cap);
+    if (h->smem > 48 * 1024) {
+        MG_CUDA(h, cudaFuncSetAttribute(mg_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        MG_CUDA(h, cudaFuncSetAttribute(mg_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        MG_CUDA(h, cudaFuncSetAttribute(mg_template_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    }
+    return MG_OK;
+}
+
+void free_templates(mg_handle h) {
+    cudaFree(h->t_xy); cudaFree(h->t_key); cudaFree(h->t_stamp); cudaFree(h->t_sc); cudaFree(h->t_obs);
+    h->t_xy = nullptr; h->t_key = nullptr; h->t_stamp = nullptr; h->t_sc = nullptr; h->t_obs = nullptr;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *mg_version(void) { return "meshgen_b200 0.1 (sm_100a)"; }
+
+const char *mg_last_error(mg_handle h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int mg_create(mg_handle *out, int device, int num_envs, int max_verts) {
+    if (!out || num_envs <= 0 || max_verts < 4 || max_verts > 8192) return fail(nullptr, MG_ERR_ARG, "mg_create: bad argument");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, MG_ERR_CUDA, std::string("mg_create: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(nullptr, MG_ERR_ARG, "mg_create: bad device index");
+    mg_handle h = new (std::nothrow) mg_env_s();
+    if (!h) return fail(nullptr, MG_ERR_ARG, "mg_create: out of host memory");
+    h->device = device; h->num_envs = num_envs; h->max_verts = max_verts;
+    MG_CUDA(h, cudaSetDevice(device));
+    Params &P = h->P;
+    P.num_envs = num_envs;
+    P.auto_reset = 1;
+    P.cap = (max_verts + 1) & ~1;
+    const size_t NC = (size_t)num_envs * P.cap;
+    P.elem_cap = P.cap;           // an episode creates at most ~n0/2 + inserted elements; capped
+    P.ins_cap = P.cap;
+    int rc = MG_OK;
+    auto A = [&](cudaError_t er, const char *what) {
+        if (er != cudaSuccess && rc == MG_OK) rc = fail(h, MG_ERR_CUDA, std::string("cudaMalloc ") + what + ": " + cudaGetErrorString(er));
+    };
+    A(dalloc(&P.xy, NC), "xy"); A(dalloc(&P.key, NC), "key"); A(dalloc(&P.stamp, NC), "stamp"); A(dalloc(&P.vid, NC), "vid");
+    A(dalloc(&P.st, (size_t)num_envs), "state"); A(dalloc(&P.stats, (size_t)num_envs), "stats");
+    A(dalloc(&P.obs_cache, (size_t)num_envs * MG_OBS_DIM), "obs");
+    A(dalloc(&P.elem, (size_t)num_envs * P.elem_cap * 4), "elem"); A(dalloc(&P.ins_xy, (size_t)num_envs * P.ins_cap), "ins_xy");
+    A(dalloc(&h->d_stats_out, 1), "stats_out");
+    A(dalloc(&h->d_act, (size_t)num_envs * 3), "act"); A(dalloc(&h->d_obs, (size_t)num_envs * MG_OBS_DIM), "obs_out");
+    A(dalloc(&h->d_term_obs, (size_t)num_envs * MG_OBS_DIM), "term_obs"); A(dalloc(&h->d_rew, (size_t)num_envs), "rew");
+    A(dalloc(&h->d_term, (size_t)num_envs), "term"); A(dalloc(&h->d_trunc, (size_t)num_envs), "trunc");
+    A(dalloc(&h->d_nel, (size_t)num_envs), "nel");
+    if (rc == MG_OK && cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking) != cudaSuccess)
+        rc = fail(h, MG_ERR_CUDA, "cudaStreamCreate");
+    if (rc == MG_OK) rc = configure_kernels(h);
+    if (rc != MG_OK) { g_err = h->err; mg_destroy(h); return rc; }
+    *out = h;
+    return MG_OK;
+}
+
+int mg_destroy(mg_handle h) {
+    if (!h) return MG_OK;
+    cudaSetDevice(h->device);
+    Params &P = h->P;
+    cudaFree(P.xy); cudaFree(P.key); cudaFree(P.stamp); cudaFree(P.vid); cudaFree(P.st); cudaFree(P.stats);
+    cudaFree(P.obs_cache); cudaFree(P.elem); cudaFree(P.ins_xy);
+    free_templates(h);
+    cudaFree(h->d_stats_out); cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_term_obs); cudaFree(h->d_rew);
+    cudaFree(h->d_term); cudaFree(h->d_trunc); cudaFree(h->d_nel);
+    if (h->host_stream) cudaStreamDestroy(h->host_stream);
+    delete h;
+    return MG_OK;
+}
+
+int mg_set_auto_reset(mg_handle h, int enabled) {
+    if (!h) return fail(h, MG_ERR_ARG, "mg_set_auto_reset: null handle");
+    h->P.auto_reset = enabled ? 1 : 0;
+    return MG_OK;
+}
+
+int mg_num_envs(mg_handle h) { return h ? h->num_envs : 0; }
+int mg_max_verts(mg_handle h) { return h ? h->max_verts : 0; }
+int64_t mg_launch_count(mg_handle h) { return h ? h->launches : 0; }
+
+int mg_set_domains(mg_handle h, const double *xy_host, const int32_t *offsets_host, int n_domains,
+                   const int32_t *env_domain_host, const double *areas_host) {
+    if (!h || !xy_host || !offsets_host || !env_domain_host || n_domains <= 0) return fail(h, MG_ERR_ARG, "mg_set_domains: bad argument");
+    MG_CUDA(h, cudaSetDevice(h->device));
+    Params &P = h->P;
+    const int cap = P.cap;
+    std::vector<double2> txy((size_t)n_domains * cap, make_double2(0, 0));
+    std::vector<DomainScalars> tsc(n_domains);
+    for (int d = 0; d < n_domains; d++) {
+        int n = offsets_host[d + 1] - offsets_host[d];
+        if (n < 3) return fail(h, MG_ERR_ARG, "mg_set_domains: polygon with fewer than 3 vertices");
+        if (n > h->max_verts) return fail(h, MG_ERR_CAPACITY, "mg_set_domains: polygon larger than max_verts");
+        for (int j = 0; j < n; j++) {
+            const double *p = xy_host + 2 * ((size_t)offsets_host[d] + j);
+            txy[(size_t)d * cap + j] = make_double2(p[0], p[1]);
+        }
+        std::memset(&tsc[d], 0, sizeof(DomainScalars));
+        tsc[d].n0 = n;
+    }
+    std::vector<EnvState> st(h->num_envs);
+    std::memset(st.data(), 0, sizeof(EnvState) * st.size());
+    for (int e = 0; e < h->num_envs; e++) {
+        int d = env_domain_host[e];
+        if (d < 0 || d >= n_domains) return fail(h, MG_ERR_ARG, "mg_set_domains: env_domain out of range");
+        st[e].domain = d;
+    }
+    free_templates(h);
+    MG_CUDA(h, dalloc(&h->t_xy, (size_t)n_domains * cap));
+    MG_CUDA(h, dalloc(&h->t_key, (size_t)n_domains * cap));
+    MG_CUDA(h, dalloc(&h->t_stamp, (size_t)n_domains * cap));
+    MG_CUDA(h, dalloc(&h->t_sc, (size_t)n_domains));
+    MG_CUDA(h, dalloc(&h->t_obs, (size_t)n_domains * MG_OBS_DIM));
+    MG_CUDA(h, cudaMemcpy(h->t_xy, txy.data(), sizeof(double2) * txy.size(), cudaMemcpyHostToDevice));
+    MG_CUDA(h, cudaMemcpy(h->t_sc, tsc.data(), sizeof(DomainScalars) * tsc.size(), cudaMemcpyHostToDevice));
+    MG_CUDA(h, cudaMemcpy(P.st, st.data(), sizeof(EnvState) * st.size(), cudaMemcpyHostToDevice));
+    double *d_areas = nullptr;
+    if (areas_host) {
+        MG_CUDA(h, cudaMalloc((void **)&d_areas, sizeof(double) * n_domains));
+        MG_CUDA(h, cudaMemcpy(d_areas, areas_host, sizeof(double) * n_domains, cudaMemcpyHostToDevice));
+    }
+    P.n_domains = n_domains; P.random_mode = 0;
+    P.t_xy = h->t_xy; P.t_key = h->t_key; P.t_stamp = h->t_stamp; P.t_sc = h->t_sc; P.t_obs = h->t_obs;
+    mg_template_kernel<<<grid_for(n_domains), WPB * 32, h->smem>>>(P, h->t_xy, h->t_key, h->t_stamp, h->t_sc, h->t_obs, d_areas);
+    h->launches++;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (d_areas) cudaFree(d_areas);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, MG_ERR_CUDA, std::string("mg_template_kernel: ") + cudaGetErrorString(e));
+    h->ready = true; h->was_reset = false;
+    return MG_OK;
+}
+
+int mg_set_random(mg_handle h, uint64_t seed, const mg_polygen_cfg *cfg, int64_t env_id_offset) {
+    if (!h) return fail(h, MG_ERR_ARG, "mg_set_random: null handle");
+    mg_polygen_cfg c;
+    if (cfg) c = *cfg;
+    else {
+        c.ctr_x = 250; c.ctr_y = 250; c.ave_radius = 100; c.irregularity = 0.55; c.spikeyness = 0.7;
+        c.min_coarse = 8; c.max_coarse = 24; c.min_verts = 64; c.max_verts = 512;
+    }
+    if (c.min_coarse < 3 || c.max_coarse < c.min_coarse || c.max_coarse > 64 || c.min_verts < 8 || c.max_verts < c.min_verts ||
+        c.max_verts > h->max_verts || c.min_verts < c.max_coarse)
+        return fail(h, MG_ERR_ARG, "mg_set_random: bad generator configuration (need 3<=min_coarse<=max_coarse<=64, "
+                                   "max_coarse<=min_verts<=max_verts<=handle max_verts)");
+    MG_CUDA(h, cudaSetDevice(h->device));
+    MG_CUDA(h, cudaMemset(h->P.st, 0, sizeof(EnvState) * h->num_envs));
+    h->P.random_mode = 1; h->P.seed = seed; h->P.gen = c; h->P.env_id_offset = env_id_offset;
+    h->ready = true; h->was_reset = false;
+    return MG_OK;
+}
+
+int mg_reset(mg_handle h, const uint8_t *mask_dev, float *obs_dev, void *stream) {
+    if (!h) return fail(h, MG_ERR_ARG, "mg_reset: null handle");
+    if (!h->ready) return fail(h, MG_ERR_STATE, "mg_reset: call mg_set_domains or mg_set_random first");
+    if (mask_dev && !h->was_reset) return fail(h, MG_ERR_STATE, "mg_reset: the first reset must cover all envs (mask = NULL)");
+    MG_CUDA(h, cudaSetDevice(h->device));
+    mg_reset_kernel<<<grid_for(h->num_envs), WPB * 32, h->smem, (cudaStream_t)stream>>>(h->P, mask_dev, obs_dev);
+    h->launches++;
+    MG_CUDA(h, cudaGetLastError());
+    h->was_reset = true;
+    return MG_OK;
+}
+
+int mg_step(mg_handle h, const float *act_dev, float *obs_dev, double *rew_dev, uint8_t *term_dev, uint8_t *trunc_dev,
+            float *term_obs_dev, int32_t *n_elem_dev, void *stream) {
+    if (!h || !act_dev || !obs_dev || !rew_dev || !term_dev || !trunc_dev) return fail(h, MG_ERR_ARG, "mg_step: null pointer");
+    if (!h->was_reset) return fail(h, MG_ERR_STATE, "mg_step: call mg_reset first");
+    MG_CUDA(h, cudaSetDevice(h->device));
+    mg_step_kernel<<<grid_for(h->num_envs), WPB * 32, h->smem, (cudaStream_t)stream>>>(h->P, act_dev, obs_dev, rew_dev, term_dev,
+                                                                                      trunc_dev, term_obs_dev, n_elem_dev);
+    h->launches++;
+    MG_CUDA(h, cudaGetLastError());
+    return MG_OK;
+}
+
+int mg_step_host(mg_handle h, const float *act_host, float *obs_host, double *rew_host, uint8_t *term_host,
+                 uint8_t *trunc_host, float *term_obs_host, int32_t *n_elem_host) {
+    if (!h || !act_host || !obs_host || !rew_host || !term_host || !trunc_host) return fail(h, MG_ERR_ARG, "mg_step_host: null pointer");
+    if (!h->was_reset) return fail(h, MG_ERR_STATE, "mg_step_host: call mg_reset first");
+    MG_CUDA(h, cudaSetDevice(h->device));
+    const size_t N = h->num_envs;
+    cudaStream_t s = h->host_stream;
+    MG_CUDA(h, cudaMemcpyAsync(h->d_act, act_host, N * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+    int rc = mg_step(h, h->d_act, h->d_obs, h->d_rew, h->d_term, h->d_trunc, h->d_term_obs, h->d_nel, s);
+    if (rc != MG_OK) return rc;
+    MG_CUDA(h, cudaMemcpyAsync(obs_host, h->d_obs, N * MG_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
+    MG_CUDA(h, cudaMemcpyAsync(rew_host, h->d_rew, N * sizeof(double), cudaMemcpyDeviceToHost, s));
+    MG_CUDA(h, cudaMemcpyAsync(term_host, h->d_term, N, cudaMemcpyDeviceToHost, s));
+    MG_CUDA(h, cudaMemcpyAsync(trunc_host, h->d_trunc, N, cudaMemcpyDeviceToHost, s));
+    if (term_obs_host) MG_CUDA(h, cudaMemcpyAsync(term_obs_host, h->d_term_obs, N * MG_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (n_elem_host) MG_CUDA(h, cudaMemcpyAsync(n_elem_host, h->d_nel, N * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    MG_CUDA(h, cudaStreamSynchronize(s));
+    return MG_OK;
+}
+
+int mg_sample_actions(mg_handle h, uint64_t seed, uint64_t step_index, float *act_dev, void *stream) {
+    if (!h || !act_dev) return fail(h, MG_ERR_ARG, "mg_sample_actions: null pointer");
+    MG_CUDA(h, cudaSetDevice(h->device));
+    mg_sample_actions_kernel<<<(h->num_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->num_envs, seed, step_index,
+                                                                                         h->P.env_id_offset, act_dev);
+    h->launches++;
+    MG_CUDA(h, cudaGetLastError());
+    return MG_OK;
+}
+
+int mg_get_state(mg_handle h, int env, mg_state_view *v) {
+    if (!h || !v || env < 0 || env >= h->num_envs) return fail(h, MG_ERR_ARG, "mg_get_state: bad argument");
+    MG_CUDA(h, cudaSetDevice(h->device));
+    MG_CUDA(h, cudaDeviceSynchronize());
+    EnvState S;
+    MG_CUDA(h, cudaMemcpy(&S, h->P.st + env, sizeof(S), cudaMemcpyDeviceToHost));
+    v->n = S.n; v->ref_index = S.ref_index; v->n_elements = S.n_elements; v->failed_num = S.failed_num; v->n0 = S.n0;
+    v->base_length = S.base_length; v->current_area = S.current_area; v->original_area = S.original_area;
+    v->area_min = S.area_min; v->area_crit = S.area_crit;
+    const size_t off = (size_t)env * h->P.cap;
+    const int n = S.n;
+    if (n < 0 || n > h->P.cap) return fail(h, MG_ERR_STATE, "mg_get_state: corrupt env state");
+    if (v->xy_host) MG_CUDA(h, cudaMemcpy(v->xy_host, h->P.xy + off, sizeof(double2) * n, cudaMemcpyDeviceToHost));
+    if (v->vertex_id_host) MG_CUDA(h, cudaMemcpy(v->vertex_id_host, h->P.vid + off, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+    if (v->cand_key_host) MG_CUDA(h, cudaMemcpy(v->cand_key_host, h->P.key + off, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    if (v->cand_stamp_host) MG_CUDA(h, cudaMemcpy(v->cand_stamp_host, h->P.stamp + off, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+    return MG_OK;
+}
+
+int mg_get_elements(mg_handle h, int env, int32_t *quads_host, int max_elements, int32_t *n_elements_out,
+                    double *vertex_xy_host, int max_vertices, int32_t *n_vertices_out) {
+    if (!h || env < 0 || env >= h->num_envs) return fail(h, MG_ERR_ARG, "mg_get_elements: bad argument");
+    MG_CUDA(h, cudaSetDevice(h->device));
+    MG_CUDA(h, cudaDeviceSynchronize());
+    EnvState S;
+    MG_CUDA(h, cudaMemcpy(&S, h->P.st + env, sizeof(S), cudaMemcpyDeviceToHost));
+    int ne = S.n_elements < h->P.elem_cap ? S.n_elements : h->P.elem_cap;
+    if (n_elements_out) *n_elements_out = S.n_elements;
+    if (quads_host && max_elements > 0) {
+        int c = ne < max_elements ? ne : max_elements;
+        MG_CUDA(h, cudaMemcpy(quads_host, h->P.elem + (size_t)env * h->P.elem_cap * 4, sizeof(int32_t) * 4 * c, cudaMemcpyDeviceToHost));
+    }
+    int nv = S.next_vid;
+    if (n_vertices_out) *n_vertices_out = nv;
+    if (vertex_xy_host && max_vertices > 0) {
+        // original vertices come from the template (domain mode); inserted ones from the log
+        int n0 = S.n0 < max_vertices ? S.n0 : max_vertices;
+        if (!h->P.random_mode)
+            MG_CUDA(h, cudaMemcpy(vertex_xy_host, h->t_xy + (size_t)S.domain * h->P.cap, sizeof(double2) * n0, cudaMemcpyDeviceToHost));
+        else std::memset(vertex_xy_host, 0, sizeof(double) * 2 * n0);
+        int ni = nv - S.n0;
+        if (ni > h->P.ins_cap) ni = h->P.ins_cap;
+        if (S.n0 + ni > max_vertices) ni = max_vertices - S.n0;
+        if (ni > 0)
+            MG_CUDA(h, cudaMemcpy(vertex_xy_host + 2 * (size_t)S.n0, h->P.ins_xy + (size_t)env * h->P.ins_cap, sizeof(double2) * ni,
+                                  cudaMemcpyDeviceToHost));
+    }
+    return MG_OK;
+}
+
+int mg_stats(mg_handle h, mg_episode_stats *out, int reset) {
+    if (!h || !out) return fail(h, MG_ERR_ARG, "mg_stats: null pointer");
+    MG_CUDA(h, cudaSetDevice(h->device));
+    MG_CUDA(h, cudaDeviceSynchronize());
+    mg_stats_kernel<<<1, 1024>>>(h->num_envs, h->P.stats, h->d_stats_out, reset);
+    h->launches++;
+    MG_CUDA(h, cudaGetLastError());
+    MG_CUDA(h, cudaMemcpy(out, h->d_stats_out, sizeof(*out), cudaMemcpyDeviceToHost));
+    return MG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1163 @@
+// Batched BoudaryEnv reset/step for sm_100a: one warp per environment.
+//
+// The active boundary (updated_boundary.vertices) of the warp's environment is staged once per
+// step from HBM into a per-warp shared-memory ring with a single 1-D bulk async copy
+// (cp.async.bulk + mbarrier, UBLKCP in SASS); every O(n) predicate then strides the ring with
+// 32 lanes (double2 loads), and the expensive quantised-angle evaluations (atan2) are batched so
+// that each lane evaluates one angle: segment-intersection tests use an aligned lane quad per
+// segment pair and exchange their collinearity bits with a ballot.
+//
+// Citations: E = v2/src/mesh_rl/envs/boundary_env.py, M = v2/src/mesh_rl/mesh_core.py,
+// C = v2/src/mesh_rl/components_core.py, D = v2/src/mesh_rl/data_core.py (reference tree).
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "mg_math.cuh"
+#include "mg_state.cuh"
+
+namespace mg {
+
+constexpr int WPB = 4;          // warps (= environments) per block
+constexpr int QCAP = 256;       // per-warp queue of "heavy" segment pairs (ints)
+constexpr int QFLUSH = 128;
+
+// ---------------------------------------------------------------------------------------------
+// per-warp view of the environment
+// ---------------------------------------------------------------------------------------------
+struct Warp {
+    double2 *ring;   // shared memory, this warp's vertex ring
+    int *queue;      // shared memory, this warp's heavy-pair queue
+    int n;           // live boundary size
+    int lane;
+    __device__ __forceinline__ int wrap(int i) const {
+        if (i < 0) i += n;
+        else if (i >= n) i -= n;
+        return i;
+    }
+    // Python list indexing B[i] for i in [-n, 2n)
+    __device__ __forceinline__ P2 at(int i) const {
+        double2 v = ring[wrap(i)];
+        return mk(v.x, v.y);
+    }
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// Stage `n` vertices (16 B each) from global memory into the warp's ring with one bulk async
+// copy issued by lane 0 and completed on a per-warp mbarrier.
+__device__ __forceinline__ void stage_ring(double2 *ring, unsigned long long *mbar, const double2 *src, int n, int lane,
+                                           unsigned parity) {
+#ifndef MG_NO_BULK_COPY
+    unsigned bar = smem_u32(mbar);
+    unsigned bytes = (unsigned)n * 16u;
+    if (lane == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(ring)),
+            "l"(src), "r"(bytes), "r"(bar)
+            : "memory");
+    }
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
+#else
+    for (int j = lane; j < n; j += 32) ring[j] = src[j];
+    __syncwarp();
+#endif
+}
+
+__device__ __forceinline__ void init_mbar(unsigned long long *mbar, int lane) {
+#ifndef MG_NO_BULK_COPY
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// candidate keys (M:228-257 check_boundary_point) and reference point (M:295-316)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double cand_key_from_angles(double a0, double a1) {
+    if (a0 >= PI * 0.972 || a0 == 0) return CUDART_INF;
+    const double lam = 0.618;
+    double sum = a0 * lam;
+    sum += a1 * (1 - lam);
+    return sum * (180.0 / PI);
+}
+
+// Full rebuild (M:259-287): key for every vertex, stamp = list index (stable sort order).
+__device__ void rebuild_candidates(const Warp &w, double *key, int32_t *stamp) {
+    for (int j = w.lane; j < w.n; j += 32) {
+        P2 c = w.at(j);
+        double a0 = cw_angle(c, w.at(j + 1), w.at(j - 1));
+        double k = CUDART_INF;
+        if (!(a0 >= PI * 0.972 || a0 == 0)) {
+            double a1 = cw_angle(c, w.at(j + 2 >= w.n ? j + 2 - w.n : j + 2), w.at(j - 2 < -w.n ? j - 2 + w.n : j - 2));
+            k = cand_key_from_angles(a0, a1);
+        }
+        key[j] = k;
+        stamp[j] = j;
+    }
+}
+
+// arg-min of (key, stamp) over the n live vertices; -1 when the candidate list is empty.
+__device__ int find_reference_index(const Warp &w, const double *key, const int32_t *stamp) {
+    double bk = CUDART_INF;
+    int bs = 0x7fffffff, bj = -1;
+    for (int j = w.lane; j < w.n; j += 32) {
+        double k = key[j];
+        int s = stamp[j];
+        if (k < bk || (k == bk && k != CUDART_INF && s < bs)) {
+            bk = k;
+            bs = s;
+            bj = j;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double ok = __shfl_xor_sync(FULL, bk, o);
+        int os = __shfl_xor_sync(FULL, bs, o);
+        int oj = __shfl_xor_sync(FULL, bj, o);
+        if (ok < bk || (ok == bk && ok != CUDART_INF && os < bs)) {
+            bk = ok;
+            bs = os;
+            bj = oj;
+        }
+    }
+    return bk == CUDART_INF ? -1 : bj;
+}
+
+// ---------------------------------------------------------------------------------------------
+// observation (C:1059-1090 PointEnvironment, C:1192-1290 get_radius_points, E:665-738)
+// returns obs[lane] for lane < 18; base length through base_out.
+// ---------------------------------------------------------------------------------------------
+__device__ float compute_obs(const Warp &w, int idx, double area_ratio, double &base_out) {
+    const int lane = w.lane, n = w.n;
+    const double radius = 4;
+    P2 ref = w.at(idx), right_p = w.at(idx - 1), left_p = w.at(idx + 1 >= n ? idx + 1 - n : idx + 1);
+
+    // --- batch 1: 6 fan distances for base_length, 6 fan distances to ref, 6 angles ---------
+    // lanes 0..5 : |N[k+1] N[k]|  with N = [i+3, i+2, i+1, i, i-1, i-2, i-3]           (C:1087-1090)
+    // lanes 8..13: angles  theta, a(i-2), a(i-3), a(i+2), a(i+3), rot                      (C:1201-1235)
+    // lanes 16..21: |ref B[i-1]|, |ref B[i+1]|, |ref B[i-2]|, |ref B[i-3]|, |ref B[i+2]|, |ref B[i+3]|
+    double val = 0;
+    if (lane < 6) {
+        int a = idx + 2 - lane, b = idx + 3 - lane;   // N[k] = at(idx+3-k); dist(N[k+1], N[k])
+        val = pdist(w.at(((a % n) + n) % n), w.at(((b % n) + n) % n));
+    } else if (lane >= 8 && lane < 14) {
+        int t = lane - 8;
+        P2 p1, p2 = right_p;
+        if (t == 0) p1 = left_p;
+        else if (t == 1) p1 = w.at((((idx - 2) % n) + n) % n);
+        else if (t == 2) p1 = w.at((((idx - 3) % n) + n) % n);
+        else if (t == 3) p1 = w.at((idx + 2) % n);
+        else if (t == 4) p1 = w.at((idx + 3) % n);
+        else {
+            p1 = right_p;
+            p2 = mk(ref.x + 1, ref.y + 0);
+        }
+        val = cw_angle(ref, p1, p2);
+    } else if (lane >= 16 && lane < 22) {
+        int t = lane - 16;
+        const int off[6] = {-1, 1, -2, -3, 2, 3};
+        val = pdist(ref, w.at((((idx + off[t]) % n) + n) % n));
+    }
+    double dl[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) dl[k] = shfl_d(val, k);
+    double base = py_round4(py_sum<6>(dl) / 6);
+    base_out = base;
+    double theta = shfl_d(val, 8), a_r1 = shfl_d(val, 9), a_r2 = shfl_d(val, 10), a_l1 = shfl_d(val, 11),
+           a_l2 = shfl_d(val, 12), rot = shfl_d(val, 13);
+    double d_r = shfl_d(val, 16), d_l = shfl_d(val, 17), d_r1 = shfl_d(val, 18), d_r2 = shfl_d(val, 19),
+           d_l1 = shfl_d(val, 20), d_l2 = shfl_d(val, 21);
+    const double T = base * radius;
+    const double clip = theta + PI / 2;
+
+    // r_points float32[9][2]; lane-uniform copies in registers
+    float r0[9], r1[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) { r0[i] = 1.0f; r1[i] = 1.0f; }
+    r0[0] = (float)((d_r / radius) / base);  r1[0] = (float)area_ratio;
+    r0[8] = (float)((d_l / radius) / base);  r1[8] = (float)theta;
+    r0[1] = (float)((d_r1 / radius) / base); r1[1] = (float)(a_r1 < PI ? a_r1 : fmax(a_r1, 1.5 * PI) - 2 * PI);
+    r0[2] = (float)((d_r2 / radius) / base); r1[2] = (float)(a_r2 < PI ? a_r2 : fmax(a_r2, 1.5 * PI) - 2 * PI);
+    r0[7] = (float)((d_l1 / radius) / base); r1[7] = (float)fmin(a_l1, clip);
+    r0[6] = (float)((d_l2 / radius) / base); r1[6] = (float)fmin(a_l2, clip);
+#pragma unroll
+    for (int j = 0; j < 3; j++) r1[3 + j] = (float)fmin((2 * j + 1) * theta / 6, clip);
+
+    // p_s = ref + rotate((T cos(theta/2), T sin(theta/2)), rot)                      (C:154-168, C:1243)
+    double sv = 0, cv = 0;
+    if (lane == 0) sincos(theta / 2, &sv, &cv);
+    if (lane == 1) sincos(rot, &sv, &cv);
+    double s_h = shfl_d(sv, 0), c_h = shfl_d(cv, 0), s_r = shfl_d(sv, 1), c_r = shfl_d(cv, 1);
+    double px = T * c_h, py = T * s_h;
+    double qx = c_r * px - s_r * py;
+    double qy = s_r * px + c_r * py;
+    P2 ps = mk(ref.x + qx, ref.y + qy);
+    double ux = ps.x - ref.x, uy = ps.y - ref.y;
+
+    // --- scan of the other n-1 vertices in the reference's order o = 1 .. n-1  (m = idx - o) --
+    const double sector = theta / 3;
+    unsigned long long best_sec[3] = {~0ull, ~0ull, ~0ull};   // (float bits of cand, order)
+    double my_ang[3] = {0, 0, 0};
+    double best_ray = CUDART_INF;                             // f64 value of the nearest bisector hit
+    int best_ray_o = 0x7fffffff;
+    for (int o = 1 + lane; o < n; o += 32) {
+        if (o == 1 || o == n - 1) continue;                   // right_p / left_p (C:1249)
+        int j = idx - o;
+        if (j < 0) j += n;
+        P2 q = w.at(j);
+        double d = pdist(ref, q);
+        double angle = cw_angle(ref, q, right_p);
+        if (angle == 0) continue;                             // C:1255
+        double kk = angle / sector;
+        int k = (kk < 3.0) ? (int)kk : 3;                     // int() truncation; NaN/inf -> no sector
+        if (k < 3 && d < T) {
+            float cand = (float)((d / radius) / base);
+            if (cand < 1.0f) {
+                unsigned long long keyv = ((unsigned long long)__float_as_uint(cand) << 32) | (unsigned)o;
+                if (keyv < best_sec[k]) {
+                    best_sec[k] = keyv;
+                    my_ang[k] = angle;
+                }
+            }
+        }
+        // C:657-676 ll.intersection_vertex(seg) with ll = (ref, p_s), seg = (B[m], B[m+1])
+        P2 q2 = w.at(j + 1 >= n ? j + 1 - n : j + 1);
+        double wx = q2.x - q.x, wy = q2.y - q.y;
+        double ss, hh;
+        if (wy == 0) {
+            if (uy == 0) continue;
+            ss = (q.y - ref.y) / uy;
+            hh = (ref.x - q.x + ss * ux) / wx;
+        } else if (wx == 0) {
+            if (ux == 0) continue;
+            ss = (q.x - ref.x) / ux;
+            hh = (ref.y - q.y + ss * uy) / wy;
+        } else {
+            ss = ((ref.x - q.x) / wx - (ref.y - q.y) / wy) / (uy / wy - ux / wx);
+            hh = (ref.x - q.x + ss * ux) / wx;
+        }
+        if (0 < ss && ss < 1 && 0 < hh && hh < 1) {
+            double v = (pdist(ref, mk(ref.x + ss * ux, ref.y + ss * uy)) / radius) / base;
+            if (v < 1.0 && (v < best_ray || (v == best_ray && o < best_ray_o))) {
+                best_ray = v;
+                best_ray_o = o;
+            }
+        }
+    }
+    // sector minima: first (in order o) strictly smaller float32 value wins (C:1259-1263)
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        unsigned long long m = warp_min_u64(best_sec[k]);
+        if (m != ~0ull) {
+            unsigned src = __ffs(__ballot_sync(FULL, best_sec[k] == m)) - 1;
+            double ang = shfl_d(my_ang[k], src);
+            r0[3 + k] = __uint_as_float((unsigned)(m >> 32));
+            r1[3 + k] = (float)fmin(ang, clip);
+        }
+    }
+    // nearest bisector hit (C:1266-1287)
+    {
+        unsigned long long kv = d2key(best_ray);
+        unsigned long long m = warp_min_u64(kv);
+        unsigned cand_mask = __ballot_sync(FULL, kv == m && best_ray < 1.0);
+        if (cand_mask) {
+            // among lanes with the same value pick the smallest order
+            unsigned oo = (kv == m && best_ray < 1.0) ? (unsigned)best_ray_o : 0xffffffffu;
+            unsigned omin = __reduce_min_sync(FULL, oo);
+            double sv2 = shfl_d(best_ray, __ffs(cand_mask) - 1);
+            if ((float)sv2 < r0[4]) {                         // float32 comparison (NEP 50)
+                int mi = idx - (int)omin;                      // _i (may be negative like in Python)
+                double v2 = 0;
+                if (lane < 3) {
+                    int jj = (((lane - 1 + mi) % n) + n) % n;
+                    v2 = pdist(ref, w.at(jj));
+                } else if (lane >= 4 && lane < 7) {
+                    int jj = (((lane - 4 - 1 + mi) % n) + n) % n;
+                    v2 = cw_angle(ref, w.at(jj), right_p);
+                }
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    r0[3 + j] = (float)((shfl_d(v2, j) / radius) / base);
+                    r1[3 + j] = (float)shfl_d(v2, 4 + j);
+                }
+            }
+        }
+    }
+    float out = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        if (lane == 2 * i) out = r0[i];
+        if (lane == 2 * i + 1) out = r1[i];
+    }
+    return np_round4f(out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// estimated_area_range (M:705-718): needs the mean, the 2nd smallest and 2nd largest edge.
+// ---------------------------------------------------------------------------------------------
+__device__ void estimate_area_range(const Warp &w, double &area_min, double &area_crit) {
+    double s = 0, lo1 = CUDART_INF, lo2 = CUDART_INF, hi1 = -CUDART_INF, hi2 = -CUDART_INF;
+    for (int j = w.lane; j < w.n; j += 32) {
+        double l = pdist(w.at(j - 1), w.at(j));
+        s += l;
+        if (l < lo1) { lo2 = lo1; lo1 = l; } else if (l < lo2) lo2 = l;
+        if (l > hi1) { hi2 = hi1; hi1 = l; } else if (l > hi2) hi2 = l;
+    }
+    s = warp_sum_d(s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double a1 = __shfl_xor_sync(FULL, lo1, o), a2 = __shfl_xor_sync(FULL, lo2, o);
+        double b1 = __shfl_xor_sync(FULL, hi1, o), b2 = __shfl_xor_sync(FULL, hi2, o);
+        double n1 = fmin(lo1, a1), n2 = fmin(fmax(lo1, a1), fmin(lo2, a2));
+        lo1 = n1; lo2 = n2;
+        double m1 = fmax(hi1, b1), m2 = fmax(fmin(hi1, b1), fmax(hi2, b2));
+        hi1 = m1; hi2 = m2;
+    }
+    double L = s / w.n;
+    double max_L = fmin(hi2, 2 * L);
+    double min_L = fmin(L / sqrt(2.0), lo2);
+    area_min = min_L;
+    area_crit = (max_L + 3 * min_L) / 4;
+}
+
+// sequential shoelace (C:485-487 up to np.dot's BLAS summation order)
+__device__ double shoelace_area(const Warp &w) {
+    double s1 = 0, s2 = 0;
+    for (int j = w.lane; j < w.n; j += 32) {
+        P2 a = w.at(j), p = w.at(j - 1);
+        s1 += a.x * p.y;
+        s2 += a.y * p.x;
+    }
+    s1 = warp_sum_d(s1);
+    s2 = warp_sum_d(s2);
+    return 0.5 * fabs(s1 - s2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// heavy-pair queue: entries are evaluated 8 at a time, one aligned lane quad per segment pair
+// ---------------------------------------------------------------------------------------------
+template <class Decode>
+__device__ int process_queue(const Warp &w, int qn, Decode decode, bool stop_on_first) {
+    int hits = 0;
+    for (int base = 0; base < qn; base += 8) {
+        int e = base + (w.lane >> 2);
+        bool active = e < qn;
+        P2 a1 = mk(0, 0), a2 = a1, b1 = a1, b2 = a1;
+        if (active) decode(w.queue[e], a1, a2, b1, b2);
+        bool c = is_cross_quad(a1, a2, b1, b2, active, w.lane);
+        unsigned m = __ballot_sync(FULL, c && (w.lane & 3) == 0);
+        hits += __popc(m);
+        if (stop_on_first && hits) break;
+    }
+    return hits;
+}
+
+template <class Decode>
+__device__ __forceinline__ void queue_push(const Warp &w, int &qn, bool flag, int value, int &hits, Decode decode,
+                                           bool stop_on_first) {
+    unsigned m = __ballot_sync(FULL, flag);
+    if (m == 0) return;
+    if (flag) w.queue[qn + __popc(m & ((1u << w.lane) - 1))] = value;
+    qn += __popc(m);
+    __syncwarp();
+    if (qn > QFLUSH) {
+        hits += process_queue(w, qn, decode, stop_on_first);
+        qn = 0;
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// point-in-polygon (M:74-128 calculate_crossing_segments, M:176-187, M:565-572)
+// ---------------------------------------------------------------------------------------------
+// rint(1e4 * dy) with the reference's rounding flavour: NumPy's when either operand is an
+// inserted vertex (np.float64), CPython's otherwise.  They only differ on exact ties after the
+// multiply, so the vertex-id lookup is deferred to that (practically unreachable) case.
+__device__ __forceinline__ double rint4_mixed(double dy, const int32_t *vid, int ja, int jb, int n0) {
+    double p = dy * 1e4;
+    double r = rint(p);
+    if (fabs(p - r) == 0.5) {
+        bool is_np = vid[ja] >= n0 || vid[jb] >= n0;
+        if (!is_np) r = py_rint4(dy);
+    }
+    return r;
+}
+
+__device__ bool point_inside(const Warp &w, P2 P, const int32_t *vid, int n0) {
+    const int n = w.n;
+    int qn = 0, hits = 0;
+    const P2 ray2 = mk(10000, P.y);
+    auto decode = [&](int j, P2 &a1, P2 &a2, P2 &b1, P2 &b2) {
+        a1 = w.at(j);
+        a2 = w.at(j - 1);
+        b1 = P;
+        b2 = ray2;
+    };
+    const bool can_prune = P.x < 9000.0;
+    for (int base = 0; base < n; base += 32) {
+        int j = base + w.lane;
+        bool need = false;
+        if (j < n) {
+            int jb = j == 0 ? n - 1 : j - 1;
+            P2 a = w.at(j), b = w.at(jb);
+            double ro = rint4_mixed(a.y - b.y, vid, j, jb, n0);
+            if (ro != 0) {
+                // would this edge be counted if it crosses the ray?  (M:91-118)
+                bool counted;
+                if (rint((a.y - P.y) * 1e4) == 0) {
+                    int jc = j + 1 == n ? 0 : j + 1;
+                    double rn = rint4_mixed(w.at(jc).y - a.y, vid, jc, j, n0);
+                    counted = !(rn == 0 || rn * ro < 0) && ro < 0;
+                } else if (rint((b.y - P.y) * 1e4) == 0) {
+                    int jc = jb == 0 ? n - 1 : jb - 1;
+                    double rp = rint4_mixed(b.y - w.at(jc).y, vid, jb, jc, n0);
+                    counted = !(rp == 0 || rp * ro < 0) && !(ro < 0);
+                } else counted = true;
+                if (counted) {
+                    // Exact early-out: if both endpoints lie strictly on the same side of the ray's
+                    // line, and at least one of them is more than 1e-4 rad off that line as seen from
+                    // P, ray.straddle(edge) is False (the collinearity pre-test C:506-508 needs both
+                    // quantised angles in {0, pi, 2pi}; the cross products then have equal signs).
+                    double dya = a.y - P.y, dyb = b.y - P.y;
+                    bool same_side = (dya > 1e-9 && dyb > 1e-9) || (dya < -1e-9 && dyb < -1e-9);
+                    bool off_axis = fabs(dya) > 1e-4 * fabs(a.x - P.x) || fabs(dyb) > 1e-4 * fabs(b.x - P.x);
+                    need = !(can_prune && same_side && off_axis);
+                }
+            }
+        }
+        queue_push(w, qn, need, j, hits, decode, false);
+    }
+    hits += process_queue(w, qn, decode, false);
+    return (hits & 1) != 0;
+}
+
+// E:766-769 find_same_point: any boundary vertex within 0.001 of P
+__device__ bool find_same_point(const Warp &w, P2 P) {
+    bool f = false;
+    for (int j = w.lane; j < w.n; j += 32) f |= pdist(w.at(j), P) < 0.001;
+    return __any_sync(FULL, f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// candidate quad: validity (C:738-757, C:814-826) + corner angles
+// ---------------------------------------------------------------------------------------------
+__device__ bool mesh_is_valid(const Warp &w, const P2 (&m)[4], double (&corner)[4]) {
+    const int lane = w.lane;
+    // lanes 0-3: is_cross((m0,m1),(m2,m3)); lanes 4-7: is_cross((m0,m3),(m1,m2)); lanes 8-11: corners
+    P2 a1 = m[0], a2 = lane < 4 ? m[1] : m[3], b1 = lane < 4 ? m[2] : m[1], b2 = lane < 4 ? m[3] : m[2];
+    double ang = 0;
+    if (lane < 8) {
+        int sub = lane & 3;
+        P2 c = sub < 2 ? a1 : b1;
+        P2 p1 = sub == 0 ? b1 : (sub == 1 ? b2 : (sub == 2 ? a1 : a2));
+        P2 p2 = sub < 2 ? a2 : b2;
+        ang = cw_angle(c, p1, p2);
+    } else if (lane < 12) {
+        int i = lane - 8;
+        P2 c = m[0], p1 = m[1], p2 = m[3];
+        if (i == 1) { c = m[1]; p1 = m[2]; p2 = m[0]; }
+        if (i == 2) { c = m[2]; p1 = m[3]; p2 = m[1]; }
+        if (i == 3) { c = m[3]; p1 = m[0]; p2 = m[2]; }
+        ang = cw_angle(c, p1, p2);
+    }
+    unsigned zb = __ballot_sync(FULL, sin_rounds_to_zero(ang));
+#pragma unroll
+    for (int i = 0; i < 4; i++) corner[i] = shfl_d(ang, 8 + i);
+    bool x0 = straddle_decide(m[0], m[1], m[2], m[3], (zb & 0x3u) == 0x3u) &&
+              straddle_decide(m[2], m[3], m[0], m[1], (zb & 0xCu) == 0xCu);
+    if (x0) return false;
+    bool x1 = straddle_decide(m[0], m[3], m[1], m[2], (zb & 0x30u) == 0x30u) &&
+              straddle_decide(m[1], m[2], m[0], m[3], (zb & 0xC0u) == 0xC0u);
+    if (x1) return false;
+    const double max_degree = 0.99 * PI, min_degree = 0.01 * PI;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        if (corner[i] > max_degree || corner[i] < min_degree) return false;
+    return true;
+}
+
+// M:536-556 check_intersection_with_boundary.  qi[] = boundary indices of the quad vertices
+// (-1 for the not-yet-inserted new vertex), ri = position of the reference point in the quad.
+__device__ bool intersects_boundary(const Warp &w, const P2 (&m)[4], const int (&qi)[4], int ri, P2 ref) {
+    const int n = w.n;
+    double max_dist = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (k != ri) max_dist = fmax(max_dist, pdist(ref, m[k]));
+    const P2 c1a = m[(ri + 3) & 3], c1b = m[(ri + 2) & 3], c2a = m[(ri + 2) & 3], c2b = m[(ri + 1) & 3];
+    auto in_mesh = [&](int j) { return j == qi[0] || j == qi[1] || j == qi[2] || j == qi[3]; };
+    auto decode = [&](int e, P2 &a1, P2 &a2, P2 &b1, P2 &b2) {
+        int j = e >> 2, t = e & 3;
+        if (t & 2) { a1 = c2a; a2 = c2b; } else { a1 = c1a; a2 = c1b; }
+        b1 = w.at(j);
+        b2 = (t & 1) ? w.at(j + 1 == n ? 0 : j + 1) : w.at(j - 1);
+    };
+    int qn = 0, hits = 0;
+    for (int base = 0; base < n && !hits; base += 32) {
+        int j = base + w.lane;
+        bool near = false, okp = false, okn = false;
+        if (j < n && !in_mesh(j)) {
+            near = pdist(ref, w.at(j)) < max_dist;
+            okp = near && !in_mesh(j == 0 ? n - 1 : j - 1);
+            okn = near && !in_mesh(j + 1 == n ? 0 : j + 1);
+        }
+        if (!__any_sync(FULL, near)) continue;
+        // reference order per vertex: (c1,prev) (c1,next) (c2,prev) (c2,next); any hit -> True
+        queue_push(w, qn, okp, j * 4 + 0, hits, decode, true);
+        queue_push(w, qn, okn, j * 4 + 1, hits, decode, true);
+        queue_push(w, qn, okp, j * 4 + 2, hits, decode, true);
+        queue_push(w, qn, okn, j * 4 + 3, hits, decode, true);
+    }
+    if (!hits) hits += process_queue(w, qn, decode, true);
+    return hits != 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// boundary quality of a freshly inserted vertex (M:355-408 compute_boundary_quality)
+// a_next / a_prev: interior angles at B[idx+1] and B[idx-1] (already evaluated for the candidates)
+// ---------------------------------------------------------------------------------------------
+__device__ double boundary_quality_new_vertex(const Warp &w, int idx, double a_next, double a_prev) {
+    const int n = w.n;
+    P2 add_v = w.at(idx);
+    double amin = CUDART_INF;
+    if (a_next < PI / 3) amin = a_next;
+    if (a_prev < PI / 3) amin = fmin(amin, a_prev);
+    double q1 = amin != CUDART_INF ? 3 * amin / PI : 1;
+    int e1 = idx + 1 >= n ? idx + 1 - n : idx + 1, e2 = (idx + 2) % n, e3 = idx - 1 < 0 ? idx - 1 + n : idx - 1,
+        e4 = (((idx - 2) % n) + n) % n;
+    double dist = pdist(add_v, w.at(e1)) + pdist(add_v, w.at(e3));
+    // close_vs: not excluded, nearer than `dist`, and not directly after an accepted index
+    double m_d = CUDART_INF;
+    unsigned carry = 0;   // parity of the run of "close" flags reaching the end of the previous chunk
+    for (int base = 0; base < n; base += 32) {
+        int j = base + w.lane;
+        bool c = false;
+        if (j < n && j != idx && j != e1 && j != e2 && j != e3 && j != e4) c = pdist(add_v, w.at(j)) < dist;
+        unsigned wbits = __ballot_sync(FULL, c);
+        if (c) {
+            unsigned below = ~wbits & ((1u << w.lane) - 1);        // zero bits below me
+            int off = below ? w.lane - (32 - __clz(below)) : w.lane + (int)carry;
+            if ((off & 1) == 0) {
+                int jn = j + 1 == n ? 0 : j + 1;
+                m_d = fmin(m_d, seg_point_distance(w.at(jn), w.at(j), add_v));
+            }
+        }
+        if (wbits == 0xffffffffu) carry = carry;                   // 32 more: parity unchanged
+        else carry = (unsigned)__clz(~wbits) & 1u;                  // length of the run of ones at the top
+    }
+    m_d = warp_min_d(m_d);
+    double targt_len = dist / 2;
+    double dl[4];
+#pragma unroll
+    for (int k = -2; k < 2; k++) {
+        int a = (((idx + k) % n) + n) % n, b = (((idx + k + 1) % n) + n) % n;
+        dl[k + 2] = pdist(w.at(a), w.at(b));
+    }
+    double mean_dist = py_sum<4>(dl) / 4;
+    double smoothness = fmin(mean_dist, targt_len) / fmax(mean_dist, targt_len);
+    double q2 = 1;
+    if (m_d != CUDART_INF) q2 = m_d < 0.5 * dist ? m_d / (0.5 * dist) : 1;
+    return pow(smoothness * q1 * q2, 1.0 / 3);
+}
+
+// M:418-452: element without a new vertex; t0,t1 = new indices of the two surviving quad vertices
+__device__ double boundary_quality_no_new(const Warp &w, int t0, int t1, double ang0, double ang1) {
+    const int n = w.n;
+    double amin = CUDART_INF;
+    if (ang0 < PI / 3) amin = ang0;
+    if (ang1 < PI / 3) amin = fmin(amin, ang1);
+    int index = t0 < t1 ? t0 : t1;
+    double targt_len = pdist(w.at(t0), w.at(t1));
+    double dl[5];
+#pragma unroll
+    for (int k = -2; k < 3; k++) {
+        int a = (((index + k) % n) + n) % n, b = (((index + k + 1) % n) + n) % n;
+        dl[k + 2] = pdist(w.at(a), w.at(b));
+    }
+    double mean_dist = py_sum<5>(dl) / 5;
+    double smoothness = fmin(mean_dist, targt_len) / fmax(mean_dist, targt_len);
+    double angle_quality = amin != CUDART_INF ? 3 * amin / PI : 1;
+    return pow(angle_quality * smoothness, 1.0 / 2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (counter-based RNG for the synthetic policy and the polygon generator)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        unsigned hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        unsigned hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+__device__ __forceinline__ double u01(unsigned a, unsigned b) {   // 53-bit uniform in [0,1)
+    return (double)((((unsigned long long)a << 32) | b) >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// random star polygon (ui/GenerateRandomPolygon.py:5-49) + densifier (ui/tk-ui.py:252-276)
+// Written by the warp into ring[0..n); returns n (even, min_verts <= n <= max_verts).
+// ---------------------------------------------------------------------------------------------
+__device__ int generate_polygon(const Params &P, Warp &w, long long global_env, int episode);
+
+// ---------------------------------------------------------------------------------------------
+// reset of one env (E:136-184): restore the polygon, rebuild candidates, first observation
+// ---------------------------------------------------------------------------------------------
+__device__ float reset_env(const Params &P, Warp &w, int env, EnvState &S) {
+    const int lane = w.lane;
+    const size_t off = (size_t)env * P.cap;
+    float obs;
+    if (!P.random_mode) {
+        const DomainScalars D = P.t_sc[S.domain];
+        const size_t toff = (size_t)S.domain * P.cap;
+        for (int j = lane; j < D.n0; j += 32) {
+            P.xy[off + j] = P.t_xy[toff + j];
+            P.key[off + j] = P.t_key[toff + j];
+            P.stamp[off + j] = P.t_stamp[toff + j];
+            P.vid[off + j] = j;
+        }
+        S.n = D.n0; S.n0 = D.n0; S.ref_index = D.ref_index;
+        S.base_length = D.base_length; S.original_area = D.original_area; S.current_area = D.original_area;
+        S.area_min = D.area_min; S.area_crit = D.area_crit;
+        obs = lane < MG_OBS_DIM ? P.t_obs[S.domain * MG_OBS_DIM + lane] : 0.0f;
+    } else {
+        int n = generate_polygon(P, w, P.env_id_offset + env, S.episode);
+        w.n = n;
+        __syncwarp();
+        for (int j = lane; j < n; j += 32) {
+            P.xy[off + j] = w.ring[j];
+            P.vid[off + j] = j;
+        }
+        rebuild_candidates(w, P.key + off, P.stamp + off);
+        __syncwarp();
+        S.n = n; S.n0 = n;
+        S.original_area = shoelace_area(w);
+        S.current_area = S.original_area;
+        estimate_area_range(w, S.area_min, S.area_crit);
+        S.ref_index = find_reference_index(w, P.key + off, P.stamp + off);
+        obs = 0.0f;
+        if (S.ref_index >= 0) obs = compute_obs(w, S.ref_index, S.current_area / S.original_area, S.base_length);
+    }
+    S.n_elements = 0; S.failed_num = 0; S.next_vid = S.n0; S.stamp_ctr = 0; S.ep_len = 0; S.ep_return = 0;
+    return obs;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+struct SmemLayout {
+    double2 *ring;
+    int *queue;
+    unsigned long long *mbar;
+};
+__device__ __forceinline__ SmemLayout carve(unsigned char *raw, int cap, int warp) {
+    SmemLayout L;
+    L.ring = reinterpret_cast<double2 *>(raw) + (size_t)warp * cap;
+    int *q = reinterpret_cast<int *>(reinterpret_cast<double2 *>(raw) + (size_t)WPB * cap);
+    L.queue = q + warp * QCAP;
+    L.mbar = reinterpret_cast<unsigned long long *>(q + WPB * QCAP) + warp;
+    return L;
+}
+size_t smem_bytes(int cap) { return (size_t)WPB * cap * 16 + (size_t)WPB * QCAP * 4 + WPB * 8; }
+
+// Per-domain reset template: one warp per domain.
+__global__ void __launch_bounds__(WPB * 32) mg_template_kernel(Params P, double2 *t_xy, double *t_key, int32_t *t_stamp,
+                                                              DomainScalars *t_sc, float *t_obs, const double *areas) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int d = blockIdx.x * WPB + warp;
+    if (d >= P.n_domains) return;
+    SmemLayout L = carve(smem_raw, P.cap, warp);
+    Warp w;
+    w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = t_sc[d].n0;
+    const size_t toff = (size_t)d * P.cap;
+    for (int j = lane; j < w.n; j += 32) w.ring[j] = t_xy[toff + j];
+    __syncwarp();
+    rebuild_candidates(w, t_key + toff, t_stamp + toff);
+    __syncwarp();
+    DomainScalars D = t_sc[d];
+    D.original_area = areas ? areas[d] : shoelace_area(w);
+    estimate_area_range(w, D.area_min, D.area_crit);
+    D.ref_index = find_reference_index(w, t_key + toff, t_stamp + toff);
+    float obs = 0.0f;
+    D.base_length = 0;
+    if (D.ref_index >= 0) obs = compute_obs(w, D.ref_index, D.original_area / D.original_area, D.base_length);
+    if (lane < MG_OBS_DIM) t_obs[d * MG_OBS_DIM + lane] = obs;
+    if (lane == 0) t_sc[d] = D;
+}
+
+__global__ void __launch_bounds__(WPB * 32) mg_reset_kernel(Params P, const uint8_t *mask, float *obs_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int env = blockIdx.x * WPB + warp;
+    if (env >= P.num_envs) return;
+    SmemLayout L = carve(smem_raw, P.cap, warp);
+    Warp w;
+    w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = 0;
+    float obs;
+    if (mask == nullptr || mask[env]) {
+        EnvState S = P.st[env];
+        obs = reset_env(P, w, env, S);
+        if (lane == 0) P.st[env] = S;
+        if (lane < MG_OBS_DIM) P.obs_cache[(size_t)env * MG_OBS_DIM + lane] = obs;
+    } else {
+        obs = lane < MG_OBS_DIM ? P.obs_cache[(size_t)env * MG_OBS_DIM + lane] : 0.0f;
+    }
+    if (obs_out && lane < MG_OBS_DIM) obs_out[(size_t)env * MG_OBS_DIM + lane] = obs;
+}
+
+// One environment transition per warp (E:388-457) + VecEnv auto-reset.
+__global__ void __launch_bounds__(WPB * 32)
+    mg_step_kernel(Params P, const float *__restrict__ act, float *__restrict__ obs_out, double *__restrict__ rew_out,
+                   uint8_t *__restrict__ term_out, uint8_t *__restrict__ trunc_out, float *__restrict__ term_obs_out,
+                   int32_t *__restrict__ n_elem_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int env = blockIdx.x * WPB + warp;
+    if (env >= P.num_envs) return;
+    SmemLayout L = carve(smem_raw, P.cap, warp);
+    init_mbar(L.mbar, lane);
+
+    EnvState S = P.st[env];
+    const size_t off = (size_t)env * P.cap;
+    Warp w;
+    w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = S.n;
+    // An env without a reference point (empty candidate list, E:736-738 returns None) has no
+    // defined continuation in the reference (its next step raises): it is reported truncated.
+    const bool dead = S.ref_index < 0 || S.n < 3;
+    if (!dead) stage_ring(w.ring, L.mbar, P.xy + off, S.n, lane, 0);
+
+    const int n = S.n, idx = dead ? 0 : S.ref_index;
+    const float a0 = act[(size_t)env * 3 + 0], a1 = act[(size_t)env * 3 + 1], a2 = act[(size_t)env * 3 + 2];
+    const P2 ref = dead ? mk(0, 0) : w.at(idx), right_p = dead ? mk(1, 0) : w.at(idx - 1);
+
+    // ---- action -> candidate vertex (E:783-792, E:202-210, D:112-137) ------------------------
+    P2 newp;
+    {
+        double ax = (double)np_round4f(a1), ay = (double)np_round4f(a2);
+        double th = 2 * PI - atan2(right_p.y - ref.y, right_p.x - ref.x);
+        double s, c;
+        sincos(th, &s, &c);
+        double ox = c * ax + s * ay;
+        double oy = -s * ax + c * ay;
+        ox *= S.base_length; oy *= S.base_length;
+        ox += ref.x; oy += ref.y;
+        newp = mk(np_round4(ox), np_round4(oy));
+    }
+
+    bool done = false, failed = true;
+    double reward = 0;
+    bool have_mesh = true, new_vertex = false;
+    int rule = 0;   // -1, +1, 0
+    if (dead) {
+        have_mesh = false;
+    } else if (n <= 5) {                            // E:428-430
+        reward = 10; done = true; have_mesh = false;
+    } else if (a0 <= -0.5f) rule = -1;
+    else if (a0 >= 0.5f) rule = 1;
+    else {
+        if (point_inside(w, newp, P.vid + off, S.n0)) {
+            if (find_same_point(w, newp)) rule = -1;
+            else new_vertex = true;
+        } else {
+            reward += S.n_elements ? -1.0 / S.n_elements : -1;      // E:279
+            have_mesh = false;
+        }
+    }
+
+    bool success = false;
+    if (have_mesh) {
+        P2 m[4]; int qi[4]; int ri;
+        const int ip1 = idx + 1 >= n ? idx + 1 - n : idx + 1, im1 = idx - 1 < 0 ? idx - 1 + n : idx - 1;
+        if (new_vertex) {
+            qi[0] = -1; qi[1] = im1; qi[2] = idx; qi[3] = ip1; ri = 2;
+        } else if (rule == -1) {
+            qi[0] = im1; qi[1] = idx; qi[2] = ip1; qi[3] = (idx + 2) % n; ri = 1;
+        } else {
+            qi[0] = (((idx - 2) % n) + n) % n; qi[1] = im1; qi[2] = idx; qi[3] = ip1; ri = 2;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) m[k] = qi[k] < 0 ? newp : w.at(qi[k]);
+        double corner[4];
+        bool valid = mesh_is_valid(w, m, corner);
+        if (valid) valid = !intersects_boundary(w, m, qi, ri, ref);
+        if (valid) {
+            success = true;
+            // ---- update_boundary (M:601-674) -----------------------------------------------
+            int nb[4];          // the four neighbours whose candidate keys are re-evaluated, in order
+            int t0 = 0, t1 = 0; // surviving quad vertices (no-new-vertex case), new indices
+            int elem_ids[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) elem_ids[k] = qi[k] < 0 ? S.next_vid : P.vid[off + qi[k]];
+            if (new_vertex) {
+                // insert P at index(ref) and remove ref: the slot is replaced in place
+                if (lane == 0) {
+                    w.ring[idx] = make_double2(newp.x, newp.y);
+                    P.xy[off + idx] = make_double2(newp.x, newp.y);
+                    P.vid[off + idx] = S.next_vid;
+                    P.key[off + idx] = CUDART_INF;
+                    if (P.ins_xy && S.next_vid - S.n0 < P.ins_cap)
+                        P.ins_xy[(size_t)env * P.ins_cap + (S.next_vid - S.n0)] = make_double2(newp.x, newp.y);
+                }
+                S.next_vid++;
+                __syncwarp();
+                nb[0] = ip1; nb[1] = im1; nb[2] = (idx + 2) % n; nb[3] = (((idx - 2) % n) + n) % n;
+            } else {
+                // remove the two middle quad vertices; compact ring + key/stamp/vid
+                const int r0 = qi[1], r1 = qi[2];
+                const int lo = r0 < r1 ? r0 : r1, hi = r0 < r1 ? r1 : r0;
+                // new index of old j (j not removed)
+                auto newpos = [&](int j) { return j - (j > lo ? 1 : 0) - (j > hi ? 1 : 0); };
+                // gather everything that moves into registers first (in-place shift)
+                for (int base = lo; base < n; base += 32) {
+                    int j = base + lane;
+                    bool mv = j < n && j != lo && j != hi;
+                    double2 v = make_double2(0, 0); double k = 0; int st = 0, id = 0;
+                    if (mv) { v = w.ring[j]; k = P.key[off + j]; st = P.stamp[off + j]; id = P.vid[off + j]; }
+                    __syncwarp();
+                    if (mv) {
+                        int q = newpos(j);
+                        w.ring[q] = v; P.xy[off + q] = v; P.key[off + q] = k; P.stamp[off + q] = st; P.vid[off + q] = id;
+                    }
+                    __syncwarp();
+                }
+                t0 = newpos(qi[0]); t1 = newpos(qi[3]);
+                w.n = n - 2;
+                const int nn = n - 2;
+                const int id = t0 > t1 ? t0 : t1;
+                nb[0] = id; nb[1] = id - 1 < 0 ? id - 1 + nn : id - 1; nb[2] = (id + 1) % nn;
+                nb[3] = (((id - 2) % nn) + nn) % nn;
+            }
+            S.n = w.n;
+            const int nn = w.n;
+            // ---- candidate keys of the four neighbours (lanes 2k, 2k+1 -> angles a0, a1 of nb[k]) --
+            double ang = 0;
+            if (lane < 8) {
+                int k = lane >> 1, v = nb[k], d = 1 + (lane & 1);
+                ang = cw_angle(w.at(v), w.at((v + d) % nn), w.at((((v - d) % nn) + nn) % nn));
+            }
+            double nb_a0[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                nb_a0[k] = shfl_d(ang, 2 * k);
+                double a1v = shfl_d(ang, 2 * k + 1);
+                double kv = cand_key_from_angles(nb_a0[k], a1v);
+                bool later_dup = false;
+#pragma unroll
+                for (int k2 = k + 1; k2 < 4; k2++) later_dup |= nb[k2] == nb[k];
+                if (lane == k && !later_dup) {
+                    P.key[off + nb[k]] = kv;
+                    P.stamp[off + nb[k]] = S.stamp_ctr - 1 - k;
+                }
+            }
+            S.stamp_ctr -= 4;
+            // ---- element log ------------------------------------------------------------------
+            if (P.elem && lane < 4 && S.n_elements < P.elem_cap)
+                P.elem[((size_t)env * P.elem_cap + S.n_elements) * 4 + lane] = elem_ids[lane];
+            S.n_elements++;
+            // ---- area (C:943-958), robust quality (C:881-892) -------------------------------
+            double e0 = pdist(m[0], m[3]), e1 = pdist(m[1], m[0]), e2 = pdist(m[2], m[1]), e3 = pdist(m[3], m[2]);
+            double sn = 0;
+            if (lane == 0) sn = sin(corner[0]);
+            if (lane == 1) sn = sin(corner[2]);
+            double mesh_area = 0.5 * e0 * e1 * shfl_d(sn, 0) + 0.5 * e2 * e3 * shfl_d(sn, 1);
+            S.current_area -= mesh_area;
+            double mn = fmin(fmin(e0, e1), fmin(e2, e3));
+            double q1 = sqrt(2.0) * mn / fmax(pdist(m[0], m[2]), pdist(m[1], m[3]));
+            double amin = fmin(fmin(corner[0], corner[1]), fmin(corner[2], corner[3]));
+            double amax = fmax(fmax(corner[0], corner[1]), fmax(corner[2], corner[3]));
+            double e_reward = sqrt(q1 * (amin / amax));
+            // ---- boundary quality (M:410-452) -----------------------------------------------
+            double b_reward;
+            __syncwarp();
+            if (new_vertex) b_reward = boundary_quality_new_vertex(w, idx, nb_a0[0], nb_a0[1]);
+            else {
+                // interior angles at the two survivors: among the re-evaluated neighbours
+                double g0 = 0, g1 = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (nb[k] == t0) g0 = nb_a0[k];
+                    if (nb[k] == t1) g1 = nb_a0[k];
+                }
+                b_reward = boundary_quality_no_new(w, t0, t1, g0, g1);
+            }
+            double quality = e_reward + 1 * (b_reward - 1);          // M:1754-1766
+            // ---- speed penalty (E:590-607) --------------------------------------------------
+            double min_area = S.area_min * S.area_min, crit = S.area_crit * S.area_crit, pen;
+            if (min_area <= mesh_area && mesh_area < crit) pen = (mesh_area - crit) / (crit - min_area);
+            else if (mesh_area < min_area) pen = -1;
+            else pen = 0;
+            reward += quality + pen;
+            failed = false;
+            if (nn <= 5) {                                   // E:345-351
+                reward += 10; done = true;
+                if (nn == 4) {
+                    if (P.elem && lane < 4 && S.n_elements < P.elem_cap)
+                        P.elem[((size_t)env * P.elem_cap + S.n_elements) * 4 + lane] = P.vid[off + lane];
+                    S.n_elements++;
+                }
+            }
+        } else {
+            reward += S.n_elements ? -1.0 / S.n_elements : -1;      // E:357
+        }
+    }
+
+    // ---- next state (E:361-386) -------------------------------------------------------------
+    float obs;
+    bool obs_none = false;
+    if (success) {
+        __syncwarp();
+        S.ref_index = find_reference_index(w, P.key + off, P.stamp + off);
+        if (S.ref_index >= 0) obs = compute_obs(w, S.ref_index, S.current_area / S.original_area, S.base_length);
+        else { obs = 0.0f; obs_none = true; }
+        S.failed_num = 0;
+    } else {
+        // nothing changed: the reference recomputes a bit-identical observation
+        obs = lane < MG_OBS_DIM ? P.obs_cache[(size_t)env * MG_OBS_DIM + lane] : 0.0f;
+        S.failed_num++;
+    }
+    bool is_complete = true;
+    if (failed && S.failed_num >= 100) { done = true; is_complete = false; }
+    bool terminated = done && is_complete, truncated = done && !is_complete;
+    if ((obs_none || dead) && !done) { done = true; truncated = true; }   // sentinel, see DESIGN.md
+    S.ep_return += reward; S.ep_len++;
+
+    // ---- statistics --------------------------------------------------------------------------
+    if (lane == 0) {
+        EnvStats T = P.stats[env];
+        T.steps++; T.sum_n += n;
+        if (success) { T.successes++; T.sum_n_success += n; }
+        if (done) {
+            T.episodes++; T.completed += terminated; T.truncated += truncated; T.elements += S.n_elements;
+            T.sum_return += S.ep_return; T.sum_length += S.ep_len;
+        }
+        P.stats[env] = T;
+        rew_out[env] = reward;
+        term_out[env] = terminated;
+        trunc_out[env] = truncated;
+        if (n_elem_out) n_elem_out[env] = S.n_elements;
+    }
+    if (term_obs_out && lane < MG_OBS_DIM) term_obs_out[(size_t)env * MG_OBS_DIM + lane] = done ? obs : 0.0f;
+
+    // ---- auto-reset (V:40-52, stock SB3 behaviour) -------------------------------------------
+    if (done && P.auto_reset) {
+        S.episode++;
+        __syncwarp();
+        obs = reset_env(P, w, env, S);
+    }
+    if (lane == 0) P.st[env] = S;
+    if (lane < MG_OBS_DIM) {
+        if (success || done) P.obs_cache[(size_t)env * MG_OBS_DIM + lane] = obs;
+        obs_out[(size_t)env * MG_OBS_DIM + lane] = obs;
+    }
+}
+
+// Uniform actions in Box([-1,-1.5,0],[1,1.5,1.5]) -- the synthetic policy of the benchmarks.
+__global__ void mg_sample_actions_kernel(int num_envs, uint64_t seed, uint64_t step, int64_t env_id_offset, float *act) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= num_envs) return;
+    unsigned long long g = (unsigned long long)(env_id_offset + e);
+    uint4 r = philox4x32(make_uint4((unsigned)step, (unsigned)(step >> 32), (unsigned)g, (unsigned)(g >> 32)),
+                         make_uint2((unsigned)seed, (unsigned)(seed >> 32) ^ 0xA5A5A5A5u));
+    const float lo[3] = {-1.0f, -1.5f, 0.0f}, hi[3] = {1.0f, 1.5f, 1.5f};
+    unsigned rr[3] = {r.x, r.y, r.z};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float u = (float)(rr[k] >> 8) * (1.0f / 16777216.0f);
+        act[(size_t)e * 3 + k] = lo[k] + (hi[k] - lo[k]) * u;
+    }
+}
+
+// Sum of the per-env counters -> one mg_episode_stats (one block).
+__global__ void mg_stats_kernel(int num_envs, EnvStats *stats, mg_episode_stats *out, int reset) {
+    long long a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double r = 0, l = 0;
+    for (int e = threadIdx.x; e < num_envs; e += blockDim.x) {
+        EnvStats T = stats[e];
+        a[0] += T.episodes; a[1] += T.completed; a[2] += T.truncated; a[3] += T.steps; a[4] += T.successes;
+        a[5] += T.elements; a[6] += T.sum_n; a[7] += T.sum_n_success; r += T.sum_return; l += T.sum_length;
+        if (reset) { EnvStats Z = {}; stats[e] = Z; }
+    }
+    __shared__ long long sa[8];
+    __shared__ double sr, sl;
+    if (threadIdx.x == 0) { for (int k = 0; k < 8; k++) sa[k] = 0; sr = 0; sl = 0; }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        long long v = a[k];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd((unsigned long long *)&sa[k], (unsigned long long)v);
+    }
+    r = warp_sum_d(r); l = warp_sum_d(l);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&sr, r); atomicAdd(&sl, l); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        out->episodes = sa[0]; out->completed = sa[1]; out->truncated = sa[2]; out->steps = sa[3];
+        out->successes = sa[4]; out->elements = sa[5]; out->sum_n = sa[6]; out->sum_n_success = sa[7];
+        out->sum_return = sr; out->sum_length = sl;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// random star polygon generator
+// ---------------------------------------------------------------------------------------------
+// Semantics of ui/GenerateRandomPolygon.py:5-49 (defaults :63) followed by the uniform densifier
+// of ui/tk-ui.py:252-276; the Python RNG stream is not reproduced, the
+// distribution is: K ~ U{min_coarse..max_coarse} angular steps ~ U(2pi/K (1-irr), 2pi/K (1+irr))
+// normalised to 2pi, start angle ~ U(0, 2pi), radius ~ clip(N(ave, spike*ave), 0.2 ave, 2 ave),
+// integer pixel coordinates (int() truncation), consecutive duplicates nudged apart, listed
+// clockwise, /100.  Each coarse edge is split into round(len/spacing) pieces with the spacing
+// chosen so that the total is even and within [min_verts, max_verts].
+__device__ int generate_polygon(const Params &P, Warp &w, long long global_env, int episode) {
+    const mg_polygen_cfg &G = P.gen;
+    const int lane = w.lane;
+    // coarse polygon lives in the warp's queue memory as ints (x, y) pairs: needs 2*max_coarse <= QCAP
+    int *cx = w.queue, *cy = w.queue + 64;
+    int *cnt = w.queue + 128;                      // pieces per coarse edge
+    uint2 key = make_uint2((unsigned)P.seed, (unsigned)(P.seed >> 32));
+    unsigned long long g = (unsigned long long)global_env;
+    auto draw = [&](unsigned slot) {
+        return philox4x32(make_uint4((unsigned)g, (unsigned)(g >> 32), (unsigned)episode, slot), key);
+    };
+    uint4 r0 = draw(0);
+    int K = G.min_coarse + (int)(u01(r0.x, r0.y) * (G.max_coarse - G.min_coarse + 1));
+    if (K > G.max_coarse) K = G.max_coarse;
+    if (K > 64) K = 64;
+    double start = 2 * PI * u01(r0.z, r0.w);
+    // angular steps
+    double irr = G.irregularity * 2 * PI / K;
+    double lower = 2 * PI / K - irr, upper = 2 * PI / K + irr;
+    double step = 0, rad = 0;
+    for (int base = 0; base < K; base += 32) {      // K <= 64: at most two rounds, kept in registers below
+        (void)base;
+    }
+    // lane handles vertices lane and lane+32
+    double st[2] = {0, 0}, rd[2] = {0, 0};
+    for (int t = 0; t < 2; t++) {
+        int i = lane + 32 * t;
+        if (i < K) {
+            uint4 r = draw(1 + i);
+            st[t] = lower + (upper - lower) * u01(r.x, r.y);
+            // Box-Muller gaussian
+            uint4 r2 = draw(100 + i);
+            double u1 = u01(r2.x, r2.y), u2 = u01(r2.z, r2.w);
+            double gs = sqrt(-2.0 * log(1.0 - u1)) * cos(2 * PI * u2);
+            double rr = G.ave_radius + gs * G.spikeyness * G.ave_radius;
+            rd[t] = fmin(fmax(rr, 0.2 * G.ave_radius), 2 * G.ave_radius);
+        }
+    }
+    (void)step; (void)rad;
+    double tot = warp_sum_d(st[0] + st[1]);
+    double kscale = tot / (2 * PI);
+    // exclusive prefix of the normalised steps -> angle of vertex i
+    for (int t = 0; t < 2; t++) {
+        double v = st[t] / kscale;
+        double inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            double y = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += y;
+        }
+        double carry = t == 0 ? 0.0 : shfl_d(st[0], 31);   // st[0] is overwritten with inclusive sums below
+        double ang = start + carry + inc - v;
+        if (t == 0) st[0] = inc; else st[1] = inc;
+        int i = lane + 32 * t;
+        if (i < K) {
+            cx[i] = (int)(G.ctr_x + rd[t] * cos(ang));
+            cy[i] = (int)(G.ctr_y + rd[t] * sin(ang));
+        }
+    }
+    __syncwarp();
+    // nudge consecutive duplicates (the reference has no defined behaviour on zero-length edges)
+    if (lane == 0) {
+        for (int i = 0; i < K; i++) {
+            int p = i == 0 ? K - 1 : i - 1;
+            if (cx[i] == cx[p] && cy[i] == cy[p]) cx[i] += 1;
+        }
+    }
+    __syncwarp();
+    // clockwise order = reversed generation order (angles increase counter-clockwise); edge e goes
+    // from coarse vertex c(e) to c(e+1) with c(e) = K-1-e
+    double len[2] = {0, 0};
+    for (int t = 0; t < 2; t++) {
+        int e = lane + 32 * t;
+        if (e < K) {
+            int a = K - 1 - e, b = a == 0 ? K - 1 : a - 1;
+            double dx = (double)(cx[b] - cx[a]), dy = (double)(cy[b] - cy[a]);
+            len[t] = sqrt(dx * dx + dy * dy);
+        }
+    }
+    double perim = warp_sum_d(len[0] + len[1]);
+    // target count ~ U{min_verts..max_verts}, then fix parity/limits by adjusting the spacing
+    uint4 r3 = draw(200);
+    int target = G.min_verts + (int)(u01(r3.x, r3.y) * (G.max_verts - G.min_verts + 1));
+    if (target > G.max_verts) target = G.max_verts;
+    int maxv = G.max_verts < P.cap ? G.max_verts : P.cap;
+    int total = 0;
+    double spacing = perim / target;
+    for (int it = 0; it < 8; it++) {
+        int c0 = 0, c1 = 0;
+        if (lane < K) c0 = max(1, (int)rint(len[0] / spacing));
+        if (lane + 32 < K) c1 = max(1, (int)rint(len[1] / spacing));
+        total = __reduce_add_sync(FULL, c0 + c1);
+        if (lane < K) cnt[lane] = c0;
+        if (lane + 32 < K) cnt[lane + 32] = c1;
+        if (total > maxv) { spacing *= 1.02 * (double)total / maxv; continue; }
+        if (total < G.min_verts) { spacing *= 0.98 * (double)total / G.min_verts; continue; }
+        break;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        // force an even total (tk-ui.py:267-269) by adding one piece to the longest-per-piece edge
+        if (total & 1) {
+            int best = 0; double bl = -1;
+            for (int e = 0; e < K; e++) {
+                int a = K - 1 - e, b = a == 0 ? K - 1 : a - 1;
+                double dx = (double)(cx[b] - cx[a]), dy = (double)(cy[b] - cy[a]);
+                double l = sqrt(dx * dx + dy * dy) / cnt[e];
+                if (l > bl) { bl = l; best = e; }
+            }
+            if (total + 1 <= maxv) { cnt[best]++; total++; }
+            else {
+                for (int e = 0; e < K; e++) if (cnt[e] > 1) { cnt[e]--; total--; break; }
+            }
+        }
+        // exclusive prefix -> start offset of each coarse edge, stored in place of cnt (cnt in cnt+64)
+        int acc = 0;
+        for (int e = 0; e < K; e++) { int c = cnt[e]; cnt[64 + e] = acc; acc += c; }
+        cnt[63] = acc;
+    }
+    __syncwarp();
+    total = cnt[63];
+    // emit the densified ring: edge e contributes cnt[e] points starting at coarse vertex c(e)
+    for (int e = 0; e < K; e++) {
+        int a = K - 1 - e, b = a == 0 ? K - 1 : a - 1;
+        int c = cnt[e], o = cnt[64 + e];
+        double xa = cx[a], ya = cy[a], xb = cx[b], yb = cy[b];
+        for (int k = lane; k < c; k += 32) {
+            double f = (double)k / c;
+            w.ring[o + k] = make_double2((xa + (xb - xa) * f) / 100.0, (ya + (yb - ya) * f) / 100.0);
+        }
+    }
+    __syncwarp();
+    return total;
+}
+
+}  // namespace mg

@@ -1,0 +1,83 @@
+// Device-resident state of the batched BoudaryEnv and the kernel parameter block.
+// Layout in HBM (env-major, `cap` = max_verts rounded up to a multiple of 2):
+//   xy    double2[num_envs][cap]   boundary vertex ring (updated_boundary.vertices), index 0 first
+//   key   double [num_envs][cap]   cached candidate key in degrees (M:228-257), +inf = not a candidate
+//   stamp int32  [num_envs][cap]   tie-break stamp: list index at rebuild, decreasing negatives later
+//   vid   int32  [num_envs][cap]   vertex ids (0..n0-1 original, n0+k k-th inserted)
+//   st    EnvState[num_envs]       scalars (128 B)
+//   stats EnvStats[num_envs]       per-env episode counters (no atomics on the step path)
+//   obs   float  [num_envs][18]    cached observation (failed steps return it unchanged)
+#pragma once
+#include <stdint.h>
+
+#include "../../include/meshgen_b200.h"
+
+namespace mg {
+
+struct __align__(16) EnvState {
+    int32_t n;            // live boundary size
+    int32_t ref_index;    // index of the reference point, -1 = none
+    int32_t n_elements;   // len(generated_meshes)
+    int32_t failed_num;   // consecutive failed steps
+    int32_t next_vid;     // id of the next inserted vertex
+    int32_t stamp_ctr;    // decreasing stamp counter for incremental candidate inserts
+    int32_t domain;       // template index (domain mode)
+    int32_t ep_len;
+    int32_t n0;           // size of the episode's original polygon
+    int32_t episode;      // episodes finished by this env (random mode: polygon counter)
+    double base_length;
+    double current_area;
+    double original_area;
+    double area_min;
+    double area_crit;
+    double ep_return;
+    int64_t pad[5];
+};
+static_assert(sizeof(EnvState) == 128, "EnvState size");
+
+struct EnvStats {
+    long long episodes, completed, truncated, steps, successes, elements, sum_n, sum_n_success;
+    double sum_return, sum_length;
+};
+
+struct DomainScalars {
+    int32_t n0;
+    int32_t ref_index;
+    double base_length;
+    double original_area;
+    double area_min;
+    double area_crit;
+};
+
+struct Params {
+    int num_envs;
+    int cap;
+    int auto_reset;      // 1 = VecEnv convention (reset in place when done), 0 = plain Gym env
+    // env state
+    double2 *xy;
+    double *key;
+    int32_t *stamp;
+    int32_t *vid;
+    EnvState *st;
+    EnvStats *stats;
+    float *obs_cache;
+    // element log: quads as 4 vertex ids, coordinates of inserted vertices
+    int32_t *elem;       // [num_envs][elem_cap][4]
+    double2 *ins_xy;     // [num_envs][ins_cap]
+    int elem_cap;
+    int ins_cap;
+    // domain templates
+    int n_domains;
+    const double2 *t_xy;      // [n_domains][cap]
+    const double *t_key;      // [n_domains][cap]
+    const int32_t *t_stamp;   // [n_domains][cap]
+    const DomainScalars *t_sc;
+    const float *t_obs;       // [n_domains][18]
+    // random-polygon mode
+    int random_mode;
+    uint64_t seed;
+    int64_t env_id_offset;
+    mg_polygen_cfg gen;
+};
+
+}  // namespace mg

@@ -1,0 +1,135 @@
+"""GPU parity (pytest -m gpu): the CUDA path, driven through the C ABI (ctypes ->
+libmeshgen_b200.so), against (a) the golden traces recorded from the live reference env and
+(b) the C oracle on fresh seeded action streams.  Bar: element counts, boundary vertex ids,
+validity decisions, done flags and float32 observations bit-exact; rewards within 1e-9 relative
+(the tolerance BASELINE.json states and the reference's own equivalence test uses,
+v2/tests/mesh_rl/test_boundary_env_equiv.py:236)."""
+import numpy as np
+import pytest
+
+from helpers import TRACES, action_stream, assert_rollout_matches, load_domains, load_trace
+
+pytestmark = pytest.mark.gpu
+
+REWARD_TOL = 1e-9
+
+
+def _mk(domains, n, **kw):
+    from reinforcementlearning4meshgeneration_b200 import BatchedBoudaryEnv
+    return BatchedBoudaryEnv(domains, num_envs=n, **kw)
+
+
+@pytest.mark.parametrize("name", TRACES)
+def test_golden_trace_and_oracle_streams(name):
+    from gpu_helpers import per_env, run_gpu
+    from oracle.c_oracle import OracleEnv
+    tr = load_trace(name)
+    T = len(tr["reward"])
+    N = 6
+    env = _mk([tr["xy0"]], N)
+    obs0 = env.reset().cpu().numpy()
+    for e in range(N):
+        assert np.array_equal(obs0[e], tr["reset_obs"]), f"{name}: reset obs differs (env {e})"
+    st = env.get_state(0)
+    assert st["ref_index"] == int(tr["reset_ref_index"]) and st["base_length"] == float(tr["reset_base_length"])
+    assert np.allclose(st["area_range"], tr["area_range"], rtol=1e-12, atol=0)
+    streams = [tr["actions"]] + [action_stream(1000 + 17 * k, T) for k in range(1, N)]
+    acts = np.stack(streams, axis=1)
+    res = run_gpu(env, acts, state_every=8, state_envs=(0, 1))
+    # (a) env 0 against the golden trace of the live reference
+    assert_rollout_matches(per_env(res, 0), tr, f"gpu vs golden[{name}]", reward_tol=REWARD_TOL)
+    # (b) envs 1.. against the C oracle
+    for e in range(1, N):
+        o = OracleEnv(tr["xy0"], original_area=float(tr["original_area"]))
+        exp = o.rollout(streams[e])
+        assert_rollout_matches(per_env(res, e), exp, f"gpu vs oracle[{name}, env {e}]", reward_tol=REWARD_TOL)
+    # (c) internal state (boundary ids + coordinates, reference index, candidate order) against a stepwise oracle
+    for e in (0, 1):
+        o = OracleEnv(tr["xy0"], original_area=float(tr["original_area"]))
+        for t in range(T):
+            obs, r, te, tru, _ = o.step(streams[e][t])
+            if te or tru or obs is None:
+                o.reset()
+            if (t, e) in res["states"]:
+                s = res["states"][(t, e)]
+                ids, xy = o.boundary()
+                assert s["n"] == o.n and np.array_equal(s["ids"], ids), f"{name}: boundary ids differ at step {t} env {e}"
+                assert np.array_equal(s["xy"], xy), f"{name}: boundary coordinates differ at step {t} env {e}"
+                assert s["ref_index"] == o.ref_index and s["n_elements"] == o.n_elements
+                assert s["failed_num"] == o.failed_num and s["base_length"] == o.base_length
+                cid, ckey = o.candidates()
+                assert [c[0] for c in s["candidates"]] == cid.tolist(), f"{name}: candidate order differs at step {t}"
+                assert [c[1] for c in s["candidates"]] == ckey.tolist(), f"{name}: candidate keys differ at step {t}"
+                assert abs(s["current_area"] - o.current_area) <= 1e-12 * max(1.0, abs(o.current_area))
+
+
+def test_mixed_domains_batch():
+    """d1/d2/d3 + others in one batch (BASELINE config 2 layout, small): every env against the oracle."""
+    from gpu_helpers import per_env, run_gpu
+    from oracle.c_oracle import OracleEnv
+    doms, areas = load_domains()
+    names = ["boundary16", "boundary15", "test1", "random1_1", "test3", "basic2", "boundary_hole_r3", "tool", "bird", "fat"]
+    N, T = 40, 300
+    env_domain = np.arange(N) % len(names)
+    env = _mk([doms[k] for k in names], N, env_domain=env_domain)
+    env.reset()
+    streams = [action_stream(500 + e, T) for e in range(N)]
+    res = run_gpu(env, np.stack(streams, axis=1))
+    for e in range(N):
+        k = names[env_domain[e]]
+        o = OracleEnv(doms[k], original_area=areas[k])
+        assert_rollout_matches(per_env(res, e), o.rollout(streams[e]), f"gpu vs oracle[{k}, env {e}]", reward_tol=REWARD_TOL)
+
+
+def test_partial_reset_and_host_step():
+    from oracle.c_oracle import OracleEnv
+    import torch
+    doms, areas = load_domains()
+    xy = doms["dolphine3"]
+    N = 5
+    env = _mk([xy], N)
+    env.reset()
+    oracles = [OracleEnv(xy, original_area=areas["dolphine3"]) for _ in range(N)]
+    streams = [action_stream(77 + e, 120) for e in range(N)]
+    for t in range(120):
+        a = np.stack([s[t] for s in streams])
+        out = env.step_host(a)
+        for e in range(N):
+            obs, r, te, tru, _ = oracles[e].step(streams[e][t])
+            if te or tru:
+                obs = oracles[e].reset()
+            assert np.array_equal(out["obs"][e], obs), f"host step obs differs t={t} env={e}"
+            assert abs(out["reward"][e] - r) <= REWARD_TOL * max(1, abs(r))
+            assert bool(out["terminated"][e]) == te and bool(out["truncated"][e]) == tru
+        if t == 60:
+            mask = torch.tensor([0, 1, 0, 1, 0], dtype=torch.uint8)
+            obs = env.reset(mask).cpu().numpy()
+            for e in (1, 3):
+                assert np.array_equal(obs[e], oracles[e].reset())
+            for e in (0, 2, 4):
+                assert np.array_equal(obs[e], oracles[e].obs())
+
+
+def test_stats_and_element_log():
+    from gpu_helpers import run_gpu
+    from oracle.c_oracle import OracleEnv
+    tr = load_trace("star")
+    T = 200
+    env = _mk([tr["xy0"]], 3)
+    env.reset()
+    streams = [tr["actions"][:T], action_stream(3, T), action_stream(4, T)]
+    res = run_gpu(env, np.stack(streams, axis=1))
+    s = env.stats()
+    assert s["steps"] == 3 * T
+    done = (res["terminated"] | res["truncated"]).astype(bool)
+    assert s["episodes"] == int(done.sum()) and s["completed"] == int(res["terminated"].sum())
+    assert s["elements"] == int(res["n_elements"][done].sum())
+    # element log of the running episode of env 1 against the oracle
+    o = OracleEnv(tr["xy0"], original_area=float(tr["original_area"]))
+    for t in range(T):
+        obs, r, te, tru, _ = o.step(streams[1][t])
+        if te or tru or obs is None:
+            o.reset()
+    quads, vxy, ne = env.get_elements(1)
+    assert ne == o.n_elements and np.array_equal(quads, o.elements())
+    assert np.array_equal(vxy, o.vertex_xy())
