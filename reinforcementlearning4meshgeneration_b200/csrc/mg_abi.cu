@@ -208,9 +208,9 @@ int mg_set_random(mg_handle h, uint64_t seed, const mg_polygen_cfg *cfg, int64_t
         c.ctr_x = 250; c.ctr_y = 250; c.ave_radius = 100; c.irregularity = 0.55; c.spikeyness = 0.7;
         c.min_coarse = 8; c.max_coarse = 24; c.min_verts = 64; c.max_verts = 512;
     }
-    if (c.min_coarse < 3 || c.max_coarse < c.min_coarse || c.max_coarse > 64 || c.min_verts < 8 || c.max_verts < c.min_verts ||
+    if (c.min_coarse < 3 || c.max_coarse < c.min_coarse || c.max_coarse > 32 || c.min_verts < 8 || c.max_verts < c.min_verts ||
         c.max_verts > h->max_verts || c.min_verts < c.max_coarse)
-        return fail(h, MG_ERR_ARG, "mg_set_random: bad generator configuration (need 3<=min_coarse<=max_coarse<=64, "
+        return fail(h, MG_ERR_ARG, "mg_set_random: bad generator configuration (need 3<=min_coarse<=max_coarse<=32, "
                                    "max_coarse<=min_verts<=max_verts<=handle max_verts)");
     MG_CUDA(h, cudaSetDevice(h->device));
     MG_CUDA(h, cudaMemset(h->P.st, 0, sizeof(EnvState) * h->num_envs));

@@ -1016,148 +1016,127 @@ __global__ void mg_stats_kernel(int num_envs, EnvStats *stats, mg_episode_stats 
 }
 
 // ---------------------------------------------------------------------------------------------
-// random star polygon generator
+// random star polygon generator (BASELINE configs 3/4)
 // ---------------------------------------------------------------------------------------------
-// Semantics of ui/GenerateRandomPolygon.py:5-49 (defaults :63) followed by the uniform densifier
-// of ui/tk-ui.py:252-276; the Python RNG stream is not reproduced, the
-// distribution is: K ~ U{min_coarse..max_coarse} angular steps ~ U(2pi/K (1-irr), 2pi/K (1+irr))
-// normalised to 2pi, start angle ~ U(0, 2pi), radius ~ clip(N(ave, spike*ave), 0.2 ave, 2 ave),
-// integer pixel coordinates (int() truncation), consecutive duplicates nudged apart, listed
-// clockwise, /100.  Each coarse edge is split into round(len/spacing) pieces with the spacing
-// chosen so that the total is even and within [min_verts, max_verts].
+// Semantics of ui/GenerateRandomPolygon.py:5-49 (defaults :63) followed by the uniform-density
+// densifier of ui/tk-ui.py:252-276; the Python RNG stream is not reproducible on a GPU
+// (SURVEY.md row 7), the distribution is:
+//   K ~ U{min_coarse..max_coarse} coarse vertices, angular steps ~ U(2pi/K -+ irr*2pi/K)
+//   normalised to 2pi, start angle ~ U(0, 2pi), radius ~ clip(N(ave, spike*ave), 0.2 ave, 2 ave)
+//   (floor 0.2 ave instead of 0: the reference crashes on zero-length edges),
+//   integer pixel coordinates by int() truncation, consecutive duplicates nudged apart, order
+//   reversed to clockwise.  Densifier with spacing A = perimeter / target, target ~ U{min..max}:
+//   coarse edge prev->cur of length L gets x = round((2L - 2A) / 2A) interior points at
+//   prev + A (j+1) dir, j < x, followed by cur; if the total is odd the middle point of the last
+//   edge is dropped (tk-ui.py:267-269).  Coordinates / 100 (geometry.py:46).
+// One coarse vertex per lane (max_coarse <= 32).  The ring is written to w.ring[0..n).
 __device__ int generate_polygon(const Params &P, Warp &w, long long global_env, int episode) {
     const mg_polygen_cfg &G = P.gen;
     const int lane = w.lane;
-    // coarse polygon lives in the warp's queue memory as ints (x, y) pairs: needs 2*max_coarse <= QCAP
-    int *cx = w.queue, *cy = w.queue + 64;
-    int *cnt = w.queue + 128;                      // pieces per coarse edge
-    uint2 key = make_uint2((unsigned)P.seed, (unsigned)(P.seed >> 32));
-    unsigned long long g = (unsigned long long)global_env;
+    int *cx = w.queue, *cy = w.queue + 32, *cnt = w.queue + 64, *offs = w.queue + 96;
+    const uint2 key = make_uint2((unsigned)P.seed, (unsigned)(P.seed >> 32));
+    const unsigned long long g = (unsigned long long)global_env;
     auto draw = [&](unsigned slot) {
         return philox4x32(make_uint4((unsigned)g, (unsigned)(g >> 32), (unsigned)episode, slot), key);
     };
-    uint4 r0 = draw(0);
-    int K = G.min_coarse + (int)(u01(r0.x, r0.y) * (G.max_coarse - G.min_coarse + 1));
-    if (K > G.max_coarse) K = G.max_coarse;
-    if (K > 64) K = 64;
-    double start = 2 * PI * u01(r0.z, r0.w);
-    // angular steps
-    double irr = G.irregularity * 2 * PI / K;
-    double lower = 2 * PI / K - irr, upper = 2 * PI / K + irr;
-    double step = 0, rad = 0;
-    for (int base = 0; base < K; base += 32) {      // K <= 64: at most two rounds, kept in registers below
-        (void)base;
+    const uint4 r0 = draw(0);
+    int K = G.min_coarse + (int)(u01(r0.x, r0.y) * (double)(G.max_coarse - G.min_coarse + 1));
+    K = min(K, G.max_coarse);
+    const double start = 2 * PI * u01(r0.z, r0.w);
+    const double irr = fmin(fmax(G.irregularity, 0.0), 1.0) * 2 * PI / K;
+    const double spike = fmin(fmax(G.spikeyness, 0.0), 1.0) * G.ave_radius;
+    const double lower = 2 * PI / K - irr, upper = 2 * PI / K + irr;
+    double step = 0, radius = 0;
+    if (lane < K) {
+        uint4 r = draw(1 + lane);
+        step = lower + (upper - lower) * u01(r.x, r.y);
+        uint4 r2 = draw(65 + lane);
+        double u1 = u01(r2.x, r2.y), u2 = u01(r2.z, r2.w);
+        double gs = sqrt(-2.0 * log(1.0 - u1)) * cos(2 * PI * u2);      // Box-Muller
+        radius = fmin(fmax(G.ave_radius + gs * spike, 0.2 * G.ave_radius), 2 * G.ave_radius);
     }
-    // lane handles vertices lane and lane+32
-    double st[2] = {0, 0}, rd[2] = {0, 0};
-    for (int t = 0; t < 2; t++) {
-        int i = lane + 32 * t;
-        if (i < K) {
-            uint4 r = draw(1 + i);
-            st[t] = lower + (upper - lower) * u01(r.x, r.y);
-            // Box-Muller gaussian
-            uint4 r2 = draw(100 + i);
-            double u1 = u01(r2.x, r2.y), u2 = u01(r2.z, r2.w);
-            double gs = sqrt(-2.0 * log(1.0 - u1)) * cos(2 * PI * u2);
-            double rr = G.ave_radius + gs * G.spikeyness * G.ave_radius;
-            rd[t] = fmin(fmax(rr, 0.2 * G.ave_radius), 2 * G.ave_radius);
-        }
-    }
-    (void)step; (void)rad;
-    double tot = warp_sum_d(st[0] + st[1]);
-    double kscale = tot / (2 * PI);
-    // exclusive prefix of the normalised steps -> angle of vertex i
-    for (int t = 0; t < 2; t++) {
-        double v = st[t] / kscale;
-        double inc = v;
+    const double ksum = warp_sum_d(step) / (2 * PI);
+    step = step / ksum;
+    double incl = step;                                // inclusive prefix of the normalised steps
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            double y = __shfl_up_sync(FULL, inc, o);
-            if (lane >= o) inc += y;
-        }
-        double carry = t == 0 ? 0.0 : shfl_d(st[0], 31);   // st[0] is overwritten with inclusive sums below
-        double ang = start + carry + inc - v;
-        if (t == 0) st[0] = inc; else st[1] = inc;
-        int i = lane + 32 * t;
-        if (i < K) {
-            cx[i] = (int)(G.ctr_x + rd[t] * cos(ang));
-            cy[i] = (int)(G.ctr_y + rd[t] * sin(ang));
-        }
+    for (int o = 1; o < 32; o <<= 1) {
+        double y = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane < K) {
+        double ang = start + (incl - step);
+        double s, c;
+        sincos(ang, &s, &c);
+        cx[lane] = (int)(G.ctr_x + radius * c);
+        cy[lane] = (int)(G.ctr_y + radius * s);
     }
     __syncwarp();
-    // nudge consecutive duplicates (the reference has no defined behaviour on zero-length edges)
-    if (lane == 0) {
+    if (lane == 0) {                                   // distinct consecutive vertices
         for (int i = 0; i < K; i++) {
             int p = i == 0 ? K - 1 : i - 1;
             if (cx[i] == cx[p] && cy[i] == cy[p]) cx[i] += 1;
         }
+        if (cx[0] == cx[K - 1] && cy[0] == cy[K - 1]) cy[0] += 1;
     }
     __syncwarp();
-    // clockwise order = reversed generation order (angles increase counter-clockwise); edge e goes
-    // from coarse vertex c(e) to c(e+1) with c(e) = K-1-e
-    double len[2] = {0, 0};
-    for (int t = 0; t < 2; t++) {
-        int e = lane + 32 * t;
-        if (e < K) {
-            int a = K - 1 - e, b = a == 0 ? K - 1 : a - 1;
-            double dx = (double)(cx[b] - cx[a]), dy = (double)(cy[b] - cy[a]);
-            len[t] = sqrt(dx * dx + dy * dy);
+    // clockwise order: c(e) = coarse[K-1-e]; edge e runs from c(e-1) to c(e)
+    double L = 0, dx = 0, dy = 0, pxv = 0, pyv = 0, cxv = 0, cyv = 0;
+    if (lane < K) {
+        int cur = K - 1 - lane, prv = lane == 0 ? 0 : K - lane;          // c(e-1) = coarse[K-e], c(-1) = coarse[0]
+        pxv = cx[prv]; pyv = cy[prv]; cxv = cx[cur]; cyv = cy[cur];
+        dx = cxv - pxv; dy = cyv - pyv;
+        L = sqrt(dx * dx + dy * dy);
+    }
+    const double perim = warp_sum_d(L);
+    const uint4 r3 = draw(200);
+    const int maxv = min(G.max_verts, P.cap);
+    int target = G.min_verts + (int)(u01(r3.x, r3.y) * (double)(maxv - G.min_verts + 1));
+    target = min(target, maxv);
+    double A = perim / target;
+    int c = 0, total = 0;
+    for (int it = 0; it < 16; it++) {
+        c = 0;
+        if (lane < K) {
+            double x = rint((2 * L - A - A) / (A + A));
+            c = (x > 0 ? (int)x : 0) + 1;
         }
+        total = __reduce_add_sync(FULL, c);
+        if (total > maxv) A *= 1.01 * (double)total / maxv;
+        else if (total < G.min_verts + 1) A *= 0.99 * (double)total / (G.min_verts + 1);
+        else break;
     }
-    double perim = warp_sum_d(len[0] + len[1]);
-    // target count ~ U{min_verts..max_verts}, then fix parity/limits by adjusting the spacing
-    uint4 r3 = draw(200);
-    int target = G.min_verts + (int)(u01(r3.x, r3.y) * (G.max_verts - G.min_verts + 1));
-    if (target > G.max_verts) target = G.max_verts;
-    int maxv = G.max_verts < P.cap ? G.max_verts : P.cap;
-    int total = 0;
-    double spacing = perim / target;
-    for (int it = 0; it < 8; it++) {
-        int c0 = 0, c1 = 0;
-        if (lane < K) c0 = max(1, (int)rint(len[0] / spacing));
-        if (lane + 32 < K) c1 = max(1, (int)rint(len[1] / spacing));
-        total = __reduce_add_sync(FULL, c0 + c1);
-        if (lane < K) cnt[lane] = c0;
-        if (lane + 32 < K) cnt[lane + 32] = c1;
-        if (total > maxv) { spacing *= 1.02 * (double)total / maxv; continue; }
-        if (total < G.min_verts) { spacing *= 0.98 * (double)total / G.min_verts; continue; }
-        break;
+    // exclusive prefix of the per-edge counts
+    int incl_c = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(FULL, incl_c, o);
+        if (lane >= o) incl_c += y;
     }
+    if (lane < K) { cnt[lane] = c; offs[lane] = incl_c - c; }
     __syncwarp();
-    if (lane == 0) {
-        // force an even total (tk-ui.py:267-269) by adding one piece to the longest-per-piece edge
-        if (total & 1) {
-            int best = 0; double bl = -1;
-            for (int e = 0; e < K; e++) {
-                int a = K - 1 - e, b = a == 0 ? K - 1 : a - 1;
-                double dx = (double)(cx[b] - cx[a]), dy = (double)(cy[b] - cy[a]);
-                double l = sqrt(dx * dx + dy * dy) / cnt[e];
-                if (l > bl) { bl = l; best = e; }
-            }
-            if (total + 1 <= maxv) { cnt[best]++; total++; }
-            else {
-                for (int e = 0; e < K; e++) if (cnt[e] > 1) { cnt[e]--; total--; break; }
-            }
-        }
-        // exclusive prefix -> start offset of each coarse edge, stored in place of cnt (cnt in cnt+64)
-        int acc = 0;
-        for (int e = 0; e < K; e++) { int c = cnt[e]; cnt[64 + e] = acc; acc += c; }
-        cnt[63] = acc;
-    }
-    __syncwarp();
-    total = cnt[63];
-    // emit the densified ring: edge e contributes cnt[e] points starting at coarse vertex c(e)
+    const bool odd = (total & 1) != 0;
+    const int c_last = cnt[K - 1];
+    const int drop = odd ? c_last / 2 : -1;             // index popped from the last edge's points
     for (int e = 0; e < K; e++) {
-        int a = K - 1 - e, b = a == 0 ? K - 1 : a - 1;
-        int c = cnt[e], o = cnt[64 + e];
-        double xa = cx[a], ya = cy[a], xb = cx[b], yb = cy[b];
-        for (int k = lane; k < c; k += 32) {
-            double f = (double)k / c;
-            w.ring[o + k] = make_double2((xa + (xb - xa) * f) / 100.0, (ya + (yb - ya) * f) / 100.0);
+        const int ce = cnt[e], oe = offs[e];
+        const double epx = shfl_d(pxv, e), epy = shfl_d(pyv, e), ecx = shfl_d(cxv, e), ecy = shfl_d(cyv, e);
+        const double eL = shfl_d(L, e);
+        const double ux = (ecx - epx) / eL, uy = (ecy - epy) / eL;
+        for (int j = lane; j < ce; j += 32) {
+            double X, Y;
+            if (j == ce - 1) { X = ecx; Y = ecy; }
+            else { double d = A * (j + 1); X = epx + d * ux; Y = epy + d * uy; }
+            int pos = oe + j;
+            if (e == K - 1 && drop >= 0) {
+                if (j == drop) continue;
+                if (j > drop) pos--;
+            }
+            if (pos < P.cap) w.ring[pos] = make_double2(X / 100.0, Y / 100.0);
         }
     }
     __syncwarp();
-    return total;
+    int n = odd ? total - 1 : total;
+    return n <= P.cap ? n : (P.cap & ~1);
 }
 
 }  // namespace mg
