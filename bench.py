@@ -222,6 +222,11 @@ def run_gpu(args):
         torch.cuda.synchronize(dev)
 
     step_idx = 0
+    # burn-in (setup, untimed): all envs start their first episode together; run until resets are
+    # spread over the steps so that the timed region sees the steady-state mix of episode phases
+    for _ in range(args.burn_in):
+        env.step(env.sample_actions(SEED, step_idx))
+        step_idx += 1
     for _ in range(args.warmup):
         env.step(env.sample_actions(SEED, step_idx))
         step_idx += 1
@@ -322,7 +327,7 @@ def run_gpu(args):
                                     "c2": "c2: paper domains d1/d2/d3 (boundary16/boundary15/test1)",
                                     "c1": "c1: BoudaryEnv(boundary()) 30 vertices"}[args.workload],
                        "envs_per_gpu": N, "global_envs": N * world, "policy": "uniform actions in the action box (Philox)",
-                       "parallelism": f"env-sharded x{world}",
+                       "parallelism": f"env-sharded x{world}", "burn_in_steps": args.burn_in,
                        "l2": "L2 flushed between timed steps" if need_flush else f"state {state_bytes >> 20} MiB > L2"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
@@ -359,6 +364,7 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's BASELINE size)")
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--burn-in", type=int, default=1500, help="untimed setup steps that de-synchronise the episodes")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3

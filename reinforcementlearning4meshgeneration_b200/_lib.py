@@ -11,7 +11,7 @@ import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_PKG, "lib", "libmeshgen_b200.so")
+LIB_PATH = os.environ.get("MESHGEN_LIB") or os.path.join(_PKG, "lib", "libmeshgen_b200.so")  # MESHGEN_LIB: tuning variants
 CSRC = os.path.join(_PKG, "csrc")
 
 NVCC_FLAGS = [

@@ -31,6 +31,8 @@ struct mg_env_s {
     bool ready = false;       // domains or generator configured
     bool was_reset = false;
     int64_t launches = 0;
+    int step_parity = 0;
+    int sm_count = 148;
     size_t smem = 0;
     std::string err;
 };
@@ -64,7 +66,9 @@ int grid_for(int n) { return (n + WPB - 1) / WPB; }
 int configure_kernels(mg_handle h) {
     h->smem = smem_bytes(h->P.cap);
     if (h->smem > 48 * 1024) {
-        MG_CUDA(h, cudaFuncSetAttribute(mg_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        MG_CUDA(h, cudaFuncSetAttribute(mg_step_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        MG_CUDA(h, cudaFuncSetAttribute(mg_step_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        MG_CUDA(h, cudaFuncSetAttribute(mg_step_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         MG_CUDA(h, cudaFuncSetAttribute(mg_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         MG_CUDA(h, cudaFuncSetAttribute(mg_template_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     }
@@ -96,6 +100,7 @@ int mg_create(mg_handle *out, int device, int num_envs, int max_verts) {
     if (!h) return fail(nullptr, MG_ERR_ARG, "mg_create: out of host memory");
     h->device = device; h->num_envs = num_envs; h->max_verts = max_verts;
     MG_CUDA(h, cudaSetDevice(device));
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     Params &P = h->P;
     P.num_envs = num_envs;
     P.auto_reset = 1;
@@ -110,6 +115,8 @@ int mg_create(mg_handle *out, int device, int num_envs, int max_verts) {
     A(dalloc(&P.xy, NC), "xy"); A(dalloc(&P.key, NC), "key"); A(dalloc(&P.stamp, NC), "stamp"); A(dalloc(&P.vid, NC), "vid");
     A(dalloc(&P.st, (size_t)num_envs), "state"); A(dalloc(&P.stats, (size_t)num_envs), "stats");
     A(dalloc(&P.obs_cache, (size_t)num_envs * MG_OBS_DIM), "obs");
+    A(dalloc(&P.pend, (size_t)num_envs), "pend"); A(dalloc(&P.succ_list, (size_t)num_envs), "succ_list");
+    A(dalloc(&P.reset_list, (size_t)num_envs), "reset_list"); A(dalloc(&P.counters, (size_t)4), "counters");
     A(dalloc(&P.elem, (size_t)num_envs * P.elem_cap * 4), "elem"); A(dalloc(&P.ins_xy, (size_t)num_envs * P.ins_cap), "ins_xy");
     A(dalloc(&h->d_stats_out, 1), "stats_out");
     A(dalloc(&h->d_act, (size_t)num_envs * 3), "act"); A(dalloc(&h->d_obs, (size_t)num_envs * MG_OBS_DIM), "obs_out");
@@ -130,6 +137,7 @@ int mg_destroy(mg_handle h) {
     Params &P = h->P;
     cudaFree(P.xy); cudaFree(P.key); cudaFree(P.stamp); cudaFree(P.vid); cudaFree(P.st); cudaFree(P.stats);
     cudaFree(P.obs_cache); cudaFree(P.elem); cudaFree(P.ins_xy);
+    cudaFree(P.pend); cudaFree(P.succ_list); cudaFree(P.reset_list); cudaFree(P.counters);
     free_templates(h);
     cudaFree(h->d_stats_out); cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_term_obs); cudaFree(h->d_rew);
     cudaFree(h->d_term); cudaFree(h->d_trunc); cudaFree(h->d_nel);
@@ -236,9 +244,19 @@ int mg_step(mg_handle h, const float *act_dev, float *obs_dev, double *rew_dev, 
     if (!h || !act_dev || !obs_dev || !rew_dev || !term_dev || !trunc_dev) return fail(h, MG_ERR_ARG, "mg_step: null pointer");
     if (!h->was_reset) return fail(h, MG_ERR_STATE, "mg_step: call mg_reset first");
     MG_CUDA(h, cudaSetDevice(h->device));
-    mg_step_kernel<<<grid_for(h->num_envs), WPB * 32, h->smem, (cudaStream_t)stream>>>(h->P, act_dev, obs_dev, rew_dev, term_dev,
-                                                                                      trunc_dev, term_obs_dev, n_elem_dev);
-    h->launches++;
+    StepIO io;
+    io.act = act_dev; io.obs_out = obs_dev; io.rew_out = rew_dev; io.term_out = term_dev; io.trunc_out = trunc_dev;
+    io.term_obs_out = term_obs_dev; io.n_elem_out = n_elem_dev;
+    const int set = h->step_parity;
+    h->step_parity ^= 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int full = grid_for(h->num_envs);
+    const int gb = full < h->sm_count * 16 ? full : h->sm_count * 16;
+    const int gc = full < h->sm_count * 4 ? full : h->sm_count * 4;
+    mg_step_decide_kernel<<<full, WPB * 32, h->smem, s>>>(h->P, io, set);
+    mg_step_apply_kernel<<<gb, WPB * 32, h->smem, s>>>(h->P, io, set);
+    mg_step_reset_kernel<<<gc, WPB * 32, h->smem, s>>>(h->P, io, set);
+    h->launches += 3;
     MG_CUDA(h, cudaGetLastError());
     return MG_OK;
 }

@@ -18,13 +18,28 @@
 
 namespace mg {
 
-constexpr int WPB = 4;          // warps (= environments) per block
+#ifndef MG_WPB
+#define MG_WPB 1
+#endif
+constexpr int WPB = MG_WPB;     // warps (= environments) per block
+#ifndef MG_MINB
+#define MG_MINB 1
+#endif
 constexpr int QCAP = 256;       // per-warp queue of "heavy" segment pairs (ints)
 constexpr int QFLUSH = 128;
 
 // ---------------------------------------------------------------------------------------------
 // per-warp view of the environment
 // ---------------------------------------------------------------------------------------------
+// i in [-2n, 3n) -> [0, n)
+__device__ __forceinline__ int wrapn(int i, int n) {
+    if (i < 0) i += n;
+    if (i < 0) i += n;
+    if (i >= n) i -= n;
+    if (i >= n) i -= n;
+    return i;
+}
+
 struct Warp {
     double2 *ring;   // shared memory, this warp's vertex ring
     int *queue;      // shared memory, this warp's heavy-pair queue
@@ -51,6 +66,9 @@ __device__ __forceinline__ void stage_ring(double2 *ring, unsigned long long *mb
 #ifndef MG_NO_BULK_COPY
     unsigned bar = smem_u32(mbar);
     unsigned bytes = (unsigned)n * 16u;
+    // order this warp's earlier generic-proxy accesses to the ring before the async-proxy write
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
     if (lane == 0) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
         asm volatile(
@@ -67,6 +85,7 @@ __device__ __forceinline__ void stage_ring(double2 *ring, unsigned long long *mb
             : "memory");
     }
 #else
+#pragma unroll 1
     for (int j = lane; j < n; j += 32) ring[j] = src[j];
     __syncwarp();
 #endif
@@ -95,7 +114,8 @@ __device__ __forceinline__ double cand_key_from_angles(double a0, double a1) {
 }
 
 // Full rebuild (M:259-287): key for every vertex, stamp = list index (stable sort order).
-__device__ void rebuild_candidates(const Warp &w, double *key, int32_t *stamp) {
+__device__ __noinline__ void rebuild_candidates(const Warp &w, double *key, int32_t *stamp) {
+#pragma unroll 1
     for (int j = w.lane; j < w.n; j += 32) {
         P2 c = w.at(j);
         double a0 = cw_angle(c, w.at(j + 1), w.at(j - 1));
@@ -110,9 +130,10 @@ __device__ void rebuild_candidates(const Warp &w, double *key, int32_t *stamp) {
 }
 
 // arg-min of (key, stamp) over the n live vertices; -1 when the candidate list is empty.
-__device__ int find_reference_index(const Warp &w, const double *key, const int32_t *stamp) {
+__device__ __noinline__ int find_reference_index(const Warp &w, const double *key, const int32_t *stamp) {
     double bk = CUDART_INF;
     int bs = 0x7fffffff, bj = -1;
+#pragma unroll 1
     for (int j = w.lane; j < w.n; j += 32) {
         double k = key[j];
         int s = stamp[j];
@@ -140,9 +161,9 @@ __device__ int find_reference_index(const Warp &w, const double *key, const int3
 // observation (C:1059-1090 PointEnvironment, C:1192-1290 get_radius_points, E:665-738)
 // returns obs[lane] for lane < 18; base length through base_out.
 // ---------------------------------------------------------------------------------------------
-__device__ float compute_obs(const Warp &w, int idx, double area_ratio, double &base_out) {
+__device__ __noinline__ float compute_obs(const Warp &w, int idx, double area_ratio, double &base_out) {
     const int lane = w.lane, n = w.n;
-    const double radius = 4;
+    const double inv_radius = 0.25;   // x / 4 == x * 0.25 exactly
     P2 ref = w.at(idx), right_p = w.at(idx - 1), left_p = w.at(idx + 1 >= n ? idx + 1 - n : idx + 1);
 
     // --- batch 1: 6 fan distances for base_length, 6 fan distances to ref, 6 angles ---------
@@ -152,15 +173,15 @@ __device__ float compute_obs(const Warp &w, int idx, double area_ratio, double &
     double val = 0;
     if (lane < 6) {
         int a = idx + 2 - lane, b = idx + 3 - lane;   // N[k] = at(idx+3-k); dist(N[k+1], N[k])
-        val = pdist(w.at(((a % n) + n) % n), w.at(((b % n) + n) % n));
+        val = pdist(w.at(wrapn(a, n)), w.at(wrapn(b, n)));
     } else if (lane >= 8 && lane < 14) {
         int t = lane - 8;
         P2 p1, p2 = right_p;
         if (t == 0) p1 = left_p;
-        else if (t == 1) p1 = w.at((((idx - 2) % n) + n) % n);
-        else if (t == 2) p1 = w.at((((idx - 3) % n) + n) % n);
-        else if (t == 3) p1 = w.at((idx + 2) % n);
-        else if (t == 4) p1 = w.at((idx + 3) % n);
+        else if (t == 1) p1 = w.at(wrapn(idx - 2, n));
+        else if (t == 2) p1 = w.at(wrapn(idx - 3, n));
+        else if (t == 3) p1 = w.at(wrapn(idx + 2, n));
+        else if (t == 4) p1 = w.at(wrapn(idx + 3, n));
         else {
             p1 = right_p;
             p2 = mk(ref.x + 1, ref.y + 0);
@@ -168,8 +189,8 @@ __device__ float compute_obs(const Warp &w, int idx, double area_ratio, double &
         val = cw_angle(ref, p1, p2);
     } else if (lane >= 16 && lane < 22) {
         int t = lane - 16;
-        const int off[6] = {-1, 1, -2, -3, 2, 3};
-        val = pdist(ref, w.at((((idx + off[t]) % n) + n) % n));
+        const int o6 = t == 0 ? -1 : (t == 1 ? 1 : (t == 2 ? -2 : (t == 3 ? -3 : (t == 4 ? 2 : 3))));
+        val = pdist(ref, w.at(wrapn(idx + o6, n)));
     }
     double dl[6];
 #pragma unroll
@@ -180,26 +201,25 @@ __device__ float compute_obs(const Warp &w, int idx, double area_ratio, double &
            a_l2 = shfl_d(val, 12), rot = shfl_d(val, 13);
     double d_r = shfl_d(val, 16), d_l = shfl_d(val, 17), d_r1 = shfl_d(val, 18), d_r2 = shfl_d(val, 19),
            d_l1 = shfl_d(val, 20), d_l2 = shfl_d(val, 21);
-    const double T = base * radius;
+    const double T = base * 4;
     const double clip = theta + PI / 2;
 
     // r_points float32[9][2]; lane-uniform copies in registers
     float r0[9], r1[9];
 #pragma unroll
     for (int i = 0; i < 9; i++) { r0[i] = 1.0f; r1[i] = 1.0f; }
-    r0[0] = (float)((d_r / radius) / base);  r1[0] = (float)area_ratio;
-    r0[8] = (float)((d_l / radius) / base);  r1[8] = (float)theta;
-    r0[1] = (float)((d_r1 / radius) / base); r1[1] = (float)(a_r1 < PI ? a_r1 : fmax(a_r1, 1.5 * PI) - 2 * PI);
-    r0[2] = (float)((d_r2 / radius) / base); r1[2] = (float)(a_r2 < PI ? a_r2 : fmax(a_r2, 1.5 * PI) - 2 * PI);
-    r0[7] = (float)((d_l1 / radius) / base); r1[7] = (float)fmin(a_l1, clip);
-    r0[6] = (float)((d_l2 / radius) / base); r1[6] = (float)fmin(a_l2, clip);
+    r0[0] = (float)((d_r * inv_radius) / base);  r1[0] = (float)area_ratio;
+    r0[8] = (float)((d_l * inv_radius) / base);  r1[8] = (float)theta;
+    r0[1] = (float)((d_r1 * inv_radius) / base); r1[1] = (float)(a_r1 < PI ? a_r1 : fmax(a_r1, 1.5 * PI) - 2 * PI);
+    r0[2] = (float)((d_r2 * inv_radius) / base); r1[2] = (float)(a_r2 < PI ? a_r2 : fmax(a_r2, 1.5 * PI) - 2 * PI);
+    r0[7] = (float)((d_l1 * inv_radius) / base); r1[7] = (float)fmin(a_l1, clip);
+    r0[6] = (float)((d_l2 * inv_radius) / base); r1[6] = (float)fmin(a_l2, clip);
 #pragma unroll
     for (int j = 0; j < 3; j++) r1[3 + j] = (float)fmin((2 * j + 1) * theta / 6, clip);
 
     // p_s = ref + rotate((T cos(theta/2), T sin(theta/2)), rot)                      (C:154-168, C:1243)
     double sv = 0, cv = 0;
-    if (lane == 0) sincos(theta / 2, &sv, &cv);
-    if (lane == 1) sincos(rot, &sv, &cv);
+    if (lane < 2) mg_sincos(lane == 0 ? theta / 2 : rot, &sv, &cv);
     double s_h = shfl_d(sv, 0), c_h = shfl_d(cv, 0), s_r = shfl_d(sv, 1), c_r = shfl_d(cv, 1);
     double px = T * c_h, py = T * s_h;
     double qx = c_r * px - s_r * py;
@@ -213,6 +233,7 @@ __device__ float compute_obs(const Warp &w, int idx, double area_ratio, double &
     double my_ang[3] = {0, 0, 0};
     double best_ray = CUDART_INF;                             // f64 value of the nearest bisector hit
     int best_ray_o = 0x7fffffff;
+#pragma unroll 1
     for (int o = 1 + lane; o < n; o += 32) {
         if (o == 1 || o == n - 1) continue;                   // right_p / left_p (C:1249)
         int j = idx - o;
@@ -224,7 +245,7 @@ __device__ float compute_obs(const Warp &w, int idx, double area_ratio, double &
         double kk = angle / sector;
         int k = (kk < 3.0) ? (int)kk : 3;                     // int() truncation; NaN/inf -> no sector
         if (k < 3 && d < T) {
-            float cand = (float)((d / radius) / base);
+            float cand = (float)((d * inv_radius) / base);
             if (cand < 1.0f) {
                 unsigned long long keyv = ((unsigned long long)__float_as_uint(cand) << 32) | (unsigned)o;
                 if (keyv < best_sec[k]) {
@@ -250,7 +271,7 @@ __device__ float compute_obs(const Warp &w, int idx, double area_ratio, double &
             hh = (ref.x - q.x + ss * ux) / wx;
         }
         if (0 < ss && ss < 1 && 0 < hh && hh < 1) {
-            double v = (pdist(ref, mk(ref.x + ss * ux, ref.y + ss * uy)) / radius) / base;
+            double v = (pdist(ref, mk(ref.x + ss * ux, ref.y + ss * uy)) * inv_radius) / base;
             if (v < 1.0 && (v < best_ray || (v == best_ray && o < best_ray_o))) {
                 best_ray = v;
                 best_ray_o = o;
@@ -282,15 +303,15 @@ __device__ float compute_obs(const Warp &w, int idx, double area_ratio, double &
                 int mi = idx - (int)omin;                      // _i (may be negative like in Python)
                 double v2 = 0;
                 if (lane < 3) {
-                    int jj = (((lane - 1 + mi) % n) + n) % n;
+                    int jj = wrapn(lane - 1 + mi, n);
                     v2 = pdist(ref, w.at(jj));
                 } else if (lane >= 4 && lane < 7) {
-                    int jj = (((lane - 4 - 1 + mi) % n) + n) % n;
+                    int jj = wrapn(lane - 4 - 1 + mi, n);
                     v2 = cw_angle(ref, w.at(jj), right_p);
                 }
 #pragma unroll
                 for (int j = 0; j < 3; j++) {
-                    r0[3 + j] = (float)((shfl_d(v2, j) / radius) / base);
+                    r0[3 + j] = (float)((shfl_d(v2, j) * inv_radius) / base);
                     r1[3 + j] = (float)shfl_d(v2, 4 + j);
                 }
             }
@@ -308,8 +329,9 @@ __device__ float compute_obs(const Warp &w, int idx, double area_ratio, double &
 // ---------------------------------------------------------------------------------------------
 // estimated_area_range (M:705-718): needs the mean, the 2nd smallest and 2nd largest edge.
 // ---------------------------------------------------------------------------------------------
-__device__ void estimate_area_range(const Warp &w, double &area_min, double &area_crit) {
+__device__ __noinline__ void estimate_area_range(const Warp &w, double &area_min, double &area_crit) {
     double s = 0, lo1 = CUDART_INF, lo2 = CUDART_INF, hi1 = -CUDART_INF, hi2 = -CUDART_INF;
+#pragma unroll 1
     for (int j = w.lane; j < w.n; j += 32) {
         double l = pdist(w.at(j - 1), w.at(j));
         s += l;
@@ -334,8 +356,9 @@ __device__ void estimate_area_range(const Warp &w, double &area_min, double &are
 }
 
 // sequential shoelace (C:485-487 up to np.dot's BLAS summation order)
-__device__ double shoelace_area(const Warp &w) {
+__device__ __noinline__ double shoelace_area(const Warp &w) {
     double s1 = 0, s2 = 0;
+#pragma unroll 1
     for (int j = w.lane; j < w.n; j += 32) {
         P2 a = w.at(j), p = w.at(j - 1);
         s1 += a.x * p.y;
@@ -349,14 +372,34 @@ __device__ double shoelace_area(const Warp &w) {
 // ---------------------------------------------------------------------------------------------
 // heavy-pair queue: entries are evaluated 8 at a time, one aligned lane quad per segment pair
 // ---------------------------------------------------------------------------------------------
-template <class Decode>
-__device__ int process_queue(const Warp &w, int qn, Decode decode, bool stop_on_first) {
+struct QCtx {
+    int mode;            // 0: point-in-polygon (entry = edge index), 1: boundary intersection (entry = 4*vertex + t)
+    P2 a, b;             // mode 0: ray (P, (10000, P.y));  mode 1: checking segment c1 = (a, b)
+    P2 c, d;             // mode 1: checking segment c2 = (c, d)
+};
+
+__device__ __forceinline__ void qdecode(const Warp &w, const QCtx &q, int e, P2 &a1, P2 &a2, P2 &b1, P2 &b2) {
+    if (q.mode == 0) {
+        a1 = w.at(e);
+        a2 = w.at(e - 1);
+        b1 = q.a;
+        b2 = q.b;
+    } else {
+        int j = e >> 2, t = e & 3;
+        if (t & 2) { a1 = q.c; a2 = q.d; } else { a1 = q.a; a2 = q.b; }
+        b1 = w.at(j);
+        b2 = (t & 1) ? w.at(j + 1) : w.at(j - 1);
+    }
+}
+
+__device__ __noinline__ int process_queue(const Warp &w, int qn, const QCtx &q, bool stop_on_first) {
     int hits = 0;
+#pragma unroll 1
     for (int base = 0; base < qn; base += 8) {
         int e = base + (w.lane >> 2);
         bool active = e < qn;
         P2 a1 = mk(0, 0), a2 = a1, b1 = a1, b2 = a1;
-        if (active) decode(w.queue[e], a1, a2, b1, b2);
+        if (active) qdecode(w, q, w.queue[e], a1, a2, b1, b2);
         bool c = is_cross_quad(a1, a2, b1, b2, active, w.lane);
         unsigned m = __ballot_sync(FULL, c && (w.lane & 3) == 0);
         hits += __popc(m);
@@ -365,8 +408,7 @@ __device__ int process_queue(const Warp &w, int qn, Decode decode, bool stop_on_
     return hits;
 }
 
-template <class Decode>
-__device__ __forceinline__ void queue_push(const Warp &w, int &qn, bool flag, int value, int &hits, Decode decode,
+__device__ __forceinline__ void queue_push(const Warp &w, int &qn, bool flag, int value, int &hits, const QCtx &q,
                                            bool stop_on_first) {
     unsigned m = __ballot_sync(FULL, flag);
     if (m == 0) return;
@@ -374,7 +416,7 @@ __device__ __forceinline__ void queue_push(const Warp &w, int &qn, bool flag, in
     qn += __popc(m);
     __syncwarp();
     if (qn > QFLUSH) {
-        hits += process_queue(w, qn, decode, stop_on_first);
+        hits += process_queue(w, qn, q, stop_on_first);
         qn = 0;
         __syncwarp();
     }
@@ -396,17 +438,13 @@ __device__ __forceinline__ double rint4_mixed(double dy, const int32_t *vid, int
     return r;
 }
 
-__device__ bool point_inside(const Warp &w, P2 P, const int32_t *vid, int n0) {
+__device__ __noinline__ bool point_inside(const Warp &w, P2 P, const int32_t *vid, int n0) {
     const int n = w.n;
     int qn = 0, hits = 0;
-    const P2 ray2 = mk(10000, P.y);
-    auto decode = [&](int j, P2 &a1, P2 &a2, P2 &b1, P2 &b2) {
-        a1 = w.at(j);
-        a2 = w.at(j - 1);
-        b1 = P;
-        b2 = ray2;
-    };
+    QCtx decode;
+    decode.mode = 0; decode.a = P; decode.b = mk(10000, P.y); decode.c = P; decode.d = P;
     const bool can_prune = P.x < 9000.0;
+#pragma unroll 1
     for (int base = 0; base < n; base += 32) {
         int j = base + w.lane;
         bool need = false;
@@ -445,8 +483,9 @@ __device__ bool point_inside(const Warp &w, P2 P, const int32_t *vid, int n0) {
 }
 
 // E:766-769 find_same_point: any boundary vertex within 0.001 of P
-__device__ bool find_same_point(const Warp &w, P2 P) {
+__device__ __noinline__ bool find_same_point(const Warp &w, P2 P) {
     bool f = false;
+#pragma unroll 1
     for (int j = w.lane; j < w.n; j += 32) f |= pdist(w.at(j), P) < 0.001;
     return __any_sync(FULL, f);
 }
@@ -454,7 +493,7 @@ __device__ bool find_same_point(const Warp &w, P2 P) {
 // ---------------------------------------------------------------------------------------------
 // candidate quad: validity (C:738-757, C:814-826) + corner angles
 // ---------------------------------------------------------------------------------------------
-__device__ bool mesh_is_valid(const Warp &w, const P2 (&m)[4], double (&corner)[4]) {
+__device__ __noinline__ bool mesh_is_valid(const Warp &w, const P2 (&m)[4], double (&corner)[4]) {
     const int lane = w.lane;
     // lanes 0-3: is_cross((m0,m1),(m2,m3)); lanes 4-7: is_cross((m0,m3),(m1,m2)); lanes 8-11: corners
     P2 a1 = m[0], a2 = lane < 4 ? m[1] : m[3], b1 = lane < 4 ? m[2] : m[1], b2 = lane < 4 ? m[3] : m[2];
@@ -491,7 +530,7 @@ __device__ bool mesh_is_valid(const Warp &w, const P2 (&m)[4], double (&corner)[
 
 // M:536-556 check_intersection_with_boundary.  qi[] = boundary indices of the quad vertices
 // (-1 for the not-yet-inserted new vertex), ri = position of the reference point in the quad.
-__device__ bool intersects_boundary(const Warp &w, const P2 (&m)[4], const int (&qi)[4], int ri, P2 ref) {
+__device__ __noinline__ bool intersects_boundary(const Warp &w, const P2 (&m)[4], const int (&qi)[4], int ri, P2 ref) {
     const int n = w.n;
     double max_dist = 0;
 #pragma unroll
@@ -499,13 +538,10 @@ __device__ bool intersects_boundary(const Warp &w, const P2 (&m)[4], const int (
         if (k != ri) max_dist = fmax(max_dist, pdist(ref, m[k]));
     const P2 c1a = m[(ri + 3) & 3], c1b = m[(ri + 2) & 3], c2a = m[(ri + 2) & 3], c2b = m[(ri + 1) & 3];
     auto in_mesh = [&](int j) { return j == qi[0] || j == qi[1] || j == qi[2] || j == qi[3]; };
-    auto decode = [&](int e, P2 &a1, P2 &a2, P2 &b1, P2 &b2) {
-        int j = e >> 2, t = e & 3;
-        if (t & 2) { a1 = c2a; a2 = c2b; } else { a1 = c1a; a2 = c1b; }
-        b1 = w.at(j);
-        b2 = (t & 1) ? w.at(j + 1 == n ? 0 : j + 1) : w.at(j - 1);
-    };
+    QCtx decode;
+    decode.mode = 1; decode.a = c1a; decode.b = c1b; decode.c = c2a; decode.d = c2b;
     int qn = 0, hits = 0;
+#pragma unroll 1
     for (int base = 0; base < n && !hits; base += 32) {
         int j = base + w.lane;
         bool near = false, okp = false, okn = false;
@@ -516,10 +552,8 @@ __device__ bool intersects_boundary(const Warp &w, const P2 (&m)[4], const int (
         }
         if (!__any_sync(FULL, near)) continue;
         // reference order per vertex: (c1,prev) (c1,next) (c2,prev) (c2,next); any hit -> True
-        queue_push(w, qn, okp, j * 4 + 0, hits, decode, true);
-        queue_push(w, qn, okn, j * 4 + 1, hits, decode, true);
-        queue_push(w, qn, okp, j * 4 + 2, hits, decode, true);
-        queue_push(w, qn, okn, j * 4 + 3, hits, decode, true);
+#pragma unroll 1
+        for (int t = 0; t < 4; t++) queue_push(w, qn, (t & 1) ? okn : okp, j * 4 + t, hits, decode, true);
     }
     if (!hits) hits += process_queue(w, qn, decode, true);
     return hits != 0;
@@ -529,19 +563,20 @@ __device__ bool intersects_boundary(const Warp &w, const P2 (&m)[4], const int (
 // boundary quality of a freshly inserted vertex (M:355-408 compute_boundary_quality)
 // a_next / a_prev: interior angles at B[idx+1] and B[idx-1] (already evaluated for the candidates)
 // ---------------------------------------------------------------------------------------------
-__device__ double boundary_quality_new_vertex(const Warp &w, int idx, double a_next, double a_prev) {
+__device__ __noinline__ double boundary_quality_new_vertex(const Warp &w, int idx, double a_next, double a_prev) {
     const int n = w.n;
     P2 add_v = w.at(idx);
     double amin = CUDART_INF;
     if (a_next < PI / 3) amin = a_next;
     if (a_prev < PI / 3) amin = fmin(amin, a_prev);
     double q1 = amin != CUDART_INF ? 3 * amin / PI : 1;
-    int e1 = idx + 1 >= n ? idx + 1 - n : idx + 1, e2 = (idx + 2) % n, e3 = idx - 1 < 0 ? idx - 1 + n : idx - 1,
-        e4 = (((idx - 2) % n) + n) % n;
+    int e1 = idx + 1 >= n ? idx + 1 - n : idx + 1, e2 = wrapn(idx + 2, n), e3 = idx - 1 < 0 ? idx - 1 + n : idx - 1,
+        e4 = wrapn(idx - 2, n);
     double dist = pdist(add_v, w.at(e1)) + pdist(add_v, w.at(e3));
     // close_vs: not excluded, nearer than `dist`, and not directly after an accepted index
     double m_d = CUDART_INF;
     unsigned carry = 0;   // parity of the run of "close" flags reaching the end of the previous chunk
+#pragma unroll 1
     for (int base = 0; base < n; base += 32) {
         int j = base + w.lane;
         bool c = false;
@@ -563,18 +598,18 @@ __device__ double boundary_quality_new_vertex(const Warp &w, int idx, double a_n
     double dl[4];
 #pragma unroll
     for (int k = -2; k < 2; k++) {
-        int a = (((idx + k) % n) + n) % n, b = (((idx + k + 1) % n) + n) % n;
+        int a = wrapn(idx + k, n), b = wrapn(idx + k + 1, n);
         dl[k + 2] = pdist(w.at(a), w.at(b));
     }
     double mean_dist = py_sum<4>(dl) / 4;
     double smoothness = fmin(mean_dist, targt_len) / fmax(mean_dist, targt_len);
     double q2 = 1;
     if (m_d != CUDART_INF) q2 = m_d < 0.5 * dist ? m_d / (0.5 * dist) : 1;
-    return pow(smoothness * q1 * q2, 1.0 / 3);
+    return mg_pow(smoothness * q1 * q2, 1.0 / 3);
 }
 
 // M:418-452: element without a new vertex; t0,t1 = new indices of the two surviving quad vertices
-__device__ double boundary_quality_no_new(const Warp &w, int t0, int t1, double ang0, double ang1) {
+__device__ __noinline__ double boundary_quality_no_new(const Warp &w, int t0, int t1, double ang0, double ang1) {
     const int n = w.n;
     double amin = CUDART_INF;
     if (ang0 < PI / 3) amin = ang0;
@@ -584,13 +619,13 @@ __device__ double boundary_quality_no_new(const Warp &w, int t0, int t1, double 
     double dl[5];
 #pragma unroll
     for (int k = -2; k < 3; k++) {
-        int a = (((index + k) % n) + n) % n, b = (((index + k + 1) % n) + n) % n;
+        int a = wrapn(index + k, n), b = wrapn(index + k + 1, n);
         dl[k + 2] = pdist(w.at(a), w.at(b));
     }
     double mean_dist = py_sum<5>(dl) / 5;
     double smoothness = fmin(mean_dist, targt_len) / fmax(mean_dist, targt_len);
     double angle_quality = amin != CUDART_INF ? 3 * amin / PI : 1;
-    return pow(angle_quality * smoothness, 1.0 / 2);
+    return mg_pow(angle_quality * smoothness, 1.0 / 2);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -615,18 +650,19 @@ __device__ __forceinline__ double u01(unsigned a, unsigned b) {   // 53-bit unif
 // random star polygon (ui/GenerateRandomPolygon.py:5-49) + densifier (ui/tk-ui.py:252-276)
 // Written by the warp into ring[0..n); returns n (even, min_verts <= n <= max_verts).
 // ---------------------------------------------------------------------------------------------
-__device__ int generate_polygon(const Params &P, Warp &w, long long global_env, int episode);
+__device__ __noinline__ int generate_polygon(const Params &P, Warp &w, long long global_env, int episode);
 
 // ---------------------------------------------------------------------------------------------
 // reset of one env (E:136-184): restore the polygon, rebuild candidates, first observation
 // ---------------------------------------------------------------------------------------------
-__device__ float reset_env(const Params &P, Warp &w, int env, EnvState &S) {
+__device__ __noinline__ float reset_env(const Params &P, Warp &w, int env, EnvState &S) {
     const int lane = w.lane;
     const size_t off = (size_t)env * P.cap;
     float obs;
     if (!P.random_mode) {
         const DomainScalars D = P.t_sc[S.domain];
         const size_t toff = (size_t)S.domain * P.cap;
+#pragma unroll 1
         for (int j = lane; j < D.n0; j += 32) {
             P.xy[off + j] = P.t_xy[toff + j];
             P.key[off + j] = P.t_key[toff + j];
@@ -641,6 +677,7 @@ __device__ float reset_env(const Params &P, Warp &w, int env, EnvState &S) {
         int n = generate_polygon(P, w, P.env_id_offset + env, S.episode);
         w.n = n;
         __syncwarp();
+#pragma unroll 1
         for (int j = lane; j < n; j += 32) {
             P.xy[off + j] = w.ring[j];
             P.vid[off + j] = j;
@@ -688,6 +725,7 @@ __global__ void __launch_bounds__(WPB * 32) mg_template_kernel(Params P, double2
     Warp w;
     w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = t_sc[d].n0;
     const size_t toff = (size_t)d * P.cap;
+#pragma unroll 1
     for (int j = lane; j < w.n; j += 32) w.ring[j] = t_xy[toff + j];
     __syncwarp();
     rebuild_candidates(w, t_key + toff, t_stamp + toff);
@@ -723,11 +761,76 @@ __global__ void __launch_bounds__(WPB * 32) mg_reset_kernel(Params P, const uint
     if (obs_out && lane < MG_OBS_DIM) obs_out[(size_t)env * MG_OBS_DIM + lane] = obs;
 }
 
-// One environment transition per warp (E:388-457) + VecEnv auto-reset.
-__global__ void __launch_bounds__(WPB * 32)
-    mg_step_kernel(Params P, const float *__restrict__ act, float *__restrict__ obs_out, double *__restrict__ rew_out,
-                   uint8_t *__restrict__ term_out, uint8_t *__restrict__ trunc_out, float *__restrict__ term_obs_out,
-                   int32_t *__restrict__ n_elem_out) {
+// ---------------------------------------------------------------------------------------------
+// One environment transition (E:388-457) + VecEnv auto-reset, as three phase kernels over
+// compacted work lists.  Every warp of a phase runs the same small piece of code (the single
+// fused kernel was instruction-fetch bound: 65 % I-cache hit rate, see profiles/):
+//   A  mg_step_decide_kernel  all envs   action -> candidate quad -> validity decision; finishes the
+//                                        step of every env whose action failed (cached observation)
+//   B  mg_step_apply_kernel   successes  boundary update, candidate keys, reward, next observation
+//   C  mg_step_reset_kernel   done envs  in-place reset (template copy or fresh random polygon)
+// Work lists are appended with one atomicAdd per warp; counter set (step & 1) is used by step s and
+// the other set is zeroed by phase C, so no memset sits between launches.
+// ---------------------------------------------------------------------------------------------
+struct StepIO {
+    const float *act;
+    float *obs_out;
+    double *rew_out;
+    uint8_t *term_out;
+    uint8_t *trunc_out;
+    float *term_obs_out;
+    int32_t *n_elem_out;
+};
+
+__device__ __forceinline__ void push_list(int *list, int *counter, int env, int lane) {
+    if (lane == 0) list[atomicAdd(counter, 1)] = env;
+}
+
+// Tail of step() shared by phases A and B (E:361-386 + outputs + statistics).
+__device__ __forceinline__ void finish_step(const Params &P, const StepIO &io, int env, int lane, EnvState &S, int n_before,
+                                            double reward, bool done, bool failed, bool success, bool force_trunc,
+                                            float obs, int set) {
+    bool is_complete = true;
+    if (failed && S.failed_num >= 100) { done = true; is_complete = false; }
+    bool terminated = done && is_complete, truncated = done && !is_complete;
+    if (force_trunc && !done) { done = true; truncated = true; }          // sentinel, see DESIGN.md
+    S.ep_return += reward; S.ep_len++;
+    if (lane == 0) {
+        EnvStats T = P.stats[env];
+        T.steps++; T.sum_n += n_before;
+        if (success) { T.successes++; T.sum_n_success += n_before; }
+        if (done) {
+            T.episodes++; T.completed += terminated; T.truncated += truncated; T.elements += S.n_elements;
+            T.sum_return += S.ep_return; T.sum_length += S.ep_len;
+        }
+        P.stats[env] = T;
+        io.rew_out[env] = reward;
+        io.term_out[env] = terminated;
+        io.trunc_out[env] = truncated;
+        if (io.n_elem_out) io.n_elem_out[env] = S.n_elements;
+        P.st[env] = S;
+    }
+    if (lane < MG_OBS_DIM) {
+        if (io.term_obs_out) io.term_obs_out[(size_t)env * MG_OBS_DIM + lane] = done ? obs : 0.0f;
+        if (success) P.obs_cache[(size_t)env * MG_OBS_DIM + lane] = obs;
+        io.obs_out[(size_t)env * MG_OBS_DIM + lane] = obs;
+    }
+    if (done && P.auto_reset) push_list(P.reset_list, P.counters + 2 * set + 1, env, lane);
+}
+
+__device__ __forceinline__ void quad_indices(int rule, bool new_vertex, int idx, int n, int (&qi)[4], int &ri) {
+    const int ip1 = idx + 1 >= n ? idx + 1 - n : idx + 1, im1 = idx - 1 < 0 ? idx - 1 + n : idx - 1;
+    if (new_vertex) {
+        qi[0] = -1; qi[1] = im1; qi[2] = idx; qi[3] = ip1; ri = 2;
+    } else if (rule == -1) {
+        qi[0] = im1; qi[1] = idx; qi[2] = ip1; qi[3] = wrapn(idx + 2, n); ri = 1;
+    } else {
+        qi[0] = wrapn(idx - 2, n); qi[1] = im1; qi[2] = idx; qi[3] = ip1; ri = 2;
+    }
+}
+
+// ---- phase A ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(WPB * 32, MG_MINB) mg_step_decide_kernel(Params P, StepIO io, int set) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * WPB + warp;
@@ -745,16 +848,16 @@ __global__ void __launch_bounds__(WPB * 32)
     if (!dead) stage_ring(w.ring, L.mbar, P.xy + off, S.n, lane, 0);
 
     const int n = S.n, idx = dead ? 0 : S.ref_index;
-    const float a0 = act[(size_t)env * 3 + 0], a1 = act[(size_t)env * 3 + 1], a2 = act[(size_t)env * 3 + 2];
+    const float a0 = io.act[(size_t)env * 3 + 0], a1 = io.act[(size_t)env * 3 + 1], a2 = io.act[(size_t)env * 3 + 2];
     const P2 ref = dead ? mk(0, 0) : w.at(idx), right_p = dead ? mk(1, 0) : w.at(idx - 1);
 
     // ---- action -> candidate vertex (E:783-792, E:202-210, D:112-137) ------------------------
     P2 newp;
     {
         double ax = (double)np_round4f(a1), ay = (double)np_round4f(a2);
-        double th = 2 * PI - atan2(right_p.y - ref.y, right_p.x - ref.x);
+        double th = 2 * PI - mg_atan2(right_p.y - ref.y, right_p.x - ref.x);
         double s, c;
-        sincos(th, &s, &c);
+        mg_sincos(th, &s, &c);
         double ox = c * ax + s * ay;
         double oy = -s * ax + c * ay;
         ox *= S.base_length; oy *= S.base_length;
@@ -762,7 +865,7 @@ __global__ void __launch_bounds__(WPB * 32)
         newp = mk(np_round4(ox), np_round4(oy));
     }
 
-    bool done = false, failed = true;
+    bool done = false;
     double reward = 0;
     bool have_mesh = true, new_vertex = false;
     int rule = 0;   // -1, +1, 0
@@ -781,191 +884,213 @@ __global__ void __launch_bounds__(WPB * 32)
             have_mesh = false;
         }
     }
-
-    bool success = false;
     if (have_mesh) {
         P2 m[4]; int qi[4]; int ri;
-        const int ip1 = idx + 1 >= n ? idx + 1 - n : idx + 1, im1 = idx - 1 < 0 ? idx - 1 + n : idx - 1;
-        if (new_vertex) {
-            qi[0] = -1; qi[1] = im1; qi[2] = idx; qi[3] = ip1; ri = 2;
-        } else if (rule == -1) {
-            qi[0] = im1; qi[1] = idx; qi[2] = ip1; qi[3] = (idx + 2) % n; ri = 1;
-        } else {
-            qi[0] = (((idx - 2) % n) + n) % n; qi[1] = im1; qi[2] = idx; qi[3] = ip1; ri = 2;
-        }
+        quad_indices(rule, new_vertex, idx, n, qi, ri);
 #pragma unroll
         for (int k = 0; k < 4; k++) m[k] = qi[k] < 0 ? newp : w.at(qi[k]);
         double corner[4];
         bool valid = mesh_is_valid(w, m, corner);
         if (valid) valid = !intersects_boundary(w, m, qi, ri, ref);
         if (valid) {
-            success = true;
-            // ---- update_boundary (M:601-674) -----------------------------------------------
-            int nb[4];          // the four neighbours whose candidate keys are re-evaluated, in order
-            int t0 = 0, t1 = 0; // surviving quad vertices (no-new-vertex case), new indices
-            int elem_ids[4];
+            // hand the element over to phase B
+            if (lane == 0) {
+                Pending Q;
+                Q.newx = newp.x; Q.newy = newp.y;
+                Q.corner[0] = corner[0]; Q.corner[1] = corner[1]; Q.corner[2] = corner[2]; Q.corner[3] = corner[3];
+                Q.rule = rule; Q.new_vertex = new_vertex ? 1 : 0; Q.pad[0] = 0; Q.pad[1] = 0;
+                P.pend[env] = Q;
+            }
+            push_list(P.succ_list, P.counters + 2 * set + 0, env, lane);
+            return;
+        }
+        reward += S.n_elements ? -1.0 / S.n_elements : -1;          // E:357
+    }
+    // failed step: nothing changed, the reference recomputes a bit-identical observation
+    float obs = lane < MG_OBS_DIM ? P.obs_cache[(size_t)env * MG_OBS_DIM + lane] : 0.0f;
+    S.failed_num++;
+    finish_step(P, io, env, lane, S, n, reward, done, true, false, dead, obs, set);
+}
+
+// ---- phase B ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(WPB * 32) mg_step_apply_kernel(Params P, StepIO io, int set) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    SmemLayout L = carve(smem_raw, P.cap, warp);
+    init_mbar(L.mbar, lane);
+    const int count = P.counters[2 * set + 0];
+    unsigned phase = 0;
+#pragma unroll 1
+    for (int item = blockIdx.x * WPB + warp; item < count; item += gridDim.x * WPB) {
+        const int env = P.succ_list[item];
+        EnvState S = P.st[env];
+        const size_t off = (size_t)env * P.cap;
+        Warp w;
+        w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = S.n;
+        __syncwarp();
+        stage_ring(w.ring, L.mbar, P.xy + off, S.n, lane, phase);
+        phase ^= 1u;
+        const Pending Q = P.pend[env];
+        const int n = S.n, idx = S.ref_index;
+        const bool new_vertex = Q.new_vertex != 0;
+        const P2 newp = mk(Q.newx, Q.newy);
+        const double corner[4] = {Q.corner[0], Q.corner[1], Q.corner[2], Q.corner[3]};
+        P2 m[4]; int qi[4]; int ri;
+        quad_indices(Q.rule, new_vertex, idx, n, qi, ri);
 #pragma unroll
-            for (int k = 0; k < 4; k++) elem_ids[k] = qi[k] < 0 ? S.next_vid : P.vid[off + qi[k]];
-            if (new_vertex) {
-                // insert P at index(ref) and remove ref: the slot is replaced in place
-                if (lane == 0) {
-                    w.ring[idx] = make_double2(newp.x, newp.y);
-                    P.xy[off + idx] = make_double2(newp.x, newp.y);
-                    P.vid[off + idx] = S.next_vid;
-                    P.key[off + idx] = CUDART_INF;
-                    if (P.ins_xy && S.next_vid - S.n0 < P.ins_cap)
-                        P.ins_xy[(size_t)env * P.ins_cap + (S.next_vid - S.n0)] = make_double2(newp.x, newp.y);
-                }
-                S.next_vid++;
+        for (int k = 0; k < 4; k++) m[k] = qi[k] < 0 ? newp : w.at(qi[k]);
+        const int ip1 = qi[3] , im1 = new_vertex ? qi[1] : (Q.rule == -1 ? qi[0] : qi[1]);
+        double reward = 0;
+        bool done = false;
+
+        // ---- update_boundary (M:601-674) ---------------------------------------------------
+        int nb[4];          // the four neighbours whose candidate keys are re-evaluated, in order
+        int t0 = 0, t1 = 0; // surviving quad vertices (no-new-vertex case), new indices
+        int elem_ids[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) elem_ids[k] = qi[k] < 0 ? S.next_vid : P.vid[off + qi[k]];
+        __syncwarp();
+        if (new_vertex) {
+            // insert P at index(ref) and remove ref: the slot is replaced in place
+            if (lane == 0) {
+                w.ring[idx] = make_double2(newp.x, newp.y);
+                P.xy[off + idx] = make_double2(newp.x, newp.y);
+                P.vid[off + idx] = S.next_vid;
+                P.key[off + idx] = CUDART_INF;
+                if (P.ins_xy && S.next_vid - S.n0 < P.ins_cap)
+                    P.ins_xy[(size_t)env * P.ins_cap + (S.next_vid - S.n0)] = make_double2(newp.x, newp.y);
+            }
+            S.next_vid++;
+            __syncwarp();
+            nb[0] = ip1; nb[1] = im1; nb[2] = wrapn(idx + 2, n); nb[3] = wrapn(idx - 2, n);
+        } else {
+            // remove the two middle quad vertices; compact ring + key/stamp/vid
+            const int r0 = qi[1], r1 = qi[2];
+            const int lo = r0 < r1 ? r0 : r1, hi = r0 < r1 ? r1 : r0;
+            auto newpos = [&](int j) { return j - (j > lo ? 1 : 0) - (j > hi ? 1 : 0); };
+#pragma unroll 1
+            for (int base = lo; base < n; base += 32) {
+                int j = base + lane;
+                bool mv = j < n && j != lo && j != hi;
+                double2 v = make_double2(0, 0); double k = 0; int st = 0, id = 0;
+                if (mv) { v = w.ring[j]; k = P.key[off + j]; st = P.stamp[off + j]; id = P.vid[off + j]; }
                 __syncwarp();
-                nb[0] = ip1; nb[1] = im1; nb[2] = (idx + 2) % n; nb[3] = (((idx - 2) % n) + n) % n;
-            } else {
-                // remove the two middle quad vertices; compact ring + key/stamp/vid
-                const int r0 = qi[1], r1 = qi[2];
-                const int lo = r0 < r1 ? r0 : r1, hi = r0 < r1 ? r1 : r0;
-                // new index of old j (j not removed)
-                auto newpos = [&](int j) { return j - (j > lo ? 1 : 0) - (j > hi ? 1 : 0); };
-                // gather everything that moves into registers first (in-place shift)
-                for (int base = lo; base < n; base += 32) {
-                    int j = base + lane;
-                    bool mv = j < n && j != lo && j != hi;
-                    double2 v = make_double2(0, 0); double k = 0; int st = 0, id = 0;
-                    if (mv) { v = w.ring[j]; k = P.key[off + j]; st = P.stamp[off + j]; id = P.vid[off + j]; }
-                    __syncwarp();
-                    if (mv) {
-                        int q = newpos(j);
-                        w.ring[q] = v; P.xy[off + q] = v; P.key[off + q] = k; P.stamp[off + q] = st; P.vid[off + q] = id;
-                    }
-                    __syncwarp();
+                if (mv) {
+                    int q = newpos(j);
+                    w.ring[q] = v; P.xy[off + q] = v; P.key[off + q] = k; P.stamp[off + q] = st; P.vid[off + q] = id;
                 }
-                t0 = newpos(qi[0]); t1 = newpos(qi[3]);
-                w.n = n - 2;
-                const int nn = n - 2;
-                const int id = t0 > t1 ? t0 : t1;
-                nb[0] = id; nb[1] = id - 1 < 0 ? id - 1 + nn : id - 1; nb[2] = (id + 1) % nn;
-                nb[3] = (((id - 2) % nn) + nn) % nn;
+                __syncwarp();
             }
-            S.n = w.n;
-            const int nn = w.n;
-            // ---- candidate keys of the four neighbours (lanes 2k, 2k+1 -> angles a0, a1 of nb[k]) --
-            double ang = 0;
-            if (lane < 8) {
-                int k = lane >> 1, v = nb[k], d = 1 + (lane & 1);
-                ang = cw_angle(w.at(v), w.at((v + d) % nn), w.at((((v - d) % nn) + nn) % nn));
+            t0 = newpos(qi[0]); t1 = newpos(qi[3]);
+            w.n = n - 2;
+            const int nn = n - 2;
+            const int id = t0 > t1 ? t0 : t1;
+            nb[0] = id; nb[1] = id - 1 < 0 ? id - 1 + nn : id - 1; nb[2] = wrapn(id + 1, nn);
+            nb[3] = wrapn(id - 2, nn);
+        }
+        S.n = w.n;
+        const int nn = w.n;
+        // ---- candidate keys of the four neighbours (lanes 2k, 2k+1 -> angles a0, a1 of nb[k]) ----
+        double ang = 0;
+        if (lane < 8) {
+            int k = lane >> 1, v = nb[k], d = 1 + (lane & 1);
+            ang = cw_angle(w.at(v), w.at(wrapn(v + d, nn)), w.at(wrapn(v - d, nn)));
+        }
+        double nb_a0[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            nb_a0[k] = shfl_d(ang, 2 * k);
+            double a1v = shfl_d(ang, 2 * k + 1);
+            double kv = cand_key_from_angles(nb_a0[k], a1v);
+            bool later_dup = false;
+#pragma unroll
+            for (int k2 = k + 1; k2 < 4; k2++) later_dup |= nb[k2] == nb[k];
+            if (lane == k && !later_dup) {
+                P.key[off + nb[k]] = kv;
+                P.stamp[off + nb[k]] = S.stamp_ctr - 1 - k;
             }
-            double nb_a0[4];
+        }
+        S.stamp_ctr -= 4;
+        // ---- element log ----------------------------------------------------------------------
+        if (P.elem && lane < 4 && S.n_elements < P.elem_cap)
+            P.elem[((size_t)env * P.elem_cap + S.n_elements) * 4 + lane] = elem_ids[lane];
+        S.n_elements++;
+        // ---- area (C:943-958), robust quality (C:881-892) -----------------------------------
+        double e0 = pdist(m[0], m[3]), e1 = pdist(m[1], m[0]), e2 = pdist(m[2], m[1]), e3 = pdist(m[3], m[2]);
+        double sn = 0;
+        if (lane < 2) sn = mg_sin(lane == 0 ? corner[0] : corner[2]);
+        double mesh_area = 0.5 * e0 * e1 * shfl_d(sn, 0) + 0.5 * e2 * e3 * shfl_d(sn, 1);
+        S.current_area -= mesh_area;
+        double mn = fmin(fmin(e0, e1), fmin(e2, e3));
+        double q1 = sqrt(2.0) * mn / fmax(pdist(m[0], m[2]), pdist(m[1], m[3]));
+        double amin = fmin(fmin(corner[0], corner[1]), fmin(corner[2], corner[3]));
+        double amax = fmax(fmax(corner[0], corner[1]), fmax(corner[2], corner[3]));
+        double e_reward = sqrt(q1 * (amin / amax));
+        // ---- boundary quality (M:410-452) ---------------------------------------------------
+        double b_reward;
+        __syncwarp();
+        if (new_vertex) b_reward = boundary_quality_new_vertex(w, idx, nb_a0[0], nb_a0[1]);
+        else {
+            double g0 = 0, g1 = 0;            // interior angles at the two survivors
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                nb_a0[k] = shfl_d(ang, 2 * k);
-                double a1v = shfl_d(ang, 2 * k + 1);
-                double kv = cand_key_from_angles(nb_a0[k], a1v);
-                bool later_dup = false;
-#pragma unroll
-                for (int k2 = k + 1; k2 < 4; k2++) later_dup |= nb[k2] == nb[k];
-                if (lane == k && !later_dup) {
-                    P.key[off + nb[k]] = kv;
-                    P.stamp[off + nb[k]] = S.stamp_ctr - 1 - k;
-                }
+                if (nb[k] == t0) g0 = nb_a0[k];
+                if (nb[k] == t1) g1 = nb_a0[k];
             }
-            S.stamp_ctr -= 4;
-            // ---- element log ------------------------------------------------------------------
-            if (P.elem && lane < 4 && S.n_elements < P.elem_cap)
-                P.elem[((size_t)env * P.elem_cap + S.n_elements) * 4 + lane] = elem_ids[lane];
-            S.n_elements++;
-            // ---- area (C:943-958), robust quality (C:881-892) -------------------------------
-            double e0 = pdist(m[0], m[3]), e1 = pdist(m[1], m[0]), e2 = pdist(m[2], m[1]), e3 = pdist(m[3], m[2]);
-            double sn = 0;
-            if (lane == 0) sn = sin(corner[0]);
-            if (lane == 1) sn = sin(corner[2]);
-            double mesh_area = 0.5 * e0 * e1 * shfl_d(sn, 0) + 0.5 * e2 * e3 * shfl_d(sn, 1);
-            S.current_area -= mesh_area;
-            double mn = fmin(fmin(e0, e1), fmin(e2, e3));
-            double q1 = sqrt(2.0) * mn / fmax(pdist(m[0], m[2]), pdist(m[1], m[3]));
-            double amin = fmin(fmin(corner[0], corner[1]), fmin(corner[2], corner[3]));
-            double amax = fmax(fmax(corner[0], corner[1]), fmax(corner[2], corner[3]));
-            double e_reward = sqrt(q1 * (amin / amax));
-            // ---- boundary quality (M:410-452) -----------------------------------------------
-            double b_reward;
-            __syncwarp();
-            if (new_vertex) b_reward = boundary_quality_new_vertex(w, idx, nb_a0[0], nb_a0[1]);
-            else {
-                // interior angles at the two survivors: among the re-evaluated neighbours
-                double g0 = 0, g1 = 0;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    if (nb[k] == t0) g0 = nb_a0[k];
-                    if (nb[k] == t1) g1 = nb_a0[k];
-                }
-                b_reward = boundary_quality_no_new(w, t0, t1, g0, g1);
-            }
-            double quality = e_reward + 1 * (b_reward - 1);          // M:1754-1766
-            // ---- speed penalty (E:590-607) --------------------------------------------------
-            double min_area = S.area_min * S.area_min, crit = S.area_crit * S.area_crit, pen;
-            if (min_area <= mesh_area && mesh_area < crit) pen = (mesh_area - crit) / (crit - min_area);
-            else if (mesh_area < min_area) pen = -1;
-            else pen = 0;
-            reward += quality + pen;
-            failed = false;
-            if (nn <= 5) {                                   // E:345-351
-                reward += 10; done = true;
-                if (nn == 4) {
-                    if (P.elem && lane < 4 && S.n_elements < P.elem_cap)
-                        P.elem[((size_t)env * P.elem_cap + S.n_elements) * 4 + lane] = P.vid[off + lane];
-                    S.n_elements++;
-                }
-            }
-        } else {
-            reward += S.n_elements ? -1.0 / S.n_elements : -1;      // E:357
+            b_reward = boundary_quality_no_new(w, t0, t1, g0, g1);
         }
-    }
-
-    // ---- next state (E:361-386) -------------------------------------------------------------
-    float obs;
-    bool obs_none = false;
-    if (success) {
+        double quality = e_reward + 1 * (b_reward - 1);              // M:1754-1766
+        // ---- speed penalty (E:590-607) ------------------------------------------------------
+        double min_area = S.area_min * S.area_min, crit = S.area_crit * S.area_crit, pen;
+        if (min_area <= mesh_area && mesh_area < crit) pen = (mesh_area - crit) / (crit - min_area);
+        else if (mesh_area < min_area) pen = -1;
+        else pen = 0;
+        reward += quality + pen;
+        if (nn <= 5) {                                       // E:345-351
+            reward += 10; done = true;
+            if (nn == 4) {
+                if (P.elem && lane < 4 && S.n_elements < P.elem_cap)
+                    P.elem[((size_t)env * P.elem_cap + S.n_elements) * 4 + lane] = P.vid[off + lane];
+                S.n_elements++;
+            }
+        }
+        // ---- next state (E:361-386) ---------------------------------------------------------
+        float obs = 0.0f;
+        bool obs_none = false;
         __syncwarp();
         S.ref_index = find_reference_index(w, P.key + off, P.stamp + off);
         if (S.ref_index >= 0) obs = compute_obs(w, S.ref_index, S.current_area / S.original_area, S.base_length);
-        else { obs = 0.0f; obs_none = true; }
+        else obs_none = true;
         S.failed_num = 0;
-    } else {
-        // nothing changed: the reference recomputes a bit-identical observation
-        obs = lane < MG_OBS_DIM ? P.obs_cache[(size_t)env * MG_OBS_DIM + lane] : 0.0f;
-        S.failed_num++;
+        finish_step(P, io, env, lane, S, n, reward, done, false, true, obs_none, obs, set);
     }
-    bool is_complete = true;
-    if (failed && S.failed_num >= 100) { done = true; is_complete = false; }
-    bool terminated = done && is_complete, truncated = done && !is_complete;
-    if ((obs_none || dead) && !done) { done = true; truncated = true; }   // sentinel, see DESIGN.md
-    S.ep_return += reward; S.ep_len++;
+}
 
-    // ---- statistics --------------------------------------------------------------------------
-    if (lane == 0) {
-        EnvStats T = P.stats[env];
-        T.steps++; T.sum_n += n;
-        if (success) { T.successes++; T.sum_n_success += n; }
-        if (done) {
-            T.episodes++; T.completed += terminated; T.truncated += truncated; T.elements += S.n_elements;
-            T.sum_return += S.ep_return; T.sum_length += S.ep_len;
-        }
-        P.stats[env] = T;
-        rew_out[env] = reward;
-        term_out[env] = terminated;
-        trunc_out[env] = truncated;
-        if (n_elem_out) n_elem_out[env] = S.n_elements;
+// ---- phase C ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(WPB * 32) mg_step_reset_kernel(Params P, StepIO io, int set) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    SmemLayout L = carve(smem_raw, P.cap, warp);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {       // the other counter set is idle during this step
+        P.counters[2 * (set ^ 1) + 0] = 0;
+        P.counters[2 * (set ^ 1) + 1] = 0;
     }
-    if (term_obs_out && lane < MG_OBS_DIM) term_obs_out[(size_t)env * MG_OBS_DIM + lane] = done ? obs : 0.0f;
-
-    // ---- auto-reset (V:40-52, stock SB3 behaviour) -------------------------------------------
-    if (done && P.auto_reset) {
+    const int count = P.counters[2 * set + 1];
+#pragma unroll 1
+    for (int item = blockIdx.x * WPB + warp; item < count; item += gridDim.x * WPB) {
+        const int env = P.reset_list[item];
+        EnvState S = P.st[env];
+        Warp w;
+        w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = 0;
         S.episode++;
         __syncwarp();
-        obs = reset_env(P, w, env, S);
-    }
-    if (lane == 0) P.st[env] = S;
-    if (lane < MG_OBS_DIM) {
-        if (success || done) P.obs_cache[(size_t)env * MG_OBS_DIM + lane] = obs;
-        obs_out[(size_t)env * MG_OBS_DIM + lane] = obs;
+        float obs = reset_env(P, w, env, S);
+        if (lane == 0) P.st[env] = S;
+        if (lane < MG_OBS_DIM) {
+            P.obs_cache[(size_t)env * MG_OBS_DIM + lane] = obs;
+            io.obs_out[(size_t)env * MG_OBS_DIM + lane] = obs;
+        }
+        __syncwarp();
     }
 }
 
@@ -1030,7 +1155,7 @@ __global__ void mg_stats_kernel(int num_envs, EnvStats *stats, mg_episode_stats 
 //   prev + A (j+1) dir, j < x, followed by cur; if the total is odd the middle point of the last
 //   edge is dropped (tk-ui.py:267-269).  Coordinates / 100 (geometry.py:46).
 // One coarse vertex per lane (max_coarse <= 32).  The ring is written to w.ring[0..n).
-__device__ int generate_polygon(const Params &P, Warp &w, long long global_env, int episode) {
+__device__ __noinline__ int generate_polygon(const Params &P, Warp &w, long long global_env, int episode) {
     const mg_polygen_cfg &G = P.gen;
     const int lane = w.lane;
     int *cx = w.queue, *cy = w.queue + 32, *cnt = w.queue + 64, *offs = w.queue + 96;
@@ -1066,7 +1191,7 @@ __device__ int generate_polygon(const Params &P, Warp &w, long long global_env, 
     if (lane < K) {
         double ang = start + (incl - step);
         double s, c;
-        sincos(ang, &s, &c);
+        mg_sincos(ang, &s, &c);
         cx[lane] = (int)(G.ctr_x + radius * c);
         cy[lane] = (int)(G.ctr_y + radius * s);
     }
@@ -1117,11 +1242,13 @@ __device__ int generate_polygon(const Params &P, Warp &w, long long global_env, 
     const bool odd = (total & 1) != 0;
     const int c_last = cnt[K - 1];
     const int drop = odd ? c_last / 2 : -1;             // index popped from the last edge's points
+#pragma unroll 1
     for (int e = 0; e < K; e++) {
         const int ce = cnt[e], oe = offs[e];
         const double epx = shfl_d(pxv, e), epy = shfl_d(pyv, e), ecx = shfl_d(cxv, e), ecy = shfl_d(cyv, e);
         const double eL = shfl_d(L, e);
         const double ux = (ecx - epx) / eL, uy = (ecy - epy) / eL;
+#pragma unroll 1
         for (int j = lane; j < ce; j += 32) {
             double X, Y;
             if (j == ce - 1) { X = ecx; Y = ecy; }

@@ -46,6 +46,13 @@ __device__ __forceinline__ double py_round4(double x) { return py_rint4(x) / 1e4
 // NumPy scalar round(x, 4) for np.float32: everything stays float32 (C:1290).
 __device__ __forceinline__ float np_round4f(float x) { return __fdiv_rn(rintf(__fmul_rn(x, 1e4f)), 1e4f); }
 
+// out-of-line wrappers: one copy of each libdevice routine in the kernel image (the step kernel is
+// instruction-fetch bound when these are inlined at every call site)
+__device__ __noinline__ void mg_sincos(double x, double *s, double *c) { sincos(x, s, c); }
+__device__ __noinline__ double mg_sin(double x) { return sin(x); }
+__device__ __noinline__ double mg_pow(double x, double y) { return pow(x, y); }
+__device__ __noinline__ double mg_atan2(double y, double x) { return atan2(y, x); }
+
 // ---- distance / angle -------------------------------------------------------------------
 // C:25-26 Point2D.distance_to.  (CPython evaluates dx ** 2 through libm pow, which is not always
 // the correctly rounded dx*dx; the difference is <= 1 ulp of the distance and never reaches a
@@ -57,12 +64,12 @@ __device__ __forceinline__ double pdist(P2 a, P2 b) {
 
 // C:99-108 Vertex.to_find_clockwise_angle(self = c, point1, point2): clockwise angle p1 -> p2
 // about c, quantised to 1e-4 rad, in [0, 6.2832]; -0.0 maps to 6.2832.
-__device__ __forceinline__ double cw_angle(P2 c, P2 p1, P2 p2) {
+__device__ __noinline__ double cw_angle(P2 c, P2 p1, P2 p2) {
     double v1x = p1.x - c.x, v1y = p1.y - c.y;
     double v2x = p2.x - c.x, v2y = p2.y - c.y;
     double cr = v1x * v2y - v1y * v2x;
     double dt = v1x * v2x + v1y * v2y;
-    double th = -atan2(cr, dt);
+    double th = -mg_atan2(cr, dt);
     if (signbit(th)) th = 2 * PI + th;
     return py_round4(th);
 }
@@ -78,7 +85,7 @@ __device__ __forceinline__ double cross_product(double v1x, double v1y, double v
 
 // C:499-524 Segment.straddle(self = (s1, s2), another = (o1, o2)) once the collinearity pre-test
 // (both quantised angles at s1 have sin rounding to 0) is known.
-__device__ __forceinline__ bool straddle_decide(P2 s1, P2 s2, P2 o1, P2 o2, bool collinear) {
+__device__ __noinline__ bool straddle_decide(P2 s1, P2 s2, P2 o1, P2 o2, bool collinear) {
     if (collinear) {
         double l1 = pdist(s1, s2), l2 = pdist(o1, o2);
         if (l1 > l2) {

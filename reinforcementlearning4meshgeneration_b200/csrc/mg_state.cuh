@@ -40,6 +40,15 @@ struct EnvStats {
     double sum_return, sum_length;
 };
 
+// element accepted by phase A of a step, applied by phase B
+struct __align__(16) Pending {
+    double newx, newy;
+    double corner[4];     // the quad's four quantised corner angles (C:752), reused for area/quality
+    int32_t rule;         // -1 / +1 (0 with new_vertex)
+    int32_t new_vertex;
+    int32_t pad[2];
+};
+
 struct DomainScalars {
     int32_t n0;
     int32_t ref_index;
@@ -61,6 +70,11 @@ struct Params {
     EnvState *st;
     EnvStats *stats;
     float *obs_cache;
+    // per-step work lists (phase kernels)
+    Pending *pend;       // [num_envs]
+    int *succ_list;      // [num_envs]
+    int *reset_list;     // [num_envs]
+    int *counters;       // [2 sets][2]: {successes, resets}
     // element log: quads as 4 vertex ids, coordinates of inserted vertices
     int32_t *elem;       // [num_envs][elem_cap][4]
     double2 *ins_xy;     // [num_envs][ins_cap]
