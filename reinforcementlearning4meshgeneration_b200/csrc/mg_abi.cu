@@ -67,8 +67,7 @@ int configure_kernels(mg_handle h) {
     h->smem = smem_bytes(h->P.cap);
     if (h->smem > 48 * 1024) {
         MG_CUDA(h, cudaFuncSetAttribute(mg_step_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-        MG_CUDA(h, cudaFuncSetAttribute(mg_step_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-        MG_CUDA(h, cudaFuncSetAttribute(mg_step_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        MG_CUDA(h, cudaFuncSetAttribute(mg_step_apply_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         MG_CUDA(h, cudaFuncSetAttribute(mg_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         MG_CUDA(h, cudaFuncSetAttribute(mg_template_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     }
@@ -254,9 +253,8 @@ int mg_step(mg_handle h, const float *act_dev, float *obs_dev, double *rew_dev, 
     const int gb = full < h->sm_count * 16 ? full : h->sm_count * 16;
     const int gc = full < h->sm_count * 4 ? full : h->sm_count * 4;
     mg_step_decide_kernel<<<full, WPB * 32, h->smem, s>>>(h->P, io, set);
-    mg_step_apply_kernel<<<gb, WPB * 32, h->smem, s>>>(h->P, io, set);
-    mg_step_reset_kernel<<<gc, WPB * 32, h->smem, s>>>(h->P, io, set);
-    h->launches += 3;
+    mg_step_apply_reset_kernel<<<gb + gc, WPB * 32, h->smem, s>>>(h->P, io, set, gb);
+    h->launches += 2;
     MG_CUDA(h, cudaGetLastError());
     return MG_OK;
 }

@@ -1,11 +1,11 @@
 // Batched BoudaryEnv reset/step for sm_100a: one warp per environment.
 //
 // The active boundary (updated_boundary.vertices) of the warp's environment is staged once per
-// step from HBM into a per-warp shared-memory ring with a single 1-D bulk async copy
+// phase from HBM into a per-warp shared-memory ring with a single 1-D bulk async copy
 // (cp.async.bulk + mbarrier, UBLKCP in SASS); every O(n) predicate then strides the ring with
-// 32 lanes (double2 loads), and the expensive quantised-angle evaluations (atan2) are batched so
-// that each lane evaluates one angle: segment-intersection tests use an aligned lane quad per
-// segment pair and exchange their collinearity bits with a ballot.
+// 32 lanes (double2 loads) and is resolved with ballots / shuffle reductions.  Angle
+// classifications use the exact-safe filters of mg_math.cuh, so atan2 only runs where the
+// quantised value itself is needed (candidate keys, observation, element quality).
 //
 // Citations: E = v2/src/mesh_rl/envs/boundary_env.py, M = v2/src/mesh_rl/mesh_core.py,
 // C = v2/src/mesh_rl/components_core.py, D = v2/src/mesh_rl/data_core.py (reference tree).
@@ -25,8 +25,7 @@ constexpr int WPB = MG_WPB;     // warps (= environments) per block
 #ifndef MG_MINB
 #define MG_MINB 1
 #endif
-constexpr int QCAP = 256;       // per-warp queue of "heavy" segment pairs (ints)
-constexpr int QFLUSH = 128;
+constexpr int QCAP = 128;       // per-warp integer scratch (coarse polygon of the generator)
 
 // ---------------------------------------------------------------------------------------------
 // per-warp view of the environment
@@ -42,7 +41,7 @@ __device__ __forceinline__ int wrapn(int i, int n) {
 
 struct Warp {
     double2 *ring;   // shared memory, this warp's vertex ring
-    int *queue;      // shared memory, this warp's heavy-pair queue
+    int *queue;      // shared memory, this warp's integer scratch
     int n;           // live boundary size
     int lane;
     __device__ __forceinline__ int wrap(int i) const {
@@ -118,11 +117,12 @@ __device__ __noinline__ void rebuild_candidates(const Warp &w, double *key, int3
 #pragma unroll 1
     for (int j = w.lane; j < w.n; j += 32) {
         P2 c = w.at(j);
-        double a0 = cw_angle(c, w.at(j + 1), w.at(j - 1));
+        double cr, dt;
+        cross_dot(c, w.at(j + 1), w.at(j - 1), cr, dt);
         double k = CUDART_INF;
-        if (!(a0 >= PI * 0.972 || a0 == 0)) {
-            double a1 = cw_angle(c, w.at(j + 2 >= w.n ? j + 2 - w.n : j + 2), w.at(j - 2 < -w.n ? j - 2 + w.n : j - 2));
-            k = cand_key_from_angles(a0, a1);
+        if (!surely_not_candidate(cr, dt)) {
+            double a0 = cw_angle_crdt(cr, dt);
+            if (!(a0 >= PI * 0.972 || a0 == 0)) k = cand_key_from_angles(a0, cw_angle(c, w.at(j + 2), w.at(j - 2)));
         }
         key[j] = k;
         stamp[j] = j;
@@ -240,8 +240,14 @@ __device__ __noinline__ float compute_obs(const Warp &w, int idx, double area_ra
         if (j < 0) j += n;
         P2 q = w.at(j);
         double d = pdist(ref, q);
-        double angle = cw_angle(ref, q, right_p);
-        if (angle == 0) continue;                             // C:1255
+        double cr, dt;
+        cross_dot(ref, q, right_p, cr, dt);
+        // the quantised angle itself is only needed inside the radius; outside, only "angle == 0"
+        double angle = 1.0;
+        if (d < T) {
+            angle = cw_angle_crdt(cr, dt);
+            if (angle == 0) continue;                         // C:1255
+        } else if (angle_is_zero(cr, dt)) continue;
         double kk = angle / sector;
         int k = (kk < 3.0) ? (int)kk : 3;                     // int() truncation; NaN/inf -> no sector
         if (k < 3 && d < T) {
@@ -370,59 +376,6 @@ __device__ __noinline__ double shoelace_area(const Warp &w) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// heavy-pair queue: entries are evaluated 8 at a time, one aligned lane quad per segment pair
-// ---------------------------------------------------------------------------------------------
-struct QCtx {
-    int mode;            // 0: point-in-polygon (entry = edge index), 1: boundary intersection (entry = 4*vertex + t)
-    P2 a, b;             // mode 0: ray (P, (10000, P.y));  mode 1: checking segment c1 = (a, b)
-    P2 c, d;             // mode 1: checking segment c2 = (c, d)
-};
-
-__device__ __forceinline__ void qdecode(const Warp &w, const QCtx &q, int e, P2 &a1, P2 &a2, P2 &b1, P2 &b2) {
-    if (q.mode == 0) {
-        a1 = w.at(e);
-        a2 = w.at(e - 1);
-        b1 = q.a;
-        b2 = q.b;
-    } else {
-        int j = e >> 2, t = e & 3;
-        if (t & 2) { a1 = q.c; a2 = q.d; } else { a1 = q.a; a2 = q.b; }
-        b1 = w.at(j);
-        b2 = (t & 1) ? w.at(j + 1) : w.at(j - 1);
-    }
-}
-
-__device__ __noinline__ int process_queue(const Warp &w, int qn, const QCtx &q, bool stop_on_first) {
-    int hits = 0;
-#pragma unroll 1
-    for (int base = 0; base < qn; base += 8) {
-        int e = base + (w.lane >> 2);
-        bool active = e < qn;
-        P2 a1 = mk(0, 0), a2 = a1, b1 = a1, b2 = a1;
-        if (active) qdecode(w, q, w.queue[e], a1, a2, b1, b2);
-        bool c = is_cross_quad(a1, a2, b1, b2, active, w.lane);
-        unsigned m = __ballot_sync(FULL, c && (w.lane & 3) == 0);
-        hits += __popc(m);
-        if (stop_on_first && hits) break;
-    }
-    return hits;
-}
-
-__device__ __forceinline__ void queue_push(const Warp &w, int &qn, bool flag, int value, int &hits, const QCtx &q,
-                                           bool stop_on_first) {
-    unsigned m = __ballot_sync(FULL, flag);
-    if (m == 0) return;
-    if (flag) w.queue[qn + __popc(m & ((1u << w.lane) - 1))] = value;
-    qn += __popc(m);
-    __syncwarp();
-    if (qn > QFLUSH) {
-        hits += process_queue(w, qn, q, stop_on_first);
-        qn = 0;
-        __syncwarp();
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 // point-in-polygon (M:74-128 calculate_crossing_segments, M:176-187, M:565-572)
 // ---------------------------------------------------------------------------------------------
 // rint(1e4 * dy) with the reference's rounding flavour: NumPy's when either operand is an
@@ -440,14 +393,13 @@ __device__ __forceinline__ double rint4_mixed(double dy, const int32_t *vid, int
 
 __device__ __noinline__ bool point_inside(const Warp &w, P2 P, const int32_t *vid, int n0) {
     const int n = w.n;
-    int qn = 0, hits = 0;
-    QCtx decode;
-    decode.mode = 0; decode.a = P; decode.b = mk(10000, P.y); decode.c = P; decode.d = P;
+    int hits = 0;
+    const P2 ray2 = mk(10000, P.y);
     const bool can_prune = P.x < 9000.0;
 #pragma unroll 1
     for (int base = 0; base < n; base += 32) {
         int j = base + w.lane;
-        bool need = false;
+        bool hit = false;
         if (j < n) {
             int jb = j == 0 ? n - 1 : j - 1;
             P2 a = w.at(j), b = w.at(jb);
@@ -472,13 +424,12 @@ __device__ __noinline__ bool point_inside(const Warp &w, P2 P, const int32_t *vi
                     double dya = a.y - P.y, dyb = b.y - P.y;
                     bool same_side = (dya > 1e-9 && dyb > 1e-9) || (dya < -1e-9 && dyb < -1e-9);
                     bool off_axis = fabs(dya) > 1e-4 * fabs(a.x - P.x) || fabs(dyb) > 1e-4 * fabs(b.x - P.x);
-                    need = !(can_prune && same_side && off_axis);
+                    if (!(can_prune && same_side && off_axis)) hit = is_cross(a, b, P, ray2);
                 }
             }
         }
-        queue_push(w, qn, need, j, hits, decode, false);
+        hits += __popc(__ballot_sync(FULL, hit));
     }
-    hits += process_queue(w, qn, decode, false);
     return (hits & 1) != 0;
 }
 
@@ -493,39 +444,25 @@ __device__ __noinline__ bool find_same_point(const Warp &w, P2 P) {
 // ---------------------------------------------------------------------------------------------
 // candidate quad: validity (C:738-757, C:814-826) + corner angles
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ bool mesh_is_valid(const Warp &w, const P2 (&m)[4], double (&corner)[4]) {
+__device__ __noinline__ bool mesh_is_valid(const Warp &w, const P2 (&m)[4]) {
     const int lane = w.lane;
-    // lanes 0-3: is_cross((m0,m1),(m2,m3)); lanes 4-7: is_cross((m0,m3),(m1,m2)); lanes 8-11: corners
-    P2 a1 = m[0], a2 = lane < 4 ? m[1] : m[3], b1 = lane < 4 ? m[2] : m[1], b2 = lane < 4 ? m[3] : m[2];
-    double ang = 0;
-    if (lane < 8) {
-        int sub = lane & 3;
-        P2 c = sub < 2 ? a1 : b1;
-        P2 p1 = sub == 0 ? b1 : (sub == 1 ? b2 : (sub == 2 ? a1 : a2));
-        P2 p2 = sub < 2 ? a2 : b2;
-        ang = cw_angle(c, p1, p2);
-    } else if (lane < 12) {
-        int i = lane - 8;
+    // lanes 0-3: corner i = m[i].angle(m[i+1], m[i-1]) outside [0.01 pi, 0.99 pi]?   (C:746-757)
+    // lanes 4-5: is_cross((m0,m1),(m2,m3)), is_cross((m0,m3),(m1,m2))                  (C:814-826)
+    // Mesh.is_valid is a pure conjunction, so the evaluation order does not matter.
+    bool bad = false;
+    if (lane < 4) {
         P2 c = m[0], p1 = m[1], p2 = m[3];
-        if (i == 1) { c = m[1]; p1 = m[2]; p2 = m[0]; }
-        if (i == 2) { c = m[2]; p1 = m[3]; p2 = m[1]; }
-        if (i == 3) { c = m[3]; p1 = m[0]; p2 = m[2]; }
-        ang = cw_angle(c, p1, p2);
+        if (lane == 1) { c = m[1]; p1 = m[2]; p2 = m[0]; }
+        if (lane == 2) { c = m[2]; p1 = m[3]; p2 = m[1]; }
+        if (lane == 3) { c = m[3]; p1 = m[0]; p2 = m[2]; }
+        double cr, dt;
+        cross_dot(c, p1, p2, cr, dt);
+        bad = corner_angle_invalid(cr, dt);
     }
-    unsigned zb = __ballot_sync(FULL, sin_rounds_to_zero(ang));
-#pragma unroll
-    for (int i = 0; i < 4; i++) corner[i] = shfl_d(ang, 8 + i);
-    bool x0 = straddle_decide(m[0], m[1], m[2], m[3], (zb & 0x3u) == 0x3u) &&
-              straddle_decide(m[2], m[3], m[0], m[1], (zb & 0xCu) == 0xCu);
-    if (x0) return false;
-    bool x1 = straddle_decide(m[0], m[3], m[1], m[2], (zb & 0x30u) == 0x30u) &&
-              straddle_decide(m[1], m[2], m[0], m[3], (zb & 0xC0u) == 0xC0u);
-    if (x1) return false;
-    const double max_degree = 0.99 * PI, min_degree = 0.01 * PI;
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-        if (corner[i] > max_degree || corner[i] < min_degree) return false;
-    return true;
+    if (__any_sync(FULL, bad)) return false;
+    if (lane == 4) bad = is_cross(m[0], m[1], m[2], m[3]);
+    if (lane == 5) bad = is_cross(m[0], m[3], m[1], m[2]);
+    return !__any_sync(FULL, bad);
 }
 
 // M:536-556 check_intersection_with_boundary.  qi[] = boundary indices of the quad vertices
@@ -538,25 +475,28 @@ __device__ __noinline__ bool intersects_boundary(const Warp &w, const P2 (&m)[4]
         if (k != ri) max_dist = fmax(max_dist, pdist(ref, m[k]));
     const P2 c1a = m[(ri + 3) & 3], c1b = m[(ri + 2) & 3], c2a = m[(ri + 2) & 3], c2b = m[(ri + 1) & 3];
     auto in_mesh = [&](int j) { return j == qi[0] || j == qi[1] || j == qi[2] || j == qi[3]; };
-    QCtx decode;
-    decode.mode = 1; decode.a = c1a; decode.b = c1b; decode.c = c2a; decode.d = c2b;
-    int qn = 0, hits = 0;
 #pragma unroll 1
-    for (int base = 0; base < n && !hits; base += 32) {
+    for (int base = 0; base < n; base += 32) {
         int j = base + w.lane;
-        bool near = false, okp = false, okn = false;
+        bool hit = false;
         if (j < n && !in_mesh(j)) {
-            near = pdist(ref, w.at(j)) < max_dist;
-            okp = near && !in_mesh(j == 0 ? n - 1 : j - 1);
-            okn = near && !in_mesh(j + 1 == n ? 0 : j + 1);
+            P2 v = w.at(j);
+            if (pdist(ref, v) < max_dist) {
+                int jp = j == 0 ? n - 1 : j - 1, jn = j + 1 == n ? 0 : j + 1;
+                // any of (c1,prev) (c1,next) (c2,prev) (c2,next) crossing -> True (order irrelevant)
+                if (!in_mesh(jp)) {
+                    P2 q = w.at(jp);
+                    hit = is_cross(c1a, c1b, v, q) || is_cross(c2a, c2b, v, q);
+                }
+                if (!hit && !in_mesh(jn)) {
+                    P2 q = w.at(jn);
+                    hit = is_cross(c1a, c1b, v, q) || is_cross(c2a, c2b, v, q);
+                }
+            }
         }
-        if (!__any_sync(FULL, near)) continue;
-        // reference order per vertex: (c1,prev) (c1,next) (c2,prev) (c2,next); any hit -> True
-#pragma unroll 1
-        for (int t = 0; t < 4; t++) queue_push(w, qn, (t & 1) ? okn : okp, j * 4 + t, hits, decode, true);
+        if (__any_sync(FULL, hit)) return true;
     }
-    if (!hits) hits += process_queue(w, qn, decode, true);
-    return hits != 0;
+    return false;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -767,8 +707,9 @@ __global__ void __launch_bounds__(WPB * 32) mg_reset_kernel(Params P, const uint
 // fused kernel was instruction-fetch bound: 65 % I-cache hit rate, see profiles/):
 //   A  mg_step_decide_kernel  all envs   action -> candidate quad -> validity decision; finishes the
 //                                        step of every env whose action failed (cached observation)
-//   B  mg_step_apply_kernel   successes  boundary update, candidate keys, reward, next observation
-//   C  mg_step_reset_kernel   done envs  in-place reset (template copy or fresh random polygon)
+//   B  apply blocks           successes  boundary update, candidate keys, reward, next observation
+//   C  reset blocks           done envs  in-place reset (template copy or fresh random polygon)
+//   (B and C share one launch, mg_step_apply_reset_kernel: their env sets are disjoint)
 // Work lists are appended with one atomicAdd per warp; counter set (step & 1) is used by step s and
 // the other set is zeroed by phase C, so no memset sits between launches.
 // ---------------------------------------------------------------------------------------------
@@ -787,9 +728,9 @@ __device__ __forceinline__ void push_list(int *list, int *counter, int env, int 
 }
 
 // Tail of step() shared by phases A and B (E:361-386 + outputs + statistics).
-__device__ __forceinline__ void finish_step(const Params &P, const StepIO &io, int env, int lane, EnvState &S, int n_before,
+__device__ __forceinline__ bool finish_step(const Params &P, const StepIO &io, int env, int lane, EnvState &S, int n_before,
                                             double reward, bool done, bool failed, bool success, bool force_trunc,
-                                            float obs, int set) {
+                                            float obs) {
     bool is_complete = true;
     if (failed && S.failed_num >= 100) { done = true; is_complete = false; }
     bool terminated = done && is_complete, truncated = done && !is_complete;
@@ -815,7 +756,7 @@ __device__ __forceinline__ void finish_step(const Params &P, const StepIO &io, i
         if (success) P.obs_cache[(size_t)env * MG_OBS_DIM + lane] = obs;
         io.obs_out[(size_t)env * MG_OBS_DIM + lane] = obs;
     }
-    if (done && P.auto_reset) push_list(P.reset_list, P.counters + 2 * set + 1, env, lane);
+    return done && P.auto_reset;
 }
 
 __device__ __forceinline__ void quad_indices(int rule, bool new_vertex, int idx, int n, int (&qi)[4], int &ri) {
@@ -852,12 +793,15 @@ __global__ void __launch_bounds__(WPB * 32, MG_MINB) mg_step_decide_kernel(Param
     const P2 ref = dead ? mk(0, 0) : w.at(idx), right_p = dead ? mk(1, 0) : w.at(idx - 1);
 
     // ---- action -> candidate vertex (E:783-792, E:202-210, D:112-137) ------------------------
+    // theta = 2 pi - atan2(dy, dx)  =>  cos(theta) = dx / r, sin(theta) = -dy / r: evaluated from the
+    // edge vector instead of through atan2 + sincos (a few ulp either way, absorbed by the 4-decimal
+    // rounding of the new vertex just like libm-vs-CUDA differences are; see DESIGN.md "numerics")
     P2 newp;
     {
         double ax = (double)np_round4f(a1), ay = (double)np_round4f(a2);
-        double th = 2 * PI - mg_atan2(right_p.y - ref.y, right_p.x - ref.x);
-        double s, c;
-        mg_sincos(th, &s, &c);
+        double dx = right_p.x - ref.x, dy = right_p.y - ref.y;
+        double r = sqrt(dx * dx + dy * dy);
+        double c = r > 0 ? dx / r : 1.0, s = r > 0 ? -(dy / r) : 0.0;
         double ox = c * ax + s * ay;
         double oy = -s * ax + c * ay;
         ox *= S.base_length; oy *= S.base_length;
@@ -889,16 +833,14 @@ __global__ void __launch_bounds__(WPB * 32, MG_MINB) mg_step_decide_kernel(Param
         quad_indices(rule, new_vertex, idx, n, qi, ri);
 #pragma unroll
         for (int k = 0; k < 4; k++) m[k] = qi[k] < 0 ? newp : w.at(qi[k]);
-        double corner[4];
-        bool valid = mesh_is_valid(w, m, corner);
+        bool valid = mesh_is_valid(w, m);
         if (valid) valid = !intersects_boundary(w, m, qi, ri, ref);
         if (valid) {
             // hand the element over to phase B
             if (lane == 0) {
                 Pending Q;
                 Q.newx = newp.x; Q.newy = newp.y;
-                Q.corner[0] = corner[0]; Q.corner[1] = corner[1]; Q.corner[2] = corner[2]; Q.corner[3] = corner[3];
-                Q.rule = rule; Q.new_vertex = new_vertex ? 1 : 0; Q.pad[0] = 0; Q.pad[1] = 0;
+                Q.rule = rule; Q.new_vertex = new_vertex ? 1 : 0;
                 P.pend[env] = Q;
             }
             push_list(P.succ_list, P.counters + 2 * set + 0, env, lane);
@@ -909,19 +851,31 @@ __global__ void __launch_bounds__(WPB * 32, MG_MINB) mg_step_decide_kernel(Param
     // failed step: nothing changed, the reference recomputes a bit-identical observation
     float obs = lane < MG_OBS_DIM ? P.obs_cache[(size_t)env * MG_OBS_DIM + lane] : 0.0f;
     S.failed_num++;
-    finish_step(P, io, env, lane, S, n, reward, done, true, false, dead, obs, set);
+    if (finish_step(P, io, env, lane, S, n, reward, done, true, false, dead, obs))
+        push_list(P.reset_list, P.counters + 2 * set + 1, env, lane);
 }
 
 // ---- phase B ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(WPB * 32) mg_step_apply_kernel(Params P, StepIO io, int set) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    SmemLayout L = carve(smem_raw, P.cap, warp);
+// in-place reset of one finished env (V:40-52): new episode, first observation to the caller
+__device__ __forceinline__ void reset_in_place(const Params &P, const StepIO &io, int env, Warp &w, EnvState &S) {
+    S.episode++;
+    __syncwarp();
+    float obs = reset_env(P, w, env, S);
+    if (w.lane == 0) P.st[env] = S;
+    if (w.lane < MG_OBS_DIM) {
+        P.obs_cache[(size_t)env * MG_OBS_DIM + w.lane] = obs;
+        io.obs_out[(size_t)env * MG_OBS_DIM + w.lane] = obs;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void apply_successes(const Params &P, const StepIO &io, int set, const SmemLayout &L, int first,
+                                                int stride, int lane) {
     init_mbar(L.mbar, lane);
     const int count = P.counters[2 * set + 0];
     unsigned phase = 0;
 #pragma unroll 1
-    for (int item = blockIdx.x * WPB + warp; item < count; item += gridDim.x * WPB) {
+    for (int item = first; item < count; item += stride) {
         const int env = P.succ_list[item];
         EnvState S = P.st[env];
         const size_t off = (size_t)env * P.cap;
@@ -934,11 +888,24 @@ __global__ void __launch_bounds__(WPB * 32) mg_step_apply_kernel(Params P, StepI
         const int n = S.n, idx = S.ref_index;
         const bool new_vertex = Q.new_vertex != 0;
         const P2 newp = mk(Q.newx, Q.newy);
-        const double corner[4] = {Q.corner[0], Q.corner[1], Q.corner[2], Q.corner[3]};
         P2 m[4]; int qi[4]; int ri;
         quad_indices(Q.rule, new_vertex, idx, n, qi, ri);
 #pragma unroll
         for (int k = 0; k < 4; k++) m[k] = qi[k] < 0 ? newp : w.at(qi[k]);
+        // the quad's four quantised corner angles (C:752, C:888, C:946-947), one per lane
+        double corner[4];
+        {
+            double ca = 0;
+            if (lane < 4) {
+                P2 c = m[0], p1 = m[1], p2 = m[3];
+                if (lane == 1) { c = m[1]; p1 = m[2]; p2 = m[0]; }
+                if (lane == 2) { c = m[2]; p1 = m[3]; p2 = m[1]; }
+                if (lane == 3) { c = m[3]; p1 = m[0]; p2 = m[2]; }
+                ca = cw_angle(c, p1, p2);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) corner[k] = shfl_d(ca, k);
+        }
         const int ip1 = qi[3] , im1 = new_vertex ? qi[1] : (Q.rule == -1 ? qi[0] : qi[1]);
         double reward = 0;
         bool done = false;
@@ -1062,35 +1029,33 @@ __global__ void __launch_bounds__(WPB * 32) mg_step_apply_kernel(Params P, StepI
         if (S.ref_index >= 0) obs = compute_obs(w, S.ref_index, S.current_area / S.original_area, S.base_length);
         else obs_none = true;
         S.failed_num = 0;
-        finish_step(P, io, env, lane, S, n, reward, done, false, true, obs_none, obs, set);
+        if (finish_step(P, io, env, lane, S, n, reward, done, false, true, obs_none, obs)) reset_in_place(P, io, env, w, S);
     }
 }
 
-// ---- phase C ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(WPB * 32) mg_step_reset_kernel(Params P, StepIO io, int set) {
+// ---- phases B + C in one launch: blocks [0, apply_blocks) apply the accepted elements, the remaining
+// blocks reset the envs that phase A finished (truncations, E:382-384); the two sets are disjoint.
+__global__ void __launch_bounds__(WPB * 32) mg_step_apply_reset_kernel(Params P, StepIO io, int set, int apply_blocks) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     SmemLayout L = carve(smem_raw, P.cap, warp);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {       // the other counter set is idle during this step
+    if ((int)blockIdx.x < apply_blocks) {
+        apply_successes(P, io, set, L, blockIdx.x * WPB + warp, apply_blocks * WPB, lane);
+        return;
+    }
+    const int rb = blockIdx.x - apply_blocks, nrb = gridDim.x - apply_blocks;
+    if (rb == 0 && threadIdx.x == 0) {               // the other counter set is idle during this step
         P.counters[2 * (set ^ 1) + 0] = 0;
         P.counters[2 * (set ^ 1) + 1] = 0;
     }
     const int count = P.counters[2 * set + 1];
 #pragma unroll 1
-    for (int item = blockIdx.x * WPB + warp; item < count; item += gridDim.x * WPB) {
+    for (int item = rb * WPB + warp; item < count; item += nrb * WPB) {
         const int env = P.reset_list[item];
         EnvState S = P.st[env];
         Warp w;
         w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = 0;
-        S.episode++;
-        __syncwarp();
-        float obs = reset_env(P, w, env, S);
-        if (lane == 0) P.st[env] = S;
-        if (lane < MG_OBS_DIM) {
-            P.obs_cache[(size_t)env * MG_OBS_DIM + lane] = obs;
-            io.obs_out[(size_t)env * MG_OBS_DIM + lane] = obs;
-        }
-        __syncwarp();
+        reset_in_place(P, io, env, w, S);
     }
 }
 

@@ -3,6 +3,12 @@
 // compiled with -fmad=false: CPython / NumPy never contract a*b+c, and the 4-decimal
 // quantisation of every angle (C:108) makes discrete decisions depend on exact IEEE results.
 //
+// The expensive primitive is the quantised clockwise angle (one atan2).  Most call sites only
+// need a *classification* of that angle (is it 0 / pi / 2pi?  is it inside [0.01pi, 0.99pi]?  is
+// it >= 0.972pi?).  Those are answered from the cross / dot products with exact-safe filters
+// (margins far wider than the 5e-5 rad quantisation) and fall back to the exact atan2 path only
+// inside the narrow undecided band, so the result is always the reference's.
+//
 // Citations: C = v2/src/mesh_rl/components_core.py (legacy twin general/components.py, -8 lines)
 #pragma once
 #include <cuda_runtime.h>
@@ -46,12 +52,11 @@ __device__ __forceinline__ double py_round4(double x) { return py_rint4(x) / 1e4
 // NumPy scalar round(x, 4) for np.float32: everything stays float32 (C:1290).
 __device__ __forceinline__ float np_round4f(float x) { return __fdiv_rn(rintf(__fmul_rn(x, 1e4f)), 1e4f); }
 
-// out-of-line wrappers: one copy of each libdevice routine in the kernel image (the step kernel is
-// instruction-fetch bound when these are inlined at every call site)
+// out-of-line wrappers: one copy of each libdevice routine per kernel image (the fused step
+// kernel was instruction-fetch bound when these were inlined at every call site)
 __device__ __noinline__ void mg_sincos(double x, double *s, double *c) { sincos(x, s, c); }
 __device__ __noinline__ double mg_sin(double x) { return sin(x); }
 __device__ __noinline__ double mg_pow(double x, double y) { return pow(x, y); }
-__device__ __noinline__ double mg_atan2(double y, double x) { return atan2(y, x); }
 
 // ---- distance / angle -------------------------------------------------------------------
 // C:25-26 Point2D.distance_to.  (CPython evaluates dx ** 2 through libm pow, which is not always
@@ -62,75 +67,95 @@ __device__ __forceinline__ double pdist(P2 a, P2 b) {
     return sqrt(dx * dx + dy * dy);
 }
 
-// C:99-108 Vertex.to_find_clockwise_angle(self = c, point1, point2): clockwise angle p1 -> p2
-// about c, quantised to 1e-4 rad, in [0, 6.2832]; -0.0 maps to 6.2832.
-__device__ __noinline__ double cw_angle(P2 c, P2 p1, P2 p2) {
+// cross / dot of (p1 - c) and (p2 - c) exactly as C:100-106 forms them
+__device__ __forceinline__ void cross_dot(P2 c, P2 p1, P2 p2, double &cr, double &dt) {
     double v1x = p1.x - c.x, v1y = p1.y - c.y;
     double v2x = p2.x - c.x, v2y = p2.y - c.y;
-    double cr = v1x * v2y - v1y * v2x;
-    double dt = v1x * v2x + v1y * v2y;
-    double th = -mg_atan2(cr, dt);
+    cr = v1x * v2y - v1y * v2x;
+    dt = v1x * v2x + v1y * v2y;
+}
+
+// C:106-108: theta = -atan2(cross, dot); round(theta, 4) if copysign(1, theta) >= 0 else
+// round(2 pi + theta, 4).  Quantised to 1e-4 rad, in [0, 6.2832]; -0.0 maps to 6.2832.
+__device__ __noinline__ double cw_angle_crdt(double cr, double dt) {
+    double th = -atan2(cr, dt);
     if (signbit(th)) th = 2 * PI + th;
     return py_round4(th);
+}
+
+// C:99-108 Vertex.to_find_clockwise_angle(self = c, point1, point2)
+__device__ __forceinline__ double cw_angle(P2 c, P2 p1, P2 p2) {
+    double cr, dt;
+    cross_dot(c, p1, p2, cr, dt);
+    return cw_angle_crdt(cr, dt);
 }
 
 // round(math.sin(angle), 4) == 0 for a quantised angle  <=>  angle in {0, 3.1416, 6.2832}
 // (sin(3.1415) = 9.3e-5 and sin(6.2831) = -8.5e-5 round to +-0.0001).  Used by C:506-508.
 __device__ __forceinline__ bool sin_rounds_to_zero(double a) { return a == 0.0 || a == 3.1416 || a == 6.2832; }
 
+// Is the quantised angle one of {0, 3.1416, 6.2832}?  Those classes cover |theta - k pi| < 5.8e-5,
+// i.e. |cross| < 5.8e-5 |dot|; outside |cross| <= 1e-4 |dot| the answer is No without an atan2.
+__device__ __forceinline__ bool angle_zero_class(double cr, double dt) {
+    if (fabs(cr) > 1e-4 * fabs(dt)) return false;
+    return sin_rounds_to_zero(cw_angle_crdt(cr, dt));
+}
+// Is the quantised angle exactly 0 (C:1255)?
+__device__ __forceinline__ bool angle_is_zero(double cr, double dt) {
+    if (fabs(cr) > 1e-4 * fabs(dt)) return false;
+    return cw_angle_crdt(cr, dt) == 0.0;
+}
+
+// C:752-757: quad corner angle outside [0.01 pi, 0.99 pi]?  theta in (0, pi) needs cross < 0;
+// 0.01 pi = 0.031416: |cross| < 0.0310 |dot| is surely outside, |cross| > 0.0318 |dot| surely inside.
+__device__ __forceinline__ bool corner_angle_invalid(double cr, double dt) {
+    if (!(cr < 0)) return true;                       // theta = 0 or theta in [pi, 2 pi]
+    double a = fabs(cr), b = fabs(dt);
+    if (a > 0.0318 * b) return false;
+    if (a < 0.0310 * b) return true;
+    double ang = cw_angle_crdt(cr, dt);
+    return ang > 0.99 * PI || ang < 0.01 * PI;
+}
+
+// M:249: not a reference candidate when the first angle is >= 0.972 pi or == 0.
+// 0.972 pi = pi - 0.08796: cross >= 0 gives theta = 0 or >= pi; for cross < 0 and dot < 0,
+// |cross| < 0.0875 |dot| puts theta within 0.0873 rad of pi.  Otherwise undecided (exact path).
+__device__ __forceinline__ bool surely_not_candidate(double cr, double dt) {
+    if (!(cr < 0)) return true;
+    return dt < 0 && fabs(cr) < 0.0875 * fabs(dt);
+}
+
 // C:490-491
 __device__ __forceinline__ double cross_product(double v1x, double v1y, double v2x, double v2y) {
     return v1x * v2y - v2x * v1y;
 }
 
-// C:499-524 Segment.straddle(self = (s1, s2), another = (o1, o2)) once the collinearity pre-test
-// (both quantised angles at s1 have sin rounding to 0) is known.
-__device__ __noinline__ bool straddle_decide(P2 s1, P2 s2, P2 o1, P2 o2, bool collinear) {
-    if (collinear) {
-        double l1 = pdist(s1, s2), l2 = pdist(o1, o2);
-        if (l1 > l2) {
-            P2 m = mk((s2.x + s1.x) / 2, (s2.y + s1.y) / 2);
-            return fmin(pdist(m, o2), pdist(m, o1)) <= l1 / 2;
-        }
-        P2 m = mk((o2.x + o1.x) / 2, (o2.y + o1.y) / 2);
-        return fmin(pdist(m, s2), pdist(m, s1)) <= l2 / 2;
+// C:509-519: the collinear branch of Segment.straddle (rare)
+__device__ __noinline__ bool straddle_collinear(P2 s1, P2 s2, P2 o1, P2 o2) {
+    double l1 = pdist(s1, s2), l2 = pdist(o1, o2);
+    if (l1 > l2) {
+        P2 m = mk((s2.x + s1.x) / 2, (s2.y + s1.y) / 2);
+        return fmin(pdist(m, o2), pdist(m, o1)) <= l1 / 2;
     }
+    P2 m = mk((o2.x + o1.x) / 2, (o2.y + o1.y) / 2);
+    return fmin(pdist(m, s2), pdist(m, s1)) <= l2 / 2;
+}
+
+// C:499-524 Segment.straddle(self = (s1, s2), another = (o1, o2))
+__device__ __forceinline__ bool straddle(P2 s1, P2 s2, P2 o1, P2 o2) {
     double v1x = o1.x - s1.x, v1y = o1.y - s1.y;
     double v2x = o2.x - s1.x, v2y = o2.y - s1.y;
     double vmx = s2.x - s1.x, vmy = s2.y - s1.y;
+    // angles at s1: (o1, s2) and (o2, s2); cross/dot in the operand order of C:100-106
+    double cr1 = v1x * vmy - v1y * vmx, dt1 = v1x * vmx + v1y * vmy;
+    double cr2 = v2x * vmy - v2y * vmx, dt2 = v2x * vmx + v2y * vmy;
+    if (angle_zero_class(cr1, dt1) && angle_zero_class(cr2, dt2)) return straddle_collinear(s1, s2, o1, o2);
     return cross_product(v1x, v1y, vmx, vmy) * cross_product(v2x, v2y, vmx, vmy) <= 0;
 }
 
-// Scalar (one-lane) C:526-541 Segment.is_cross(self = (a1, a2), another = (b1, b2)).
-__device__ __forceinline__ bool is_cross_scalar(P2 a1, P2 a2, P2 b1, P2 b2) {
-    bool z0 = sin_rounds_to_zero(cw_angle(a1, b1, a2));
-    bool z1 = sin_rounds_to_zero(cw_angle(a1, b2, a2));
-    if (!straddle_decide(a1, a2, b1, b2, z0 && z1)) return false;
-    bool z2 = sin_rounds_to_zero(cw_angle(b1, a1, b2));
-    bool z3 = sin_rounds_to_zero(cw_angle(b1, a2, b2));
-    return straddle_decide(b1, b2, a1, a2, z2 && z3);
-}
-
-// Quad-lane is_cross: the four lanes of an aligned lane quad each evaluate ONE of the four
-// quantised angles of is_cross(A, B) (the atan2 is the expensive part) and exchange the
-// collinearity bits with a ballot.  Must be called by all 32 lanes; `active` says whether this
-// quad holds a real segment pair.  Returns the predicate in every lane of the quad.
-// The reference short-circuits `straddle(A,B) and straddle(B,A)`; both operands are pure, so
-// evaluating all four angles is equivalent.
-__device__ __forceinline__ bool is_cross_quad(P2 a1, P2 a2, P2 b1, P2 b2, bool active, int lane) {
-    int sub = lane & 3;
-    bool z = false;
-    if (active) {
-        P2 c = sub < 2 ? a1 : b1;
-        P2 p1 = sub == 0 ? b1 : (sub == 1 ? b2 : (sub == 2 ? a1 : a2));
-        P2 p2 = sub < 2 ? a2 : b2;
-        z = sin_rounds_to_zero(cw_angle(c, p1, p2));
-    }
-    unsigned zb = (__ballot_sync(FULL, z) >> (lane & ~3)) & 0xFu;
-    if (!active) return false;
-    bool sab = straddle_decide(a1, a2, b1, b2, (zb & 3u) == 3u);
-    bool sba = straddle_decide(b1, b2, a1, a2, (zb & 12u) == 12u);
-    return sab && sba;
+// C:526-541 Segment.is_cross(self = (a1, a2), another = (b1, b2)), one lane.
+__device__ __forceinline__ bool is_cross(P2 a1, P2 a2, P2 b1, P2 b2) {
+    return straddle(a1, a2, b1, b2) && straddle(b1, b2, a1, a2);
 }
 
 // C:678-692 Segment(p1, p2).distance(point a)
@@ -160,7 +185,6 @@ __device__ __forceinline__ double py_sum(const double (&x)[K]) {
 
 // ---- warp helpers ----------------------------------------------------------------------
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(FULL, v, src); }
-__device__ __forceinline__ P2 shfl_p(P2 v, int src) { return mk(__shfl_sync(FULL, v.x, src), __shfl_sync(FULL, v.y, src)); }
 
 __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
 #pragma unroll
@@ -173,11 +197,6 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
 __device__ __forceinline__ double warp_min_d(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
-    return v;
-}
-__device__ __forceinline__ double warp_max_d(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
     return v;
 }
 __device__ __forceinline__ double warp_sum_d(double v) {

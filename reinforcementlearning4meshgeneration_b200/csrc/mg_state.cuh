@@ -42,11 +42,10 @@ struct EnvStats {
 
 // element accepted by phase A of a step, applied by phase B
 struct __align__(16) Pending {
-    double newx, newy;
-    double corner[4];     // the quad's four quantised corner angles (C:752), reused for area/quality
+    double newx, newy;    // the candidate vertex (used when new_vertex != 0)
     int32_t rule;         // -1 / +1 (0 with new_vertex)
     int32_t new_vertex;
-    int32_t pad[2];
+    int64_t pad;
 };
 
 struct DomainScalars {
