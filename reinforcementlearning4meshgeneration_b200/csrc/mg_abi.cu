@@ -71,6 +71,10 @@ int configure_kernels(mg_handle h) {
         MG_CUDA(h, cudaFuncSetAttribute(mg_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         MG_CUDA(h, cudaFuncSetAttribute(mg_template_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     }
+    // the vertex rings want shared memory, not L1: ask for the largest carve-out so that the number of
+    // resident warps is set by registers, not by the driver's default split
+    MG_CUDA(h, cudaFuncSetAttribute(mg_step_decide_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    MG_CUDA(h, cudaFuncSetAttribute(mg_step_apply_reset_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     return MG_OK;
 }
 

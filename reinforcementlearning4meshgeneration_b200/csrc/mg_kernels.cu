@@ -19,13 +19,13 @@
 namespace mg {
 
 #ifndef MG_WPB
-#define MG_WPB 1
+#define MG_WPB 2     // tuned on B200 (profiles/): 2 warps per block, >= 8 blocks per SM
 #endif
 constexpr int WPB = MG_WPB;     // warps (= environments) per block
 #ifndef MG_MINB
-#define MG_MINB 1
+#define MG_MINB 8
 #endif
-constexpr int QCAP = 128;       // per-warp integer scratch (coarse polygon of the generator)
+constexpr int QCAP = 128 + 256;  // per-warp scratch: 4x32 ints + 32x4 doubles (coarse polygon of the generator)
 
 // ---------------------------------------------------------------------------------------------
 // per-warp view of the environment
@@ -1033,17 +1033,18 @@ __device__ __forceinline__ void apply_successes(const Params &P, const StepIO &i
     }
 }
 
-// ---- phases B + C in one launch: blocks [0, apply_blocks) apply the accepted elements, the remaining
+// ---- phases B + C in one launch: the last apply_blocks blocks apply the accepted elements, the first
 // blocks reset the envs that phase A finished (truncations, E:382-384); the two sets are disjoint.
 __global__ void __launch_bounds__(WPB * 32) mg_step_apply_reset_kernel(Params P, StepIO io, int set, int apply_blocks) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     SmemLayout L = carve(smem_raw, P.cap, warp);
-    if ((int)blockIdx.x < apply_blocks) {
-        apply_successes(P, io, set, L, blockIdx.x * WPB + warp, apply_blocks * WPB, lane);
+    const int reset_blocks = gridDim.x - apply_blocks;     // scheduled first: one reset is the longest item
+    if ((int)blockIdx.x >= reset_blocks) {
+        apply_successes(P, io, set, L, (blockIdx.x - reset_blocks) * WPB + warp, apply_blocks * WPB, lane);
         return;
     }
-    const int rb = blockIdx.x - apply_blocks, nrb = gridDim.x - apply_blocks;
+    const int rb = blockIdx.x, nrb = reset_blocks;
     if (rb == 0 && threadIdx.x == 0) {               // the other counter set is idle during this step
         P.counters[2 * (set ^ 1) + 0] = 0;
         P.counters[2 * (set ^ 1) + 1] = 0;
@@ -1206,25 +1207,34 @@ __device__ __noinline__ int generate_polygon(const Params &P, Warp &w, long long
     __syncwarp();
     const bool odd = (total & 1) != 0;
     const int c_last = cnt[K - 1];
-    const int drop = odd ? c_last / 2 : -1;             // index popped from the last edge's points
+    const int drop = odd ? offs[K - 1] + c_last / 2 : -1;   // flat index popped from the last edge (tk-ui.py:267-269)
+    // coarse edge data in shared scratch so that any lane can emit any point
+    double *edge = reinterpret_cast<double *>(w.queue + 128);            // [K][4]: prev x, prev y, unit x, unit y
+    if (lane < K) {
+        edge[4 * lane + 0] = pxv; edge[4 * lane + 1] = pyv;
+        edge[4 * lane + 2] = (cxv - pxv) / L; edge[4 * lane + 3] = (cyv - pyv) / L;
+    }
+    __syncwarp();
 #pragma unroll 1
-    for (int e = 0; e < K; e++) {
-        const int ce = cnt[e], oe = offs[e];
-        const double epx = shfl_d(pxv, e), epy = shfl_d(pyv, e), ecx = shfl_d(cxv, e), ecy = shfl_d(cyv, e);
-        const double eL = shfl_d(L, e);
-        const double ux = (ecx - epx) / eL, uy = (ecy - epy) / eL;
-#pragma unroll 1
-        for (int j = lane; j < ce; j += 32) {
-            double X, Y;
-            if (j == ce - 1) { X = ecx; Y = ecy; }
-            else { double d = A * (j + 1); X = epx + d * ux; Y = epy + d * uy; }
-            int pos = oe + j;
-            if (e == K - 1 && drop >= 0) {
-                if (j == drop) continue;
-                if (j > drop) pos--;
-            }
-            if (pos < P.cap) w.ring[pos] = make_double2(X / 100.0, Y / 100.0);
+    for (int f = lane; f < total; f += 32) {
+        if (f == drop) continue;
+        int lo = 0, hi = K - 1;                       // last edge e with offs[e] <= f
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (offs[mid] <= f) lo = mid; else hi = mid - 1;
         }
+        const int e = lo, j = f - offs[e], ce = cnt[e];
+        double X, Y;
+        if (j == ce - 1) {                            // the coarse vertex itself
+            int cur = K - 1 - e;
+            X = cx[cur]; Y = cy[cur];
+        } else {
+            double d = A * (j + 1);
+            X = edge[4 * e + 0] + d * edge[4 * e + 2];
+            Y = edge[4 * e + 1] + d * edge[4 * e + 3];
+        }
+        int pos = (drop >= 0 && f > drop) ? f - 1 : f;
+        if (pos < P.cap) w.ring[pos] = make_double2(X / 100.0, Y / 100.0);
     }
     __syncwarp();
     int n = odd ? total - 1 : total;
