@@ -190,3 +190,60 @@ def test_random_polygons_sharding_invariance():
         ra = a.step(a.sample_actions(11, t)).obs.cpu().numpy()
         rb = b.step(b.sample_actions(11, t)).obs.cpu().numpy()
         assert np.array_equal(ra[8:], rb), f"step {t}"
+
+
+def test_gymnasium_facade_matches_golden_trace():
+    """BoudaryEnv (single-env Gymnasium facade, auto-reset off like the reference env) replays the
+    golden trace of BoudaryEnv(boundary()) -- config 1 of BASELINE.json."""
+    from reinforcementlearning4meshgeneration_b200.boundary_env import BoudaryEnv, boundary
+    tr = load_trace("boundary0")
+    env = BoudaryEnv(boundary())
+    assert env.observation_space.shape == (18,) and env.action_space.shape == (3,)
+    obs, info = env.reset()
+    assert info == {} and obs.dtype == np.float32 and np.array_equal(obs, tr["reset_obs"])
+    T = 1500
+    for t in range(T):
+        obs, rew, term, trunc, info = env.step(tr["actions"][t])
+        assert isinstance(rew, np.float64) and isinstance(term, bool) and isinstance(trunc, bool)
+        assert term == bool(tr["terminated"][t]) and trunc == bool(tr["truncated"][t]), f"flags differ at {t}"
+        assert abs(rew - tr["reward"][t]) <= REWARD_TOL * max(1.0, abs(tr["reward"][t])), f"reward differs at {t}"
+        assert info["is_complete"] == (not trunc)
+        assert len(env.generated_meshes) == int(tr["n_elements"][t]), f"element count differs at {t}"
+        if term or trunc:
+            exp = tr["terminal_obs"][t]
+            if not tr["obs_none"][t]:
+                assert np.array_equal(obs, exp), f"terminal obs differs at {t}"
+            obs, _ = env.reset()
+        assert np.array_equal(obs, tr["obs"][t]) or (term or trunc), f"obs differs at {t}"
+    env.close()
+
+
+def test_sb3_vecenv_adapter_on_device():
+    from reinforcementlearning4meshgeneration_b200.vec_env import SB3VecEnv
+    from oracle.c_oracle import OracleEnv
+    tr = load_trace("half_wheel")
+    N, T = 4, 300
+    venv = SB3VecEnv([tr["xy0"]], num_envs=N)
+    obs = venv.reset()
+    oracles = [OracleEnv(tr["xy0"], original_area=float(tr["original_area"])) for _ in range(N)]
+    streams = [action_stream(40 + e, T) for e in range(N)]
+    ep_r = np.zeros(N)
+    n_done = 0
+    for t in range(T):
+        obs, rew, dones, infos = venv.step(np.stack([s[t] for s in streams]))
+        for e in range(N):
+            eo, er, te, tru, _ = oracles[e].step(streams[e][t])
+            ep_r[e] += er
+            assert dones[e] == (te or tru)
+            assert abs(float(rew[e]) - er) <= 1e-6 * max(1.0, abs(er))      # VecEnv rewards are float32
+            if te or tru:
+                n_done += 1
+                assert np.array_equal(infos[e]["terminal_observation"], np.zeros(18, np.float32) if eo is None else eo)
+                assert infos[e]["TimeLimit.truncated"] == tru and infos[e]["is_complete"] == (not tru)
+                assert infos[e]["n_elements"] == oracles[e].n_elements
+                assert abs(infos[e]["episode"]["r"] - ep_r[e]) <= 1e-6 * max(1.0, abs(ep_r[e]))
+                ep_r[e] = 0
+                eo = oracles[e].reset()
+            assert np.array_equal(obs[e], eo)
+    assert n_done > 3
+    venv.close()
