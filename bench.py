@@ -72,7 +72,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
@@ -221,6 +221,9 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()          # sampled under the same load from burn-in to the end of the timed region
     step_idx = 0
     # burn-in (setup, untimed): all envs start their first episode together; run until resets are
     # spread over the steps so that the timed region sees the steady-state mix of episode phases
@@ -233,9 +236,6 @@ def run_gpu(args):
     env.stats(reset=True)
     launches0 = env.launch_count
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     K = args.steps
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(K)]
@@ -358,7 +358,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--workload", choices=["c1", "c2", "c3"], default="c3")
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's BASELINE size)")

@@ -396,35 +396,36 @@ __device__ __noinline__ bool point_inside(const Warp &w, P2 P, const int32_t *vi
     int hits = 0;
     const P2 ray2 = mk(10000, P.y);
     const bool can_prune = P.x < 9000.0;
-#pragma unroll 1
+#pragma unroll 2
     for (int base = 0; base < n; base += 32) {
         int j = base + w.lane;
         bool hit = false;
         if (j < n) {
             int jb = j == 0 ? n - 1 : j - 1;
             P2 a = w.at(j), b = w.at(jb);
-            double ro = rint4_mixed(a.y - b.y, vid, j, jb, n0);
-            if (ro != 0) {
-                // would this edge be counted if it crosses the ray?  (M:91-118)
-                bool counted;
-                if (rint((a.y - P.y) * 1e4) == 0) {
-                    int jc = j + 1 == n ? 0 : j + 1;
-                    double rn = rint4_mixed(w.at(jc).y - a.y, vid, jc, j, n0);
-                    counted = !(rn == 0 || rn * ro < 0) && ro < 0;
-                } else if (rint((b.y - P.y) * 1e4) == 0) {
-                    int jc = jb == 0 ? n - 1 : jb - 1;
-                    double rp = rint4_mixed(b.y - w.at(jc).y, vid, jb, jc, n0);
-                    counted = !(rp == 0 || rp * ro < 0) && !(ro < 0);
-                } else counted = true;
-                if (counted) {
-                    // Exact early-out: if both endpoints lie strictly on the same side of the ray's
-                    // line, and at least one of them is more than 1e-4 rad off that line as seen from
-                    // P, ray.straddle(edge) is False (the collinearity pre-test C:506-508 needs both
-                    // quantised angles in {0, pi, 2pi}; the cross products then have equal signs).
-                    double dya = a.y - P.y, dyb = b.y - P.y;
-                    bool same_side = (dya > 1e-9 && dyb > 1e-9) || (dya < -1e-9 && dyb < -1e-9);
-                    bool off_axis = fabs(dya) > 1e-4 * fabs(a.x - P.x) || fabs(dyb) > 1e-4 * fabs(b.x - P.x);
-                    if (!(can_prune && same_side && off_axis)) hit = is_cross(a, b, P, ray2);
+            // Exact early-out, evaluated first because it removes ~97 % of the edges: an edge is
+            // counted only if edge.is_cross(ray) (M:90).  If both endpoints lie strictly on the same
+            // side of the ray's line and at least one of them is more than 1e-4 rad off that line as
+            // seen from P, ray.straddle(edge) is False (the collinearity pre-test C:506-508 needs both
+            // quantised angles in {0, pi, 2 pi}; the cross products then have equal signs).
+            double dya = a.y - P.y, dyb = b.y - P.y;
+            bool same_side = (dya > 1e-9 && dyb > 1e-9) || (dya < -1e-9 && dyb < -1e-9);
+            bool off_axis = fabs(dya) > 1e-4 * fabs(a.x - P.x) || fabs(dyb) > 1e-4 * fabs(b.x - P.x);
+            if (!(can_prune && same_side && off_axis)) {
+                double ro = rint4_mixed(a.y - b.y, vid, j, jb, n0);
+                if (ro != 0) {
+                    // would this edge be counted if it crosses the ray?  (M:91-118)
+                    bool counted;
+                    if (rint(dya * 1e4) == 0) {
+                        int jc = j + 1 == n ? 0 : j + 1;
+                        double rn = rint4_mixed(w.at(jc).y - a.y, vid, jc, j, n0);
+                        counted = !(rn == 0 || rn * ro < 0) && ro < 0;
+                    } else if (rint(dyb * 1e4) == 0) {
+                        int jc = jb == 0 ? n - 1 : jb - 1;
+                        double rp = rint4_mixed(b.y - w.at(jc).y, vid, jb, jc, n0);
+                        counted = !(rp == 0 || rp * ro < 0) && !(ro < 0);
+                    } else counted = true;
+                    if (counted) hit = is_cross(a, b, P, ray2);
                 }
             }
         }
@@ -475,7 +476,7 @@ __device__ __noinline__ bool intersects_boundary(const Warp &w, const P2 (&m)[4]
         if (k != ri) max_dist = fmax(max_dist, pdist(ref, m[k]));
     const P2 c1a = m[(ri + 3) & 3], c1b = m[(ri + 2) & 3], c2a = m[(ri + 2) & 3], c2b = m[(ri + 1) & 3];
     auto in_mesh = [&](int j) { return j == qi[0] || j == qi[1] || j == qi[2] || j == qi[3]; };
-#pragma unroll 1
+#pragma unroll 2
     for (int base = 0; base < n; base += 32) {
         int j = base + w.lane;
         bool hit = false;
@@ -730,14 +731,14 @@ __device__ __forceinline__ void push_list(int *list, int *counter, int env, int 
 // Tail of step() shared by phases A and B (E:361-386 + outputs + statistics).
 __device__ __forceinline__ bool finish_step(const Params &P, const StepIO &io, int env, int lane, EnvState &S, int n_before,
                                             double reward, bool done, bool failed, bool success, bool force_trunc,
-                                            float obs) {
+                                            float obs, const EnvStats *preloaded = nullptr) {
     bool is_complete = true;
     if (failed && S.failed_num >= 100) { done = true; is_complete = false; }
     bool terminated = done && is_complete, truncated = done && !is_complete;
     if (force_trunc && !done) { done = true; truncated = true; }          // sentinel, see DESIGN.md
     S.ep_return += reward; S.ep_len++;
     if (lane == 0) {
-        EnvStats T = P.stats[env];
+        EnvStats T = preloaded ? *preloaded : P.stats[env];
         T.steps++; T.sum_n += n_before;
         if (success) { T.successes++; T.sum_n_success += n_before; }
         if (done) {
@@ -771,25 +772,27 @@ __device__ __forceinline__ void quad_indices(int rule, bool new_vertex, int idx,
 }
 
 // ---- phase A ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(WPB * 32, MG_MINB) mg_step_decide_kernel(Params P, StepIO io, int set) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.x * WPB + warp;
-    if (env >= P.num_envs) return;
-    SmemLayout L = carve(smem_raw, P.cap, warp);
-    init_mbar(L.mbar, lane);
-
+__device__ __forceinline__ void decide_one(const Params &P, const StepIO &io, int set, const SmemLayout &L, int env, int lane,
+                                           unsigned parity) {
     EnvState S = P.st[env];
+    // everything the step will need from HBM is requested now, so that the tail of a failed step
+    // (cached observation, statistics) does not pay a second and third DRAM round trip
+    const float a0 = io.act[(size_t)env * 3 + 0], a1 = io.act[(size_t)env * 3 + 1], a2 = io.act[(size_t)env * 3 + 2];
+    const float obs_cached = lane < MG_OBS_DIM ? P.obs_cache[(size_t)env * MG_OBS_DIM + lane] : 0.0f;
+    EnvStats T0;
+    if (lane == 0) T0 = P.stats[env];
     const size_t off = (size_t)env * P.cap;
     Warp w;
     w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = S.n;
     // An env without a reference point (empty candidate list, E:736-738 returns None) has no
     // defined continuation in the reference (its next step raises): it is reported truncated.
     const bool dead = S.ref_index < 0 || S.n < 3;
-    if (!dead) stage_ring(w.ring, L.mbar, P.xy + off, S.n, lane, 0);
+    if (!dead) stage_ring(w.ring, L.mbar, P.xy + off, S.n, lane, parity);
+    else if (lane == 0) {     // keep the barrier phase in step with the caller's parity
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(L.mbar)) : "memory");
+    }
 
     const int n = S.n, idx = dead ? 0 : S.ref_index;
-    const float a0 = io.act[(size_t)env * 3 + 0], a1 = io.act[(size_t)env * 3 + 1], a2 = io.act[(size_t)env * 3 + 2];
     const P2 ref = dead ? mk(0, 0) : w.at(idx), right_p = dead ? mk(1, 0) : w.at(idx - 1);
 
     // ---- action -> candidate vertex (E:783-792, E:202-210, D:112-137) ------------------------
@@ -849,10 +852,24 @@ __global__ void __launch_bounds__(WPB * 32, MG_MINB) mg_step_decide_kernel(Param
         reward += S.n_elements ? -1.0 / S.n_elements : -1;          // E:357
     }
     // failed step: nothing changed, the reference recomputes a bit-identical observation
-    float obs = lane < MG_OBS_DIM ? P.obs_cache[(size_t)env * MG_OBS_DIM + lane] : 0.0f;
     S.failed_num++;
-    if (finish_step(P, io, env, lane, S, n, reward, done, true, false, dead, obs))
+    if (finish_step(P, io, env, lane, S, n, reward, done, true, false, dead, obs_cached, &T0))
         push_list(P.reset_list, P.counters + 2 * set + 1, env, lane);
+}
+
+// Persistent grid (resident blocks only): warp k handles envs k, k + W, k + 2W, ...
+__global__ void __launch_bounds__(WPB * 32, MG_MINB) mg_step_decide_kernel(Params P, StepIO io, int set) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    SmemLayout L = carve(smem_raw, P.cap, warp);
+    init_mbar(L.mbar, lane);
+    unsigned parity = 0;
+#pragma unroll 1
+    for (int env = blockIdx.x * WPB + warp; env < P.num_envs; env += gridDim.x * WPB) {
+        decide_one(P, io, set, L, env, lane, parity);
+        parity ^= 1u;
+        __syncwarp();
+    }
 }
 
 // ---- phase B ---------------------------------------------------------------------------------
