@@ -176,3 +176,16 @@ class BoudaryEnv(_EnvBase):
     def render(self, mode: str = "human") -> None:
         print(f"Generated elements: {len(self.generated_meshes)}")
 
+    # -- element export (rl/boundary_env.py:648-669, general/mesh.py:1842-1864) ---------------
+    def _mesh(self):
+        quads, vxy, _ = self._batched.get_elements(0)
+        return len(self._xy), quads, vxy
+
+    def write_2_file(self, filename) -> None:
+        from .export import write_2_file
+        write_2_file(filename, *self._mesh())
+
+    def write_generated_elements_2_file(self, filename, format: str = "inp") -> None:
+        from .export import write_inp
+        write_inp(filename, *self._mesh())
+

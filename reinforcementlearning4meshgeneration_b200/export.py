@@ -1,0 +1,78 @@
+"""Element-log export: the generated quads of an episode in the
+reference's two on-disk formats, built from the device element log (mg_get_elements).
+
+* ``write_2_file``  -- JSON ``{"nodes": {i: {"coordinates": [x, y], "connected": [...]}},
+  "elements": {k: [i0, i1, i2, i3]}}`` as ``BoudaryEnv.write_2_file`` (rl/boundary_env.py:648-669):
+  node index = position in ``boundary.vertices`` = original vertices followed by the inserted ones
+  in insertion order, which is exactly this package's vertex-id convention; ``connected`` lists the
+  partners in segment order (the two polygon neighbours first, then element edges as they were
+  connected, general/components.py:832-837).
+* ``write_inp``     -- Abaqus ``.inp`` as ``write_generated_elements_2_file`` (general/mesh.py:1842-1864).
+"""
+from __future__ import annotations
+
+import json
+from typing import Dict, List
+
+import numpy as np
+
+
+def connectivity(n0: int, quads: np.ndarray, n_vertices: int) -> List[List[int]]:
+    """Per-vertex partner lists in the order the reference's Vertex.segments would hold them:
+    deep_copy links i-1 <-> i for the polygon (components.py:213-220), then every element calls
+    connect_vertices, which links v[i] <-> v[i-1] unless a segment already exists."""
+    adj: List[List[int]] = [[] for _ in range(n_vertices)]
+    for i in range(n0):
+        a = (i - 1) % n0
+        adj[a].append(i)
+        adj[i].append(a)
+    for q in quads:
+        for i in range(4):
+            a, b = int(q[i]), int(q[i - 1])
+            if b not in adj[a]:
+                adj[a].append(b)
+                adj[b].append(a)
+    return adj
+
+
+def mesh_dict(n0: int, quads: np.ndarray, vertex_xy: np.ndarray) -> Dict:
+    adj = connectivity(n0, quads, len(vertex_xy))
+    nodes = {}
+    for i, (x, y) in enumerate(vertex_xy):
+        conn: List[int] = []
+        for p in adj[i]:
+            if p not in conn:
+                conn.append(p)
+        nodes[i] = {"coordinates": [float(x), float(y)], "connected": conn}
+    elements = {k: [int(v) for v in q] for k, q in enumerate(quads)}
+    return {"nodes": nodes, "elements": elements}
+
+
+def write_2_file(filename, n0: int, quads: np.ndarray, vertex_xy: np.ndarray) -> None:
+    with open(filename, "w") as fw:
+        json.dump(mesh_dict(n0, quads, vertex_xy), fw)
+
+
+def write_inp(filename, n0: int, quads: np.ndarray, vertex_xy: np.ndarray) -> None:
+    if len(quads) == 0:
+        print("There are no elements generated!")
+        return
+    order: List[int] = []
+    for q in quads:
+        for v in q:
+            if int(v) not in order:
+                order.append(int(v))
+    for v in range(n0):            # the reference indexes every original vertex (mesh.py:1856-1857)
+        if v not in order:
+            order.append(v)
+    pos = {v: k + 1 for k, v in enumerate(order)}
+    with open(filename, "w") as fw:
+        fw.write("*NODE, NSET=ALLNODES\n")
+        for v in order:
+            fw.write(f"{pos[v]}, {vertex_xy[v][0]}, {vertex_xy[v][1]}\n")
+        i = 0
+        for i in range(1, n0):
+            fw.write(f"*ELEMENT, TYPE=B21, ELSET=EB{i}\n {i+1}, {pos[i-1]}, {pos[i]}\n")
+        fw.write(f"*ELEMENT, TYPE=S4R, ELSET=EB{i+1} \n")
+        for k, q in enumerate(quads):
+            fw.write(f"{k+1}, {pos[int(q[0])]}, {pos[int(q[1])]}, {pos[int(q[2])]}, {pos[int(q[3])]}\n")

@@ -247,3 +247,39 @@ def test_sb3_vecenv_adapter_on_device():
             assert np.array_equal(obs[e], eo)
     assert n_done > 3
     venv.close()
+
+
+def test_element_export_formats(tmp_path):
+    """write_2_file JSON / .inp export against the oracle's element log and segment graph."""
+    import json
+    from reinforcementlearning4meshgeneration_b200.boundary_env import BoudaryEnv
+    from oracle.c_oracle import OracleEnv
+    tr = load_trace("boundary0")
+    env = BoudaryEnv(tr["xy0"])
+    env.reset()
+    o = OracleEnv(tr["xy0"], original_area=float(tr["original_area"]))
+    for t in range(120):
+        env.step(tr["actions"][t])
+        o.step(tr["actions"][t])
+    f = tmp_path / "mesh.json"
+    env.write_2_file(f)
+    d = json.load(open(f))
+    quads, vxy = o.elements(), o.vertex_xy()
+    assert len(d["elements"]) == len(quads) > 5
+    for k, q in enumerate(quads):
+        assert d["elements"][str(k)] == q.tolist()
+    assert len(d["nodes"]) == len(vxy)
+    for i, p in enumerate(vxy):
+        assert d["nodes"][str(i)]["coordinates"] == p.tolist()
+    # every element edge is a connection; polygon neighbours come first
+    n0 = len(tr["xy0"])
+    assert d["nodes"]["3"]["connected"][:2] == [2, 4]
+    for q in quads:
+        for i in range(4):
+            assert int(q[i - 1]) in d["nodes"][str(int(q[i]))]["connected"]
+    g = tmp_path / "mesh.inp"
+    env.write_generated_elements_2_file(g)
+    txt = open(g).read()
+    assert txt.startswith("*NODE, NSET=ALLNODES") and txt.count("TYPE=B21") == n0 - 1 and "TYPE=S4R" in txt
+    assert len(txt.strip().splitlines()) == 1 + len(vxy) + 2 * (n0 - 1) + 1 + len(quads)
+    env.close()
