@@ -33,7 +33,6 @@ struct mg_env_s {
     int64_t launches = 0;
     int step_parity = 0;
     int sm_count = 148;
-    int decide_grid = 0;      // resident blocks of the persistent phase-A kernel
     size_t smem = 0;
     std::string err;
 };
@@ -76,10 +75,6 @@ int configure_kernels(mg_handle h) {
     // resident warps is set by registers, not by the driver's default split
     MG_CUDA(h, cudaFuncSetAttribute(mg_step_decide_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     MG_CUDA(h, cudaFuncSetAttribute(mg_step_apply_reset_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    int per_sm = 0;
-    MG_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mg_step_decide_kernel, WPB * 32, h->smem));
-    if (per_sm < 1) per_sm = 1;
-    h->decide_grid = per_sm * h->sm_count;
     return MG_OK;
 }
 
@@ -261,8 +256,7 @@ int mg_step(mg_handle h, const float *act_dev, float *obs_dev, double *rew_dev, 
     const int full = grid_for(h->num_envs);
     const int gb = full < h->sm_count * 16 ? full : h->sm_count * 16;
     const int gc = full < h->sm_count * 4 ? full : h->sm_count * 4;
-    const int ga = full < h->decide_grid ? full : h->decide_grid;
-    mg_step_decide_kernel<<<ga, WPB * 32, h->smem, s>>>(h->P, io, set);
+    mg_step_decide_kernel<<<full, WPB * 32, h->smem, s>>>(h->P, io, set);
     mg_step_apply_reset_kernel<<<gb + gc, WPB * 32, h->smem, s>>>(h->P, io, set, gb);
     h->launches += 2;
     MG_CUDA(h, cudaGetLastError());

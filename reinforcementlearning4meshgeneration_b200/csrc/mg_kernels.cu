@@ -133,7 +133,7 @@ __device__ __noinline__ void rebuild_candidates(const Warp &w, double *key, int3
 __device__ __noinline__ int find_reference_index(const Warp &w, const double *key, const int32_t *stamp) {
     double bk = CUDART_INF;
     int bs = 0x7fffffff, bj = -1;
-#pragma unroll 1
+#pragma unroll 4
     for (int j = w.lane; j < w.n; j += 32) {
         double k = key[j];
         int s = stamp[j];
@@ -263,6 +263,18 @@ __device__ __noinline__ float compute_obs(const Warp &w, int idx, double area_ra
         // C:657-676 ll.intersection_vertex(seg) with ll = (ref, p_s), seg = (B[m], B[m+1])
         P2 q2 = w.at(j + 1 >= n ? j + 1 - n : j + 1);
         double wx = q2.x - q.x, wy = q2.y - q.y;
+        {
+            // Exact-safe early-out: a hit needs the ray's line to cross the edge (0 < h < 1).  With
+            // sa, sb = signed offsets of the edge's endpoints from that line, h = sa / (sa - sb); both on
+            // the same side by a 1e-6 relative margin puts h at least ~5e-7 outside [0, 1], far beyond
+            // the rounding error of C:663-674 for an edge that is not degenerate in x or y.
+            double ax = q.x - ref.x, ay = q.y - ref.y;
+            double sa = ux * ay - uy * ax;
+            double sb = ux * (q2.y - ref.y) - uy * (q2.x - ref.x);
+            double tol = 1e-6 * (fabs(ux) + fabs(uy)) * (fabs(ax) + fabs(ay) + fabs(wx) + fabs(wy));
+            bool conditioned = (wx == 0 || fabs(wx) > 1e-6 * fabs(wy)) && (wy == 0 || fabs(wy) > 1e-6 * fabs(wx));
+            if (conditioned && ((sa > tol && sb > tol) || (sa < -tol && sb < -tol))) continue;
+        }
         double ss, hh;
         if (wy == 0) {
             if (uy == 0) continue;
@@ -396,36 +408,35 @@ __device__ __noinline__ bool point_inside(const Warp &w, P2 P, const int32_t *vi
     int hits = 0;
     const P2 ray2 = mk(10000, P.y);
     const bool can_prune = P.x < 9000.0;
-#pragma unroll 2
+#pragma unroll 1
     for (int base = 0; base < n; base += 32) {
         int j = base + w.lane;
         bool hit = false;
         if (j < n) {
             int jb = j == 0 ? n - 1 : j - 1;
             P2 a = w.at(j), b = w.at(jb);
-            // Exact early-out, evaluated first because it removes ~97 % of the edges: an edge is
-            // counted only if edge.is_cross(ray) (M:90).  If both endpoints lie strictly on the same
-            // side of the ray's line and at least one of them is more than 1e-4 rad off that line as
-            // seen from P, ray.straddle(edge) is False (the collinearity pre-test C:506-508 needs both
-            // quantised angles in {0, pi, 2 pi}; the cross products then have equal signs).
-            double dya = a.y - P.y, dyb = b.y - P.y;
-            bool same_side = (dya > 1e-9 && dyb > 1e-9) || (dya < -1e-9 && dyb < -1e-9);
-            bool off_axis = fabs(dya) > 1e-4 * fabs(a.x - P.x) || fabs(dyb) > 1e-4 * fabs(b.x - P.x);
-            if (!(can_prune && same_side && off_axis)) {
-                double ro = rint4_mixed(a.y - b.y, vid, j, jb, n0);
-                if (ro != 0) {
-                    // would this edge be counted if it crosses the ray?  (M:91-118)
-                    bool counted;
-                    if (rint(dya * 1e4) == 0) {
-                        int jc = j + 1 == n ? 0 : j + 1;
-                        double rn = rint4_mixed(w.at(jc).y - a.y, vid, jc, j, n0);
-                        counted = !(rn == 0 || rn * ro < 0) && ro < 0;
-                    } else if (rint(dyb * 1e4) == 0) {
-                        int jc = jb == 0 ? n - 1 : jb - 1;
-                        double rp = rint4_mixed(b.y - w.at(jc).y, vid, jb, jc, n0);
-                        counted = !(rp == 0 || rp * ro < 0) && !(ro < 0);
-                    } else counted = true;
-                    if (counted) hit = is_cross(a, b, P, ray2);
+            double ro = rint4_mixed(a.y - b.y, vid, j, jb, n0);
+            if (ro != 0) {
+                // would this edge be counted if it crosses the ray?  (M:91-118)
+                bool counted;
+                if (rint((a.y - P.y) * 1e4) == 0) {
+                    int jc = j + 1 == n ? 0 : j + 1;
+                    double rn = rint4_mixed(w.at(jc).y - a.y, vid, jc, j, n0);
+                    counted = !(rn == 0 || rn * ro < 0) && ro < 0;
+                } else if (rint((b.y - P.y) * 1e4) == 0) {
+                    int jc = jb == 0 ? n - 1 : jb - 1;
+                    double rp = rint4_mixed(b.y - w.at(jc).y, vid, jb, jc, n0);
+                    counted = !(rp == 0 || rp * ro < 0) && !(ro < 0);
+                } else counted = true;
+                if (counted) {
+                    // Exact early-out: if both endpoints lie strictly on the same side of the ray's
+                    // line, and at least one of them is more than 1e-4 rad off that line as seen from
+                    // P, ray.straddle(edge) is False (the collinearity pre-test C:506-508 needs both
+                    // quantised angles in {0, pi, 2pi}; the cross products then have equal signs).
+                    double dya = a.y - P.y, dyb = b.y - P.y;
+                    bool same_side = (dya > 1e-9 && dyb > 1e-9) || (dya < -1e-9 && dyb < -1e-9);
+                    bool off_axis = fabs(dya) > 1e-4 * fabs(a.x - P.x) || fabs(dyb) > 1e-4 * fabs(b.x - P.x);
+                    if (!(can_prune && same_side && off_axis)) hit = is_cross(a, b, P, ray2);
                 }
             }
         }
@@ -476,7 +487,7 @@ __device__ __noinline__ bool intersects_boundary(const Warp &w, const P2 (&m)[4]
         if (k != ri) max_dist = fmax(max_dist, pdist(ref, m[k]));
     const P2 c1a = m[(ri + 3) & 3], c1b = m[(ri + 2) & 3], c2a = m[(ri + 2) & 3], c2b = m[(ri + 1) & 3];
     auto in_mesh = [&](int j) { return j == qi[0] || j == qi[1] || j == qi[2] || j == qi[3]; };
-#pragma unroll 2
+#pragma unroll 1
     for (int base = 0; base < n; base += 32) {
         int j = base + w.lane;
         bool hit = false;
@@ -731,14 +742,14 @@ __device__ __forceinline__ void push_list(int *list, int *counter, int env, int 
 // Tail of step() shared by phases A and B (E:361-386 + outputs + statistics).
 __device__ __forceinline__ bool finish_step(const Params &P, const StepIO &io, int env, int lane, EnvState &S, int n_before,
                                             double reward, bool done, bool failed, bool success, bool force_trunc,
-                                            float obs, const EnvStats *preloaded = nullptr) {
+                                            float obs) {
     bool is_complete = true;
     if (failed && S.failed_num >= 100) { done = true; is_complete = false; }
     bool terminated = done && is_complete, truncated = done && !is_complete;
     if (force_trunc && !done) { done = true; truncated = true; }          // sentinel, see DESIGN.md
     S.ep_return += reward; S.ep_len++;
     if (lane == 0) {
-        EnvStats T = preloaded ? *preloaded : P.stats[env];
+        EnvStats T = P.stats[env];
         T.steps++; T.sum_n += n_before;
         if (success) { T.successes++; T.sum_n_success += n_before; }
         if (done) {
@@ -772,27 +783,25 @@ __device__ __forceinline__ void quad_indices(int rule, bool new_vertex, int idx,
 }
 
 // ---- phase A ---------------------------------------------------------------------------------
-__device__ __forceinline__ void decide_one(const Params &P, const StepIO &io, int set, const SmemLayout &L, int env, int lane,
-                                           unsigned parity) {
+__global__ void __launch_bounds__(WPB * 32, MG_MINB) mg_step_decide_kernel(Params P, StepIO io, int set) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int env = blockIdx.x * WPB + warp;
+    if (env >= P.num_envs) return;
+    SmemLayout L = carve(smem_raw, P.cap, warp);
+    init_mbar(L.mbar, lane);
+
     EnvState S = P.st[env];
-    // everything the step will need from HBM is requested now, so that the tail of a failed step
-    // (cached observation, statistics) does not pay a second and third DRAM round trip
-    const float a0 = io.act[(size_t)env * 3 + 0], a1 = io.act[(size_t)env * 3 + 1], a2 = io.act[(size_t)env * 3 + 2];
-    const float obs_cached = lane < MG_OBS_DIM ? P.obs_cache[(size_t)env * MG_OBS_DIM + lane] : 0.0f;
-    EnvStats T0;
-    if (lane == 0) T0 = P.stats[env];
     const size_t off = (size_t)env * P.cap;
     Warp w;
     w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = S.n;
     // An env without a reference point (empty candidate list, E:736-738 returns None) has no
     // defined continuation in the reference (its next step raises): it is reported truncated.
     const bool dead = S.ref_index < 0 || S.n < 3;
-    if (!dead) stage_ring(w.ring, L.mbar, P.xy + off, S.n, lane, parity);
-    else if (lane == 0) {     // keep the barrier phase in step with the caller's parity
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(L.mbar)) : "memory");
-    }
+    if (!dead) stage_ring(w.ring, L.mbar, P.xy + off, S.n, lane, 0);
 
     const int n = S.n, idx = dead ? 0 : S.ref_index;
+    const float a0 = io.act[(size_t)env * 3 + 0], a1 = io.act[(size_t)env * 3 + 1], a2 = io.act[(size_t)env * 3 + 2];
     const P2 ref = dead ? mk(0, 0) : w.at(idx), right_p = dead ? mk(1, 0) : w.at(idx - 1);
 
     // ---- action -> candidate vertex (E:783-792, E:202-210, D:112-137) ------------------------
@@ -852,24 +861,10 @@ __device__ __forceinline__ void decide_one(const Params &P, const StepIO &io, in
         reward += S.n_elements ? -1.0 / S.n_elements : -1;          // E:357
     }
     // failed step: nothing changed, the reference recomputes a bit-identical observation
+    float obs = lane < MG_OBS_DIM ? P.obs_cache[(size_t)env * MG_OBS_DIM + lane] : 0.0f;
     S.failed_num++;
-    if (finish_step(P, io, env, lane, S, n, reward, done, true, false, dead, obs_cached, &T0))
+    if (finish_step(P, io, env, lane, S, n, reward, done, true, false, dead, obs))
         push_list(P.reset_list, P.counters + 2 * set + 1, env, lane);
-}
-
-// Persistent grid (resident blocks only): warp k handles envs k, k + W, k + 2W, ...
-__global__ void __launch_bounds__(WPB * 32, MG_MINB) mg_step_decide_kernel(Params P, StepIO io, int set) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    SmemLayout L = carve(smem_raw, P.cap, warp);
-    init_mbar(L.mbar, lane);
-    unsigned parity = 0;
-#pragma unroll 1
-    for (int env = blockIdx.x * WPB + warp; env < P.num_envs; env += gridDim.x * WPB) {
-        decide_one(P, io, set, L, env, lane, parity);
-        parity ^= 1u;
-        __syncwarp();
-    }
 }
 
 // ---- phase B ---------------------------------------------------------------------------------
@@ -953,15 +948,25 @@ __device__ __forceinline__ void apply_successes(const Params &P, const StepIO &i
             const int lo = r0 < r1 ? r0 : r1, hi = r0 < r1 ? r1 : r0;
             auto newpos = [&](int j) { return j - (j > lo ? 1 : 0) - (j > hi ? 1 : 0); };
 #pragma unroll 1
-            for (int base = lo; base < n; base += 32) {
-                int j = base + lane;
-                bool mv = j < n && j != lo && j != hi;
-                double2 v = make_double2(0, 0); double k = 0; int st = 0, id = 0;
-                if (mv) { v = w.ring[j]; k = P.key[off + j]; st = P.stamp[off + j]; id = P.vid[off + j]; }
+            for (int base = lo; base < n; base += 128) {
+                // every element moves left by at most 2, so a group only overwrites slots that it (or an
+                // earlier group) has already read; 4 chunks of loads are in flight per DRAM round trip
+                double2 v[4]; double k[4]; int st[4], id[4];
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    int j = base + 32 * c + lane;
+                    bool mv = j < n && j != lo && j != hi;
+                    v[c] = make_double2(0, 0); k[c] = 0; st[c] = 0; id[c] = 0;
+                    if (mv) { v[c] = w.ring[j]; k[c] = P.key[off + j]; st[c] = P.stamp[off + j]; id[c] = P.vid[off + j]; }
+                }
                 __syncwarp();
-                if (mv) {
-                    int q = newpos(j);
-                    w.ring[q] = v; P.xy[off + q] = v; P.key[off + q] = k; P.stamp[off + q] = st; P.vid[off + q] = id;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    int j = base + 32 * c + lane;
+                    if (j < n && j != lo && j != hi) {
+                        int q = newpos(j);
+                        w.ring[q] = v[c]; P.xy[off + q] = v[c]; P.key[off + q] = k[c]; P.stamp[off + q] = st[c]; P.vid[off + q] = id[c];
+                    }
                 }
                 __syncwarp();
             }
