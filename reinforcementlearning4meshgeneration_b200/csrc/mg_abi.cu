@@ -28,6 +28,11 @@ struct mg_env_s {
     uint8_t *d_term = nullptr, *d_trunc = nullptr;
     int32_t *d_nel = nullptr;
     cudaStream_t host_stream = nullptr;
+    // mg_step_host: terminal observations travel compacted (only finished envs)
+    int32_t *d_pack_idx = nullptr, *d_pack_cnt = nullptr, *h_pack_idx = nullptr, *h_pack_cnt = nullptr;
+    float *d_pack_obs = nullptr, *h_pack_obs = nullptr;
+    float *last_term_obs_host = nullptr;
+    std::vector<int32_t> prev_done;
     bool ready = false;       // domains or generator configured
     bool was_reset = false;
     int64_t launches = 0;
@@ -126,6 +131,11 @@ int mg_create(mg_handle *out, int device, int num_envs, int max_verts) {
     A(dalloc(&h->d_term_obs, (size_t)num_envs * MG_OBS_DIM), "term_obs"); A(dalloc(&h->d_rew, (size_t)num_envs), "rew");
     A(dalloc(&h->d_term, (size_t)num_envs), "term"); A(dalloc(&h->d_trunc, (size_t)num_envs), "trunc");
     A(dalloc(&h->d_nel, (size_t)num_envs), "nel");
+    A(dalloc(&h->d_pack_idx, (size_t)num_envs), "pack_idx"); A(dalloc(&h->d_pack_cnt, (size_t)1), "pack_cnt");
+    A(dalloc(&h->d_pack_obs, (size_t)num_envs * MG_OBS_DIM), "pack_obs");
+    A(cudaMallocHost((void **)&h->h_pack_idx, sizeof(int32_t) * num_envs), "h_pack_idx");
+    A(cudaMallocHost((void **)&h->h_pack_cnt, sizeof(int32_t)), "h_pack_cnt");
+    A(cudaMallocHost((void **)&h->h_pack_obs, sizeof(float) * MG_OBS_DIM * num_envs), "h_pack_obs");
     if (rc == MG_OK && cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking) != cudaSuccess)
         rc = fail(h, MG_ERR_CUDA, "cudaStreamCreate");
     if (rc == MG_OK) rc = configure_kernels(h);
@@ -144,6 +154,8 @@ int mg_destroy(mg_handle h) {
     free_templates(h);
     cudaFree(h->d_stats_out); cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_term_obs); cudaFree(h->d_rew);
     cudaFree(h->d_term); cudaFree(h->d_trunc); cudaFree(h->d_nel);
+    cudaFree(h->d_pack_idx); cudaFree(h->d_pack_cnt); cudaFree(h->d_pack_obs);
+    cudaFreeHost(h->h_pack_idx); cudaFreeHost(h->h_pack_cnt); cudaFreeHost(h->h_pack_obs);
     if (h->host_stream) cudaStreamDestroy(h->host_stream);
     delete h;
     return MG_OK;
@@ -273,13 +285,38 @@ int mg_step_host(mg_handle h, const float *act_host, float *obs_host, double *re
     MG_CUDA(h, cudaMemcpyAsync(h->d_act, act_host, N * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
     int rc = mg_step(h, h->d_act, h->d_obs, h->d_rew, h->d_term, h->d_trunc, h->d_term_obs, h->d_nel, s);
     if (rc != MG_OK) return rc;
+    if (term_obs_host) {
+        MG_CUDA(h, cudaMemsetAsync(h->d_pack_cnt, 0, sizeof(int32_t), s));
+        mg_pack_terminal_kernel<<<(h->num_envs + 255) / 256, 256, 0, s>>>(h->num_envs, h->d_term, h->d_trunc, h->d_term_obs,
+                                                                           h->d_pack_idx, h->d_pack_obs, h->d_pack_cnt);
+        h->launches++;
+        MG_CUDA(h, cudaMemcpyAsync(h->h_pack_cnt, h->d_pack_cnt, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    }
     MG_CUDA(h, cudaMemcpyAsync(obs_host, h->d_obs, N * MG_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
     MG_CUDA(h, cudaMemcpyAsync(rew_host, h->d_rew, N * sizeof(double), cudaMemcpyDeviceToHost, s));
     MG_CUDA(h, cudaMemcpyAsync(term_host, h->d_term, N, cudaMemcpyDeviceToHost, s));
     MG_CUDA(h, cudaMemcpyAsync(trunc_host, h->d_trunc, N, cudaMemcpyDeviceToHost, s));
-    if (term_obs_host) MG_CUDA(h, cudaMemcpyAsync(term_obs_host, h->d_term_obs, N * MG_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (n_elem_host) MG_CUDA(h, cudaMemcpyAsync(n_elem_host, h->d_nel, N * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     MG_CUDA(h, cudaStreamSynchronize(s));
+    if (term_obs_host) {
+        // terminal observations are only defined where done: ship those rows compacted instead of N*72 bytes
+        const int c = *h->h_pack_cnt;
+        if (c > 0) {
+            MG_CUDA(h, cudaMemcpyAsync(h->h_pack_idx, h->d_pack_idx, sizeof(int32_t) * c, cudaMemcpyDeviceToHost, s));
+            MG_CUDA(h, cudaMemcpyAsync(h->h_pack_obs, h->d_pack_obs, sizeof(float) * MG_OBS_DIM * c, cudaMemcpyDeviceToHost, s));
+            MG_CUDA(h, cudaStreamSynchronize(s));
+        }
+        if (h->last_term_obs_host != term_obs_host) {
+            std::memset(term_obs_host, 0, sizeof(float) * MG_OBS_DIM * N);
+            h->last_term_obs_host = term_obs_host;
+        } else {
+            for (int32_t e : h->prev_done) std::memset(term_obs_host + (size_t)e * MG_OBS_DIM, 0, sizeof(float) * MG_OBS_DIM);
+        }
+        h->prev_done.assign(h->h_pack_idx, h->h_pack_idx + c);
+        for (int i = 0; i < c; i++)
+            std::memcpy(term_obs_host + (size_t)h->h_pack_idx[i] * MG_OBS_DIM, h->h_pack_obs + (size_t)i * MG_OBS_DIM,
+                        sizeof(float) * MG_OBS_DIM);
+    }
     return MG_OK;
 }
 

@@ -113,20 +113,42 @@ __device__ __forceinline__ double cand_key_from_angles(double a0, double a1) {
 }
 
 // Full rebuild (M:259-287): key for every vertex, stamp = list index (stable sort order).
+// Two passes so that the atan2 work runs on full warps: pass 1 classifies every vertex from its
+// cross/dot products (most vertices of a densified polygon are surely not candidates) and compacts
+// the undecided ones into a small queue; the queue is drained 32 entries at a time.
 __device__ __noinline__ void rebuild_candidates(const Warp &w, double *key, int32_t *stamp) {
-#pragma unroll 1
-    for (int j = w.lane; j < w.n; j += 32) {
-        P2 c = w.at(j);
-        double cr, dt;
-        cross_dot(c, w.at(j + 1), w.at(j - 1), cr, dt);
-        double k = CUDART_INF;
-        if (!surely_not_candidate(cr, dt)) {
-            double a0 = cw_angle_crdt(cr, dt);
+    const int n = w.n, lane = w.lane;
+    int qn = 0;
+    auto drain = [&](int count) {           // exact keys for queue[qn - count .. qn), one vertex per lane
+        int j = lane < count ? w.queue[qn - count + lane] : -1;
+        if (j >= 0) {
+            P2 c = w.at(j);
+            double k = CUDART_INF;
+            double a0 = cw_angle(c, w.at(j + 1), w.at(j - 1));
             if (!(a0 >= PI * 0.972 || a0 == 0)) k = cand_key_from_angles(a0, cw_angle(c, w.at(j + 2), w.at(j - 2)));
+            key[j] = k;
         }
-        key[j] = k;
-        stamp[j] = j;
+        qn -= count;
+        __syncwarp();
+    };
+#pragma unroll 1
+    for (int base = 0; base < n; base += 32) {
+        int j = base + lane;
+        bool undecided = false;
+        if (j < n) {
+            double cr, dt;
+            cross_dot(w.at(j), w.at(j + 1), w.at(j - 1), cr, dt);
+            undecided = !surely_not_candidate(cr, dt);
+            if (!undecided) key[j] = CUDART_INF;
+            stamp[j] = j;
+        }
+        unsigned m = __ballot_sync(FULL, undecided);
+        if (undecided) w.queue[qn + __popc(m & ((1u << lane) - 1))] = j;
+        qn += __popc(m);
+        __syncwarp();
+        if (qn >= 32) drain(32);
     }
+    if (qn > 0) drain(qn);
 }
 
 // arg-min of (key, stamp) over the n live vertices; -1 when the candidate list is empty.
@@ -1096,6 +1118,17 @@ __global__ void mg_sample_actions_kernel(int num_envs, uint64_t seed, uint64_t s
         float u = (float)(rr[k] >> 8) * (1.0f / 16777216.0f);
         act[(size_t)e * 3 + k] = lo[k] + (hi[k] - lo[k]) * u;
     }
+}
+
+// mg_step_host: gather the terminal observations of the envs that finished this step.
+__global__ void mg_pack_terminal_kernel(int num_envs, const uint8_t *term, const uint8_t *trunc, const float *term_obs,
+                                        int32_t *idx, float *packed, int32_t *count) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= num_envs || !(term[e] | trunc[e])) return;
+    int i = atomicAdd(count, 1);
+    idx[i] = e;
+#pragma unroll
+    for (int k = 0; k < MG_OBS_DIM; k++) packed[(size_t)i * MG_OBS_DIM + k] = term_obs[(size_t)e * MG_OBS_DIM + k];
 }
 
 // Sum of the per-env counters -> one mg_episode_stats (one block).
