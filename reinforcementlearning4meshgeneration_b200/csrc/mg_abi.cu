@@ -121,7 +121,7 @@ int mg_create(mg_handle *out, int device, int num_envs, int max_verts) {
         if (er != cudaSuccess && rc == MG_OK) rc = fail(h, MG_ERR_CUDA, std::string("cudaMalloc ") + what + ": " + cudaGetErrorString(er));
     };
     A(dalloc(&P.xy, NC), "xy"); A(dalloc(&P.key, NC), "key"); A(dalloc(&P.stamp, NC), "stamp"); A(dalloc(&P.vid, NC), "vid");
-    A(dalloc(&P.st, (size_t)num_envs), "state"); A(dalloc(&P.stats, (size_t)num_envs), "stats");
+    A(dalloc(&P.st, (size_t)num_envs), "state"); A(dalloc(&P.stats, (size_t)STAT_SLOTS), "stats");
     A(dalloc(&P.obs_cache, (size_t)num_envs * MG_OBS_DIM), "obs");
     A(dalloc(&P.pend, (size_t)num_envs), "pend"); A(dalloc(&P.succ_list, (size_t)num_envs), "succ_list");
     A(dalloc(&P.reset_list, (size_t)num_envs), "reset_list"); A(dalloc(&P.counters, (size_t)4), "counters");
@@ -384,7 +384,7 @@ int mg_stats(mg_handle h, mg_episode_stats *out, int reset) {
     if (!h || !out) return fail(h, MG_ERR_ARG, "mg_stats: null pointer");
     MG_CUDA(h, cudaSetDevice(h->device));
     MG_CUDA(h, cudaDeviceSynchronize());
-    mg_stats_kernel<<<1, 1024>>>(h->num_envs, h->P.stats, h->d_stats_out, reset);
+    mg_stats_kernel<<<1, 32>>>(h->P.stats, h->d_stats_out, reset);
     h->launches++;
     MG_CUDA(h, cudaGetLastError());
     MG_CUDA(h, cudaMemcpy(out, h->d_stats_out, sizeof(*out), cudaMemcpyDeviceToHost));

@@ -437,28 +437,29 @@ __device__ __noinline__ bool point_inside(const Warp &w, P2 P, const int32_t *vi
         if (j < n) {
             int jb = j == 0 ? n - 1 : j - 1;
             P2 a = w.at(j), b = w.at(jb);
-            double ro = rint4_mixed(a.y - b.y, vid, j, jb, n0);
-            if (ro != 0) {
-                // would this edge be counted if it crosses the ray?  (M:91-118)
-                bool counted;
-                if (rint((a.y - P.y) * 1e4) == 0) {
-                    int jc = j + 1 == n ? 0 : j + 1;
-                    double rn = rint4_mixed(w.at(jc).y - a.y, vid, jc, j, n0);
-                    counted = !(rn == 0 || rn * ro < 0) && ro < 0;
-                } else if (rint((b.y - P.y) * 1e4) == 0) {
-                    int jc = jb == 0 ? n - 1 : jb - 1;
-                    double rp = rint4_mixed(b.y - w.at(jc).y, vid, jb, jc, n0);
-                    counted = !(rp == 0 || rp * ro < 0) && !(ro < 0);
-                } else counted = true;
-                if (counted) {
-                    // Exact early-out: if both endpoints lie strictly on the same side of the ray's
-                    // line, and at least one of them is more than 1e-4 rad off that line as seen from
-                    // P, ray.straddle(edge) is False (the collinearity pre-test C:506-508 needs both
-                    // quantised angles in {0, pi, 2pi}; the cross products then have equal signs).
-                    double dya = a.y - P.y, dyb = b.y - P.y;
-                    bool same_side = (dya > 1e-9 && dyb > 1e-9) || (dya < -1e-9 && dyb < -1e-9);
-                    bool off_axis = fabs(dya) > 1e-4 * fabs(a.x - P.x) || fabs(dyb) > 1e-4 * fabs(b.x - P.x);
-                    if (!(can_prune && same_side && off_axis)) hit = is_cross(a, b, P, ray2);
+            // Exact early-out, evaluated first because it removes ~97 % of the edges: an edge is only
+            // counted if edge.is_cross(ray) (M:90).  If both endpoints lie strictly on the same side of
+            // the ray's line and at least one of them is more than 1e-4 rad off that line as seen from
+            // P, ray.straddle(edge) is False (the collinearity pre-test C:506-508 needs both quantised
+            // angles in {0, pi, 2 pi}; the cross products then have equal signs).
+            double dya = a.y - P.y, dyb = b.y - P.y;
+            bool same_side = (dya > 1e-9 && dyb > 1e-9) || (dya < -1e-9 && dyb < -1e-9);
+            bool off_axis = fabs(dya) > 1e-4 * fabs(a.x - P.x) || fabs(dyb) > 1e-4 * fabs(b.x - P.x);
+            if (!(can_prune && same_side && off_axis)) {
+                double ro = rint4_mixed(a.y - b.y, vid, j, jb, n0);
+                if (ro != 0) {
+                    // would this edge be counted if it crosses the ray?  (M:91-118)
+                    bool counted;
+                    if (rint(dya * 1e4) == 0) {
+                        int jc = j + 1 == n ? 0 : j + 1;
+                        double rn = rint4_mixed(w.at(jc).y - a.y, vid, jc, j, n0);
+                        counted = !(rn == 0 || rn * ro < 0) && ro < 0;
+                    } else if (rint(dyb * 1e4) == 0) {
+                        int jc = jb == 0 ? n - 1 : jb - 1;
+                        double rp = rint4_mixed(b.y - w.at(jc).y, vid, jb, jc, n0);
+                        counted = !(rp == 0 || rp * ro < 0) && !(ro < 0);
+                    } else counted = true;
+                    if (counted) hit = is_cross(a, b, P, ray2);
                 }
             }
         }
@@ -761,8 +762,18 @@ __device__ __forceinline__ void push_list(int *list, int *counter, int env, int 
     if (lane == 0) list[atomicAdd(counter, 1)] = env;
 }
 
+__device__ __forceinline__ void store_state(const Params &P, int env, const EnvState &S) { P.st[env] = S; }
+// phase A only changes failed_num, ep_len, ep_return: chunks 1 and 2 of the record
+__device__ __forceinline__ void store_state(const Params &P, int env, const EnvHot &S) {
+    int4 *dst = reinterpret_cast<int4 *>(P.st + env);
+    const int4 *src = reinterpret_cast<const int4 *>(&S);
+    dst[1] = src[1];
+    dst[2] = src[2];
+}
+
 // Tail of step() shared by phases A and B (E:361-386 + outputs + statistics).
-__device__ __forceinline__ bool finish_step(const Params &P, const StepIO &io, int env, int lane, EnvState &S, int n_before,
+template <class State>
+__device__ __forceinline__ bool finish_step(const Params &P, const StepIO &io, int env, int lane, State &S, int n_before,
                                             double reward, bool done, bool failed, bool success, bool force_trunc,
                                             float obs) {
     bool is_complete = true;
@@ -771,19 +782,23 @@ __device__ __forceinline__ bool finish_step(const Params &P, const StepIO &io, i
     if (force_trunc && !done) { done = true; truncated = true; }          // sentinel, see DESIGN.md
     S.ep_return += reward; S.ep_len++;
     if (lane == 0) {
-        EnvStats T = P.stats[env];
-        T.steps++; T.sum_n += n_before;
-        if (success) { T.successes++; T.sum_n_success += n_before; }
+        StatsAcc *T = P.stats + ((env / WPB) & (STAT_SLOTS - 1));
+        atomicAdd(&T->steps, 1ull);
+        atomicAdd(&T->sum_n, (unsigned long long)n_before);
+        if (success) { atomicAdd(&T->successes, 1ull); atomicAdd(&T->sum_n_success, (unsigned long long)n_before); }
         if (done) {
-            T.episodes++; T.completed += terminated; T.truncated += truncated; T.elements += S.n_elements;
-            T.sum_return += S.ep_return; T.sum_length += S.ep_len;
+            atomicAdd(&T->episodes, 1ull);
+            atomicAdd(&T->completed, (unsigned long long)terminated);
+            atomicAdd(&T->truncated, (unsigned long long)truncated);
+            atomicAdd(&T->elements, (unsigned long long)S.n_elements);
+            atomicAdd(&T->sum_return, S.ep_return);
+            atomicAdd(&T->sum_length, (double)S.ep_len);
         }
-        P.stats[env] = T;
         io.rew_out[env] = reward;
         io.term_out[env] = terminated;
         io.trunc_out[env] = truncated;
         if (io.n_elem_out) io.n_elem_out[env] = S.n_elements;
-        P.st[env] = S;
+        store_state(P, env, S);
     }
     if (lane < MG_OBS_DIM) {
         if (io.term_obs_out) io.term_obs_out[(size_t)env * MG_OBS_DIM + lane] = done ? obs : 0.0f;
@@ -813,7 +828,8 @@ __global__ void __launch_bounds__(WPB * 32, MG_MINB) mg_step_decide_kernel(Param
     SmemLayout L = carve(smem_raw, P.cap, warp);
     init_mbar(L.mbar, lane);
 
-    EnvState S = P.st[env];
+    const EnvHot S0 = *reinterpret_cast<const EnvHot *>(P.st + env);      // 3 x 16 B, the rest is phase B/C's
+    EnvHot S = S0;
     const size_t off = (size_t)env * P.cap;
     Warp w;
     w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = S.n;
@@ -1131,33 +1147,25 @@ __global__ void mg_pack_terminal_kernel(int num_envs, const uint8_t *term, const
     for (int k = 0; k < MG_OBS_DIM; k++) packed[(size_t)i * MG_OBS_DIM + k] = term_obs[(size_t)e * MG_OBS_DIM + k];
 }
 
-// Sum of the per-env counters -> one mg_episode_stats (one block).
-__global__ void mg_stats_kernel(int num_envs, EnvStats *stats, mg_episode_stats *out, int reset) {
-    long long a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+// Sum of the accumulator slots -> one mg_episode_stats (one warp).
+__global__ void mg_stats_kernel(StatsAcc *stats, mg_episode_stats *out, int reset) {
+    unsigned long long a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double r = 0, l = 0;
-    for (int e = threadIdx.x; e < num_envs; e += blockDim.x) {
-        EnvStats T = stats[e];
+    for (int e = threadIdx.x; e < STAT_SLOTS; e += 32) {
+        StatsAcc T = stats[e];
         a[0] += T.episodes; a[1] += T.completed; a[2] += T.truncated; a[3] += T.steps; a[4] += T.successes;
         a[5] += T.elements; a[6] += T.sum_n; a[7] += T.sum_n_success; r += T.sum_return; l += T.sum_length;
-        if (reset) { EnvStats Z = {}; stats[e] = Z; }
+        if (reset) { StatsAcc Z = {}; stats[e] = Z; }
     }
-    __shared__ long long sa[8];
-    __shared__ double sr, sl;
-    if (threadIdx.x == 0) { for (int k = 0; k < 8; k++) sa[k] = 0; sr = 0; sl = 0; }
-    __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        long long v = a[k];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-        if ((threadIdx.x & 31) == 0) atomicAdd((unsigned long long *)&sa[k], (unsigned long long)v);
-    }
+    for (int k = 0; k < 8; k++)
+        for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_xor_sync(FULL, a[k], o);
     r = warp_sum_d(r); l = warp_sum_d(l);
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&sr, r); atomicAdd(&sl, l); }
-    __syncthreads();
     if (threadIdx.x == 0) {
-        out->episodes = sa[0]; out->completed = sa[1]; out->truncated = sa[2]; out->steps = sa[3];
-        out->successes = sa[4]; out->elements = sa[5]; out->sum_n = sa[6]; out->sum_n_success = sa[7];
-        out->sum_return = sr; out->sum_length = sl;
+        out->episodes = (long long)a[0]; out->completed = (long long)a[1]; out->truncated = (long long)a[2];
+        out->steps = (long long)a[3]; out->successes = (long long)a[4]; out->elements = (long long)a[5];
+        out->sum_n = (long long)a[6]; out->sum_n_success = (long long)a[7];
+        out->sum_return = r; out->sum_length = l;
     }
 }
 

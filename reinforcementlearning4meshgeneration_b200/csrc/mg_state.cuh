@@ -5,7 +5,7 @@
 //   stamp int32  [num_envs][cap]   tie-break stamp: list index at rebuild, decreasing negatives later
 //   vid   int32  [num_envs][cap]   vertex ids (0..n0-1 original, n0+k k-th inserted)
 //   st    EnvState[num_envs]       scalars (128 B)
-//   stats EnvStats[num_envs]       per-env episode counters (no atomics on the step path)
+//   stats StatsAcc[64]             episode counters (fire-and-forget atomics, 64 slots)
 //   obs   float  [num_envs][18]    cached observation (failed steps return it unchanged)
 #pragma once
 #include <stdint.h>
@@ -14,31 +14,52 @@
 
 namespace mg {
 
-struct __align__(16) EnvState {
+// The first 48 bytes are everything phase A (the all-envs kernel) reads, and the second and third
+// 16-byte chunks are everything it writes back on a failed step.
+struct __align__(16) EnvHot {
     int32_t n;            // live boundary size
     int32_t ref_index;    // index of the reference point, -1 = none
     int32_t n_elements;   // len(generated_meshes)
-    int32_t failed_num;   // consecutive failed steps
-    int32_t next_vid;     // id of the next inserted vertex
-    int32_t stamp_ctr;    // decreasing stamp counter for incremental candidate inserts
-    int32_t domain;       // template index (domain mode)
-    int32_t ep_len;
     int32_t n0;           // size of the episode's original polygon
-    int32_t episode;      // episodes finished by this env (random mode: polygon counter)
     double base_length;
+    int32_t failed_num;   // consecutive failed steps
+    int32_t ep_len;
+    double ep_return;
     double current_area;
+};
+static_assert(sizeof(EnvHot) == 48, "EnvHot size");
+
+struct __align__(16) EnvState {
+    int32_t n;
+    int32_t ref_index;
+    int32_t n_elements;
+    int32_t n0;
+    double base_length;
+    int32_t failed_num;
+    int32_t ep_len;
+    double ep_return;
+    double current_area;
+    // ---- not touched by phase A ----
     double original_area;
     double area_min;
     double area_crit;
-    double ep_return;
+    int32_t next_vid;     // id of the next inserted vertex
+    int32_t stamp_ctr;    // decreasing stamp counter for incremental candidate inserts
+    int32_t domain;       // template index (domain mode)
+    int32_t episode;      // episodes finished by this env (random mode: polygon counter)
     int64_t pad[5];
 };
 static_assert(sizeof(EnvState) == 128, "EnvState size");
 
-struct EnvStats {
-    long long episodes, completed, truncated, steps, successes, elements, sum_n, sum_n_success;
+// Episode statistics: 64 accumulator slots updated with fire-and-forget atomics (slot = warp id & 63),
+// summed on demand by mg_stats.  Same fields as mg_episode_stats.
+constexpr int STAT_SLOTS = 64;
+struct __align__(16) StatsAcc {
+    unsigned long long episodes, completed, truncated, steps, successes, elements, sum_n, sum_n_success;
     double sum_return, sum_length;
+    unsigned long long pad[6];       // 128 bytes: one slot per L2 line
 };
+static_assert(sizeof(StatsAcc) == 128, "StatsAcc size");
 
 // element accepted by phase A of a step, applied by phase B
 struct __align__(16) Pending {
@@ -67,7 +88,7 @@ struct Params {
     int32_t *stamp;
     int32_t *vid;
     EnvState *st;
-    EnvStats *stats;
+    StatsAcc *stats;     // [STAT_SLOTS]
     float *obs_cache;
     // per-step work lists (phase kernels)
     Pending *pend;       // [num_envs]
