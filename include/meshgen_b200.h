@@ -124,8 +124,8 @@ int mg_reset(mg_handle h, const uint8_t *mask_dev, float *obs_dev, void *stream)
  *   rew_dev      out num_envs float64      reward (the reference returns np.float64)
  *   term_dev     out num_envs uint8        terminated = done and is_complete
  *   trunc_dev    out num_envs uint8        truncated  = done and not is_complete
- *   term_obs_dev out num_envs*18 float32   observation before the auto-reset (valid where done;
- *                                          may be NULL)
+ *   term_obs_dev out num_envs*18 float32   observation before the auto-reset; rows are written only
+ *                                          where done (others keep their content); may be NULL
  *   n_elem_dev   out num_envs int32        len(generated_meshes) after the step, before reset
  *                                          (may be NULL) */
 int mg_step(mg_handle h, const float *act_dev, float *obs_dev, double *rew_dev, uint8_t *term_dev,

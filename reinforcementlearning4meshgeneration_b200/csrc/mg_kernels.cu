@@ -801,7 +801,7 @@ __device__ __forceinline__ bool finish_step(const Params &P, const StepIO &io, i
         store_state(P, env, S);
     }
     if (lane < MG_OBS_DIM) {
-        if (io.term_obs_out) io.term_obs_out[(size_t)env * MG_OBS_DIM + lane] = done ? obs : 0.0f;
+        if (io.term_obs_out && done) io.term_obs_out[(size_t)env * MG_OBS_DIM + lane] = obs;
         if (success) P.obs_cache[(size_t)env * MG_OBS_DIM + lane] = obs;
         io.obs_out[(size_t)env * MG_OBS_DIM + lane] = obs;
     }
@@ -830,6 +830,8 @@ __global__ void __launch_bounds__(WPB * 32, MG_MINB) mg_step_decide_kernel(Param
 
     const EnvHot S0 = *reinterpret_cast<const EnvHot *>(P.st + env);      // 3 x 16 B, the rest is phase B/C's
     EnvHot S = S0;
+    // requested now so that the tail of a failed step does not pay another DRAM round trip
+    const float obs_cached = lane < MG_OBS_DIM ? P.obs_cache[(size_t)env * MG_OBS_DIM + lane] : 0.0f;
     const size_t off = (size_t)env * P.cap;
     Warp w;
     w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = S.n;
@@ -899,7 +901,7 @@ __global__ void __launch_bounds__(WPB * 32, MG_MINB) mg_step_decide_kernel(Param
         reward += S.n_elements ? -1.0 / S.n_elements : -1;          // E:357
     }
     // failed step: nothing changed, the reference recomputes a bit-identical observation
-    float obs = lane < MG_OBS_DIM ? P.obs_cache[(size_t)env * MG_OBS_DIM + lane] : 0.0f;
+    const float obs = obs_cached;
     S.failed_num++;
     if (finish_step(P, io, env, lane, S, n, reward, done, true, false, dead, obs))
         push_list(P.reset_list, P.counters + 2 * set + 1, env, lane);
@@ -1095,7 +1097,10 @@ __device__ __forceinline__ void apply_successes(const Params &P, const StepIO &i
 
 // ---- phases B + C in one launch: the last apply_blocks blocks apply the accepted elements, the first
 // blocks reset the envs that phase A finished (truncations, E:382-384); the two sets are disjoint.
-__global__ void __launch_bounds__(WPB * 32) mg_step_apply_reset_kernel(Params P, StepIO io, int set, int apply_blocks) {
+#ifndef MG_MINB_APPLY
+#define MG_MINB_APPLY 12    // tuned on B200: 80 registers, 24 warps per SM for the latency-bound apply phase
+#endif
+__global__ void __launch_bounds__(WPB * 32, MG_MINB_APPLY) mg_step_apply_reset_kernel(Params P, StepIO io, int set, int apply_blocks) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     SmemLayout L = carve(smem_raw, P.cap, warp);

@@ -41,10 +41,14 @@ def assert_rollout_matches(got, exp, what, reward_tol=1e-9, reward_exact=False):
             g, e = np.asarray(got[key]).astype(np.int64), np.asarray(exp[key]).astype(np.int64)
             bad = np.nonzero(g != e)[0]
             assert bad.size == 0, f"{what}: {key} differs first at step {bad[0]}: got {g[bad[0]]} expected {e[bad[0]]}"
+    done = (np.asarray(exp["terminated"]).astype(bool) | np.asarray(exp["truncated"]).astype(bool))
     for key in ("obs", "terminal_obs"):
         if key in got and key in exp:
             g, e = np.asarray(got[key], np.float32), np.asarray(exp[key], np.float32)
-            bad = np.nonzero((g.view(np.uint32) != e.view(np.uint32)).any(axis=1) & ~((g == e).all(axis=1)))[0]
+            bad = (g.view(np.uint32) != e.view(np.uint32)).any(axis=1) & ~((g == e).all(axis=1))
+            if key == "terminal_obs":
+                bad &= done            # the terminal observation is only defined where the episode ended
+            bad = np.nonzero(bad)[0]
             assert bad.size == 0, f"{what}: {key} differs first at step {bad[0]}:\n got {g[bad[0]]}\n exp {e[bad[0]]}"
     g, e = np.asarray(got["reward"], np.float64), np.asarray(exp["reward"], np.float64)
     ok = (g == e) if reward_exact else rel_close(g, e, reward_tol)
