@@ -269,8 +269,27 @@ def run_gpu(args):
     launches = env.launch_count - launches0
     stats = env.stats(reset=True)
 
+    # ---- optional: device time of phase A alone (state frozen at steady state), B+C by difference ----
+    phase_times = None
+    if args.phase_times:
+        from reinforcementlearning4meshgeneration_b200._lib import check
+        check(env._L.mg_set_phase_mask(env._h, 1), env._h, "mg_set_phase_mask")
+        a = env.sample_actions(SEED, step_idx)
+        for _ in range(5):
+            env.step(a)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            env.step(a)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        check(env._L.mg_set_phase_mask(env._h, 3), env._h, "mg_set_phase_mask")
+        ta = e0.elapsed_time(e1) / 50
+        phase_times = {"decide_ms": ta, "apply_reset_ms": kern_ms / K - ta}
+        env.stats(reset=True)
+
     # ---- e2e: host buffers through the C ABI (mg_step_host), H2D + D2H inside the timed region ----
-    Ke = max(3, min(K, 20))
+    Ke = max(3, min(K, 100))
     pinned = dict(
         act=torch.empty((N, 3), dtype=torch.float32).pin_memory(), obs=torch.empty((N, 18), dtype=torch.float32).pin_memory(),
         reward=torch.empty(N, dtype=torch.float64).pin_memory(), terminated=torch.empty(N, dtype=torch.uint8).pin_memory(),
@@ -343,6 +362,8 @@ def run_gpu(args):
             "success_rate": gstats["successes"] / max(1, gstats["steps"]),
             "wall_s_timed_region": t_wall,
         }
+        if phase_times:
+            line["phase_times"] = phase_times
         if world == 1 and not args.no_cpu_baseline:
             polys, sample = sample_polygons(args.workload)
             v, threads, steps, dt = cpu_port_throughput(polys, seconds_budget=10.0)
@@ -366,6 +387,7 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's BASELINE size)")
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--phase-times", action="store_true", help="also time phase A alone (profiling aid)")
     ap.add_argument("--burn-in", type=int, default=1500, help="untimed setup steps that de-synchronise the episodes")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":

@@ -153,6 +153,10 @@ int mg_get_elements(mg_handle h, int env, int32_t *quads_host, int max_elements,
  * reset != 0 zeroes the counters afterwards. */
 int mg_stats(mg_handle h, mg_episode_stats *out, int reset);
 
+/* Profiling aid (bench.py --phase-times): restrict mg_step to phase A (bit 0) and/or phases B+C
+ * (bit 1).  With a partial mask the environments do not advance correctly; restore 3 afterwards. */
+int mg_set_phase_mask(mg_handle h, int mask);
+
 int mg_num_envs(mg_handle h);
 int mg_max_verts(mg_handle h);
 /* number of kernel launches issued by this handle so far (bench.py's gpu_launches) */

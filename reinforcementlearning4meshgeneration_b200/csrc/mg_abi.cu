@@ -37,6 +37,7 @@ struct mg_env_s {
     bool was_reset = false;
     int64_t launches = 0;
     int step_parity = 0;
+    int phase_mask = 3;       // profiling aid: bit 0 = phase A launch, bit 1 = phase B+C launch
     int sm_count = 148;
     size_t smem = 0;
     std::string err;
@@ -167,6 +168,12 @@ int mg_set_auto_reset(mg_handle h, int enabled) {
     return MG_OK;
 }
 
+int mg_set_phase_mask(mg_handle h, int mask) {
+    if (!h) return fail(h, MG_ERR_ARG, "mg_set_phase_mask: null handle");
+    h->phase_mask = mask & 3;
+    return MG_OK;
+}
+
 int mg_num_envs(mg_handle h) { return h ? h->num_envs : 0; }
 int mg_max_verts(mg_handle h) { return h ? h->max_verts : 0; }
 int64_t mg_launch_count(mg_handle h) { return h ? h->launches : 0; }
@@ -268,8 +275,8 @@ int mg_step(mg_handle h, const float *act_dev, float *obs_dev, double *rew_dev, 
     const int full = grid_for(h->num_envs);
     const int gb = full < h->sm_count * 16 ? full : h->sm_count * 16;
     const int gc = full < h->sm_count * 4 ? full : h->sm_count * 4;
-    mg_step_decide_kernel<<<full, WPB * 32, h->smem, s>>>(h->P, io, set);
-    mg_step_apply_reset_kernel<<<gb + gc, WPB * 32, h->smem, s>>>(h->P, io, set, gb);
+    if (h->phase_mask & 1) mg_step_decide_kernel<<<full, WPB * 32, h->smem, s>>>(h->P, io, set);
+    if (h->phase_mask & 2) mg_step_apply_reset_kernel<<<gb + gc, WPB * 32, h->smem, s>>>(h->P, io, set, gb);
     h->launches += 2;
     MG_CUDA(h, cudaGetLastError());
     return MG_OK;

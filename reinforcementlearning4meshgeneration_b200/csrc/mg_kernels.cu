@@ -23,7 +23,7 @@ namespace mg {
 #endif
 constexpr int WPB = MG_WPB;     // warps (= environments) per block
 #ifndef MG_MINB
-#define MG_MINB 8
+#define MG_MINB 10
 #endif
 constexpr int QCAP = 128 + 256;  // per-warp scratch: 4x32 ints + 32x4 doubles (coarse polygon of the generator)
 
