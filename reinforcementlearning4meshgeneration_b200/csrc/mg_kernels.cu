@@ -471,7 +471,7 @@ __device__ __noinline__ bool point_inside(const Warp &w, P2 P, const int32_t *vi
 // E:766-769 find_same_point: any boundary vertex within 0.001 of P
 __device__ __noinline__ bool find_same_point(const Warp &w, P2 P) {
     bool f = false;
-#pragma unroll 1
+#pragma unroll 4
     for (int j = w.lane; j < w.n; j += 32) f |= pdist(w.at(j), P) < 0.001;
     return __any_sync(FULL, f);
 }
@@ -510,7 +510,7 @@ __device__ __noinline__ bool intersects_boundary(const Warp &w, const P2 (&m)[4]
         if (k != ri) max_dist = fmax(max_dist, pdist(ref, m[k]));
     const P2 c1a = m[(ri + 3) & 3], c1b = m[(ri + 2) & 3], c2a = m[(ri + 2) & 3], c2b = m[(ri + 1) & 3];
     auto in_mesh = [&](int j) { return j == qi[0] || j == qi[1] || j == qi[2] || j == qi[3]; };
-#pragma unroll 1
+#pragma unroll 2
     for (int base = 0; base < n; base += 32) {
         int j = base + w.lane;
         bool hit = false;
@@ -826,12 +826,13 @@ __global__ void __launch_bounds__(WPB * 32, MG_MINB) mg_step_decide_kernel(Param
     const int env = blockIdx.x * WPB + warp;
     if (env >= P.num_envs) return;
     SmemLayout L = carve(smem_raw, P.cap, warp);
-    init_mbar(L.mbar, lane);
 
     const EnvHot S0 = *reinterpret_cast<const EnvHot *>(P.st + env);      // 3 x 16 B, the rest is phase B/C's
     EnvHot S = S0;
     // requested now so that the tail of a failed step does not pay another DRAM round trip
     const float obs_cached = lane < MG_OBS_DIM ? P.obs_cache[(size_t)env * MG_OBS_DIM + lane] : 0.0f;
+    const float a0 = io.act[(size_t)env * 3 + 0], a1 = io.act[(size_t)env * 3 + 1], a2 = io.act[(size_t)env * 3 + 2];
+    init_mbar(L.mbar, lane);                 // barrier set-up overlaps the loads above
     const size_t off = (size_t)env * P.cap;
     Warp w;
     w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = S.n;
@@ -841,7 +842,6 @@ __global__ void __launch_bounds__(WPB * 32, MG_MINB) mg_step_decide_kernel(Param
     if (!dead) stage_ring(w.ring, L.mbar, P.xy + off, S.n, lane, 0);
 
     const int n = S.n, idx = dead ? 0 : S.ref_index;
-    const float a0 = io.act[(size_t)env * 3 + 0], a1 = io.act[(size_t)env * 3 + 1], a2 = io.act[(size_t)env * 3 + 2];
     const P2 ref = dead ? mk(0, 0) : w.at(idx), right_p = dead ? mk(1, 0) : w.at(idx - 1);
 
     // ---- action -> candidate vertex (E:783-792, E:202-210, D:112-137) ------------------------
