@@ -283,3 +283,98 @@ def test_element_export_formats(tmp_path):
     assert txt.startswith("*NODE, NSET=ALLNODES") and txt.count("TYPE=B21") == n0 - 1 and "TYPE=S4R" in txt
     assert len(txt.strip().splitlines()) == 1 + len(vxy) + 2 * (n0 - 1) + 1 + len(quads)
     env.close()
+
+
+def _spot_check_against_oracle(env, polys_areas, pick, T, seed, what):
+    """Run T steps of the whole batch with the library's Philox policy, record the picked envs'
+    actions/outputs on the device, replay them through the CPU oracle."""
+    import torch
+    from oracle.c_oracle import OracleEnv
+    dev = env.device
+    idx = torch.tensor(pick, device=dev, dtype=torch.long)
+    K = len(pick)
+    rec = dict(act=torch.zeros((T, K, 3), device=dev), obs=torch.zeros((T, K, 18), device=dev),
+               tobs=torch.zeros((T, K, 18), device=dev), rew=torch.zeros((T, K), dtype=torch.float64, device=dev),
+               te=torch.zeros((T, K), dtype=torch.uint8, device=dev), tr=torch.zeros((T, K), dtype=torch.uint8, device=dev),
+               ne=torch.zeros((T, K), dtype=torch.int32, device=dev))
+    for t in range(T):
+        a = env.sample_actions(seed, t)
+        rec["act"][t] = a[idx]
+        r = env.step(a)
+        rec["obs"][t] = r.obs[idx]; rec["tobs"][t] = r.terminal_obs[idx]; rec["rew"][t] = r.reward[idx]
+        rec["te"][t] = r.terminated[idx]; rec["tr"][t] = r.truncated[idx]; rec["ne"][t] = r.n_elements[idx]
+    rec = {k: v.cpu().numpy() for k, v in rec.items()}
+    for k, e in enumerate(pick):
+        xy, area = polys_areas(e)
+        o = OracleEnv(xy, original_area=area)
+        stop_at_done = getattr(env, "random_mode", False)      # a fresh polygon follows: replay the first episode only
+        L = T
+        exp = o.rollout(rec["act"][:, k])
+        if stop_at_done:
+            d = np.nonzero(exp["terminated"] | exp["truncated"])[0]
+            L = int(d[0]) + 1 if d.size else T
+        got = dict(obs=rec["obs"][:L, k], terminal_obs=rec["tobs"][:L, k], reward=rec["rew"][:L, k], terminated=rec["te"][:L, k],
+                   truncated=rec["tr"][:L, k], n_elements=rec["ne"][:L, k])
+        exp = {kk: v[:L] for kk, v in exp.items()}
+        if stop_at_done and L < T + 1 and (exp["terminated"][L - 1] or exp["truncated"][L - 1]):
+            got["obs"] = got["obs"][:L - 1]; exp["obs"] = exp["obs"][:L - 1]    # the reset obs belongs to a new polygon
+            for kk in ("terminal_obs", "reward", "terminated", "truncated", "n_elements"):
+                pass
+            g2 = {kk: (v if kk == "obs" else v) for kk, v in got.items()}
+            # compare obs on the shorter range, everything else on the full first episode
+            assert_rollout_matches({kk: v for kk, v in g2.items() if kk != "obs"}, {kk: v for kk, v in exp.items() if kk != "obs"},
+                                   f"{what}[env {e}]", reward_tol=REWARD_TOL)
+            assert np.array_equal(got["obs"], exp["obs"]), f"{what}[env {e}]: obs differ"
+        else:
+            assert_rollout_matches(got, exp, f"{what}[env {e}]", reward_tol=REWARD_TOL)
+
+
+def test_full_size_config2_spot_check():
+    """BASELINE config 2 at full size: d1/d2/d3, 4096 envs (1365/1365/1366), device Philox actions
+    (seed 1234); 64 envs x 256 steps replayed through the oracle."""
+    doms, areas = load_domains()
+    names = ["boundary16", "boundary15", "test1"]
+    N = 4096
+    env_domain = np.concatenate([np.full(1365, 0), np.full(1365, 1), np.full(1366, 2)])
+    env = _mk([doms[k] for k in names], N, env_domain=env_domain)
+    env.reset()
+    rng = np.random.default_rng(0)
+    pick = sorted(rng.choice(N, size=64, replace=False).tolist())
+    _spot_check_against_oracle(env, lambda e: (doms[names[env_domain[e]]], areas[names[env_domain[e]]]), pick, 256, 1234,
+                               "config 2 spot check")
+    s = env.stats()
+    assert s["steps"] == N * 256
+
+
+def test_full_size_config3_properties_and_spot_check():
+    """BASELINE config 3 at full size (65536 envs, random polygons 64..512 vertices, in-kernel
+    auto-reset): size-independent properties + oracle replay of 48 envs' first episodes + determinism."""
+    import torch
+    N, T = 65536, 220
+    kw = dict(random_polygons=dict(min_verts=64, max_verts=512), seed=2026)
+    env = _mk(None, N, **kw)
+    obs0 = env.reset().clone()
+    rng = np.random.default_rng(1)
+    pick = sorted(rng.choice(N, size=48, replace=False).tolist())
+    states = {e: env.get_state(e) for e in pick}
+    for e in pick:
+        assert 64 <= states[e]["n"] <= 512 and states[e]["n"] % 2 == 0
+    _spot_check_against_oracle(env, lambda e: (states[e]["xy"], states[e]["original_area"]), pick, T, 2026, "config 3 spot check")
+    s = env.stats()
+    assert s["steps"] == N * T and s["sum_n"] >= 64 * N * T * 0.5
+    assert s["episodes"] == s["completed"] + s["truncated"] and s["episodes"] > 0
+    assert s["successes"] <= s["steps"] and s["sum_n_success"] <= s["sum_n"]
+    o = env.obs
+    assert torch.isfinite(o).all() and (o.abs() <= 999).all()
+    assert (o[:, 1] >= 0).all() and (o[:, 1] <= 1.0001).all()           # area ratio
+    assert torch.isfinite(env.reward).all() and (env.reward <= 21).all()
+    # determinism: the same seed reproduces the run bit for bit
+    env2 = _mk(None, N, **kw)
+    assert torch.equal(env2.reset(), obs0)
+    for t in range(40):
+        r2 = env2.step(env2.sample_actions(2026, t))
+    env3 = _mk(None, N, **kw)
+    env3.reset()
+    for t in range(40):
+        r3 = env3.step(env3.sample_actions(2026, t))
+    assert torch.equal(r2.obs, r3.obs) and torch.equal(r2.reward, r3.reward) and torch.equal(r2.n_elements, r3.n_elements)
