@@ -39,6 +39,11 @@ __device__ __forceinline__ int wrapn(int i, int n) {
     return i;
 }
 
+struct Quad {
+    double x[4], y[4];        // candidate quad, passed by value (registers) to the out-of-line predicates
+    __device__ __forceinline__ P2 at(int k) const { return mk(x[k], y[k]); }
+};
+
 struct Warp {
     double2 *ring;   // shared memory, this warp's vertex ring
     int *queue;      // shared memory, this warp's integer scratch
@@ -60,9 +65,7 @@ __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)_
 
 // Stage `n` vertices (16 B each) from global memory into the warp's ring with one bulk async
 // copy issued by lane 0 and completed on a per-warp mbarrier.
-__device__ __forceinline__ void stage_ring(double2 *ring, unsigned long long *mbar, const double2 *src, int n, int lane,
-                                           unsigned parity) {
-#ifndef MG_NO_BULK_COPY
+__device__ __forceinline__ void stage_issue(double2 *ring, unsigned long long *mbar, const double2 *src, int n, int lane) {
     unsigned bar = smem_u32(mbar);
     unsigned bytes = (unsigned)n * 16u;
     // order this warp's earlier generic-proxy accesses to the ring before the async-proxy write
@@ -75,6 +78,9 @@ __device__ __forceinline__ void stage_ring(double2 *ring, unsigned long long *mb
             "l"(src), "r"(bytes), "r"(bar)
             : "memory");
     }
+}
+__device__ __forceinline__ void stage_wait(unsigned long long *mbar, unsigned parity) {
+    unsigned bar = smem_u32(mbar);
     unsigned done = 0;
     while (!done) {
         asm volatile(
@@ -83,11 +89,13 @@ __device__ __forceinline__ void stage_ring(double2 *ring, unsigned long long *mb
             : "r"(bar), "r"(parity)
             : "memory");
     }
-#else
-#pragma unroll 1
-    for (int j = lane; j < n; j += 32) ring[j] = src[j];
-    __syncwarp();
-#endif
+}
+// Stage `n` vertices (16 B each) from global memory into the warp's ring with one bulk async
+// copy issued by lane 0 and completed on a per-warp mbarrier.
+__device__ __forceinline__ void stage_ring(double2 *ring, unsigned long long *mbar, const double2 *src, int n, int lane,
+                                           unsigned parity) {
+    stage_issue(ring, mbar, src, n, lane);
+    stage_wait(mbar, parity);
 }
 
 __device__ __forceinline__ void init_mbar(unsigned long long *mbar, int lane) {
@@ -116,7 +124,7 @@ __device__ __forceinline__ double cand_key_from_angles(double a0, double a1) {
 // Two passes so that the atan2 work runs on full warps: pass 1 classifies every vertex from its
 // cross/dot products (most vertices of a densified polygon are surely not candidates) and compacts
 // the undecided ones into a small queue; the queue is drained 32 entries at a time.
-__device__ __noinline__ void rebuild_candidates(const Warp &w, double *key, int32_t *stamp) {
+__device__ __noinline__ void rebuild_candidates(const Warp w, double *key, int32_t *stamp) {
     const int n = w.n, lane = w.lane;
     int qn = 0;
     auto drain = [&](int count) {           // exact keys for queue[qn - count .. qn), one vertex per lane
@@ -152,7 +160,7 @@ __device__ __noinline__ void rebuild_candidates(const Warp &w, double *key, int3
 }
 
 // arg-min of (key, stamp) over the n live vertices; -1 when the candidate list is empty.
-__device__ __noinline__ int find_reference_index(const Warp &w, const double *key, const int32_t *stamp) {
+__device__ __noinline__ int find_reference_index(const Warp w, const double *key, const int32_t *stamp) {
     double bk = CUDART_INF;
     int bs = 0x7fffffff, bj = -1;
 #pragma unroll 4
@@ -183,7 +191,7 @@ __device__ __noinline__ int find_reference_index(const Warp &w, const double *ke
 // observation (C:1059-1090 PointEnvironment, C:1192-1290 get_radius_points, E:665-738)
 // returns obs[lane] for lane < 18; base length through base_out.
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ float compute_obs(const Warp &w, int idx, double area_ratio, double &base_out) {
+__device__ __noinline__ float compute_obs(const Warp w, int idx, double area_ratio, double &base_out) {
     const int lane = w.lane, n = w.n;
     const double inv_radius = 0.25;   // x / 4 == x * 0.25 exactly
     P2 ref = w.at(idx), right_p = w.at(idx - 1), left_p = w.at(idx + 1 >= n ? idx + 1 - n : idx + 1);
@@ -369,7 +377,7 @@ __device__ __noinline__ float compute_obs(const Warp &w, int idx, double area_ra
 // ---------------------------------------------------------------------------------------------
 // estimated_area_range (M:705-718): needs the mean, the 2nd smallest and 2nd largest edge.
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ void estimate_area_range(const Warp &w, double &area_min, double &area_crit) {
+__device__ __noinline__ void estimate_area_range(const Warp w, double &area_min, double &area_crit) {
     double s = 0, lo1 = CUDART_INF, lo2 = CUDART_INF, hi1 = -CUDART_INF, hi2 = -CUDART_INF;
 #pragma unroll 1
     for (int j = w.lane; j < w.n; j += 32) {
@@ -396,7 +404,7 @@ __device__ __noinline__ void estimate_area_range(const Warp &w, double &area_min
 }
 
 // sequential shoelace (C:485-487 up to np.dot's BLAS summation order)
-__device__ __noinline__ double shoelace_area(const Warp &w) {
+__device__ __noinline__ double shoelace_area(const Warp w) {
     double s1 = 0, s2 = 0;
 #pragma unroll 1
     for (int j = w.lane; j < w.n; j += 32) {
@@ -425,7 +433,7 @@ __device__ __forceinline__ double rint4_mixed(double dy, const int32_t *vid, int
     return r;
 }
 
-__device__ __noinline__ bool point_inside(const Warp &w, P2 P, const int32_t *vid, int n0) {
+__device__ __noinline__ bool point_inside(const Warp w, P2 P, const int32_t *vid, int n0) {
     const int n = w.n;
     int hits = 0;
     const P2 ray2 = mk(10000, P.y);
@@ -469,7 +477,7 @@ __device__ __noinline__ bool point_inside(const Warp &w, P2 P, const int32_t *vi
 }
 
 // E:766-769 find_same_point: any boundary vertex within 0.001 of P
-__device__ __noinline__ bool find_same_point(const Warp &w, P2 P) {
+__device__ __noinline__ bool find_same_point(const Warp w, P2 P) {
     bool f = false;
 #pragma unroll 4
     for (int j = w.lane; j < w.n; j += 32) f |= pdist(w.at(j), P) < 0.001;
@@ -479,8 +487,9 @@ __device__ __noinline__ bool find_same_point(const Warp &w, P2 P) {
 // ---------------------------------------------------------------------------------------------
 // candidate quad: validity (C:738-757, C:814-826) + corner angles
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ bool mesh_is_valid(const Warp &w, const P2 (&m)[4]) {
+__device__ __noinline__ bool mesh_is_valid(const Warp w, const Quad Q) {
     const int lane = w.lane;
+    const P2 m[4] = {Q.at(0), Q.at(1), Q.at(2), Q.at(3)};
     // lanes 0-3: corner i = m[i].angle(m[i+1], m[i-1]) outside [0.01 pi, 0.99 pi]?   (C:746-757)
     // lanes 4-5: is_cross((m0,m1),(m2,m3)), is_cross((m0,m3),(m1,m2))                  (C:814-826)
     // Mesh.is_valid is a pure conjunction, so the evaluation order does not matter.
@@ -502,8 +511,10 @@ __device__ __noinline__ bool mesh_is_valid(const Warp &w, const P2 (&m)[4]) {
 
 // M:536-556 check_intersection_with_boundary.  qi[] = boundary indices of the quad vertices
 // (-1 for the not-yet-inserted new vertex), ri = position of the reference point in the quad.
-__device__ __noinline__ bool intersects_boundary(const Warp &w, const P2 (&m)[4], const int (&qi)[4], int ri, P2 ref) {
+__device__ __noinline__ bool intersects_boundary(const Warp w, const Quad Q, const int4 qv, int ri, P2 ref) {
     const int n = w.n;
+    const P2 m[4] = {Q.at(0), Q.at(1), Q.at(2), Q.at(3)};
+    const int qi[4] = {qv.x, qv.y, qv.z, qv.w};
     double max_dist = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++)
@@ -538,7 +549,7 @@ __device__ __noinline__ bool intersects_boundary(const Warp &w, const P2 (&m)[4]
 // boundary quality of a freshly inserted vertex (M:355-408 compute_boundary_quality)
 // a_next / a_prev: interior angles at B[idx+1] and B[idx-1] (already evaluated for the candidates)
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ double boundary_quality_new_vertex(const Warp &w, int idx, double a_next, double a_prev) {
+__device__ __noinline__ double boundary_quality_new_vertex(const Warp w, int idx, double a_next, double a_prev) {
     const int n = w.n;
     P2 add_v = w.at(idx);
     double amin = CUDART_INF;
@@ -584,7 +595,7 @@ __device__ __noinline__ double boundary_quality_new_vertex(const Warp &w, int id
 }
 
 // M:418-452: element without a new vertex; t0,t1 = new indices of the two surviving quad vertices
-__device__ __noinline__ double boundary_quality_no_new(const Warp &w, int t0, int t1, double ang0, double ang1) {
+__device__ __noinline__ double boundary_quality_no_new(const Warp w, int t0, int t1, double ang0, double ang1) {
     const int n = w.n;
     double amin = CUDART_INF;
     if (ang0 < PI / 3) amin = ang0;
@@ -826,20 +837,23 @@ __global__ void __launch_bounds__(WPB * 32, MG_MINB) mg_step_decide_kernel(Param
     const int env = blockIdx.x * WPB + warp;
     if (env >= P.num_envs) return;
     SmemLayout L = carve(smem_raw, P.cap, warp);
+    // the ring copy does not depend on the env record: copy the whole `cap`-slot slab right away (entries
+    // past n are stale and never read) so that its DRAM round trip overlaps the record's
+    init_mbar(L.mbar, lane);
+    stage_issue(L.ring, L.mbar, P.xy + (size_t)env * P.cap, P.cap, lane);
 
     const EnvHot S0 = *reinterpret_cast<const EnvHot *>(P.st + env);      // 3 x 16 B, the rest is phase B/C's
     EnvHot S = S0;
     // requested now so that the tail of a failed step does not pay another DRAM round trip
     const float obs_cached = lane < MG_OBS_DIM ? P.obs_cache[(size_t)env * MG_OBS_DIM + lane] : 0.0f;
     const float a0 = io.act[(size_t)env * 3 + 0], a1 = io.act[(size_t)env * 3 + 1], a2 = io.act[(size_t)env * 3 + 2];
-    init_mbar(L.mbar, lane);                 // barrier set-up overlaps the loads above
     const size_t off = (size_t)env * P.cap;
     Warp w;
     w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = S.n;
     // An env without a reference point (empty candidate list, E:736-738 returns None) has no
     // defined continuation in the reference (its next step raises): it is reported truncated.
     const bool dead = S.ref_index < 0 || S.n < 3;
-    if (!dead) stage_ring(w.ring, L.mbar, P.xy + off, S.n, lane, 0);
+    stage_wait(L.mbar, 0);
 
     const int n = S.n, idx = dead ? 0 : S.ref_index;
     const P2 ref = dead ? mk(0, 0) : w.at(idx), right_p = dead ? mk(1, 0) : w.at(idx - 1);
@@ -885,8 +899,11 @@ __global__ void __launch_bounds__(WPB * 32, MG_MINB) mg_step_decide_kernel(Param
         quad_indices(rule, new_vertex, idx, n, qi, ri);
 #pragma unroll
         for (int k = 0; k < 4; k++) m[k] = qi[k] < 0 ? newp : w.at(qi[k]);
-        bool valid = mesh_is_valid(w, m);
-        if (valid) valid = !intersects_boundary(w, m, qi, ri, ref);
+        Quad Q;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { Q.x[k] = m[k].x; Q.y[k] = m[k].y; }
+        bool valid = mesh_is_valid(w, Q);
+        if (valid) valid = !intersects_boundary(w, Q, make_int4(qi[0], qi[1], qi[2], qi[3]), ri, ref);
         if (valid) {
             // hand the element over to phase B
             if (lane == 0) {
@@ -929,12 +946,13 @@ __device__ __forceinline__ void apply_successes(const Params &P, const StepIO &i
 #pragma unroll 1
     for (int item = first; item < count; item += stride) {
         const int env = P.succ_list[item];
-        EnvState S = P.st[env];
         const size_t off = (size_t)env * P.cap;
+        __syncwarp();
+        stage_issue(L.ring, L.mbar, P.xy + off, P.cap, lane);      // whole slab, overlaps the record load
+        EnvState S = P.st[env];
         Warp w;
         w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = S.n;
-        __syncwarp();
-        stage_ring(w.ring, L.mbar, P.xy + off, S.n, lane, phase);
+        stage_wait(L.mbar, phase);
         phase ^= 1u;
         const Pending Q = P.pend[env];
         const int n = S.n, idx = S.ref_index;
