@@ -259,8 +259,8 @@ __device__ __noinline__ float compute_obs(const Warp w, int idx, double area_rat
 
     // --- scan of the other n-1 vertices in the reference's order o = 1 .. n-1  (m = idx - o) --
     const double sector = theta / 3;
-    unsigned long long best_sec[3] = {~0ull, ~0ull, ~0ull};   // (float bits of cand, order)
-    double my_ang[3] = {0, 0, 0};
+    unsigned long long bs0 = ~0ull, bs1 = ~0ull, bs2 = ~0ull;  // per sector: (float bits of cand, order)
+    double ma0 = 0, ma1 = 0, ma2 = 0;
     double best_ray = CUDART_INF;                             // f64 value of the nearest bisector hit
     int best_ray_o = 0x7fffffff;
 #pragma unroll 1
@@ -284,10 +284,9 @@ __device__ __noinline__ float compute_obs(const Warp w, int idx, double area_rat
             float cand = (float)((d * inv_radius) / base);
             if (cand < 1.0f) {
                 unsigned long long keyv = ((unsigned long long)__float_as_uint(cand) << 32) | (unsigned)o;
-                if (keyv < best_sec[k]) {
-                    best_sec[k] = keyv;
-                    my_ang[k] = angle;
-                }
+                if (k == 0) { if (keyv < bs0) { bs0 = keyv; ma0 = angle; } }
+                else if (k == 1) { if (keyv < bs1) { bs1 = keyv; ma1 = angle; } }
+                else { if (keyv < bs2) { bs2 = keyv; ma2 = angle; } }
             }
         }
         // C:657-676 ll.intersection_vertex(seg) with ll = (ref, p_s), seg = (B[m], B[m+1])
@@ -329,10 +328,12 @@ __device__ __noinline__ float compute_obs(const Warp w, int idx, double area_rat
     // sector minima: first (in order o) strictly smaller float32 value wins (C:1259-1263)
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        unsigned long long m = warp_min_u64(best_sec[k]);
+        const unsigned long long mine = k == 0 ? bs0 : (k == 1 ? bs1 : bs2);
+        const double mine_ang = k == 0 ? ma0 : (k == 1 ? ma1 : ma2);
+        unsigned long long m = warp_min_u64(mine);
         if (m != ~0ull) {
-            unsigned src = __ffs(__ballot_sync(FULL, best_sec[k] == m)) - 1;
-            double ang = shfl_d(my_ang[k], src);
+            unsigned src = __ffs(__ballot_sync(FULL, mine == m)) - 1;
+            double ang = shfl_d(mine_ang, src);
             r0[3 + k] = __uint_as_float((unsigned)(m >> 32));
             r1[3 + k] = (float)fmin(ang, clip);
         }
@@ -926,9 +927,9 @@ __global__ void __launch_bounds__(WPB * 32, MG_MINB) mg_step_decide_kernel(Param
 
 // ---- phase B ---------------------------------------------------------------------------------
 // in-place reset of one finished env (V:40-52): new episode, first observation to the caller
-__device__ __forceinline__ void reset_in_place(const Params &P, const StepIO &io, int env, Warp &w, EnvState &S) {
+__device__ __noinline__ void reset_in_place(const Params &P, const StepIO &io, int env, Warp w) {
+    EnvState S = P.st[env];                      // reloaded here: the caller's copy stays in registers
     S.episode++;
-    __syncwarp();
     float obs = reset_env(P, w, env, S);
     if (w.lane == 0) P.st[env] = S;
     if (w.lane < MG_OBS_DIM) {
@@ -1060,7 +1061,8 @@ __device__ __forceinline__ void apply_successes(const Params &P, const StepIO &i
         S.stamp_ctr -= 4;
         // ---- element log ----------------------------------------------------------------------
         if (P.elem && lane < 4 && S.n_elements < P.elem_cap)
-            P.elem[((size_t)env * P.elem_cap + S.n_elements) * 4 + lane] = elem_ids[lane];
+            P.elem[((size_t)env * P.elem_cap + S.n_elements) * 4 + lane] =
+                lane == 0 ? elem_ids[0] : (lane == 1 ? elem_ids[1] : (lane == 2 ? elem_ids[2] : elem_ids[3]));
         S.n_elements++;
         // ---- area (C:943-958), robust quality (C:881-892) -----------------------------------
         double e0 = pdist(m[0], m[3]), e1 = pdist(m[1], m[0]), e2 = pdist(m[2], m[1]), e3 = pdist(m[3], m[2]);
@@ -1109,7 +1111,10 @@ __device__ __forceinline__ void apply_successes(const Params &P, const StepIO &i
         if (S.ref_index >= 0) obs = compute_obs(w, S.ref_index, S.current_area / S.original_area, S.base_length);
         else obs_none = true;
         S.failed_num = 0;
-        if (finish_step(P, io, env, lane, S, n, reward, done, false, true, obs_none, obs)) reset_in_place(P, io, env, w, S);
+        if (finish_step(P, io, env, lane, S, n, reward, done, false, true, obs_none, obs)) {
+            __syncwarp();                        // lane 0's record store is visible to the warp
+            reset_in_place(P, io, env, w);
+        }
     }
 }
 
@@ -1136,10 +1141,9 @@ __global__ void __launch_bounds__(WPB * 32, MG_MINB_APPLY) mg_step_apply_reset_k
 #pragma unroll 1
     for (int item = rb * WPB + warp; item < count; item += nrb * WPB) {
         const int env = P.reset_list[item];
-        EnvState S = P.st[env];
         Warp w;
         w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = 0;
-        reset_in_place(P, io, env, w, S);
+        reset_in_place(P, io, env, w);
     }
 }
 
