@@ -136,6 +136,16 @@ int mg_step(mg_handle h, const float *act_dev, float *obs_dev, double *rew_dev, 
 int mg_step_host(mg_handle h, const float *act_host, float *obs_host, double *rew_host,
                  uint8_t *term_host, uint8_t *trunc_host, float *term_obs_host, int32_t *n_elem_host);
 
+/* Delta transfers for mg_step_host: enabled != 0 lets the library ship observations
+ * only for the envs whose state changed in the step (an element was created or the env was reset -- on a
+ * failed step the reference itself returns a bit-identical observation).  Requires the caller to pass the
+ * same, unmodified obs_host buffer on every call (the first call, a pointer change or an
+ * mg_reset fall back to a full copy). */
+int mg_set_host_delta(mg_handle h, int enabled);
+
+/* Bytes moved host->device and device->host by the last mg_step_host call. */
+int mg_last_host_bytes(mg_handle h, int64_t *h2d, int64_t *d2h);
+
 /* Uniform actions in the action box (E:78-80) from the handle's Philox stream -- the synthetic
  * policy used by the benchmarks.  act_dev: out num_envs*3 float32. */
 int mg_sample_actions(mg_handle h, uint64_t seed, uint64_t step_index, float *act_dev, void *stream);

@@ -20,7 +20,7 @@ NVCC_FLAGS = [
 ]
 
 SYMBOLS = [
-    "mg_create", "mg_set_domains", "mg_set_random", "mg_set_auto_reset", "mg_reset", "mg_step", "mg_step_host", "mg_sample_actions",
+    "mg_create", "mg_set_domains", "mg_set_random", "mg_set_auto_reset", "mg_reset", "mg_step", "mg_step_host", "mg_set_host_delta", "mg_last_host_bytes", "mg_sample_actions",
     "mg_get_state", "mg_get_elements", "mg_stats", "mg_set_phase_mask", "mg_num_envs", "mg_max_verts", "mg_launch_count", "mg_destroy",
     "mg_last_error", "mg_version",
 ]
@@ -82,6 +82,8 @@ def load():
     L.mg_reset.argtypes = [vp, vp, vp, vp]
     L.mg_step.argtypes = [vp] + [vp] * 7 + [vp]
     L.mg_step_host.argtypes = [vp] + [vp] * 7
+    L.mg_set_host_delta.argtypes = [vp, i32]
+    L.mg_last_host_bytes.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.mg_sample_actions.argtypes = [vp, u64, u64, vp, vp]
     L.mg_get_state.argtypes = [vp, i32, C.POINTER(StateView)]
     L.mg_get_elements.argtypes = [vp, i32, vp, i32, C.POINTER(C.c_int32), vp, i32, C.POINTER(C.c_int32)]

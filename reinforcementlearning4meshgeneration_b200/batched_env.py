@@ -177,6 +177,16 @@ class BatchedBoudaryEnv:
               self._h, "mg_step_host")
         return out
 
+    def set_host_delta(self, enabled: bool = True) -> None:
+        """step_host ships only the observation rows that changed (see mg_set_host_delta); the caller
+        must then pass the same, unmodified ``out`` buffers on every call."""
+        check(self._L.mg_set_host_delta(self._h, int(enabled)), self._h, "mg_set_host_delta")
+
+    def last_host_bytes(self):
+        h2d, d2h = C.c_int64(), C.c_int64()
+        check(self._L.mg_last_host_bytes(self._h, C.byref(h2d), C.byref(d2h)), self._h, "mg_last_host_bytes")
+        return h2d.value, d2h.value
+
     def sample_actions(self, seed: int, step_index: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Uniform actions in the action box from the library's Philox stream (synthetic policy)."""
         out = self._act if out is None else out

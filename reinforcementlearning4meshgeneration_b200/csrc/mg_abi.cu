@@ -32,6 +32,13 @@ struct mg_env_s {
     int32_t *d_pack_idx = nullptr, *d_pack_cnt = nullptr, *h_pack_idx = nullptr, *h_pack_cnt = nullptr;
     float *d_pack_obs = nullptr, *h_pack_obs = nullptr;
     float *last_term_obs_host = nullptr;
+    // delta mode (mg_set_host_delta): observations / element counts travel only for the envs whose state changed
+    bool host_delta = false;
+    float *last_obs_host = nullptr;
+    int32_t *last_nel_host = nullptr;
+    int32_t *d_chg_idx = nullptr, *d_chg_nel = nullptr, *h_chg_idx = nullptr, *h_chg_nel = nullptr;
+    float *d_chg_obs = nullptr, *h_chg_obs = nullptr;
+    int64_t last_h2d = 0, last_d2h = 0;
     std::vector<int32_t> prev_done;
     bool ready = false;       // domains or generator configured
     bool was_reset = false;
@@ -132,11 +139,16 @@ int mg_create(mg_handle *out, int device, int num_envs, int max_verts) {
     A(dalloc(&h->d_term_obs, (size_t)num_envs * MG_OBS_DIM), "term_obs"); A(dalloc(&h->d_rew, (size_t)num_envs), "rew");
     A(dalloc(&h->d_term, (size_t)num_envs), "term"); A(dalloc(&h->d_trunc, (size_t)num_envs), "trunc");
     A(dalloc(&h->d_nel, (size_t)num_envs), "nel");
-    A(dalloc(&h->d_pack_idx, (size_t)num_envs), "pack_idx"); A(dalloc(&h->d_pack_cnt, (size_t)1), "pack_cnt");
+    A(dalloc(&h->d_pack_idx, (size_t)num_envs), "pack_idx"); A(dalloc(&h->d_pack_cnt, (size_t)2), "pack_cnt");
     A(dalloc(&h->d_pack_obs, (size_t)num_envs * MG_OBS_DIM), "pack_obs");
     A(cudaMallocHost((void **)&h->h_pack_idx, sizeof(int32_t) * num_envs), "h_pack_idx");
-    A(cudaMallocHost((void **)&h->h_pack_cnt, sizeof(int32_t)), "h_pack_cnt");
+    A(cudaMallocHost((void **)&h->h_pack_cnt, 2 * sizeof(int32_t)), "h_pack_cnt");
     A(cudaMallocHost((void **)&h->h_pack_obs, sizeof(float) * MG_OBS_DIM * num_envs), "h_pack_obs");
+    A(dalloc(&h->d_chg_idx, (size_t)num_envs), "chg_idx"); A(dalloc(&h->d_chg_nel, (size_t)num_envs), "chg_nel");
+    A(dalloc(&h->d_chg_obs, (size_t)num_envs * MG_OBS_DIM), "chg_obs");
+    A(cudaMallocHost((void **)&h->h_chg_idx, sizeof(int32_t) * num_envs), "h_chg_idx");
+    A(cudaMallocHost((void **)&h->h_chg_nel, sizeof(int32_t) * num_envs), "h_chg_nel");
+    A(cudaMallocHost((void **)&h->h_chg_obs, sizeof(float) * MG_OBS_DIM * num_envs), "h_chg_obs");
     if (rc == MG_OK && cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking) != cudaSuccess)
         rc = fail(h, MG_ERR_CUDA, "cudaStreamCreate");
     if (rc == MG_OK) rc = configure_kernels(h);
@@ -157,6 +169,8 @@ int mg_destroy(mg_handle h) {
     cudaFree(h->d_term); cudaFree(h->d_trunc); cudaFree(h->d_nel);
     cudaFree(h->d_pack_idx); cudaFree(h->d_pack_cnt); cudaFree(h->d_pack_obs);
     cudaFreeHost(h->h_pack_idx); cudaFreeHost(h->h_pack_cnt); cudaFreeHost(h->h_pack_obs);
+    cudaFree(h->d_chg_idx); cudaFree(h->d_chg_nel); cudaFree(h->d_chg_obs);
+    cudaFreeHost(h->h_chg_idx); cudaFreeHost(h->h_chg_nel); cudaFreeHost(h->h_chg_obs);
     if (h->host_stream) cudaStreamDestroy(h->host_stream);
     delete h;
     return MG_OK;
@@ -258,6 +272,8 @@ int mg_reset(mg_handle h, const uint8_t *mask_dev, float *obs_dev, void *stream)
     h->launches++;
     MG_CUDA(h, cudaGetLastError());
     h->was_reset = true;
+    h->last_obs_host = nullptr;          // host-side delta copies are stale after a reset
+    h->last_nel_host = nullptr;
     return MG_OK;
 }
 
@@ -290,40 +306,90 @@ int mg_step_host(mg_handle h, const float *act_host, float *obs_host, double *re
     const size_t N = h->num_envs;
     cudaStream_t s = h->host_stream;
     MG_CUDA(h, cudaMemcpyAsync(h->d_act, act_host, N * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+    const int set = h->step_parity;                 // work lists of the step enqueued next
     int rc = mg_step(h, h->d_act, h->d_obs, h->d_rew, h->d_term, h->d_trunc, h->d_term_obs, h->d_nel, s);
     if (rc != MG_OK) return rc;
+    int64_t d2h = 0;
+    // observations (and element counts) only change for envs that created an element or were reset: in delta
+    // mode, with the caller's buffers unchanged since the previous call, only those rows cross PCIe
+    const bool delta_obs = h->host_delta && h->last_obs_host == obs_host;
+    // (element counts are not delta-coded: a reset env reports the finished episode's count in the reset
+    // step and 0 from the next step on, whatever that step does)
+    const bool delta_nel = false;
+    MG_CUDA(h, cudaMemsetAsync(h->d_pack_cnt, 0, 2 * sizeof(int32_t), s));
     if (term_obs_host) {
-        MG_CUDA(h, cudaMemsetAsync(h->d_pack_cnt, 0, sizeof(int32_t), s));
         mg_pack_terminal_kernel<<<(h->num_envs + 255) / 256, 256, 0, s>>>(h->num_envs, h->d_term, h->d_trunc, h->d_term_obs,
                                                                            h->d_pack_idx, h->d_pack_obs, h->d_pack_cnt);
         h->launches++;
-        MG_CUDA(h, cudaMemcpyAsync(h->h_pack_cnt, h->d_pack_cnt, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     }
-    MG_CUDA(h, cudaMemcpyAsync(obs_host, h->d_obs, N * MG_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (delta_obs) {
+        mg_pack_changed_kernel<<<h->sm_count * 2, 256, 0, s>>>(h->P, set, h->d_obs, h->d_nel, h->d_chg_idx, h->d_chg_obs,
+                                                              h->d_chg_nel, h->d_pack_cnt + 1);
+        h->launches++;
+    } else {
+        MG_CUDA(h, cudaMemcpyAsync(obs_host, h->d_obs, N * MG_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
+        d2h += N * MG_OBS_DIM * sizeof(float);
+    }
+    MG_CUDA(h, cudaMemcpyAsync(h->h_pack_cnt, h->d_pack_cnt, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     MG_CUDA(h, cudaMemcpyAsync(rew_host, h->d_rew, N * sizeof(double), cudaMemcpyDeviceToHost, s));
     MG_CUDA(h, cudaMemcpyAsync(term_host, h->d_term, N, cudaMemcpyDeviceToHost, s));
     MG_CUDA(h, cudaMemcpyAsync(trunc_host, h->d_trunc, N, cudaMemcpyDeviceToHost, s));
-    if (n_elem_host) MG_CUDA(h, cudaMemcpyAsync(n_elem_host, h->d_nel, N * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    d2h += N * (sizeof(double) + 2) + 2 * sizeof(int32_t);
+    if (n_elem_host && !delta_nel) {
+        MG_CUDA(h, cudaMemcpyAsync(n_elem_host, h->d_nel, N * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        d2h += N * sizeof(int32_t);
+    }
     MG_CUDA(h, cudaStreamSynchronize(s));
+    const int c_term = term_obs_host ? h->h_pack_cnt[0] : 0, c_chg = delta_obs ? h->h_pack_cnt[1] : 0;
+    if (c_term > 0) {
+        MG_CUDA(h, cudaMemcpyAsync(h->h_pack_idx, h->d_pack_idx, sizeof(int32_t) * c_term, cudaMemcpyDeviceToHost, s));
+        MG_CUDA(h, cudaMemcpyAsync(h->h_pack_obs, h->d_pack_obs, sizeof(float) * MG_OBS_DIM * c_term, cudaMemcpyDeviceToHost, s));
+        d2h += (int64_t)c_term * (4 + 4 * MG_OBS_DIM);
+    }
+    if (c_chg > 0) {
+        MG_CUDA(h, cudaMemcpyAsync(h->h_chg_idx, h->d_chg_idx, sizeof(int32_t) * c_chg, cudaMemcpyDeviceToHost, s));
+        MG_CUDA(h, cudaMemcpyAsync(h->h_chg_obs, h->d_chg_obs, sizeof(float) * MG_OBS_DIM * c_chg, cudaMemcpyDeviceToHost, s));
+        if (delta_nel) MG_CUDA(h, cudaMemcpyAsync(h->h_chg_nel, h->d_chg_nel, sizeof(int32_t) * c_chg, cudaMemcpyDeviceToHost, s));
+        d2h += (int64_t)c_chg * (4 + 4 * MG_OBS_DIM + (delta_nel ? 4 : 0));
+    }
+    if (c_term > 0 || c_chg > 0) MG_CUDA(h, cudaStreamSynchronize(s));
+    for (int i = 0; i < c_chg; i++) {
+        const size_t e = (size_t)h->h_chg_idx[i];
+        std::memcpy(obs_host + e * MG_OBS_DIM, h->h_chg_obs + (size_t)i * MG_OBS_DIM, sizeof(float) * MG_OBS_DIM);
+        if (delta_nel) n_elem_host[e] = h->h_chg_nel[i];
+    }
     if (term_obs_host) {
-        // terminal observations are only defined where done: ship those rows compacted instead of N*72 bytes
-        const int c = *h->h_pack_cnt;
-        if (c > 0) {
-            MG_CUDA(h, cudaMemcpyAsync(h->h_pack_idx, h->d_pack_idx, sizeof(int32_t) * c, cudaMemcpyDeviceToHost, s));
-            MG_CUDA(h, cudaMemcpyAsync(h->h_pack_obs, h->d_pack_obs, sizeof(float) * MG_OBS_DIM * c, cudaMemcpyDeviceToHost, s));
-            MG_CUDA(h, cudaStreamSynchronize(s));
-        }
+        // terminal observations are only defined where done: those rows travel compacted instead of N*72 bytes
         if (h->last_term_obs_host != term_obs_host) {
             std::memset(term_obs_host, 0, sizeof(float) * MG_OBS_DIM * N);
             h->last_term_obs_host = term_obs_host;
         } else {
             for (int32_t e : h->prev_done) std::memset(term_obs_host + (size_t)e * MG_OBS_DIM, 0, sizeof(float) * MG_OBS_DIM);
         }
-        h->prev_done.assign(h->h_pack_idx, h->h_pack_idx + c);
-        for (int i = 0; i < c; i++)
+        h->prev_done.assign(h->h_pack_idx, h->h_pack_idx + c_term);
+        for (int i = 0; i < c_term; i++)
             std::memcpy(term_obs_host + (size_t)h->h_pack_idx[i] * MG_OBS_DIM, h->h_pack_obs + (size_t)i * MG_OBS_DIM,
                         sizeof(float) * MG_OBS_DIM);
     }
+    h->last_obs_host = obs_host;
+    h->last_nel_host = n_elem_host;
+    h->last_h2d = (int64_t)(N * 3 * sizeof(float));
+    h->last_d2h = d2h;
+    return MG_OK;
+}
+
+int mg_set_host_delta(mg_handle h, int enabled) {
+    if (!h) return fail(h, MG_ERR_ARG, "mg_set_host_delta: null handle");
+    h->host_delta = enabled != 0;
+    h->last_obs_host = nullptr;
+    h->last_nel_host = nullptr;
+    return MG_OK;
+}
+
+int mg_last_host_bytes(mg_handle h, int64_t *h2d, int64_t *d2h) {
+    if (!h) return fail(h, MG_ERR_ARG, "mg_last_host_bytes: null handle");
+    if (h2d) *h2d = h->last_h2d;
+    if (d2h) *d2h = h->last_d2h;
     return MG_OK;
 }
 

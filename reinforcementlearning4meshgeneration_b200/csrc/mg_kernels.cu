@@ -1174,6 +1174,21 @@ __global__ void mg_pack_terminal_kernel(int num_envs, const uint8_t *term, const
     for (int k = 0; k < MG_OBS_DIM; k++) packed[(size_t)i * MG_OBS_DIM + k] = term_obs[(size_t)e * MG_OBS_DIM + k];
 }
 
+// mg_step_host, delta mode: gather observation + element count of every env that changed in this step
+// (accepted elements and resets: exactly the two work lists of the step), one warp per entry.
+__global__ void mg_pack_changed_kernel(Params P, int set, const float *obs, const int32_t *nel, int32_t *idx, float *pobs,
+                                       int32_t *pnel, int32_t *count) {
+    const int cs = P.counters[2 * set + 0], cr = P.counters[2 * set + 1];
+    const int lane = threadIdx.x & 31;
+    const int warps = gridDim.x * (blockDim.x >> 5);
+    for (int it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < cs + cr; it += warps) {
+        const int env = it < cs ? P.succ_list[it] : P.reset_list[it - cs];
+        if (lane == 0) { idx[it] = env; pnel[it] = nel[env]; }
+        if (lane < MG_OBS_DIM) pobs[(size_t)it * MG_OBS_DIM + lane] = obs[(size_t)env * MG_OBS_DIM + lane];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *count = cs + cr;
+}
+
 // Sum of the accumulator slots -> one mg_episode_stats (one warp).
 __global__ void mg_stats_kernel(StatsAcc *stats, mg_episode_stats *out, int reset) {
     unsigned long long a[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -57,6 +57,8 @@ class _VecEnvCore:
                          terminated=_pinned((N,), torch.uint8), truncated=_pinned((N,), torch.uint8),
                          terminal_obs=_pinned((N, OBS_DIM), torch.float32), n_elements=_pinned((N,), torch.int32))
         self._monitor = monitor
+        if hasattr(batched, "set_host_delta"):
+            batched.set_host_delta(True)      # the adapter owns its pinned buffers and hands out copies
         self._ep_ret = np.zeros(N, np.float64)
         self._ep_len = np.zeros(N, np.int64)
         self._t0 = time.time()

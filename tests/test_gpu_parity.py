@@ -12,6 +12,8 @@ from helpers import TRACES, action_stream, assert_rollout_matches, load_domains,
 pytestmark = pytest.mark.gpu
 
 REWARD_TOL = 1e-9
+LOW_A = np.array([-1.0, -1.5, 0.0], np.float32)
+HIGH_A = np.array([1.0, 1.5, 1.5], np.float32)
 
 
 def _mk(domains, n, **kw):
@@ -378,3 +380,34 @@ def test_full_size_config3_properties_and_spot_check():
     for t in range(40):
         r3 = env3.step(env3.sample_actions(2026, t))
     assert torch.equal(r2.obs, r3.obs) and torch.equal(r2.reward, r3.reward) and torch.equal(r2.n_elements, r3.n_elements)
+
+
+def test_host_step_delta_transfers_equal_full_copies():
+    """mg_step_host in delta mode (only changed observation rows cross PCIe) delivers exactly the same
+    host arrays as the full-copy mode, including across a mid-run reset."""
+    import torch
+    doms, _ = load_domains()
+    N, T = 96, 260
+    envs = [_mk([doms["star"], doms["half_wheel"], doms["boundary16"]], N) for _ in range(2)]
+    envs[1].set_host_delta(True)
+    outs = [None, None]
+    for e in envs:
+        e.reset()
+    rng = np.random.default_rng(3)
+    moved = []
+    for t in range(T):
+        a = rng.uniform(LOW_A, HIGH_A, size=(N, 3)).astype(np.float32)
+        outs[0] = envs[0].step_host(a, outs[0])
+        outs[1] = envs[1].step_host(a, outs[1])
+        moved.append(envs[1].last_host_bytes()[1])
+        for k in ("obs", "reward", "terminated", "truncated", "n_elements"):
+            assert np.array_equal(outs[0][k], outs[1][k]), f"{k} differs at step {t}"
+        d = (outs[0]["terminated"] | outs[0]["truncated"]).astype(bool)
+        assert np.array_equal(outs[0]["terminal_obs"][d], outs[1]["terminal_obs"][d])
+        if t == 100:
+            m = torch.zeros(N, dtype=torch.uint8)
+            m[::3] = 1
+            for e in envs:
+                e.reset(m)
+    full = N * (72 + 8 + 2 + 4)
+    assert moved[0] >= full and np.median(moved[5:]) < 0.5 * full
