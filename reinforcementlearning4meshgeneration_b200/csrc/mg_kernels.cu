@@ -831,6 +831,23 @@ __device__ __forceinline__ void quad_indices(int rule, bool new_vertex, int idx,
     }
 }
 
+// |x * 1e4 - (k + 0.5)| < tol for some integer k: np_round4(x) could flip under a perturbation of x
+__device__ __forceinline__ bool near_round4_tie(double x, double tol) {
+    double p = x * 1e4;
+    return 0.5 - fabs(p - rint(p)) < tol;
+}
+// E:202-210 / D:112-137 exactly as written: theta = 2 pi - atan2(dy, dx), cos/sin of that double
+__device__ __noinline__ void action_frame_exact(double ax, double ay, double dx, double dy, double base, P2 ref, double &ox,
+                                                double &oy) {
+    double th = 2 * PI - atan2(dy, dx);
+    double s, c;
+    mg_sincos(th, &s, &c);
+    ox = c * ax + s * ay;
+    oy = -s * ax + c * ay;
+    ox *= base; oy *= base;
+    ox += ref.x; oy += ref.y;
+}
+
 // ---- phase A ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(WPB * 32, MG_MINB) mg_step_decide_kernel(Params P, StepIO io, int set) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -860,9 +877,12 @@ __global__ void __launch_bounds__(WPB * 32, MG_MINB) mg_step_decide_kernel(Param
     const P2 ref = dead ? mk(0, 0) : w.at(idx), right_p = dead ? mk(1, 0) : w.at(idx - 1);
 
     // ---- action -> candidate vertex (E:783-792, E:202-210, D:112-137) ------------------------
-    // theta = 2 pi - atan2(dy, dx)  =>  cos(theta) = dx / r, sin(theta) = -dy / r: evaluated from the
-    // edge vector instead of through atan2 + sincos (a few ulp either way, absorbed by the 4-decimal
-    // rounding of the new vertex just like libm-vs-CUDA differences are; see DESIGN.md "numerics")
+    // theta = 2 pi - atan2(dy, dx)  =>  cos(theta) ~ dx / r, sin(theta) ~ -dy / r.  The frame is first
+    // evaluated from the edge vector (no atan2 / sincos); that value is within ~1e-14 of the reference's,
+    // so both round to the same 4-decimal vertex unless a coordinate sits next to a rounding tie.  Ties
+    // are NOT rare on axis-aligned domains (dyadic action components times a short base length land
+    // exactly on k + 0.5, and the reference's sin(fl(2 pi)) = -2.4e-16 then decides): in that band the
+    // reference's own expression is evaluated (exact-safe filter, like the angle classes of mg_math.cuh).
     P2 newp;
     {
         double ax = (double)np_round4f(a1), ay = (double)np_round4f(a2);
@@ -873,6 +893,8 @@ __global__ void __launch_bounds__(WPB * 32, MG_MINB) mg_step_decide_kernel(Param
         double oy = -s * ax + c * ay;
         ox *= S.base_length; oy *= S.base_length;
         ox += ref.x; oy += ref.y;
+        const double tol = 1e-8 * (3 * fabs(S.base_length) + fabs(ref.x) + fabs(ref.y) + 1);   // in units of 1e-4
+        if (near_round4_tie(ox, tol) || near_round4_tie(oy, tol)) action_frame_exact(ax, ay, dx, dy, S.base_length, ref, ox, oy);
         newp = mk(np_round4(ox), np_round4(oy));
     }
 

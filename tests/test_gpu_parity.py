@@ -411,3 +411,74 @@ def test_host_step_delta_transfers_equal_full_copies():
                 e.reset(m)
     full = N * (72 + 8 + 2 + 4)
     assert moved[0] >= full and np.median(moved[5:]) < 0.5 * full
+
+
+def test_soak_all_golden_domains_against_oracle():
+    """Differential soak: every committed domain (5..628 vertices, axis-aligned and curved), 24 envs
+    each, 400 steps of device-sampled actions, every env replayed through the CPU oracle in parallel
+    threads (~160 k env-steps, ~11 k accepted elements)."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle.c_oracle import OracleEnv
+    doms, areas = load_domains()
+    names = sorted(doms)
+    per, T = 24, 400
+    N = per * len(names)
+    env_domain = np.repeat(np.arange(len(names)), per)
+    env = _mk([doms[k] for k in names], N, env_domain=env_domain)
+    env.reset()
+    dev = env.device
+    rec = dict(act=torch.zeros((T, N, 3), device=dev), obs=torch.zeros((T, N, 18), device=dev),
+               tobs=torch.zeros((T, N, 18), device=dev), rew=torch.zeros((T, N), dtype=torch.float64, device=dev),
+               te=torch.zeros((T, N), dtype=torch.uint8, device=dev), tr=torch.zeros((T, N), dtype=torch.uint8, device=dev),
+               ne=torch.zeros((T, N), dtype=torch.int32, device=dev))
+    for t in range(T):
+        a = env.sample_actions(99, t)
+        rec["act"][t] = a
+        r = env.step(a)
+        rec["obs"][t] = r.obs; rec["tobs"][t] = r.terminal_obs; rec["rew"][t] = r.reward
+        rec["te"][t] = r.terminated; rec["tr"][t] = r.truncated; rec["ne"][t] = r.n_elements
+    rec = {k: v.cpu().numpy() for k, v in rec.items()}
+
+    def check(e):
+        k = names[env_domain[e]]
+        o = OracleEnv(doms[k], original_area=areas[k])
+        exp = o.rollout(rec["act"][:, e])
+        got = dict(obs=rec["obs"][:, e], terminal_obs=rec["tobs"][:, e], reward=rec["rew"][:, e], terminated=rec["te"][:, e],
+                   truncated=rec["tr"][:, e], n_elements=rec["ne"][:, e])
+        assert_rollout_matches(got, exp, f"soak[{k}, env {e}]", reward_tol=REWARD_TOL)
+        return int(exp["success"].sum())
+
+    with ThreadPoolExecutor(max_workers=16) as ex:
+        n_el = sum(ex.map(check, range(N)))
+    assert n_el > 5000
+
+
+def test_rounding_ties_of_the_new_vertex_on_axis_aligned_domains():
+    """Dyadic action components (k/16 is exact in float32 and in 4 decimals) times a short base length put the
+    new vertex exactly on a 4-decimal rounding tie; on axis-aligned frames the reference's own
+    sin(fl(2 pi)) = -2.4e-16 then decides the digit (E:202-210).  Found by the soak test (easy1_1, step 347)."""
+    from gpu_helpers import per_env, run_gpu
+    from oracle.c_oracle import OracleEnv
+    doms, areas = load_domains()
+    names = ["easy1_1", "boundary0", "basic2", "half_wheel"]
+    per, T = 16, 500
+    N = per * len(names)
+    env_domain = np.repeat(np.arange(len(names)), per)
+    env = _mk([doms[k] for k in names], N, env_domain=env_domain)
+    env.reset()
+    rng = np.random.default_rng(4242)
+    acts = rng.uniform(LOW_A, HIGH_A, size=(T, N, 3)).astype(np.float32)
+    dyadic = rng.random((T, N)) < 0.4
+    acts[..., 1] = np.where(dyadic, rng.integers(-24, 25, size=(T, N)) / 16.0, acts[..., 1]).astype(np.float32)
+    acts[..., 2] = np.where(dyadic, rng.integers(0, 25, size=(T, N)) / 16.0, acts[..., 2]).astype(np.float32)
+    acts[..., 0] = np.where(dyadic, 0.0, acts[..., 0]).astype(np.float32)          # rule 0: the new-vertex path
+    res = run_gpu(env, acts)
+    n_el = 0
+    for e in range(N):
+        k = names[env_domain[e]]
+        o = OracleEnv(doms[k], original_area=areas[k])
+        exp = o.rollout(acts[:, e])
+        assert_rollout_matches(per_env(res, e), exp, f"ties[{k}, env {e}]", reward_tol=REWARD_TOL)
+        n_el += int(exp["success"].sum())
+    assert n_el > 500
