@@ -1,5 +1,6 @@
 // C ABI of libmeshgen_b200.so (include/meshgen_b200.h): handle management, device memory,
 // kernel launches.  No torch types, no exceptions across the boundary, no CPU fallback.
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -22,6 +23,7 @@ struct mg_env_s {
     DomainScalars *t_sc = nullptr;
     float *t_obs = nullptr;
     mg_episode_stats *d_stats_out = nullptr;
+    double2 *sc_tab = nullptr;      // [2][ANGLE_TAB_N] host-libm {sin, cos} of the quantised angles and their halves
     // staging buffers for mg_step_host
     float *d_act = nullptr, *d_obs = nullptr, *d_term_obs = nullptr;
     double *d_rew = nullptr;
@@ -91,6 +93,24 @@ int configure_kernels(mg_handle h) {
     return MG_OK;
 }
 
+// sin / cos of the quantised angles with the host's libm -- the library CPython's math.sin / math.cos call in the
+// reference (C:154-168, C:946-947, C:1243).  Called through volatile pointers so that the compiler neither folds
+// them nor merges the pair into sincos().
+int upload_angle_table(mg_handle h) {
+    double (*volatile fsin)(double) = ::sin;
+    double (*volatile fcos)(double) = ::cos;
+    std::vector<double2> tab((size_t)2 * ANGLE_TAB_N);
+    for (int k = 0; k < ANGLE_TAB_N; k++) {
+        const double a = (double)k / 1e4;             // == round(theta, 4) for every quantised angle
+        tab[k] = make_double2(fsin(a), fcos(a));
+        tab[(size_t)ANGLE_TAB_N + k] = make_double2(fsin(a / 2), fcos(a / 2));
+    }
+    MG_CUDA(h, cudaMemcpy(h->sc_tab, tab.data(), tab.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    h->P.sc_full = h->sc_tab;
+    h->P.sc_half = h->sc_tab + ANGLE_TAB_N;
+    return MG_OK;
+}
+
 void free_templates(mg_handle h) {
     cudaFree(h->t_xy); cudaFree(h->t_key); cudaFree(h->t_stamp); cudaFree(h->t_sc); cudaFree(h->t_obs);
     h->t_xy = nullptr; h->t_key = nullptr; h->t_stamp = nullptr; h->t_sc = nullptr; h->t_obs = nullptr;
@@ -135,6 +155,7 @@ int mg_create(mg_handle *out, int device, int num_envs, int max_verts) {
     A(dalloc(&P.reset_list, (size_t)num_envs), "reset_list"); A(dalloc(&P.counters, (size_t)4), "counters");
     A(dalloc(&P.elem, (size_t)num_envs * P.elem_cap * 4), "elem"); A(dalloc(&P.ins_xy, (size_t)num_envs * P.ins_cap), "ins_xy");
     A(dalloc(&h->d_stats_out, 1), "stats_out");
+    A(dalloc(&h->sc_tab, (size_t)2 * ANGLE_TAB_N), "angle table");
     A(dalloc(&h->d_act, (size_t)num_envs * 3), "act"); A(dalloc(&h->d_obs, (size_t)num_envs * MG_OBS_DIM), "obs_out");
     A(dalloc(&h->d_term_obs, (size_t)num_envs * MG_OBS_DIM), "term_obs"); A(dalloc(&h->d_rew, (size_t)num_envs), "rew");
     A(dalloc(&h->d_term, (size_t)num_envs), "term"); A(dalloc(&h->d_trunc, (size_t)num_envs), "trunc");
@@ -152,6 +173,7 @@ int mg_create(mg_handle *out, int device, int num_envs, int max_verts) {
     if (rc == MG_OK && cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking) != cudaSuccess)
         rc = fail(h, MG_ERR_CUDA, "cudaStreamCreate");
     if (rc == MG_OK) rc = configure_kernels(h);
+    if (rc == MG_OK) rc = upload_angle_table(h);
     if (rc != MG_OK) { g_err = h->err; mg_destroy(h); return rc; }
     *out = h;
     return MG_OK;
@@ -165,6 +187,7 @@ int mg_destroy(mg_handle h) {
     cudaFree(P.obs_cache); cudaFree(P.elem); cudaFree(P.ins_xy);
     cudaFree(P.pend); cudaFree(P.succ_list); cudaFree(P.reset_list); cudaFree(P.counters);
     free_templates(h);
+    cudaFree(h->sc_tab);
     cudaFree(h->d_stats_out); cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_term_obs); cudaFree(h->d_rew);
     cudaFree(h->d_term); cudaFree(h->d_trunc); cudaFree(h->d_nel);
     cudaFree(h->d_pack_idx); cudaFree(h->d_pack_cnt); cudaFree(h->d_pack_obs);

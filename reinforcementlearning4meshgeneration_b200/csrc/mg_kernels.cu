@@ -49,6 +49,7 @@ struct Warp {
     int *queue;      // shared memory, this warp's integer scratch
     int n;           // live boundary size
     int lane;
+    const double2 *sc_full, *sc_half;   // Params::sc_full / sc_half
     __device__ __forceinline__ int wrap(int i) const {
         if (i < 0) i += n;
         else if (i >= n) i -= n;
@@ -60,6 +61,18 @@ struct Warp {
         return mk(v.x, v.y);
     }
 };
+
+// {sin, cos} of a quantised angle (or of its half with tab = sc_half) from the host-libm table; any other
+// argument falls back to the device routines
+__device__ __forceinline__ void sincos_quantised(const double2 *tab, double angle, bool half, double &s, double &c) {
+    const double kf = rint(angle * 1e4);
+    if (tab != nullptr && kf >= 0.0 && kf <= (double)(ANGLE_TAB_N - 1) && kf / 1e4 == angle) {
+        const double2 v = __ldg(tab + (int)kf);
+        s = v.x; c = v.y;
+    } else {
+        mg_sincos(half ? angle / 2 : angle, &s, &c);
+    }
+}
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -248,9 +261,9 @@ __device__ __noinline__ float compute_obs(const Warp w, int idx, double area_rat
     for (int j = 0; j < 3; j++) r1[3 + j] = (float)fmin((2 * j + 1) * theta / 6, clip);
 
     // p_s = ref + rotate((T cos(theta/2), T sin(theta/2)), rot)                      (C:154-168, C:1243)
-    double sv = 0, cv = 0;
-    if (lane < 2) mg_sincos(lane == 0 ? theta / 2 : rot, &sv, &cv);
-    double s_h = shfl_d(sv, 0), c_h = shfl_d(cv, 0), s_r = shfl_d(sv, 1), c_r = shfl_d(cv, 1);
+    double s_h, c_h, s_r, c_r;
+    sincos_quantised(w.sc_half, theta, true, s_h, c_h);
+    sincos_quantised(w.sc_full, rot, false, s_r, c_r);
     double px = T * c_h, py = T * s_h;
     double qx = c_r * px - s_r * py;
     double qy = s_r * px + c_r * py;
@@ -710,7 +723,7 @@ __global__ void __launch_bounds__(WPB * 32) mg_template_kernel(Params P, double2
     if (d >= P.n_domains) return;
     SmemLayout L = carve(smem_raw, P.cap, warp);
     Warp w;
-    w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = t_sc[d].n0;
+    w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.sc_full = P.sc_full; w.sc_half = P.sc_half; w.n = t_sc[d].n0;
     const size_t toff = (size_t)d * P.cap;
 #pragma unroll 1
     for (int j = lane; j < w.n; j += 32) w.ring[j] = t_xy[toff + j];
@@ -735,7 +748,7 @@ __global__ void __launch_bounds__(WPB * 32) mg_reset_kernel(Params P, const uint
     if (env >= P.num_envs) return;
     SmemLayout L = carve(smem_raw, P.cap, warp);
     Warp w;
-    w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = 0;
+    w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.sc_full = P.sc_full; w.sc_half = P.sc_half; w.n = 0;
     float obs;
     if (mask == nullptr || mask[env]) {
         EnvState S = P.st[env];
@@ -867,7 +880,7 @@ __global__ void __launch_bounds__(WPB * 32, MG_MINB) mg_step_decide_kernel(Param
     const float a0 = io.act[(size_t)env * 3 + 0], a1 = io.act[(size_t)env * 3 + 1], a2 = io.act[(size_t)env * 3 + 2];
     const size_t off = (size_t)env * P.cap;
     Warp w;
-    w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = S.n;
+    w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.sc_full = P.sc_full; w.sc_half = P.sc_half; w.n = S.n;
     // An env without a reference point (empty candidate list, E:736-738 returns None) has no
     // defined continuation in the reference (its next step raises): it is reported truncated.
     const bool dead = S.ref_index < 0 || S.n < 3;
@@ -974,7 +987,7 @@ __device__ __forceinline__ void apply_successes(const Params &P, const StepIO &i
         stage_issue(L.ring, L.mbar, P.xy + off, P.cap, lane);      // whole slab, overlaps the record load
         EnvState S = P.st[env];
         Warp w;
-        w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = S.n;
+        w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.sc_full = P.sc_full; w.sc_half = P.sc_half; w.n = S.n;
         stage_wait(L.mbar, phase);
         phase ^= 1u;
         const Pending Q = P.pend[env];
@@ -1088,9 +1101,10 @@ __device__ __forceinline__ void apply_successes(const Params &P, const StepIO &i
         S.n_elements++;
         // ---- area (C:943-958), robust quality (C:881-892) -----------------------------------
         double e0 = pdist(m[0], m[3]), e1 = pdist(m[1], m[0]), e2 = pdist(m[2], m[1]), e3 = pdist(m[3], m[2]);
-        double sn = 0;
-        if (lane < 2) sn = mg_sin(lane == 0 ? corner[0] : corner[2]);
-        double mesh_area = 0.5 * e0 * e1 * shfl_d(sn, 0) + 0.5 * e2 * e3 * shfl_d(sn, 1);
+        double sn0, sn2, cs_unused;
+        sincos_quantised(w.sc_full, corner[0], false, sn0, cs_unused);
+        sincos_quantised(w.sc_full, corner[2], false, sn2, cs_unused);
+        double mesh_area = 0.5 * e0 * e1 * sn0 + 0.5 * e2 * e3 * sn2;
         S.current_area -= mesh_area;
         double mn = fmin(fmin(e0, e1), fmin(e2, e3));
         double q1 = sqrt(2.0) * mn / fmax(pdist(m[0], m[2]), pdist(m[1], m[3]));
@@ -1164,7 +1178,7 @@ __global__ void __launch_bounds__(WPB * 32, MG_MINB_APPLY) mg_step_apply_reset_k
     for (int item = rb * WPB + warp; item < count; item += nrb * WPB) {
         const int env = P.reset_list[item];
         Warp w;
-        w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = 0;
+        w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.sc_full = P.sc_full; w.sc_half = P.sc_half; w.n = 0;
         reset_in_place(P, io, env, w);
     }
 }

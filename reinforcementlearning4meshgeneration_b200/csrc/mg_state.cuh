@@ -69,6 +69,8 @@ struct __align__(16) Pending {
     int64_t pad;
 };
 
+constexpr int ANGLE_TAB_N = 62833;      // round(2 pi, 4) = 6.2832
+
 struct DomainScalars {
     int32_t n0;
     int32_t ref_index;
@@ -107,6 +109,11 @@ struct Params {
     const int32_t *t_stamp;   // [n_domains][cap]
     const DomainScalars *t_sc;
     const float *t_obs;       // [n_domains][18]
+    // {sin, cos} of every quantised angle k * 1e-4 (k = 0..62832) and of its half, evaluated by the HOST libm at
+    // mg_create: sin/cos on this path only ever see quantised angles (C:154-168, C:946-947, C:1243), and the
+    // bisector ray test (C:657-676) is chaotic in the last bit of sin/cos on near-degenerate edges
+    const double2 *sc_full;   // [ANGLE_TAB_N]
+    const double2 *sc_half;   // [ANGLE_TAB_N]
     // random-polygon mode
     int random_mode;
     uint64_t seed;

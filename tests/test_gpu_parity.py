@@ -482,3 +482,22 @@ def test_rounding_ties_of_the_new_vertex_on_axis_aligned_domains():
         assert_rollout_matches(per_env(res, e), exp, f"ties[{k}, env {e}]", reward_tol=REWARD_TOL)
         n_el += int(exp["success"].sum())
     assert n_el > 500
+
+
+def test_regression_bisector_ray_on_near_degenerate_edge():
+    """Found by tests/soak.py (basic2, step 733): the bisector ray test (C:657-676) against an edge with
+    dx ~ 1e-17 is chaotic in the last bit of sin/cos(theta/2), sin/cos(rot); those come from the host-libm table
+    of quantised angles, so the hit decision is the reference's."""
+    import os
+    from gpu_helpers import per_env, run_gpu
+    from helpers import GOLDEN
+    from oracle.c_oracle import OracleEnv
+    z = np.load(os.path.join(GOLDEN, "regress_basic2_raytest.npz"))
+    acts = z["actions"]
+    env = _mk([z["xy"]], 2)
+    env.reset()
+    res = run_gpu(env, np.stack([acts, acts], axis=1))
+    exp = OracleEnv(z["xy"], original_area=float(z["area"])).rollout(acts)
+    assert_rollout_matches(per_env(res, 0), exp, "regression basic2 ray test", reward_tol=REWARD_TOL)
+    # sin of the quantised corner angles comes from the same table: rewards agree to the last bits
+    assert np.allclose(per_env(res, 1)["reward"], exp["reward"], rtol=1e-12, atol=0)
