@@ -49,7 +49,6 @@ struct Warp {
     int *queue;      // shared memory, this warp's integer scratch
     int n;           // live boundary size
     int lane;
-    const double2 *sc_full, *sc_half;   // Params::sc_full / sc_half
     __device__ __forceinline__ int wrap(int i) const {
         if (i < 0) i += n;
         else if (i >= n) i -= n;
@@ -70,7 +69,8 @@ __device__ __forceinline__ void sincos_quantised(const double2 *tab, double angl
         const double2 v = __ldg(tab + (int)kf);
         s = v.x; c = v.y;
     } else {
-        mg_sincos(half ? angle / 2 : angle, &s, &c);
+        const double2 v = mg_sincos(half ? angle / 2 : angle);
+        s = v.x; c = v.y;
     }
 }
 
@@ -86,11 +86,32 @@ __device__ __forceinline__ void stage_issue(double2 *ring, unsigned long long *m
     __syncwarp();
     if (lane == 0) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+#ifndef MG_NO_RING_EVICT_FIRST
+        // the rings are streamed once per phase (state >> L2): do not let them displace the small hot records
+        unsigned long long pol;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                smem_u32(ring)),
+            "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+            : "memory");
+#else
         asm volatile(
             "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(ring)),
             "l"(src), "r"(bytes), "r"(bar)
             : "memory");
+#endif
     }
+}
+// 16-byte load that asks L2 to keep the line (the 48-byte hot records, 3 MB at 65 536 envs, are re-read every step)
+__device__ __forceinline__ int4 ldg_keep(const void *p) {
+    int4 v;
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.L2::cache_hint.v4.s32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p), "l"(pol));
+    return v;
 }
 __device__ __forceinline__ void stage_wait(unsigned long long *mbar, unsigned parity) {
     unsigned bar = smem_u32(mbar);
@@ -204,7 +225,7 @@ __device__ __noinline__ int find_reference_index(const Warp w, const double *key
 // observation (C:1059-1090 PointEnvironment, C:1192-1290 get_radius_points, E:665-738)
 // returns obs[lane] for lane < 18; base length through base_out.
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ float compute_obs(const Warp w, int idx, double area_ratio, double &base_out) {
+__device__ __noinline__ float compute_obs(const Warp w, const double2 *sc, int idx, double area_ratio, double &base_out) {
     const int lane = w.lane, n = w.n;
     const double inv_radius = 0.25;   // x / 4 == x * 0.25 exactly
     P2 ref = w.at(idx), right_p = w.at(idx - 1), left_p = w.at(idx + 1 >= n ? idx + 1 - n : idx + 1);
@@ -262,8 +283,8 @@ __device__ __noinline__ float compute_obs(const Warp w, int idx, double area_rat
 
     // p_s = ref + rotate((T cos(theta/2), T sin(theta/2)), rot)                      (C:154-168, C:1243)
     double s_h, c_h, s_r, c_r;
-    sincos_quantised(w.sc_half, theta, true, s_h, c_h);
-    sincos_quantised(w.sc_full, rot, false, s_r, c_r);
+    sincos_quantised(sc ? sc + ANGLE_TAB_N : nullptr, theta, true, s_h, c_h);      // sc = Params::sc_full; the half table follows
+    sincos_quantised(sc, rot, false, s_r, c_r);
     double px = T * c_h, py = T * s_h;
     double qx = c_r * px - s_r * py;
     double qy = s_r * px + c_r * py;
@@ -447,7 +468,7 @@ __device__ __forceinline__ double rint4_mixed(double dy, const int32_t *vid, int
     return r;
 }
 
-__device__ __noinline__ bool point_inside(const Warp w, P2 P, const int32_t *vid, int n0) {
+__device__ __forceinline__ bool point_inside(const Warp w, P2 P, const int32_t *vid, int n0) {
     const int n = w.n;
     int hits = 0;
     const P2 ray2 = mk(10000, P.y);
@@ -491,7 +512,7 @@ __device__ __noinline__ bool point_inside(const Warp w, P2 P, const int32_t *vid
 }
 
 // E:766-769 find_same_point: any boundary vertex within 0.001 of P
-__device__ __noinline__ bool find_same_point(const Warp w, P2 P) {
+__device__ __forceinline__ bool find_same_point(const Warp w, P2 P) {
     bool f = false;
 #pragma unroll 4
     for (int j = w.lane; j < w.n; j += 32) f |= pdist(w.at(j), P) < 0.001;
@@ -501,7 +522,7 @@ __device__ __noinline__ bool find_same_point(const Warp w, P2 P) {
 // ---------------------------------------------------------------------------------------------
 // candidate quad: validity (C:738-757, C:814-826) + corner angles
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ bool mesh_is_valid(const Warp w, const Quad Q) {
+__device__ __forceinline__ bool mesh_is_valid(const Warp w, const Quad Q) {
     const int lane = w.lane;
     const P2 m[4] = {Q.at(0), Q.at(1), Q.at(2), Q.at(3)};
     // lanes 0-3: corner i = m[i].angle(m[i+1], m[i-1]) outside [0.01 pi, 0.99 pi]?   (C:746-757)
@@ -525,7 +546,7 @@ __device__ __noinline__ bool mesh_is_valid(const Warp w, const Quad Q) {
 
 // M:536-556 check_intersection_with_boundary.  qi[] = boundary indices of the quad vertices
 // (-1 for the not-yet-inserted new vertex), ri = position of the reference point in the quad.
-__device__ __noinline__ bool intersects_boundary(const Warp w, const Quad Q, const int4 qv, int ri, P2 ref) {
+__device__ __forceinline__ bool intersects_boundary(const Warp w, const Quad Q, const int4 qv, int ri, P2 ref) {
     const int n = w.n;
     const P2 m[4] = {Q.at(0), Q.at(1), Q.at(2), Q.at(3)};
     const int qi[4] = {qv.x, qv.y, qv.z, qv.w};
@@ -533,7 +554,9 @@ __device__ __noinline__ bool intersects_boundary(const Warp w, const Quad Q, con
 #pragma unroll
     for (int k = 0; k < 4; k++)
         if (k != ri) max_dist = fmax(max_dist, pdist(ref, m[k]));
-    const P2 c1a = m[(ri + 3) & 3], c1b = m[(ri + 2) & 3], c2a = m[(ri + 2) & 3], c2b = m[(ri + 1) & 3];
+    // ri is 1 or 2 (quad_indices); selects instead of m[(ri + k) & 3] keep the quad in registers
+    const bool r1 = ri == 1;
+    const P2 c1a = r1 ? m[0] : m[1], c1b = r1 ? m[3] : m[0], c2a = c1b, c2b = r1 ? m[2] : m[3];
     auto in_mesh = [&](int j) { return j == qi[0] || j == qi[1] || j == qi[2] || j == qi[3]; };
 #pragma unroll 2
     for (int base = 0; base < n; base += 32) {
@@ -690,7 +713,7 @@ __device__ __noinline__ float reset_env(const Params &P, Warp &w, int env, EnvSt
         estimate_area_range(w, S.area_min, S.area_crit);
         S.ref_index = find_reference_index(w, P.key + off, P.stamp + off);
         obs = 0.0f;
-        if (S.ref_index >= 0) obs = compute_obs(w, S.ref_index, S.current_area / S.original_area, S.base_length);
+        if (S.ref_index >= 0) obs = compute_obs(w, P.sc_full, S.ref_index, S.current_area / S.original_area, S.base_length);
     }
     S.n_elements = 0; S.failed_num = 0; S.next_vid = S.n0; S.stamp_ctr = 0; S.ep_len = 0; S.ep_return = 0;
     return obs;
@@ -723,7 +746,7 @@ __global__ void __launch_bounds__(WPB * 32) mg_template_kernel(Params P, double2
     if (d >= P.n_domains) return;
     SmemLayout L = carve(smem_raw, P.cap, warp);
     Warp w;
-    w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.sc_full = P.sc_full; w.sc_half = P.sc_half; w.n = t_sc[d].n0;
+    w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = t_sc[d].n0;
     const size_t toff = (size_t)d * P.cap;
 #pragma unroll 1
     for (int j = lane; j < w.n; j += 32) w.ring[j] = t_xy[toff + j];
@@ -736,7 +759,7 @@ __global__ void __launch_bounds__(WPB * 32) mg_template_kernel(Params P, double2
     D.ref_index = find_reference_index(w, t_key + toff, t_stamp + toff);
     float obs = 0.0f;
     D.base_length = 0;
-    if (D.ref_index >= 0) obs = compute_obs(w, D.ref_index, D.original_area / D.original_area, D.base_length);
+    if (D.ref_index >= 0) obs = compute_obs(w, P.sc_full, D.ref_index, D.original_area / D.original_area, D.base_length);
     if (lane < MG_OBS_DIM) t_obs[d * MG_OBS_DIM + lane] = obs;
     if (lane == 0) t_sc[d] = D;
 }
@@ -748,7 +771,7 @@ __global__ void __launch_bounds__(WPB * 32) mg_reset_kernel(Params P, const uint
     if (env >= P.num_envs) return;
     SmemLayout L = carve(smem_raw, P.cap, warp);
     Warp w;
-    w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.sc_full = P.sc_full; w.sc_half = P.sc_half; w.n = 0;
+    w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = 0;
     float obs;
     if (mask == nullptr || mask[env]) {
         EnvState S = P.st[env];
@@ -788,12 +811,20 @@ __device__ __forceinline__ void push_list(int *list, int *counter, int env, int 
 }
 
 __device__ __forceinline__ void store_state(const Params &P, int env, const EnvState &S) { P.st[env] = S; }
-// phase A only changes failed_num, ep_len, ep_return: chunks 1 and 2 of the record
+// phase A only changes failed_num, ep_len, ep_return: chunks 1 and 2 of the record.  Packed from registers (taking
+// the address of the record would force it into local memory).
 __device__ __forceinline__ void store_state(const Params &P, int env, const EnvHot &S) {
     int4 *dst = reinterpret_cast<int4 *>(P.st + env);
-    const int4 *src = reinterpret_cast<const int4 *>(&S);
-    dst[1] = src[1];
-    dst[2] = src[2];
+    dst[1] = make_int4(__double2loint(S.base_length), __double2hiint(S.base_length), S.failed_num, S.ep_len);
+    dst[2] = make_int4(__double2loint(S.ep_return), __double2hiint(S.ep_return), __double2loint(S.current_area),
+                       __double2hiint(S.current_area));
+}
+__device__ __forceinline__ EnvHot unpack_hot(int4 c0, int4 c1, int4 c2) {
+    EnvHot S;
+    S.n = c0.x; S.ref_index = c0.y; S.n_elements = c0.z; S.n0 = c0.w;
+    S.base_length = __hiloint2double(c1.y, c1.x); S.failed_num = c1.z; S.ep_len = c1.w;
+    S.ep_return = __hiloint2double(c2.y, c2.x); S.current_area = __hiloint2double(c2.w, c2.z);
+    return S;
 }
 
 // Tail of step() shared by phases A and B (E:361-386 + outputs + statistics).
@@ -850,15 +881,15 @@ __device__ __forceinline__ bool near_round4_tie(double x, double tol) {
     return 0.5 - fabs(p - rint(p)) < tol;
 }
 // E:202-210 / D:112-137 exactly as written: theta = 2 pi - atan2(dy, dx), cos/sin of that double
-__device__ __noinline__ void action_frame_exact(double ax, double ay, double dx, double dy, double base, P2 ref, double &ox,
-                                                double &oy) {
+__device__ __noinline__ double2 action_frame_exact(double ax, double ay, double dx, double dy, double base, P2 ref) {
     double th = 2 * PI - atan2(dy, dx);
-    double s, c;
-    mg_sincos(th, &s, &c);
-    ox = c * ax + s * ay;
-    oy = -s * ax + c * ay;
+    const double2 sc = mg_sincos(th);
+    const double s = sc.x, c = sc.y;
+    double ox = c * ax + s * ay;
+    double oy = -s * ax + c * ay;
     ox *= base; oy *= base;
     ox += ref.x; oy += ref.y;
+    return make_double2(ox, oy);
 }
 
 // ---- phase A ---------------------------------------------------------------------------------
@@ -871,16 +902,27 @@ __global__ void __launch_bounds__(WPB * 32, MG_MINB) mg_step_decide_kernel(Param
     // the ring copy does not depend on the env record: copy the whole `cap`-slot slab right away (entries
     // past n are stale and never read) so that its DRAM round trip overlaps the record's
     init_mbar(L.mbar, lane);
-    stage_issue(L.ring, L.mbar, P.xy + (size_t)env * P.cap, P.cap, lane);
-
-    const EnvHot S0 = *reinterpret_cast<const EnvHot *>(P.st + env);      // 3 x 16 B, the rest is phase B/C's
-    EnvHot S = S0;
+    // the record first (kept L2-resident by its evict_last hint), then exactly n vertices: copying the whole
+    // `cap` slab before the record arrives hides one L2 round trip but doubles the DRAM traffic of the phase for
+    // the same time (profiles/README.md, A/B v1)
+    const int4 *rec = reinterpret_cast<const int4 *>(P.st + env);
+    const int4 rec0 = ldg_keep(rec), rec1 = ldg_keep(rec + 1), rec2 = ldg_keep(rec + 2);
     // requested now so that the tail of a failed step does not pay another DRAM round trip
     const float obs_cached = lane < MG_OBS_DIM ? P.obs_cache[(size_t)env * MG_OBS_DIM + lane] : 0.0f;
+    EnvHot S = unpack_hot(rec0, rec1, rec1);
+    stage_issue(L.ring, L.mbar, P.xy + (size_t)env * P.cap, S.n > 0 ? S.n : 2, lane);
+    // Everything only the tail of the step needs (failed_num, ep_len, ep_return, current_area, the cached
+    // observation) is parked in this warp's shared scratch instead of being carried -- and spilled to local
+    // memory -- across the predicate calls: with the shared-memory carve-out at its maximum L1 is tiny and every
+    // spill reload was an L2 round trip (profiles/r1_ncu_step_v9.txt).
+    int4 *stash = reinterpret_cast<int4 *>(L.queue);
+    float *stash_obs = reinterpret_cast<float *>(L.queue) + 8;
+    if (lane == 0) { stash[0] = rec1; stash[1] = rec2; }
+    if (lane < MG_OBS_DIM) stash_obs[lane] = obs_cached;
     const float a0 = io.act[(size_t)env * 3 + 0], a1 = io.act[(size_t)env * 3 + 1], a2 = io.act[(size_t)env * 3 + 2];
     const size_t off = (size_t)env * P.cap;
     Warp w;
-    w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.sc_full = P.sc_full; w.sc_half = P.sc_half; w.n = S.n;
+    w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = S.n;
     // An env without a reference point (empty candidate list, E:736-738 returns None) has no
     // defined continuation in the reference (its next step raises): it is reported truncated.
     const bool dead = S.ref_index < 0 || S.n < 3;
@@ -907,7 +949,10 @@ __global__ void __launch_bounds__(WPB * 32, MG_MINB) mg_step_decide_kernel(Param
         ox *= S.base_length; oy *= S.base_length;
         ox += ref.x; oy += ref.y;
         const double tol = 1e-8 * (3 * fabs(S.base_length) + fabs(ref.x) + fabs(ref.y) + 1);   // in units of 1e-4
-        if (near_round4_tie(ox, tol) || near_round4_tie(oy, tol)) action_frame_exact(ax, ay, dx, dy, S.base_length, ref, ox, oy);
+        if (near_round4_tie(ox, tol) || near_round4_tie(oy, tol)) {
+            const double2 o = action_frame_exact(ax, ay, dx, dy, S.base_length, ref);
+            ox = o.x; oy = o.y;
+        }
         newp = mk(np_round4(ox), np_round4(oy));
     }
 
@@ -954,7 +999,13 @@ __global__ void __launch_bounds__(WPB * 32, MG_MINB) mg_step_decide_kernel(Param
         reward += S.n_elements ? -1.0 / S.n_elements : -1;          // E:357
     }
     // failed step: nothing changed, the reference recomputes a bit-identical observation
-    const float obs = obs_cached;
+    __syncwarp();
+    const float obs = lane < MG_OBS_DIM ? stash_obs[lane] : 0.0f;
+    {
+        const int4 r1 = stash[0], r2 = stash[1];
+        S.base_length = __hiloint2double(r1.y, r1.x); S.failed_num = r1.z; S.ep_len = r1.w;
+        S.ep_return = __hiloint2double(r2.y, r2.x); S.current_area = __hiloint2double(r2.w, r2.z);
+    }
     S.failed_num++;
     if (finish_step(P, io, env, lane, S, n, reward, done, true, false, dead, obs))
         push_list(P.reset_list, P.counters + 2 * set + 1, env, lane);
@@ -987,7 +1038,7 @@ __device__ __forceinline__ void apply_successes(const Params &P, const StepIO &i
         stage_issue(L.ring, L.mbar, P.xy + off, P.cap, lane);      // whole slab, overlaps the record load
         EnvState S = P.st[env];
         Warp w;
-        w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.sc_full = P.sc_full; w.sc_half = P.sc_half; w.n = S.n;
+        w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = S.n;
         stage_wait(L.mbar, phase);
         phase ^= 1u;
         const Pending Q = P.pend[env];
@@ -1102,8 +1153,8 @@ __device__ __forceinline__ void apply_successes(const Params &P, const StepIO &i
         // ---- area (C:943-958), robust quality (C:881-892) -----------------------------------
         double e0 = pdist(m[0], m[3]), e1 = pdist(m[1], m[0]), e2 = pdist(m[2], m[1]), e3 = pdist(m[3], m[2]);
         double sn0, sn2, cs_unused;
-        sincos_quantised(w.sc_full, corner[0], false, sn0, cs_unused);
-        sincos_quantised(w.sc_full, corner[2], false, sn2, cs_unused);
+        sincos_quantised(P.sc_full, corner[0], false, sn0, cs_unused);
+        sincos_quantised(P.sc_full, corner[2], false, sn2, cs_unused);
         double mesh_area = 0.5 * e0 * e1 * sn0 + 0.5 * e2 * e3 * sn2;
         S.current_area -= mesh_area;
         double mn = fmin(fmin(e0, e1), fmin(e2, e3));
@@ -1144,7 +1195,7 @@ __device__ __forceinline__ void apply_successes(const Params &P, const StepIO &i
         bool obs_none = false;
         __syncwarp();
         S.ref_index = find_reference_index(w, P.key + off, P.stamp + off);
-        if (S.ref_index >= 0) obs = compute_obs(w, S.ref_index, S.current_area / S.original_area, S.base_length);
+        if (S.ref_index >= 0) obs = compute_obs(w, P.sc_full, S.ref_index, S.current_area / S.original_area, S.base_length);
         else obs_none = true;
         S.failed_num = 0;
         if (finish_step(P, io, env, lane, S, n, reward, done, false, true, obs_none, obs)) {
@@ -1178,7 +1229,7 @@ __global__ void __launch_bounds__(WPB * 32, MG_MINB_APPLY) mg_step_apply_reset_k
     for (int item = rb * WPB + warp; item < count; item += nrb * WPB) {
         const int env = P.reset_list[item];
         Warp w;
-        w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.sc_full = P.sc_full; w.sc_half = P.sc_half; w.n = 0;
+        w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = 0;
         reset_in_place(P, io, env, w);
     }
 }
@@ -1297,8 +1348,8 @@ __device__ __noinline__ int generate_polygon(const Params &P, Warp &w, long long
     }
     if (lane < K) {
         double ang = start + (incl - step);
-        double s, c;
-        mg_sincos(ang, &s, &c);
+        const double2 sc = mg_sincos(ang);
+        const double s = sc.x, c = sc.y;
         cx[lane] = (int)(G.ctr_x + radius * c);
         cy[lane] = (int)(G.ctr_y + radius * s);
     }

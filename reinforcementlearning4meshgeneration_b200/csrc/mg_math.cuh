@@ -54,7 +54,13 @@ __device__ __forceinline__ float np_round4f(float x) { return __fdiv_rn(rintf(__
 
 // out-of-line wrappers: one copy of each libdevice routine per kernel image (the fused step
 // kernel was instruction-fetch bound when these were inlined at every call site)
-__device__ __noinline__ void mg_sincos(double x, double *s, double *c) { sincos(x, s, c); }
+// {sin, cos} returned by value: pointer outputs would live in local memory, and with the shared-memory carve-out
+// at its maximum L1 is tiny, so every local access is an L2 round trip
+__device__ __noinline__ double2 mg_sincos(double x) {
+    double s, c;
+    sincos(x, &s, &c);
+    return make_double2(s, c);
+}
 __device__ __noinline__ double mg_sin(double x) { return sin(x); }
 __device__ __noinline__ double mg_pow(double x, double y) { return pow(x, y); }
 
