@@ -48,7 +48,7 @@ struct mg_env_s {
     int step_parity = 0;
     int phase_mask = 3;       // profiling aid: bit 0 = phase A launch, bit 1 = phase B+C launch
     int sm_count = 148;
-    size_t smem = 0;
+    size_t smem = 0, smem_a = 0;
     std::string err;
 };
 
@@ -80,8 +80,10 @@ int grid_for(int n) { return (n + WPB - 1) / WPB; }
 
 int configure_kernels(mg_handle h) {
     h->smem = smem_bytes(h->P.cap);
+    h->smem_a = smem_bytes_a(h->P.cap);
+    if (h->smem_a > 48 * 1024)
+        MG_CUDA(h, cudaFuncSetAttribute(mg_step_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_a));
     if (h->smem > 48 * 1024) {
-        MG_CUDA(h, cudaFuncSetAttribute(mg_step_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         MG_CUDA(h, cudaFuncSetAttribute(mg_step_apply_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         MG_CUDA(h, cudaFuncSetAttribute(mg_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         MG_CUDA(h, cudaFuncSetAttribute(mg_template_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
@@ -314,7 +316,7 @@ int mg_step(mg_handle h, const float *act_dev, float *obs_dev, double *rew_dev, 
     const int full = grid_for(h->num_envs);
     const int gb = full < h->sm_count * 16 ? full : h->sm_count * 16;
     const int gc = full < h->sm_count * 4 ? full : h->sm_count * 4;
-    if (h->phase_mask & 1) mg_step_decide_kernel<<<full, WPB * 32, h->smem, s>>>(h->P, io, set);
+    if (h->phase_mask & 1) mg_step_decide_kernel<<<(h->num_envs + WPB_A - 1) / WPB_A, WPB_A * 32, h->smem_a, s>>>(h->P, io, set);
     if (h->phase_mask & 2) mg_step_apply_reset_kernel<<<gb + gc, WPB * 32, h->smem, s>>>(h->P, io, set, gb);
     h->launches += 2;
     MG_CUDA(h, cudaGetLastError());

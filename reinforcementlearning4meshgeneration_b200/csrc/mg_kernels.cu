@@ -23,8 +23,13 @@ namespace mg {
 #endif
 constexpr int WPB = MG_WPB;     // warps (= environments) per block
 #ifndef MG_MINB
-#define MG_MINB 10
+#define MG_MINB 20
 #endif
+#ifndef MG_WPB_A
+#define MG_WPB_A 1   // phase A (decide): one env per block (no slot held by the slower of two envs), 128-byte scratch
+#endif
+constexpr int WPB_A = MG_WPB_A;
+constexpr int QCAP_A = 32;       // phase A scratch: the parked record chunks + cached observation (26 words)
 constexpr int QCAP = 128 + 256;  // per-warp scratch: 4x32 ints + 32x4 doubles (coarse polygon of the generator)
 
 // ---------------------------------------------------------------------------------------------
@@ -223,9 +228,14 @@ __device__ __noinline__ int find_reference_index(const Warp w, const double *key
 
 // ---------------------------------------------------------------------------------------------
 // observation (C:1059-1090 PointEnvironment, C:1192-1290 get_radius_points, E:665-738)
-// returns obs[lane] for lane < 18; base length through base_out.
+// returns obs[lane] for lane < 18 and the base length (by value: reference outputs of an out-of-line function live
+// in local memory, an L2 round trip with the shared-memory carve-out at its maximum).
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ float compute_obs(const Warp w, const double2 *sc, int idx, double area_ratio, double &base_out) {
+struct ObsOut {
+    double base;
+    float obs;
+};
+__device__ __noinline__ ObsOut compute_obs(const Warp w, const double2 *sc, int idx, double area_ratio) {
     const int lane = w.lane, n = w.n;
     const double inv_radius = 0.25;   // x / 4 == x * 0.25 exactly
     P2 ref = w.at(idx), right_p = w.at(idx - 1), left_p = w.at(idx + 1 >= n ? idx + 1 - n : idx + 1);
@@ -260,7 +270,6 @@ __device__ __noinline__ float compute_obs(const Warp w, const double2 *sc, int i
 #pragma unroll
     for (int k = 0; k < 6; k++) dl[k] = shfl_d(val, k);
     double base = py_round4(py_sum<6>(dl) / 6);
-    base_out = base;
     double theta = shfl_d(val, 8), a_r1 = shfl_d(val, 9), a_r2 = shfl_d(val, 10), a_l1 = shfl_d(val, 11),
            a_l2 = shfl_d(val, 12), rot = shfl_d(val, 13);
     double d_r = shfl_d(val, 16), d_l = shfl_d(val, 17), d_r1 = shfl_d(val, 18), d_r2 = shfl_d(val, 19),
@@ -406,13 +415,16 @@ __device__ __noinline__ float compute_obs(const Warp w, const double2 *sc, int i
         if (lane == 2 * i) out = r0[i];
         if (lane == 2 * i + 1) out = r1[i];
     }
-    return np_round4f(out);
+    ObsOut R;
+    R.base = base;
+    R.obs = np_round4f(out);
+    return R;
 }
 
 // ---------------------------------------------------------------------------------------------
 // estimated_area_range (M:705-718): needs the mean, the 2nd smallest and 2nd largest edge.
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ void estimate_area_range(const Warp w, double &area_min, double &area_crit) {
+__device__ __noinline__ double2 estimate_area_range(const Warp w) {   // {area_min, area_crit}
     double s = 0, lo1 = CUDART_INF, lo2 = CUDART_INF, hi1 = -CUDART_INF, hi2 = -CUDART_INF;
 #pragma unroll 1
     for (int j = w.lane; j < w.n; j += 32) {
@@ -434,8 +446,7 @@ __device__ __noinline__ void estimate_area_range(const Warp w, double &area_min,
     double L = s / w.n;
     double max_L = fmin(hi2, 2 * L);
     double min_L = fmin(L / sqrt(2.0), lo2);
-    area_min = min_L;
-    area_crit = (max_L + 3 * min_L) / 4;
+    return make_double2(min_L, (max_L + 3 * min_L) / 4);
 }
 
 // sequential shoelace (C:485-487 up to np.dot's BLAS summation order)
@@ -673,12 +684,12 @@ __device__ __forceinline__ double u01(unsigned a, unsigned b) {   // 53-bit unif
 // random star polygon (ui/GenerateRandomPolygon.py:5-49) + densifier (ui/tk-ui.py:252-276)
 // Written by the warp into ring[0..n); returns n (even, min_verts <= n <= max_verts).
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ int generate_polygon(const Params &P, Warp &w, long long global_env, int episode);
+__device__ __noinline__ int generate_polygon(const Params &P, const Warp w, long long global_env, int episode);
 
 // ---------------------------------------------------------------------------------------------
 // reset of one env (E:136-184): restore the polygon, rebuild candidates, first observation
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ float reset_env(const Params &P, Warp &w, int env, EnvState &S) {
+__device__ __forceinline__ float reset_env(const Params &P, Warp &w, int env, EnvState &S) {
     const int lane = w.lane;
     const size_t off = (size_t)env * P.cap;
     float obs;
@@ -710,10 +721,13 @@ __device__ __noinline__ float reset_env(const Params &P, Warp &w, int env, EnvSt
         S.n = n; S.n0 = n;
         S.original_area = shoelace_area(w);
         S.current_area = S.original_area;
-        estimate_area_range(w, S.area_min, S.area_crit);
+        { const double2 ar = estimate_area_range(w); S.area_min = ar.x; S.area_crit = ar.y; }
         S.ref_index = find_reference_index(w, P.key + off, P.stamp + off);
         obs = 0.0f;
-        if (S.ref_index >= 0) obs = compute_obs(w, P.sc_full, S.ref_index, S.current_area / S.original_area, S.base_length);
+        if (S.ref_index >= 0) {
+            const ObsOut R = compute_obs(w, P.sc_full, S.ref_index, S.current_area / S.original_area);
+            obs = R.obs; S.base_length = R.base;
+        }
     }
     S.n_elements = 0; S.failed_num = 0; S.next_vid = S.n0; S.stamp_ctr = 0; S.ep_len = 0; S.ep_return = 0;
     return obs;
@@ -736,9 +750,18 @@ __device__ __forceinline__ SmemLayout carve(unsigned char *raw, int cap, int war
     return L;
 }
 size_t smem_bytes(int cap) { return (size_t)WPB * cap * 16 + (size_t)WPB * QCAP * 4 + WPB * 8; }
+__device__ __forceinline__ SmemLayout carve_a(unsigned char *raw, int cap, int warp) {
+    SmemLayout L;
+    L.ring = reinterpret_cast<double2 *>(raw) + (size_t)warp * cap;
+    int *q = reinterpret_cast<int *>(reinterpret_cast<double2 *>(raw) + (size_t)WPB_A * cap);
+    L.queue = q + warp * QCAP_A;
+    L.mbar = reinterpret_cast<unsigned long long *>(q + WPB_A * QCAP_A) + warp;
+    return L;
+}
+size_t smem_bytes_a(int cap) { return (size_t)WPB_A * cap * 16 + (size_t)WPB_A * QCAP_A * 4 + WPB_A * 8; }
 
 // Per-domain reset template: one warp per domain.
-__global__ void __launch_bounds__(WPB * 32) mg_template_kernel(Params P, double2 *t_xy, double *t_key, int32_t *t_stamp,
+__global__ void __launch_bounds__(WPB * 32) mg_template_kernel(const __grid_constant__ Params P, double2 *t_xy, double *t_key, int32_t *t_stamp,
                                                               DomainScalars *t_sc, float *t_obs, const double *areas) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -755,16 +778,19 @@ __global__ void __launch_bounds__(WPB * 32) mg_template_kernel(Params P, double2
     __syncwarp();
     DomainScalars D = t_sc[d];
     D.original_area = areas ? areas[d] : shoelace_area(w);
-    estimate_area_range(w, D.area_min, D.area_crit);
+    { const double2 ar = estimate_area_range(w); D.area_min = ar.x; D.area_crit = ar.y; }
     D.ref_index = find_reference_index(w, t_key + toff, t_stamp + toff);
     float obs = 0.0f;
     D.base_length = 0;
-    if (D.ref_index >= 0) obs = compute_obs(w, P.sc_full, D.ref_index, D.original_area / D.original_area, D.base_length);
+    if (D.ref_index >= 0) {
+        const ObsOut R = compute_obs(w, P.sc_full, D.ref_index, D.original_area / D.original_area);
+        obs = R.obs; D.base_length = R.base;
+    }
     if (lane < MG_OBS_DIM) t_obs[d * MG_OBS_DIM + lane] = obs;
     if (lane == 0) t_sc[d] = D;
 }
 
-__global__ void __launch_bounds__(WPB * 32) mg_reset_kernel(Params P, const uint8_t *mask, float *obs_out) {
+__global__ void __launch_bounds__(WPB * 32) mg_reset_kernel(const __grid_constant__ Params P, const uint8_t *mask, float *obs_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * WPB + warp;
@@ -838,7 +864,7 @@ __device__ __forceinline__ bool finish_step(const Params &P, const StepIO &io, i
     if (force_trunc && !done) { done = true; truncated = true; }          // sentinel, see DESIGN.md
     S.ep_return += reward; S.ep_len++;
     if (lane == 0) {
-        StatsAcc *T = P.stats + ((env / WPB) & (STAT_SLOTS - 1));
+        StatsAcc *T = P.stats + ((env >> 1) & (STAT_SLOTS - 1));
         atomicAdd(&T->steps, 1ull);
         atomicAdd(&T->sum_n, (unsigned long long)n_before);
         if (success) { atomicAdd(&T->successes, 1ull); atomicAdd(&T->sum_n_success, (unsigned long long)n_before); }
@@ -893,12 +919,12 @@ __device__ __noinline__ double2 action_frame_exact(double ax, double ay, double 
 }
 
 // ---- phase A ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(WPB * 32, MG_MINB) mg_step_decide_kernel(Params P, StepIO io, int set) {
+__global__ void __launch_bounds__(WPB_A * 32, MG_MINB) mg_step_decide_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io, int set) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.x * WPB + warp;
+    const int env = blockIdx.x * WPB_A + warp;
     if (env >= P.num_envs) return;
-    SmemLayout L = carve(smem_raw, P.cap, warp);
+    SmemLayout L = carve_a(smem_raw, P.cap, warp);
     // the ring copy does not depend on the env record: copy the whole `cap`-slot slab right away (entries
     // past n are stale and never read) so that its DRAM round trip overlaps the record's
     init_mbar(L.mbar, lane);
@@ -1195,8 +1221,10 @@ __device__ __forceinline__ void apply_successes(const Params &P, const StepIO &i
         bool obs_none = false;
         __syncwarp();
         S.ref_index = find_reference_index(w, P.key + off, P.stamp + off);
-        if (S.ref_index >= 0) obs = compute_obs(w, P.sc_full, S.ref_index, S.current_area / S.original_area, S.base_length);
-        else obs_none = true;
+        if (S.ref_index >= 0) {
+            const ObsOut R = compute_obs(w, P.sc_full, S.ref_index, S.current_area / S.original_area);
+            obs = R.obs; S.base_length = R.base;
+        } else obs_none = true;
         S.failed_num = 0;
         if (finish_step(P, io, env, lane, S, n, reward, done, false, true, obs_none, obs)) {
             __syncwarp();                        // lane 0's record store is visible to the warp
@@ -1210,7 +1238,7 @@ __device__ __forceinline__ void apply_successes(const Params &P, const StepIO &i
 #ifndef MG_MINB_APPLY
 #define MG_MINB_APPLY 12    // tuned on B200: 80 registers, 24 warps per SM for the latency-bound apply phase
 #endif
-__global__ void __launch_bounds__(WPB * 32, MG_MINB_APPLY) mg_step_apply_reset_kernel(Params P, StepIO io, int set, int apply_blocks) {
+__global__ void __launch_bounds__(WPB * 32, MG_MINB_APPLY) mg_step_apply_reset_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io, int set, int apply_blocks) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     SmemLayout L = carve(smem_raw, P.cap, warp);
@@ -1263,7 +1291,7 @@ __global__ void mg_pack_terminal_kernel(int num_envs, const uint8_t *term, const
 
 // mg_step_host, delta mode: gather observation + element count of every env that changed in this step
 // (accepted elements and resets: exactly the two work lists of the step), one warp per entry.
-__global__ void mg_pack_changed_kernel(Params P, int set, const float *obs, const int32_t *nel, int32_t *idx, float *pobs,
+__global__ void mg_pack_changed_kernel(const __grid_constant__ Params P, int set, const float *obs, const int32_t *nel, int32_t *idx, float *pobs,
                                        int32_t *pnel, int32_t *count) {
     const int cs = P.counters[2 * set + 0], cr = P.counters[2 * set + 1];
     const int lane = threadIdx.x & 31;
@@ -1313,7 +1341,7 @@ __global__ void mg_stats_kernel(StatsAcc *stats, mg_episode_stats *out, int rese
 //   prev + A (j+1) dir, j < x, followed by cur; if the total is odd the middle point of the last
 //   edge is dropped (tk-ui.py:267-269).  Coordinates / 100 (geometry.py:46).
 // One coarse vertex per lane (max_coarse <= 32).  The ring is written to w.ring[0..n).
-__device__ __noinline__ int generate_polygon(const Params &P, Warp &w, long long global_env, int episode) {
+__device__ __noinline__ int generate_polygon(const Params &P, const Warp w, long long global_env, int episode) {
     const mg_polygen_cfg &G = P.gen;
     const int lane = w.lane;
     int *cx = w.queue, *cy = w.queue + 32, *cnt = w.queue + 64, *offs = w.queue + 96;
