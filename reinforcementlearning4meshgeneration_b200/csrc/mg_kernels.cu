@@ -25,6 +25,16 @@ constexpr int WPB = MG_WPB;     // warps (= environments) per block
 #ifndef MG_MINB
 #define MG_MINB 20
 #endif
+#ifndef MG_UNROLL_OBS
+#define MG_UNROLL_OBS 1
+#endif
+#ifndef MG_UNROLL_BQ
+#define MG_UNROLL_BQ 1
+#endif
+#ifndef MG_UNROLL_PIP
+#define MG_UNROLL_PIP 1
+#endif
+constexpr int UNROLL_OBS = MG_UNROLL_OBS, UNROLL_BQ = MG_UNROLL_BQ, UNROLL_PIP = MG_UNROLL_PIP;   // tuning knobs (profiles/README.md)
 #ifndef MG_WPB_A
 #define MG_WPB_A 1   // phase A (decide): one env per block (no slot held by the slower of two envs), 128-byte scratch
 #endif
@@ -306,7 +316,7 @@ __device__ __noinline__ ObsOut compute_obs(const Warp w, const double2 *sc, int 
     double ma0 = 0, ma1 = 0, ma2 = 0;
     double best_ray = CUDART_INF;                             // f64 value of the nearest bisector hit
     int best_ray_o = 0x7fffffff;
-#pragma unroll 1
+#pragma unroll UNROLL_OBS
     for (int o = 1 + lane; o < n; o += 32) {
         if (o == 1 || o == n - 1) continue;                   // right_p / left_p (C:1249)
         int j = idx - o;
@@ -484,7 +494,7 @@ __device__ __forceinline__ bool point_inside(const Warp w, P2 P, const int32_t *
     int hits = 0;
     const P2 ray2 = mk(10000, P.y);
     const bool can_prune = P.x < 9000.0;
-#pragma unroll 1
+#pragma unroll UNROLL_PIP
     for (int base = 0; base < n; base += 32) {
         int j = base + w.lane;
         bool hit = false;
@@ -610,7 +620,7 @@ __device__ __noinline__ double boundary_quality_new_vertex(const Warp w, int idx
     // close_vs: not excluded, nearer than `dist`, and not directly after an accepted index
     double m_d = CUDART_INF;
     unsigned carry = 0;   // parity of the run of "close" flags reaching the end of the previous chunk
-#pragma unroll 1
+#pragma unroll UNROLL_BQ
     for (int base = 0; base < n; base += 32) {
         int j = base + w.lane;
         bool c = false;
