@@ -163,6 +163,21 @@ int mg_get_elements(mg_handle h, int env, int32_t *quads_host, int max_elements,
  * reset != 0 zeroes the counters afterwards. */
 int mg_stats(mg_handle h, mg_episode_stats *out, int reset);
 
+/* Device-resident replay buffer write (replaces, for a batched env, what SB3's
+ * OffPolicyAlgorithm._store_transition + ReplayBuffer.add do on the host -- the callers named in
+ * rl/baselines/RL_Mesh.py:186-197 and v2 training/train_loop.py:132): one launch stores the N transitions of a
+ * step into slot `slot` of a ring of `capacity_steps` slots, layout [slot][env][...]:
+ *   buf_obs[slot][e]      = prev_obs[e]              (observation the action was computed from)
+ *   buf_next_obs[slot][e] = done ? term_obs[e] : new_obs[e]   (SB3 stores the terminal observation, not the reset one)
+ *   buf_act[slot][e]      = act[e];  buf_rew[slot][e] = (float) rew[e]
+ *   buf_done[slot][e]     = terminated | truncated;  buf_timeout[slot][e] = truncated
+ *                           (handle_timeout_termination: the learner bootstraps unless done & !timeout)
+ * All pointers are device pointers; work is enqueued on `stream`; no synchronisation. */
+int mg_replay_add(mg_handle h, int64_t capacity_steps, int64_t slot, float *buf_obs, float *buf_next_obs, float *buf_act,
+                  float *buf_rew, uint8_t *buf_done, uint8_t *buf_timeout, const float *prev_obs, const float *act,
+                  const float *new_obs, const double *rew, const uint8_t *term, const uint8_t *trunc,
+                  const float *term_obs, void *stream);
+
 /* Profiling aid (bench.py --phase-times): restrict mg_step to phase A (bit 0) and/or phases B+C
  * (bit 1).  With a partial mask the environments do not advance correctly; restore 3 afterwards. */
 int mg_set_phase_mask(mg_handle h, int mask);

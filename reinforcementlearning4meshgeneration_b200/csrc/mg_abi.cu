@@ -207,6 +207,25 @@ int mg_set_auto_reset(mg_handle h, int enabled) {
     return MG_OK;
 }
 
+int mg_replay_add(mg_handle h, int64_t capacity_steps, int64_t slot, float *buf_obs, float *buf_next_obs, float *buf_act,
+                  float *buf_rew, uint8_t *buf_done, uint8_t *buf_timeout, const float *prev_obs, const float *act,
+                  const float *new_obs, const double *rew, const uint8_t *term, const uint8_t *trunc,
+                  const float *term_obs, void *stream) {
+    if (!h || !buf_obs || !buf_next_obs || !buf_act || !buf_rew || !buf_done || !buf_timeout || !prev_obs || !act || !new_obs ||
+        !rew || !term || !trunc || !term_obs)
+        return fail(h, MG_ERR_ARG, "mg_replay_add: null pointer");
+    if (capacity_steps <= 0 || slot < 0 || slot >= capacity_steps) return fail(h, MG_ERR_ARG, "mg_replay_add: slot out of range");
+    MG_CUDA(h, cudaSetDevice(h->device));
+    const size_t N = (size_t)h->num_envs, s = (size_t)slot;
+    const int total = h->num_envs * MG_OBS_DIM;
+    mg_replay_add_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        h->num_envs, buf_obs + s * N * MG_OBS_DIM, buf_next_obs + s * N * MG_OBS_DIM, buf_act + s * N * MG_ACT_DIM, buf_rew + s * N,
+        buf_done + s * N, buf_timeout + s * N, prev_obs, act, new_obs, rew, term, trunc, term_obs);
+    h->launches += 1;
+    MG_CUDA(h, cudaGetLastError());
+    return MG_OK;
+}
+
 int mg_set_phase_mask(mg_handle h, int mask) {
     if (!h) return fail(h, MG_ERR_ARG, "mg_set_phase_mask: null handle");
     h->phase_mask = mask & 3;

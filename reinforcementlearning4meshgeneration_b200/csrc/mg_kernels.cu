@@ -1314,6 +1314,26 @@ __global__ void mg_pack_changed_kernel(const __grid_constant__ Params P, int set
     if (blockIdx.x == 0 && threadIdx.x == 0) *count = cs + cr;
 }
 
+// mg_replay_add: the N transitions of one step into slot `slot` of the replay ring (coalesced: one thread per
+// observation element, the first threads of every env also move the action / reward / flags).
+__global__ void mg_replay_add_kernel(int num_envs, float *__restrict__ b_obs, float *__restrict__ b_next, float *__restrict__ b_act,
+                                     float *__restrict__ b_rew, uint8_t *__restrict__ b_done, uint8_t *__restrict__ b_to,
+                                     const float *__restrict__ prev_obs, const float *__restrict__ act,
+                                     const float *__restrict__ new_obs, const double *__restrict__ rew,
+                                     const uint8_t *__restrict__ term, const uint8_t *__restrict__ trunc,
+                                     const float *__restrict__ term_obs) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_envs * MG_OBS_DIM) return;
+    const int e = t / MG_OBS_DIM, k = t - e * MG_OBS_DIM;
+    const bool te = term[e] != 0, tr = trunc[e] != 0, done = te || tr;
+    b_obs[t] = prev_obs[t];
+    b_next[t] = done ? term_obs[t] : new_obs[t];
+    if (k < MG_ACT_DIM) b_act[e * MG_ACT_DIM + k] = act[e * MG_ACT_DIM + k];
+    if (k == 3) b_rew[e] = (float)rew[e];
+    if (k == 4) b_done[e] = done ? 1 : 0;
+    if (k == 5) b_to[e] = tr ? 1 : 0;
+}
+
 // Sum of the accumulator slots -> one mg_episode_stats (one warp).
 __global__ void mg_stats_kernel(StatsAcc *stats, mg_episode_stats *out, int reset) {
     unsigned long long a[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -501,3 +501,47 @@ def test_regression_bisector_ray_on_near_degenerate_edge():
     assert_rollout_matches(per_env(res, 0), exp, "regression basic2 ray test", reward_tol=REWARD_TOL)
     # sin of the quantised corner angles comes from the same table: rewards agree to the last bits
     assert np.allclose(per_env(res, 1)["reward"], exp["reward"], rtol=1e-12, atol=0)
+
+
+def test_device_replay_buffer_stores_what_sb3_would():
+    """mg_replay_add against a numpy restatement of SB3's OffPolicyAlgorithm._store_transition +
+    ReplayBuffer.add/_get_samples: terminal observation swapped in for finished envs, rewards as float32,
+    done masked by the time-limit flag, ring wrap-around."""
+    import torch
+    from reinforcementlearning4meshgeneration_b200.replay import DeviceReplayBuffer
+    doms, _ = load_domains()
+    N, S, T = 64, 40, 100
+    env = _mk([doms["star"], doms["boundary0"]], N)
+    obs = env.reset().clone()
+    buf = DeviceReplayBuffer(env, S)
+    ref = dict(obs=np.zeros((S, N, 18), np.float32), nxt=np.zeros((S, N, 18), np.float32), act=np.zeros((S, N, 3), np.float32),
+               rew=np.zeros((S, N), np.float32), done=np.zeros((S, N), np.uint8), to=np.zeros((S, N), np.uint8))
+    n_done = 0
+    for t in range(T):
+        a = env.sample_actions(5, t)
+        prev = obs.cpu().numpy()
+        r = env.step(a)
+        buf.add(obs, a, r)
+        done = (r.terminated | r.truncated).bool().cpu().numpy()
+        s = t % S
+        ref["obs"][s] = prev
+        ref["nxt"][s] = np.where(done[:, None], r.terminal_obs.cpu().numpy(), r.obs.cpu().numpy())
+        ref["act"][s] = a.cpu().numpy()
+        ref["rew"][s] = r.reward.cpu().numpy().astype(np.float32)
+        ref["done"][s] = done
+        ref["to"][s] = r.truncated.cpu().numpy()
+        n_done += int(done.sum())
+        obs.copy_(r.obs)
+    assert n_done > 0 and buf.full and len(buf) == S * N and buf.pos == T % S
+    for k, tns in (("obs", buf.obs), ("nxt", buf.next_obs), ("act", buf.actions), ("rew", buf.rewards), ("done", buf.dones), ("to", buf.timeouts)):
+        assert np.array_equal(tns.cpu().numpy(), ref[k]), k
+    g = torch.Generator(device=env.device)
+    g.manual_seed(3)
+    b = buf.sample(4096, generator=g)
+    g.manual_seed(3)
+    idx = torch.randint(0, S * N, (4096,), device=env.device, generator=g).cpu().numpy()
+    assert np.array_equal(b.observations.cpu().numpy(), ref["obs"].reshape(-1, 18)[idx])
+    assert np.array_equal(b.next_observations.cpu().numpy(), ref["nxt"].reshape(-1, 18)[idx])
+    assert np.array_equal(b.rewards.cpu().numpy()[:, 0], ref["rew"].reshape(-1)[idx])
+    exp_done = ref["done"].reshape(-1)[idx].astype(np.float32) * (1 - ref["to"].reshape(-1)[idx].astype(np.float32))
+    assert np.array_equal(b.dones.cpu().numpy()[:, 0], exp_done)
