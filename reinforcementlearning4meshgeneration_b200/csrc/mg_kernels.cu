@@ -316,9 +316,13 @@ __device__ __noinline__ ObsOut compute_obs(const Warp w, const double2 *sc, int 
     double ma0 = 0, ma1 = 0, ma2 = 0;
     double best_ray = CUDART_INF;                             // f64 value of the nearest bisector hit
     int best_ray_o = 0x7fffffff;
-#pragma unroll UNROLL_OBS
-    for (int o = 1 + lane; o < n; o += 32) {
-        if (o == 1 || o == n - 1) continue;                   // right_p / left_p (C:1249)
+    // Two passes (like rebuild_candidates): pass 1 is a light filter that keeps the few vertices that can matter --
+    // inside the radius (sector candidates, C:1255-1263) or with an edge the bisector's line may cross (C:657-676) --
+    // and compacts their order numbers into the warp's queue; pass 2 runs the reference's per-vertex body on full
+    // warps of queued entries.  A vertex is dropped only when it is surely outside the radius (1e-12 relative
+    // margin on the squared distance) AND its edge passes the exact-safe early-out below: the body would do
+    // nothing for it.  Both per-lane accumulators are (value, order) minima, so the evaluation order is free.
+    auto body = [&](const int o) {
         int j = idx - o;
         if (j < 0) j += n;
         P2 q = w.at(j);
@@ -329,8 +333,8 @@ __device__ __noinline__ ObsOut compute_obs(const Warp w, const double2 *sc, int 
         double angle = 1.0;
         if (d < T) {
             angle = cw_angle_crdt(cr, dt);
-            if (angle == 0) continue;                         // C:1255
-        } else if (angle_is_zero(cr, dt)) continue;
+            if (angle == 0) return;                         // C:1255
+        } else if (angle_is_zero(cr, dt)) return;
         double kk = angle / sector;
         int k = (kk < 3.0) ? (int)kk : 3;                     // int() truncation; NaN/inf -> no sector
         if (k < 3 && d < T) {
@@ -355,15 +359,15 @@ __device__ __noinline__ ObsOut compute_obs(const Warp w, const double2 *sc, int 
             double sb = ux * (q2.y - ref.y) - uy * (q2.x - ref.x);
             double tol = 1e-6 * (fabs(ux) + fabs(uy)) * (fabs(ax) + fabs(ay) + fabs(wx) + fabs(wy));
             bool conditioned = (wx == 0 || fabs(wx) > 1e-6 * fabs(wy)) && (wy == 0 || fabs(wy) > 1e-6 * fabs(wx));
-            if (conditioned && ((sa > tol && sb > tol) || (sa < -tol && sb < -tol))) continue;
+            if (conditioned && ((sa > tol && sb > tol) || (sa < -tol && sb < -tol))) return;
         }
         double ss, hh;
         if (wy == 0) {
-            if (uy == 0) continue;
+            if (uy == 0) return;
             ss = (q.y - ref.y) / uy;
             hh = (ref.x - q.x + ss * ux) / wx;
         } else if (wx == 0) {
-            if (ux == 0) continue;
+            if (ux == 0) return;
             ss = (q.x - ref.x) / ux;
             hh = (ref.y - q.y + ss * uy) / wy;
         } else {
@@ -376,6 +380,44 @@ __device__ __noinline__ ObsOut compute_obs(const Warp w, const double2 *sc, int 
                 best_ray = v;
                 best_ray_o = o;
             }
+        }
+    };
+    {
+        const double T2_far = (T * T) * (1.0 + 1e-12);
+        const double ur = 1e-6 * (fabs(ux) + fabs(uy));
+        int qn = 0, base_o = 1;
+#pragma unroll 1
+        while (true) {
+            if (base_o < n) {
+                const int o = base_o + lane;
+                bool keep = false;
+                if (o < n && o != 1 && o != n - 1) {              // right_p / left_p (C:1249)
+                    int j = idx - o;
+                    if (j < 0) j += n;
+                    const P2 q = w.at(j), q2 = w.at(j + 1 >= n ? j + 1 - n : j + 1);
+                    const double ax = q.x - ref.x, ay = q.y - ref.y, wx = q2.x - q.x, wy = q2.y - q.y;
+                    const bool far = ax * ax + ay * ay > T2_far;
+                    const double sa = ux * ay - uy * ax;
+                    const double sb = ux * (q2.y - ref.y) - uy * (q2.x - ref.x);
+                    const double tol = ur * (fabs(ax) + fabs(ay) + fabs(wx) + fabs(wy));
+                    const bool conditioned = (wx == 0 || fabs(wx) > 1e-6 * fabs(wy)) && (wy == 0 || fabs(wy) > 1e-6 * fabs(wx));
+                    const bool off_line = conditioned && ((sa > tol && sb > tol) || (sa < -tol && sb < -tol));
+                    keep = !(far && off_line);
+                }
+                const unsigned m = __ballot_sync(FULL, keep);
+                if (keep) w.queue[qn + __popc(m & ((1u << lane) - 1))] = o;
+                qn += __popc(m);
+                base_o += 32;
+                __syncwarp();
+            }
+            const bool scanning = base_o < n;
+            if (qn >= 32 || (!scanning && qn > 0)) {          // one call site: the body is big
+                const int cnt = qn < 32 ? qn : 32;
+                if (lane < cnt) body(w.queue[qn - cnt + lane]);
+                qn -= cnt;
+                __syncwarp();
+            }
+            if (!scanning && qn == 0) break;
         }
     }
     // sector minima: first (in order o) strictly smaller float32 value wins (C:1259-1263)
