@@ -577,8 +577,9 @@ __device__ __forceinline__ bool point_inside(const Warp w, P2 P, const int32_t *
 // E:766-769 find_same_point: any boundary vertex within 0.001 of P
 __device__ __forceinline__ bool find_same_point(const Warp w, P2 P) {
     bool f = false;
+    const DistBound B = dist_bound(0.001);
 #pragma unroll 4
-    for (int j = w.lane; j < w.n; j += 32) f |= pdist(w.at(j), P) < 0.001;
+    for (int j = w.lane; j < w.n; j += 32) f |= dist_less(w.at(j), P, B);
     return __any_sync(FULL, f);
 }
 
@@ -620,6 +621,7 @@ __device__ __forceinline__ bool intersects_boundary(const Warp w, const Quad Q, 
     // ri is 1 or 2 (quad_indices); selects instead of m[(ri + k) & 3] keep the quad in registers
     const bool r1 = ri == 1;
     const P2 c1a = r1 ? m[0] : m[1], c1b = r1 ? m[3] : m[0], c2a = c1b, c2b = r1 ? m[2] : m[3];
+    const DistBound MD = dist_bound(max_dist);
     auto in_mesh = [&](int j) { return j == qi[0] || j == qi[1] || j == qi[2] || j == qi[3]; };
 #pragma unroll 2
     for (int base = 0; base < n; base += 32) {
@@ -627,7 +629,7 @@ __device__ __forceinline__ bool intersects_boundary(const Warp w, const Quad Q, 
         bool hit = false;
         if (j < n && !in_mesh(j)) {
             P2 v = w.at(j);
-            if (pdist(ref, v) < max_dist) {
+            if (dist_less(ref, v, MD)) {
                 int jp = j == 0 ? n - 1 : j - 1, jn = j + 1 == n ? 0 : j + 1;
                 // any of (c1,prev) (c1,next) (c2,prev) (c2,next) crossing -> True (order irrelevant)
                 if (!in_mesh(jp)) {
@@ -659,6 +661,7 @@ __device__ __noinline__ double boundary_quality_new_vertex(const Warp w, int idx
     int e1 = idx + 1 >= n ? idx + 1 - n : idx + 1, e2 = wrapn(idx + 2, n), e3 = idx - 1 < 0 ? idx - 1 + n : idx - 1,
         e4 = wrapn(idx - 2, n);
     double dist = pdist(add_v, w.at(e1)) + pdist(add_v, w.at(e3));
+    const DistBound DB = dist_bound(dist);
     // close_vs: not excluded, nearer than `dist`, and not directly after an accepted index
     double m_d = CUDART_INF;
     unsigned carry = 0;   // parity of the run of "close" flags reaching the end of the previous chunk
@@ -666,7 +669,7 @@ __device__ __noinline__ double boundary_quality_new_vertex(const Warp w, int idx
     for (int base = 0; base < n; base += 32) {
         int j = base + w.lane;
         bool c = false;
-        if (j < n && j != idx && j != e1 && j != e2 && j != e3 && j != e4) c = pdist(add_v, w.at(j)) < dist;
+        if (j < n && j != idx && j != e1 && j != e2 && j != e3 && j != e4) c = dist_less(add_v, w.at(j), DB);
         unsigned wbits = __ballot_sync(FULL, c);
         if (c) {
             unsigned below = ~wbits & ((1u << w.lane) - 1);        // zero bits below me
@@ -1020,8 +1023,9 @@ __global__ void __launch_bounds__(WPB_A * 32, MG_MINB) mg_step_decide_kernel(con
     {
         double ax = (double)np_round4f(a1), ay = (double)np_round4f(a2);
         double dx = right_p.x - ref.x, dy = right_p.y - ref.y;
-        double r = sqrt(dx * dx + dy * dy);
-        double c = r > 0 ? dx / r : 1.0, s = r > 0 ? -(dy / r) : 0.0;
+        double r2 = dx * dx + dy * dy;
+        double rinv = rsqrt(r2);                        // estimate only: the tie band below is > 1000x wider than its error
+        double c = r2 > 0 ? dx * rinv : 1.0, s = r2 > 0 ? -(dy * rinv) : 0.0;
         double ox = c * ax + s * ay;
         double oy = -s * ax + c * ay;
         ox *= S.base_length; oy *= S.base_length;

@@ -73,6 +73,26 @@ __device__ __forceinline__ double pdist(P2 a, P2 b) {
     return sqrt(dx * dx + dy * dy);
 }
 
+// pdist(a, b) < r decided from the squared distance: sqrt is monotonic and correctly rounded, so outside a 1e-12
+// relative band around r^2 the comparison is already decided; the exact sqrt only runs inside the band.
+struct DistBound {
+    double r, lo, hi;
+};
+__device__ __forceinline__ DistBound dist_bound(double r) {
+    DistBound b;
+    b.r = r;
+    b.lo = (r * r) * (1.0 - 1e-12);
+    b.hi = (r * r) * (1.0 + 1e-12);
+    return b;
+}
+__device__ __forceinline__ bool dist_less(P2 a, P2 b, const DistBound &B) {
+    double dx = a.x - b.x, dy = a.y - b.y;
+    double s = dx * dx + dy * dy;
+    if (s < B.lo) return true;
+    if (s > B.hi) return false;
+    return sqrt(s) < B.r;
+}
+
 // cross / dot of (p1 - c) and (p2 - c) exactly as C:100-106 forms them
 __device__ __forceinline__ void cross_dot(P2 c, P2 p1, P2 p2, double &cr, double &dt) {
     double v1x = p1.x - c.x, v1y = p1.y - c.y;
