@@ -2,6 +2,7 @@
 // kernel launches.  No torch types, no exceptions across the boundary, no CPU fallback.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>

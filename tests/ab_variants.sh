@@ -1,4 +1,4 @@
-for v in base u2b9 u2b12 u2qb9 p2 u2b8; do
+for v in base ns20 ns24 ns28 ns32; do
   if [ $v = base ]; then unset MESHGEN_LIB; else export MESHGEN_LIB=$PWD/reinforcementlearning4meshgeneration_b200/lib/variants/$v.so; fi
   python bench.py --no-cpu-baseline --phase-times --steps 500 > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
   python - <<PY
