@@ -299,6 +299,7 @@ def run_gpu(args):
     lo, hi = np.array([-1, -1.5, 0], np.float32), np.array([1, 1.5, 1.5], np.float32)
     host_actions = [torch.from_numpy(rng.uniform(lo, hi, size=(N, 3)).astype(np.float32)) for _ in range(4)]
     out = {k: v for k, v in pinned.items() if k != "act"}
+    reward_view = out["reward"].numpy()                       # host view the caller reads its results through
     env.set_host_delta(True)      # persistent pinned result buffers: only the rows that changed cross PCIe
     for k in range(2):
         pinned["act"].copy_(host_actions[k % 4])
@@ -308,7 +309,7 @@ def run_gpu(args):
     for k in range(Ke):
         pinned["act"].copy_(host_actions[k % 4])             # the policy's output lands in pinned host memory
         env.step_host(pinned["act"], out)
-        _ = float(out["reward"][0])                           # the caller reads the result on the host
+        _ = float(reward_view[0])                             # the caller reads the result on the host
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     h2d_meas, d2h_meas = env.last_host_bytes()

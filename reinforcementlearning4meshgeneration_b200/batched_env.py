@@ -160,8 +160,15 @@ class BatchedBoudaryEnv:
 
     def step_host(self, actions: np.ndarray, out: Optional[dict] = None) -> dict:
         """Same transition through host (numpy / pinned) buffers: H2D + step + D2H + sync inside the
-        library (mg_step_host) -- the path a numpy-facing caller such as SB3 pays."""
-        a = np.ascontiguousarray(actions, dtype=np.float32)
+        library (mg_step_host) -- the path a numpy-facing caller such as SB3 pays.  With pinned ``out`` buffers
+        (torch ``.pin_memory()``) and ``set_host_delta(True)`` the rows that changed are written by the GPU straight
+        into them."""
+        is_t = isinstance(actions, torch.Tensor)
+        if is_t:
+            if actions.dtype != torch.float32 or not actions.is_contiguous() or actions.device.type != "cpu":
+                raise ValueError("actions tensor must be a contiguous float32 CPU tensor (pinned for the fastest path)")
+        else:
+            a = np.ascontiguousarray(actions, dtype=np.float32)
         N = self.num_envs
         if out is None:
             out = dict(obs=np.empty((N, OBS_DIM), np.float32), reward=np.empty(N, np.float64),
@@ -171,7 +178,7 @@ class BatchedBoudaryEnv:
         def ptr(x):
             return C.c_void_p(x.data_ptr()) if isinstance(x, torch.Tensor) else C.c_void_p(x.ctypes.data)
 
-        aptr = ptr(actions) if isinstance(actions, torch.Tensor) else C.c_void_p(a.ctypes.data)
+        aptr = ptr(actions) if is_t else C.c_void_p(a.ctypes.data)
         check(self._L.mg_step_host(self._h, aptr, ptr(out["obs"]), ptr(out["reward"]), ptr(out["terminated"]),
                                    ptr(out["truncated"]), ptr(out["terminal_obs"]), ptr(out["n_elements"])),
               self._h, "mg_step_host")

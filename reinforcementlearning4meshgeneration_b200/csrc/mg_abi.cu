@@ -32,17 +32,21 @@ struct mg_env_s {
     int32_t *d_nel = nullptr;
     cudaStream_t host_stream = nullptr;
     // mg_step_host: terminal observations travel compacted (only finished envs)
-    int32_t *d_pack_idx = nullptr, *d_pack_cnt = nullptr, *h_pack_idx = nullptr, *h_pack_cnt = nullptr;
-    float *d_pack_obs = nullptr, *h_pack_obs = nullptr;
+    int32_t *d_pack_cnt = nullptr, *h_pack_idx = nullptr, *h_pack_cnt = nullptr;
+    float *h_pack_obs = nullptr;
     float *last_term_obs_host = nullptr;
     // delta mode (mg_set_host_delta): observations / element counts travel only for the envs whose state changed
     bool host_delta = false;
     float *last_obs_host = nullptr;
     int32_t *last_nel_host = nullptr;
-    int32_t *d_chg_idx = nullptr, *d_chg_nel = nullptr, *h_chg_idx = nullptr, *h_chg_nel = nullptr;
-    float *d_chg_obs = nullptr, *h_chg_obs = nullptr;
+    int32_t *h_chg_idx = nullptr, *h_chg_nel = nullptr;
+    float *h_chg_obs = nullptr;
+    // device-side aliases of the mapped pinned buffers above
+    int32_t *m_pack_idx = nullptr, *m_chg_idx = nullptr, *m_chg_nel = nullptr;
+    float *m_pack_obs = nullptr, *m_chg_obs = nullptr;
     int64_t last_h2d = 0, last_d2h = 0;
     std::vector<int32_t> prev_done;
+    void *alias_host[2] = {nullptr, nullptr}, *alias_dev[2] = {nullptr, nullptr};   // obs_host, term_obs_host
     bool ready = false;       // domains or generator configured
     bool was_reset = false;
     int64_t launches = 0;
@@ -114,6 +118,21 @@ int upload_angle_table(mg_handle h) {
     return MG_OK;
 }
 
+// Device alias of a caller's host buffer when it is pinned / registered (torch .pin_memory(), cudaHostAlloc,
+// cudaHostRegister); nullptr for pageable memory.  Cached per pointer: the query costs a few microseconds.
+template <class T>
+T *pinned_alias(mg_handle h, T *host, int slot) {
+    if (!host) return nullptr;
+    if (h->alias_host[slot] == (void *)host) return (T *)h->alias_dev[slot];
+    cudaPointerAttributes a{};
+    void *dev = nullptr;
+    if (cudaPointerGetAttributes(&a, host) == cudaSuccess && a.type == cudaMemoryTypeHost) dev = a.devicePointer;
+    cudaGetLastError();
+    h->alias_host[slot] = (void *)host;
+    h->alias_dev[slot] = dev;
+    return (T *)dev;
+}
+
 void free_templates(mg_handle h) {
     cudaFree(h->t_xy); cudaFree(h->t_key); cudaFree(h->t_stamp); cudaFree(h->t_sc); cudaFree(h->t_obs);
     h->t_xy = nullptr; h->t_key = nullptr; h->t_stamp = nullptr; h->t_sc = nullptr; h->t_obs = nullptr;
@@ -163,16 +182,22 @@ int mg_create(mg_handle *out, int device, int num_envs, int max_verts) {
     A(dalloc(&h->d_term_obs, (size_t)num_envs * MG_OBS_DIM), "term_obs"); A(dalloc(&h->d_rew, (size_t)num_envs), "rew");
     A(dalloc(&h->d_term, (size_t)num_envs), "term"); A(dalloc(&h->d_trunc, (size_t)num_envs), "trunc");
     A(dalloc(&h->d_nel, (size_t)num_envs), "nel");
-    A(dalloc(&h->d_pack_idx, (size_t)num_envs), "pack_idx"); A(dalloc(&h->d_pack_cnt, (size_t)2), "pack_cnt");
-    A(dalloc(&h->d_pack_obs, (size_t)num_envs * MG_OBS_DIM), "pack_obs");
-    A(cudaMallocHost((void **)&h->h_pack_idx, sizeof(int32_t) * num_envs), "h_pack_idx");
-    A(cudaMallocHost((void **)&h->h_pack_cnt, 2 * sizeof(int32_t)), "h_pack_cnt");
-    A(cudaMallocHost((void **)&h->h_pack_obs, sizeof(float) * MG_OBS_DIM * num_envs), "h_pack_obs");
-    A(dalloc(&h->d_chg_idx, (size_t)num_envs), "chg_idx"); A(dalloc(&h->d_chg_nel, (size_t)num_envs), "chg_nel");
-    A(dalloc(&h->d_chg_obs, (size_t)num_envs * MG_OBS_DIM), "chg_obs");
-    A(cudaMallocHost((void **)&h->h_chg_idx, sizeof(int32_t) * num_envs), "h_chg_idx");
-    A(cudaMallocHost((void **)&h->h_chg_nel, sizeof(int32_t) * num_envs), "h_chg_nel");
-    A(cudaMallocHost((void **)&h->h_chg_obs, sizeof(float) * MG_OBS_DIM * num_envs), "h_chg_obs");
+    A(dalloc(&h->d_pack_cnt, (size_t)2), "pack_cnt");
+    // packed rows are written by the pack kernels straight into mapped pinned host memory (coalesced rows over
+    // PCIe): no second copy + synchronise round once the counts are known
+    A(cudaHostAlloc((void **)&h->h_pack_idx, sizeof(int32_t) * num_envs, cudaHostAllocMapped), "h_pack_idx");
+    A(cudaMallocHost((void **)&h->h_pack_cnt, 4 * sizeof(int32_t)), "h_pack_cnt");
+    A(cudaHostAlloc((void **)&h->h_pack_obs, sizeof(float) * MG_OBS_DIM * num_envs, cudaHostAllocMapped), "h_pack_obs");
+    A(cudaHostAlloc((void **)&h->h_chg_idx, sizeof(int32_t) * num_envs, cudaHostAllocMapped), "h_chg_idx");
+    A(cudaHostAlloc((void **)&h->h_chg_nel, sizeof(int32_t) * num_envs, cudaHostAllocMapped), "h_chg_nel");
+    A(cudaHostAlloc((void **)&h->h_chg_obs, sizeof(float) * MG_OBS_DIM * num_envs, cudaHostAllocMapped), "h_chg_obs");
+    if (rc == MG_OK) {
+        A(cudaHostGetDevicePointer((void **)&h->m_pack_idx, h->h_pack_idx, 0), "map pack_idx");
+        A(cudaHostGetDevicePointer((void **)&h->m_pack_obs, h->h_pack_obs, 0), "map pack_obs");
+        A(cudaHostGetDevicePointer((void **)&h->m_chg_idx, h->h_chg_idx, 0), "map chg_idx");
+        A(cudaHostGetDevicePointer((void **)&h->m_chg_nel, h->h_chg_nel, 0), "map chg_nel");
+        A(cudaHostGetDevicePointer((void **)&h->m_chg_obs, h->h_chg_obs, 0), "map chg_obs");
+    }
     if (rc == MG_OK && cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking) != cudaSuccess)
         rc = fail(h, MG_ERR_CUDA, "cudaStreamCreate");
     if (rc == MG_OK) rc = configure_kernels(h);
@@ -193,9 +218,8 @@ int mg_destroy(mg_handle h) {
     cudaFree(h->sc_tab);
     cudaFree(h->d_stats_out); cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_term_obs); cudaFree(h->d_rew);
     cudaFree(h->d_term); cudaFree(h->d_trunc); cudaFree(h->d_nel);
-    cudaFree(h->d_pack_idx); cudaFree(h->d_pack_cnt); cudaFree(h->d_pack_obs);
+    cudaFree(h->d_pack_cnt);
     cudaFreeHost(h->h_pack_idx); cudaFreeHost(h->h_pack_cnt); cudaFreeHost(h->h_pack_obs);
-    cudaFree(h->d_chg_idx); cudaFree(h->d_chg_nel); cudaFree(h->d_chg_obs);
     cudaFreeHost(h->h_chg_idx); cudaFreeHost(h->h_chg_nel); cudaFreeHost(h->h_chg_obs);
     if (h->host_stream) cudaStreamDestroy(h->host_stream);
     delete h;
@@ -361,19 +385,32 @@ int mg_step_host(mg_handle h, const float *act_host, float *obs_host, double *re
     // (element counts are not delta-coded: a reset env reports the finished episode's count in the reset
     // step and 0 from the next step on, whatever that step does)
     const bool delta_nel = false;
+    // pinned caller buffers: changed rows go straight into them (no staging, no host-side scatter)
+    float *obs_alias = delta_obs ? pinned_alias(h, obs_host, 0) : nullptr;
+    float *tobs_alias = pinned_alias(h, term_obs_host, 1);
+    const bool direct_obs = obs_alias != nullptr, direct_tobs = tobs_alias != nullptr;
     MG_CUDA(h, cudaMemsetAsync(h->d_pack_cnt, 0, 2 * sizeof(int32_t), s));
-    if (term_obs_host) {
-        mg_pack_terminal_kernel<<<(h->num_envs + 255) / 256, 256, 0, s>>>(h->num_envs, h->d_term, h->d_trunc, h->d_term_obs,
-                                                                           h->d_pack_idx, h->d_pack_obs, h->d_pack_cnt);
+    if (direct_obs || direct_tobs) {
+        mg_scatter_rows_host_kernel<<<h->sm_count * 2, 256, 0, s>>>(h->P, set, h->d_obs, direct_obs ? obs_alias : nullptr, h->d_term,
+                                                                   h->d_trunc, h->d_term_obs, direct_tobs ? tobs_alias : nullptr,
+                                                                   h->d_pack_cnt);
         h->launches++;
     }
-    if (delta_obs) {
-        mg_pack_changed_kernel<<<h->sm_count * 2, 256, 0, s>>>(h->P, set, h->d_obs, h->d_nel, h->d_chg_idx, h->d_chg_obs,
-                                                              h->d_chg_nel, h->d_pack_cnt + 1);
+    if (term_obs_host && !direct_tobs) {
+        mg_pack_terminal_kernel<<<(h->num_envs + 255) / 256, 256, 0, s>>>(h->num_envs, h->d_term, h->d_trunc, h->d_term_obs,
+                                                                           h->m_pack_idx, h->m_pack_obs, h->d_pack_cnt);
         h->launches++;
-    } else {
+    }
+    if (delta_obs && !direct_obs) {
+        mg_pack_changed_kernel<<<h->sm_count * 2, 256, 0, s>>>(h->P, set, h->d_obs, h->d_nel, h->m_chg_idx, h->m_chg_obs,
+                                                              h->m_chg_nel, h->d_pack_cnt + 1);
+        h->launches++;
+    } else if (!delta_obs) {
         MG_CUDA(h, cudaMemcpyAsync(obs_host, h->d_obs, N * MG_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
         d2h += N * MG_OBS_DIM * sizeof(float);
+    }
+    if (direct_obs || direct_tobs) {      // row counts for the byte accounting (the work-list counters of this step)
+        MG_CUDA(h, cudaMemcpyAsync(h->h_pack_cnt + 2, h->P.counters + 2 * set, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     }
     MG_CUDA(h, cudaMemcpyAsync(h->h_pack_cnt, h->d_pack_cnt, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     MG_CUDA(h, cudaMemcpyAsync(rew_host, h->d_rew, N * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -385,25 +422,16 @@ int mg_step_host(mg_handle h, const float *act_host, float *obs_host, double *re
         d2h += N * sizeof(int32_t);
     }
     MG_CUDA(h, cudaStreamSynchronize(s));
-    const int c_term = term_obs_host ? h->h_pack_cnt[0] : 0, c_chg = delta_obs ? h->h_pack_cnt[1] : 0;
-    if (c_term > 0) {
-        MG_CUDA(h, cudaMemcpyAsync(h->h_pack_idx, h->d_pack_idx, sizeof(int32_t) * c_term, cudaMemcpyDeviceToHost, s));
-        MG_CUDA(h, cudaMemcpyAsync(h->h_pack_obs, h->d_pack_obs, sizeof(float) * MG_OBS_DIM * c_term, cudaMemcpyDeviceToHost, s));
-        d2h += (int64_t)c_term * (4 + 4 * MG_OBS_DIM);
-    }
-    if (c_chg > 0) {
-        MG_CUDA(h, cudaMemcpyAsync(h->h_chg_idx, h->d_chg_idx, sizeof(int32_t) * c_chg, cudaMemcpyDeviceToHost, s));
-        MG_CUDA(h, cudaMemcpyAsync(h->h_chg_obs, h->d_chg_obs, sizeof(float) * MG_OBS_DIM * c_chg, cudaMemcpyDeviceToHost, s));
-        if (delta_nel) MG_CUDA(h, cudaMemcpyAsync(h->h_chg_nel, h->d_chg_nel, sizeof(int32_t) * c_chg, cudaMemcpyDeviceToHost, s));
-        d2h += (int64_t)c_chg * (4 + 4 * MG_OBS_DIM + (delta_nel ? 4 : 0));
-    }
-    if (c_term > 0 || c_chg > 0) MG_CUDA(h, cudaStreamSynchronize(s));
+    const int c_term = (term_obs_host && !direct_tobs) ? h->h_pack_cnt[0] : 0, c_chg = (delta_obs && !direct_obs) ? h->h_pack_cnt[1] : 0;
+    d2h += (int64_t)c_term * (4 + 4 * MG_OBS_DIM) + (int64_t)c_chg * (4 + 4 * MG_OBS_DIM + 4);    // written by the pack kernels
+    if (direct_obs) d2h += (int64_t)(h->h_pack_cnt[2] + h->h_pack_cnt[3]) * 4 * MG_OBS_DIM;
+    if (direct_tobs) d2h += (int64_t)h->h_pack_cnt[0] * 4 * MG_OBS_DIM;
     for (int i = 0; i < c_chg; i++) {
         const size_t e = (size_t)h->h_chg_idx[i];
         std::memcpy(obs_host + e * MG_OBS_DIM, h->h_chg_obs + (size_t)i * MG_OBS_DIM, sizeof(float) * MG_OBS_DIM);
         if (delta_nel) n_elem_host[e] = h->h_chg_nel[i];
     }
-    if (term_obs_host) {
+    if (term_obs_host && !direct_tobs) {
         // terminal observations are only defined where done: those rows travel compacted instead of N*72 bytes
         if (h->last_term_obs_host != term_obs_host) {
             std::memset(term_obs_host, 0, sizeof(float) * MG_OBS_DIM * N);

@@ -1380,6 +1380,36 @@ __global__ void mg_replay_add_kernel(int num_envs, float *__restrict__ b_obs, fl
     if (k == 5) b_to[e] = tr ? 1 : 0;
 }
 
+// mg_step_host with PINNED caller buffers: the rows that changed are written straight into the caller's host arrays
+// through their device aliases (one 72-byte row per warp: coalesced PCIe writes, no staging copy, no host-side
+// scatter).  `obs_host` rows for the step's two work lists, `term_obs_host` rows for the envs that finished.
+__global__ void mg_scatter_rows_host_kernel(const __grid_constant__ Params P, int set, const float *obs, float *obs_host,
+                                            const uint8_t *term, const uint8_t *trunc, const float *term_obs, float *term_obs_host,
+                                            int32_t *n_done_rows) {
+    const int lane = threadIdx.x & 31;
+    const int warps = gridDim.x * (blockDim.x >> 5), w0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (obs_host) {
+        const int cs = P.counters[2 * set + 0], cr = P.counters[2 * set + 1];
+        for (int it = w0; it < cs + cr; it += warps) {
+            const int env = it < cs ? P.succ_list[it] : P.reset_list[it - cs];
+            if (lane < MG_OBS_DIM) obs_host[(size_t)env * MG_OBS_DIM + lane] = obs[(size_t)env * MG_OBS_DIM + lane];
+        }
+    }
+    if (term_obs_host) {
+        // finished envs: one flag byte per lane, then one row per set bit
+        for (int base = w0 * 32; base < P.num_envs; base += warps * 32) {
+            const int e = base + lane;
+            unsigned m = __ballot_sync(FULL, e < P.num_envs && (term[e] | trunc[e]));
+            if (m && lane == 0) atomicAdd(n_done_rows, __popc(m));      // byte accounting of mg_last_host_bytes
+            while (m) {
+                const int env = base + __ffs(m) - 1;
+                m &= m - 1;
+                if (lane < MG_OBS_DIM) term_obs_host[(size_t)env * MG_OBS_DIM + lane] = term_obs[(size_t)env * MG_OBS_DIM + lane];
+            }
+        }
+    }
+}
+
 // Sum of the accumulator slots -> one mg_episode_stats (one warp).
 __global__ void mg_stats_kernel(StatsAcc *stats, mg_episode_stats *out, int reset) {
     unsigned long long a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
