@@ -34,6 +34,7 @@ struct mg_env_s {
     // mg_step_host: terminal observations travel compacted (only finished envs)
     int32_t *d_pack_cnt = nullptr, *h_pack_idx = nullptr, *h_pack_cnt = nullptr;
     float *h_pack_obs = nullptr;
+    int32_t *h_cnt_all = nullptr;
     float *last_term_obs_host = nullptr;
     // delta mode (mg_set_host_delta): observations / element counts travel only for the envs whose state changed
     bool host_delta = false;
@@ -50,7 +51,6 @@ struct mg_env_s {
     bool ready = false;       // domains or generator configured
     bool was_reset = false;
     int64_t launches = 0;
-    int step_parity = 0;
     int phase_mask = 3;       // profiling aid: bit 0 = phase A launch, bit 1 = phase B+C launch
     int sm_count = 148;
     size_t smem = 0, smem_a = 0;
@@ -174,7 +174,7 @@ int mg_create(mg_handle *out, int device, int num_envs, int max_verts) {
     A(dalloc(&P.st, (size_t)num_envs), "state"); A(dalloc(&P.stats, (size_t)STAT_SLOTS), "stats");
     A(dalloc(&P.obs_cache, (size_t)num_envs * MG_OBS_DIM), "obs");
     A(dalloc(&P.pend, (size_t)num_envs), "pend"); A(dalloc(&P.succ_list, (size_t)num_envs), "succ_list");
-    A(dalloc(&P.reset_list, (size_t)num_envs), "reset_list"); A(dalloc(&P.counters, (size_t)4), "counters");
+    A(dalloc(&P.reset_list, (size_t)num_envs), "reset_list"); A(dalloc(&P.counters, (size_t)CNT_N), "counters");
     A(dalloc(&P.elem, (size_t)num_envs * P.elem_cap * 4), "elem"); A(dalloc(&P.ins_xy, (size_t)num_envs * P.ins_cap), "ins_xy");
     A(dalloc(&h->d_stats_out, 1), "stats_out");
     A(dalloc(&h->sc_tab, (size_t)2 * ANGLE_TAB_N), "angle table");
@@ -187,6 +187,7 @@ int mg_create(mg_handle *out, int device, int num_envs, int max_verts) {
     // PCIe): no second copy + synchronise round once the counts are known
     A(cudaHostAlloc((void **)&h->h_pack_idx, sizeof(int32_t) * num_envs, cudaHostAllocMapped), "h_pack_idx");
     A(cudaMallocHost((void **)&h->h_pack_cnt, 4 * sizeof(int32_t)), "h_pack_cnt");
+    A(cudaMallocHost((void **)&h->h_cnt_all, CNT_N * sizeof(int32_t)), "h_cnt_all");
     A(cudaHostAlloc((void **)&h->h_pack_obs, sizeof(float) * MG_OBS_DIM * num_envs, cudaHostAllocMapped), "h_pack_obs");
     A(cudaHostAlloc((void **)&h->h_chg_idx, sizeof(int32_t) * num_envs, cudaHostAllocMapped), "h_chg_idx");
     A(cudaHostAlloc((void **)&h->h_chg_nel, sizeof(int32_t) * num_envs, cudaHostAllocMapped), "h_chg_nel");
@@ -219,7 +220,7 @@ int mg_destroy(mg_handle h) {
     cudaFree(h->d_stats_out); cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_term_obs); cudaFree(h->d_rew);
     cudaFree(h->d_term); cudaFree(h->d_trunc); cudaFree(h->d_nel);
     cudaFree(h->d_pack_cnt);
-    cudaFreeHost(h->h_pack_idx); cudaFreeHost(h->h_pack_cnt); cudaFreeHost(h->h_pack_obs);
+    cudaFreeHost(h->h_pack_idx); cudaFreeHost(h->h_pack_cnt); cudaFreeHost(h->h_pack_obs); cudaFreeHost(h->h_cnt_all);
     cudaFreeHost(h->h_chg_idx); cudaFreeHost(h->h_chg_nel); cudaFreeHost(h->h_chg_obs);
     if (h->host_stream) cudaStreamDestroy(h->host_stream);
     delete h;
@@ -254,6 +255,10 @@ int mg_replay_add(mg_handle h, int64_t capacity_steps, int64_t slot, float *buf_
 int mg_set_phase_mask(mg_handle h, int mask) {
     if (!h) return fail(h, MG_ERR_ARG, "mg_set_phase_mask: null handle");
     h->phase_mask = mask & 3;
+    // masked steps leave entries in the work lists: start clean on every change of the mask
+    MG_CUDA(h, cudaSetDevice(h->device));
+    MG_CUDA(h, cudaDeviceSynchronize());
+    MG_CUDA(h, cudaMemset(h->P.counters, 0, 4 * sizeof(int)));
     return MG_OK;
 }
 
@@ -354,14 +359,12 @@ int mg_step(mg_handle h, const float *act_dev, float *obs_dev, double *rew_dev, 
     StepIO io;
     io.act = act_dev; io.obs_out = obs_dev; io.rew_out = rew_dev; io.term_out = term_dev; io.trunc_out = trunc_dev;
     io.term_obs_out = term_obs_dev; io.n_elem_out = n_elem_dev;
-    const int set = h->step_parity;
-    h->step_parity ^= 1;
     cudaStream_t s = (cudaStream_t)stream;
     const int full = grid_for(h->num_envs);
     const int gb = full < h->sm_count * 16 ? full : h->sm_count * 16;
     const int gc = full < h->sm_count * 4 ? full : h->sm_count * 4;
-    if (h->phase_mask & 1) mg_step_decide_kernel<<<(h->num_envs + WPB_A - 1) / WPB_A, WPB_A * 32, h->smem_a, s>>>(h->P, io, set);
-    if (h->phase_mask & 2) mg_step_apply_reset_kernel<<<gb + gc, WPB * 32, h->smem, s>>>(h->P, io, set, gb);
+    if (h->phase_mask & 1) mg_step_decide_kernel<<<(h->num_envs + WPB_A - 1) / WPB_A, WPB_A * 32, h->smem_a, s>>>(h->P, io);
+    if (h->phase_mask & 2) mg_step_apply_reset_kernel<<<gb + gc, WPB * 32, h->smem, s>>>(h->P, io, gb);
     h->launches += 2;
     MG_CUDA(h, cudaGetLastError());
     return MG_OK;
@@ -375,7 +378,6 @@ int mg_step_host(mg_handle h, const float *act_host, float *obs_host, double *re
     const size_t N = h->num_envs;
     cudaStream_t s = h->host_stream;
     MG_CUDA(h, cudaMemcpyAsync(h->d_act, act_host, N * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
-    const int set = h->step_parity;                 // work lists of the step enqueued next
     int rc = mg_step(h, h->d_act, h->d_obs, h->d_rew, h->d_term, h->d_trunc, h->d_term_obs, h->d_nel, s);
     if (rc != MG_OK) return rc;
     int64_t d2h = 0;
@@ -391,7 +393,7 @@ int mg_step_host(mg_handle h, const float *act_host, float *obs_host, double *re
     const bool direct_obs = obs_alias != nullptr, direct_tobs = tobs_alias != nullptr;
     MG_CUDA(h, cudaMemsetAsync(h->d_pack_cnt, 0, 2 * sizeof(int32_t), s));
     if (direct_obs || direct_tobs) {
-        mg_scatter_rows_host_kernel<<<h->sm_count * 2, 256, 0, s>>>(h->P, set, h->d_obs, direct_obs ? obs_alias : nullptr, h->d_term,
+        mg_scatter_rows_host_kernel<<<h->sm_count * 2, 256, 0, s>>>(h->P, h->d_obs, direct_obs ? obs_alias : nullptr, h->d_term,
                                                                    h->d_trunc, h->d_term_obs, direct_tobs ? tobs_alias : nullptr,
                                                                    h->d_pack_cnt);
         h->launches++;
@@ -402,15 +404,15 @@ int mg_step_host(mg_handle h, const float *act_host, float *obs_host, double *re
         h->launches++;
     }
     if (delta_obs && !direct_obs) {
-        mg_pack_changed_kernel<<<h->sm_count * 2, 256, 0, s>>>(h->P, set, h->d_obs, h->d_nel, h->m_chg_idx, h->m_chg_obs,
+        mg_pack_changed_kernel<<<h->sm_count * 2, 256, 0, s>>>(h->P, h->d_obs, h->d_nel, h->m_chg_idx, h->m_chg_obs,
                                                               h->m_chg_nel, h->d_pack_cnt + 1);
         h->launches++;
     } else if (!delta_obs) {
         MG_CUDA(h, cudaMemcpyAsync(obs_host, h->d_obs, N * MG_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
         d2h += N * MG_OBS_DIM * sizeof(float);
     }
-    if (direct_obs || direct_tobs) {      // row counts for the byte accounting (the work-list counters of this step)
-        MG_CUDA(h, cudaMemcpyAsync(h->h_pack_cnt + 2, h->P.counters + 2 * set, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (direct_obs || direct_tobs) {      // row counts for the byte accounting (both counter sets + the current set)
+        MG_CUDA(h, cudaMemcpyAsync(h->h_cnt_all, h->P.counters, CNT_N * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     }
     MG_CUDA(h, cudaMemcpyAsync(h->h_pack_cnt, h->d_pack_cnt, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     MG_CUDA(h, cudaMemcpyAsync(rew_host, h->d_rew, N * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -424,7 +426,10 @@ int mg_step_host(mg_handle h, const float *act_host, float *obs_host, double *re
     MG_CUDA(h, cudaStreamSynchronize(s));
     const int c_term = (term_obs_host && !direct_tobs) ? h->h_pack_cnt[0] : 0, c_chg = (delta_obs && !direct_obs) ? h->h_pack_cnt[1] : 0;
     d2h += (int64_t)c_term * (4 + 4 * MG_OBS_DIM) + (int64_t)c_chg * (4 + 4 * MG_OBS_DIM + 4);    // written by the pack kernels
-    if (direct_obs) d2h += (int64_t)(h->h_pack_cnt[2] + h->h_pack_cnt[3]) * 4 * MG_OBS_DIM;
+    if (direct_obs) {
+        const int cur = h->h_cnt_all[CNT_CUR] & 1;
+        d2h += (int64_t)(h->h_cnt_all[2 * cur] + h->h_cnt_all[2 * cur + 1]) * 4 * MG_OBS_DIM;
+    }
     if (direct_tobs) d2h += (int64_t)h->h_pack_cnt[0] * 4 * MG_OBS_DIM;
     for (int i = 0; i < c_chg; i++) {
         const size_t e = (size_t)h->h_chg_idx[i];

@@ -874,8 +874,11 @@ __global__ void __launch_bounds__(WPB * 32) mg_reset_kernel(const __grid_constan
 //   B  apply blocks           successes  boundary update, candidate keys, reward, next observation
 //   C  reset blocks           done envs  in-place reset (template copy or fresh random polygon)
 //   (B and C share one launch, mg_step_apply_reset_kernel: their env sets are disjoint)
-// Work lists are appended with one atomicAdd per warp; counter set (step & 1) is used by step s and
-// the other set is zeroed by phase C, so no memset sits between launches.
+// Work lists are appended with one atomicAdd per warp.  Two sets of list sizes alternate: phase A of step s uses
+// set (CNT_STEP & 1) and records it in CNT_CUR; the B/C launch reads CNT_CUR, and its first thread clears the
+// other (idle) set and advances CNT_STEP for the next step.  The parity lives in device memory, so no memset sits
+// between launches and any sequence of mg_step calls can be captured in a CUDA graph (a ticket that lets the last
+// block clear one set cost 5 us per step, an 8-byte memset node 2 us).
 // ---------------------------------------------------------------------------------------------
 struct StepIO {
     const float *act;
@@ -887,8 +890,11 @@ struct StepIO {
     int32_t *n_elem_out;
 };
 
-__device__ __forceinline__ void push_list(int *list, int *counter, int env, int lane) {
-    if (lane == 0) list[atomicAdd(counter, 1)] = env;
+__device__ __forceinline__ void push_list(int *list, int *counter, int env, int lane, int cap) {
+    if (lane == 0) {
+        const int i = atomicAdd(counter, 1);
+        if (i < cap) list[i] = env;          // (only a profiling run with phase B masked off can overrun the list)
+    }
 }
 
 __device__ __forceinline__ void store_state(const Params &P, int env, const EnvState &S) { P.st[env] = S; }
@@ -974,7 +980,7 @@ __device__ __noinline__ double2 action_frame_exact(double ax, double ay, double 
 }
 
 // ---- phase A ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(WPB_A * 32, MG_MINB) mg_step_decide_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io, int set) {
+__global__ void __launch_bounds__(WPB_A * 32, MG_MINB) mg_step_decide_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * WPB_A + warp;
@@ -988,6 +994,7 @@ __global__ void __launch_bounds__(WPB_A * 32, MG_MINB) mg_step_decide_kernel(con
     // the same time (profiles/README.md, A/B v1)
     const int4 *rec = reinterpret_cast<const int4 *>(P.st + env);
     const int4 rec0 = ldg_keep(rec), rec1 = ldg_keep(rec + 1), rec2 = ldg_keep(rec + 2);
+    if (env == 0 && lane == 0) P.counters[CNT_CUR] = P.counters[CNT_STEP] & 1;    // the set this step's lists use
     // requested now so that the tail of a failed step does not pay another DRAM round trip
     const float obs_cached = lane < MG_OBS_DIM ? P.obs_cache[(size_t)env * MG_OBS_DIM + lane] : 0.0f;
     EnvHot S = unpack_hot(rec0, rec1, rec1);
@@ -1001,7 +1008,6 @@ __global__ void __launch_bounds__(WPB_A * 32, MG_MINB) mg_step_decide_kernel(con
     if (lane == 0) { stash[0] = rec1; stash[1] = rec2; }
     if (lane < MG_OBS_DIM) stash_obs[lane] = obs_cached;
     const float a0 = io.act[(size_t)env * 3 + 0], a1 = io.act[(size_t)env * 3 + 1], a2 = io.act[(size_t)env * 3 + 2];
-    const size_t off = (size_t)env * P.cap;
     Warp w;
     w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = S.n;
     // An env without a reference point (empty candidate list, E:736-738 returns None) has no
@@ -1049,7 +1055,7 @@ __global__ void __launch_bounds__(WPB_A * 32, MG_MINB) mg_step_decide_kernel(con
     } else if (a0 <= -0.5f) rule = -1;
     else if (a0 >= 0.5f) rule = 1;
     else {
-        if (point_inside(w, newp, P.vid + off, S.n0)) {
+        if (point_inside(w, newp, P.vid + (size_t)env * P.cap, S.n0)) {
             if (find_same_point(w, newp)) rule = -1;
             else new_vertex = true;
         } else {
@@ -1075,7 +1081,7 @@ __global__ void __launch_bounds__(WPB_A * 32, MG_MINB) mg_step_decide_kernel(con
                 Q.rule = rule; Q.new_vertex = new_vertex ? 1 : 0;
                 P.pend[env] = Q;
             }
-            push_list(P.succ_list, P.counters + 2 * set + 0, env, lane);
+            push_list(P.succ_list, P.counters + 2 * (P.counters[CNT_STEP] & 1) + 0, env, lane, P.num_envs);
             return;
         }
         reward += S.n_elements ? -1.0 / S.n_elements : -1;          // E:357
@@ -1090,7 +1096,7 @@ __global__ void __launch_bounds__(WPB_A * 32, MG_MINB) mg_step_decide_kernel(con
     }
     S.failed_num++;
     if (finish_step(P, io, env, lane, S, n, reward, done, true, false, dead, obs))
-        push_list(P.reset_list, P.counters + 2 * set + 1, env, lane);
+        push_list(P.reset_list, P.counters + 2 * (P.counters[CNT_STEP] & 1) + 1, env, lane, P.num_envs);
 }
 
 // ---- phase B ---------------------------------------------------------------------------------
@@ -1110,7 +1116,7 @@ __device__ __noinline__ void reset_in_place(const Params &P, const StepIO &io, i
 __device__ __forceinline__ void apply_successes(const Params &P, const StepIO &io, int set, const SmemLayout &L, int first,
                                                 int stride, int lane) {
     init_mbar(L.mbar, lane);
-    const int count = P.counters[2 * set + 0];
+    const int count = min(P.counters[2 * set + 0], P.num_envs);
     unsigned phase = 0;
 #pragma unroll 1
     for (int item = first; item < count; item += stride) {
@@ -1294,27 +1300,29 @@ __device__ __forceinline__ void apply_successes(const Params &P, const StepIO &i
 #ifndef MG_MINB_APPLY
 #define MG_MINB_APPLY 12    // tuned on B200: 80 registers, 24 warps per SM for the latency-bound apply phase
 #endif
-__global__ void __launch_bounds__(WPB * 32, MG_MINB_APPLY) mg_step_apply_reset_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io, int set, int apply_blocks) {
+__global__ void __launch_bounds__(WPB * 32, MG_MINB_APPLY) mg_step_apply_reset_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io, int apply_blocks) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     SmemLayout L = carve(smem_raw, P.cap, warp);
     const int reset_blocks = gridDim.x - apply_blocks;     // scheduled first: one reset is the longest item
+    const int set = P.counters[CNT_CUR];                   // written by phase A of this step
     if ((int)blockIdx.x >= reset_blocks) {
         apply_successes(P, io, set, L, (blockIdx.x - reset_blocks) * WPB + warp, apply_blocks * WPB, lane);
-        return;
-    }
-    const int rb = blockIdx.x, nrb = reset_blocks;
-    if (rb == 0 && threadIdx.x == 0) {               // the other counter set is idle during this step
-        P.counters[2 * (set ^ 1) + 0] = 0;
-        P.counters[2 * (set ^ 1) + 1] = 0;
-    }
-    const int count = P.counters[2 * set + 1];
+    } else {
+        const int rb = blockIdx.x, nrb = reset_blocks;
+        if (rb == 0 && threadIdx.x == 0) {               // the other counter set is idle during this step
+            P.counters[2 * (set ^ 1) + 0] = 0;
+            P.counters[2 * (set ^ 1) + 1] = 0;
+            P.counters[CNT_STEP] = (set ^ 1);            // parity of the next step; only phase A reads it
+        }
+        const int count = min(P.counters[2 * set + 1], P.num_envs);
 #pragma unroll 1
-    for (int item = rb * WPB + warp; item < count; item += nrb * WPB) {
-        const int env = P.reset_list[item];
-        Warp w;
-        w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = 0;
-        reset_in_place(P, io, env, w);
+        for (int item = rb * WPB + warp; item < count; item += nrb * WPB) {
+            const int env = P.reset_list[item];
+            Warp w;
+            w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = 0;
+            reset_in_place(P, io, env, w);
+        }
     }
 }
 
@@ -1347,9 +1355,10 @@ __global__ void mg_pack_terminal_kernel(int num_envs, const uint8_t *term, const
 
 // mg_step_host, delta mode: gather observation + element count of every env that changed in this step
 // (accepted elements and resets: exactly the two work lists of the step), one warp per entry.
-__global__ void mg_pack_changed_kernel(const __grid_constant__ Params P, int set, const float *obs, const int32_t *nel, int32_t *idx, float *pobs,
+__global__ void mg_pack_changed_kernel(const __grid_constant__ Params P, const float *obs, const int32_t *nel, int32_t *idx, float *pobs,
                                        int32_t *pnel, int32_t *count) {
-    const int cs = P.counters[2 * set + 0], cr = P.counters[2 * set + 1];
+    const int set = P.counters[CNT_CUR];
+    const int cs = min(P.counters[2 * set + 0], P.num_envs), cr = min(P.counters[2 * set + 1], P.num_envs);
     const int lane = threadIdx.x & 31;
     const int warps = gridDim.x * (blockDim.x >> 5);
     for (int it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < cs + cr; it += warps) {
@@ -1383,13 +1392,14 @@ __global__ void mg_replay_add_kernel(int num_envs, float *__restrict__ b_obs, fl
 // mg_step_host with PINNED caller buffers: the rows that changed are written straight into the caller's host arrays
 // through their device aliases (one 72-byte row per warp: coalesced PCIe writes, no staging copy, no host-side
 // scatter).  `obs_host` rows for the step's two work lists, `term_obs_host` rows for the envs that finished.
-__global__ void mg_scatter_rows_host_kernel(const __grid_constant__ Params P, int set, const float *obs, float *obs_host,
+__global__ void mg_scatter_rows_host_kernel(const __grid_constant__ Params P, const float *obs, float *obs_host,
                                             const uint8_t *term, const uint8_t *trunc, const float *term_obs, float *term_obs_host,
                                             int32_t *n_done_rows) {
     const int lane = threadIdx.x & 31;
     const int warps = gridDim.x * (blockDim.x >> 5), w0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (obs_host) {
-        const int cs = P.counters[2 * set + 0], cr = P.counters[2 * set + 1];
+        const int set = P.counters[CNT_CUR];
+    const int cs = min(P.counters[2 * set + 0], P.num_envs), cr = min(P.counters[2 * set + 1], P.num_envs);
         for (int it = w0; it < cs + cr; it += warps) {
             const int env = it < cs ? P.succ_list[it] : P.reset_list[it - cs];
             if (lane < MG_OBS_DIM) obs_host[(size_t)env * MG_OBS_DIM + lane] = obs[(size_t)env * MG_OBS_DIM + lane];

@@ -69,6 +69,10 @@ struct __align__(16) Pending {
     int64_t pad;
 };
 
+// counters[2 * set + {0, 1}] = sizes of the success / reset lists of counter set `set`; CNT_STEP = steps completed
+// (set of a step = CNT_STEP & 1 when its phase A starts); CNT_CUR = the set phase A of the current step used
+enum { CNT_STEP = 4, CNT_CUR = 5, CNT_N = 8 };
+
 constexpr int ANGLE_TAB_N = 62833;      // round(2 pi, 4) = 6.2832
 
 struct DomainScalars {
@@ -96,7 +100,7 @@ struct Params {
     Pending *pend;       // [num_envs]
     int *succ_list;      // [num_envs]
     int *reset_list;     // [num_envs]
-    int *counters;       // [2 sets][2]: {successes, resets}
+    int *counters;       // [CNT_N]: two sets of list sizes + the device-side step parity (see the enum above)
     // element log: quads as 4 vertex ids, coordinates of inserted vertices
     int32_t *elem;       // [num_envs][elem_cap][4]
     double2 *ins_xy;     // [num_envs][ins_cap]

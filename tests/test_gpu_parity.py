@@ -545,3 +545,47 @@ def test_device_replay_buffer_stores_what_sb3_would():
     assert np.array_equal(b.rewards.cpu().numpy()[:, 0], ref["rew"].reshape(-1)[idx])
     exp_done = ref["done"].reshape(-1)[idx].astype(np.float32) * (1 - ref["to"].reshape(-1)[idx].astype(np.float32))
     assert np.array_equal(b.dones.cpu().numpy()[:, 0], exp_done)
+
+
+def test_step_sequences_replay_from_a_cuda_graph():
+    """mg_step keeps no step state on the host (the work lists are emptied by the last block of the B/C launch), so
+    any number of steps -- here an odd one -- can be captured in a CUDA graph and replayed; the replayed rollout is
+    bit-identical to the eager one."""
+    import torch
+    doms, _ = load_domains()
+    N, K, R = 256, 3, 40
+    rng = np.random.default_rng(8)
+    acts = torch.from_numpy(rng.uniform(LOW_A, HIGH_A, size=(R * K, N, 3)).astype(np.float32)).cuda()
+    eager = _mk([doms["star"], doms["boundary16"]], N)
+    eager.reset()
+    exp_obs, exp_rew = [], []
+    for t in range(R * K):
+        r = eager.step(acts[t])
+        exp_obs.append(r.obs.clone()); exp_rew.append(r.reward.clone())
+    env = _mk([doms["star"], doms["boundary16"]], N)
+    env.reset()
+    a_buf = torch.zeros((K, N, 3), device=env.device)
+    obs_buf = torch.zeros((K, N, 18), device=env.device)
+    rew_buf = torch.zeros((K, N), dtype=torch.float64, device=env.device)
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        a_buf.copy_(acts[0:K])
+        for k in range(K):                       # warm-up outside the capture, then rewind
+            env.step(a_buf[k])
+    torch.cuda.synchronize()
+    env.reset()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for k in range(K):
+            r = env.step(a_buf[k])
+            obs_buf[k].copy_(r.obs); rew_buf[k].copy_(r.reward)
+    env.reset()
+    for rep in range(R):
+        a_buf.copy_(acts[rep * K:(rep + 1) * K])
+        g.replay()
+        for k in range(K):
+            t = rep * K + k
+            assert torch.equal(obs_buf[k], exp_obs[t]), f"obs differ at step {t}"
+            assert torch.equal(rew_buf[k], exp_rew[t]), f"reward differs at step {t}"
+    assert env.stats()["steps"] > 0
