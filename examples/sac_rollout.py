@@ -47,6 +47,8 @@ def main():
     ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")
     ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--stats-every", type=int, default=64)
+    ap.add_argument("--graph", action="store_true", help="capture policy + env step in one CUDA graph (mg_step is capturable)")
+    ap.add_argument("--tf32", action="store_true", help="TF32 matmuls for the policy (the env stays FP64)")
     args = ap.parse_args()
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", 1), ("RANK", 0), ("LOCAL_RANK", 0)))
     if world > 1:
@@ -58,12 +60,27 @@ def main():
     actor = Actor().to(dev)
     env = BatchedBoudaryEnv(None, num_envs=args.envs, device=dev, random_polygons=dict(min_verts=64, max_verts=512),
                             seed=2026, env_id_offset=rank * args.envs)
+    if args.tf32:
+        torch.backends.cuda.matmul.allow_tf32 = True
     obs = env.reset()
+    graph = None
+    if args.graph:
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            for _ in range(3):                               # warm-up outside the capture
+                env.step(actor(env.obs))
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            env.step(actor(env.obs))                         # env.obs is the env's persistent output buffer
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for t in range(args.steps):
-        r = env.step(actor(obs))
-        obs = r.obs
+        if graph is not None:
+            graph.replay()
+        else:
+            r = env.step(actor(obs))
+            obs = r.obs
         if (t + 1) % args.stats_every == 0:
             s = allreduce_stats(env.stats(reset=True), dev)
             if rank == 0 and s["episodes"]:
