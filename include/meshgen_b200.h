@@ -178,6 +178,15 @@ int mg_replay_add(mg_handle h, int64_t capacity_steps, int64_t slot, float *buf_
                   const float *new_obs, const double *rew, const uint8_t *term, const uint8_t *trunc,
                   const float *term_obs, void *stream);
 
+/* Snapshot / restore of the complete environment state (boundary rings, candidate keys, per-env scalars, element
+ * log, statistics, cached observations) -- the reference never checkpoints its env; with a
+ * batched env this is what makes long rollouts resumable and lets a caller branch from a state.  The blob is
+ * mg_snapshot_bytes(h) bytes of DEVICE memory owned by the caller; copies are enqueued on `stream`.  A blob can be
+ * loaded into any handle created with the same num_envs / max_verts and the same domains or generator settings. */
+int64_t mg_snapshot_bytes(mg_handle h);
+int mg_snapshot_save(mg_handle h, void *blob_dev, void *stream);
+int mg_snapshot_load(mg_handle h, const void *blob_dev, void *stream);
+
 /* Profiling aid (bench.py --phase-times): restrict mg_step to phase A (bit 0) and/or phases B+C
  * (bit 1).  With a partial mask the environments do not advance correctly; restore 3 afterwards. */
 int mg_set_phase_mask(mg_handle h, int mask);

@@ -184,6 +184,22 @@ class BatchedBoudaryEnv:
               self._h, "mg_step_host")
         return out
 
+    def snapshot(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Complete env state as one uint8 device tensor (mg_snapshot_save); ``.cpu()`` it to persist."""
+        nbytes = int(self._L.mg_snapshot_bytes(self._h))
+        if out is None:
+            out = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        if out.numel() != nbytes or out.device != self.device or out.dtype != torch.uint8:
+            raise ValueError(f"snapshot buffer must be a uint8 tensor of {nbytes} bytes on {self.device}")
+        check(self._L.mg_snapshot_save(self._h, C.c_void_p(out.data_ptr()), self._stream()), self._h, "mg_snapshot_save")
+        return out
+
+    def restore(self, blob: torch.Tensor) -> torch.Tensor:
+        """Load a ``snapshot()`` (same num_envs / max_verts / domains or generator); returns the current obs."""
+        blob = blob.to(device=self.device, dtype=torch.uint8).contiguous()
+        check(self._L.mg_snapshot_load(self._h, C.c_void_p(blob.data_ptr()), self._stream()), self._h, "mg_snapshot_load")
+        return self.reset(torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device))   # empty mask: reads the cached obs
+
     def set_host_delta(self, enabled: bool = True) -> None:
         """step_host ships only the observation rows that changed (see mg_set_host_delta); the caller
         must then pass the same, unmodified ``out`` buffers on every call."""

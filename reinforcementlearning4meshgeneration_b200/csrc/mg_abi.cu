@@ -252,6 +252,66 @@ int mg_replay_add(mg_handle h, int64_t capacity_steps, int64_t slot, float *buf_
     return MG_OK;
 }
 
+namespace {
+struct Piece { void *ptr; size_t bytes; };
+std::vector<Piece> snapshot_pieces(mg_handle h) {
+    Params &P = h->P;
+    const size_t N = (size_t)h->num_envs, NC = N * P.cap;
+    return {
+        {P.xy, NC * sizeof(double2)}, {P.key, NC * sizeof(double)}, {P.stamp, NC * sizeof(int32_t)}, {P.vid, NC * sizeof(int32_t)},
+        {P.st, N * sizeof(EnvState)}, {P.stats, STAT_SLOTS * sizeof(StatsAcc)}, {P.obs_cache, N * MG_OBS_DIM * sizeof(float)},
+        {P.elem, N * P.elem_cap * 4 * sizeof(int32_t)}, {P.ins_xy, N * P.ins_cap * sizeof(double2)},
+        {P.counters, CNT_N * sizeof(int)},
+    };
+}
+constexpr size_t SNAP_ALIGN = 256;
+size_t snap_round(size_t b) { return (b + SNAP_ALIGN - 1) / SNAP_ALIGN * SNAP_ALIGN; }
+}  // namespace
+
+int64_t mg_snapshot_bytes(mg_handle h) {
+    if (!h) return 0;
+    size_t total = SNAP_ALIGN;                       // header: num_envs, cap, was_reset
+    for (const Piece &p : snapshot_pieces(h)) total += snap_round(p.bytes);
+    return (int64_t)total;
+}
+
+int mg_snapshot_save(mg_handle h, void *blob_dev, void *stream) {
+    if (!h || !blob_dev) return fail(h, MG_ERR_ARG, "mg_snapshot_save: null pointer");
+    if (!h->was_reset) return fail(h, MG_ERR_STATE, "mg_snapshot_save: call mg_reset first");
+    MG_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int32_t hdr[4] = {0x4d475331, h->num_envs, h->P.cap, h->P.random_mode};
+    MG_CUDA(h, cudaMemcpyAsync(blob_dev, hdr, sizeof(hdr), cudaMemcpyHostToDevice, s));
+    MG_CUDA(h, cudaStreamSynchronize(s));            // hdr is a stack object
+    char *dst = (char *)blob_dev + SNAP_ALIGN;
+    for (const Piece &p : snapshot_pieces(h)) {
+        MG_CUDA(h, cudaMemcpyAsync(dst, p.ptr, p.bytes, cudaMemcpyDeviceToDevice, s));
+        dst += snap_round(p.bytes);
+    }
+    return MG_OK;
+}
+
+int mg_snapshot_load(mg_handle h, const void *blob_dev, void *stream) {
+    if (!h || !blob_dev) return fail(h, MG_ERR_ARG, "mg_snapshot_load: null pointer");
+    if (!h->ready) return fail(h, MG_ERR_STATE, "mg_snapshot_load: configure domains or the generator first");
+    MG_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int32_t hdr[4] = {0, 0, 0, 0};
+    MG_CUDA(h, cudaMemcpyAsync(hdr, blob_dev, sizeof(hdr), cudaMemcpyDeviceToHost, s));
+    MG_CUDA(h, cudaStreamSynchronize(s));
+    if (hdr[0] != 0x4d475331 || hdr[1] != h->num_envs || hdr[2] != h->P.cap || hdr[3] != h->P.random_mode)
+        return fail(h, MG_ERR_ARG, "mg_snapshot_load: blob does not match this handle (num_envs / max_verts / mode)");
+    const char *src = (const char *)blob_dev + SNAP_ALIGN;
+    for (const Piece &p : snapshot_pieces(h)) {
+        MG_CUDA(h, cudaMemcpyAsync(p.ptr, src, p.bytes, cudaMemcpyDeviceToDevice, s));
+        src += snap_round(p.bytes);
+    }
+    h->was_reset = true;
+    h->last_obs_host = nullptr;          // host-side delta copies are stale
+    h->last_nel_host = nullptr;
+    return MG_OK;
+}
+
 int mg_set_phase_mask(mg_handle h, int mask) {
     if (!h) return fail(h, MG_ERR_ARG, "mg_set_phase_mask: null handle");
     h->phase_mask = mask & 3;
