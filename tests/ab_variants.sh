@@ -1,4 +1,7 @@
-for v in base ns20 ns24 ns28 ns32; do
+# A/B of tuning variants in one gpurun call (profiling aid): build variant libraries into
+# reinforcementlearning4meshgeneration_b200/lib/variants/<name>.so (nvcc ... -DMG_...=...), then
+#   gpurun -- 'bash tests/ab_variants.sh <name> <name> ...'
+for v in base "$@"; do
   if [ $v = base ]; then unset MESHGEN_LIB; else export MESHGEN_LIB=$PWD/reinforcementlearning4meshgeneration_b200/lib/variants/$v.so; fi
   python bench.py --no-cpu-baseline --phase-times --steps 500 > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
   python - <<PY
