@@ -3,7 +3,7 @@
 
     python tests/soak.py [--per-domain 256] [--steps 1000] [--random-envs 8192] [--random-steps 400] [--seed 99]
 
-(a) every committed domain x `per-domain` envs x `steps` steps with auto-reset, device Philox actions with a
+(a) every committed domain (or, with --all-domains, all 58 usable domains of the reference) x `per-domain` envs x `steps` steps with auto-reset, device Philox actions with a
     share of dyadic action components (exact rounding ties of the new vertex, E:202-210);
 (b) `random-envs` random star polygons (BASELINE config 3 generator), first episode of each env.
 Every env is replayed through oracle/liboracle.so on all host threads; every mismatch is listed (not just the
@@ -79,6 +79,7 @@ def main():
     ap.add_argument("--random-steps", type=int, default=400)
     ap.add_argument("--seed", type=int, default=99)
     ap.add_argument("--dyadic", type=float, default=0.15)
+    ap.add_argument("--all-domains", action="store_true", help="all 58 usable reference domains (tests/golden/domains_all.npz)")
     ap.add_argument("--threads", type=int, default=os.cpu_count() or 8)
     ap.add_argument("--out", default=os.path.join(os.path.dirname(HERE), "gpurun_out", "soak_report.json"))
     args = ap.parse_args()
@@ -90,6 +91,10 @@ def main():
 
     if args.per_domain > 0:
         doms, areas = load_domains()
+        if args.all_domains:
+            z = np.load(os.path.join(HERE, "golden", "domains_all.npz"))
+            doms = {k: z[k] for k in z.files if not k.startswith("area__")}
+            areas = {k[6:]: float(z[k]) for k in z.files if k.startswith("area__")}
         names = sorted(doms)
         N = args.per_domain * len(names)
         env_domain = np.repeat(np.arange(len(names)), args.per_domain)
