@@ -986,8 +986,6 @@ __global__ void __launch_bounds__(WPB_A * 32, MG_MINB) mg_step_decide_kernel(con
     const int env = blockIdx.x * WPB_A + warp;
     if (env >= P.num_envs) return;
     SmemLayout L = carve_a(smem_raw, P.cap, warp);
-    // the ring copy does not depend on the env record: copy the whole `cap`-slot slab right away (entries
-    // past n are stale and never read) so that its DRAM round trip overlaps the record's
     init_mbar(L.mbar, lane);
     // the record first (kept L2-resident by its evict_last hint), then exactly n vertices: copying the whole
     // `cap` slab before the record arrives hides one L2 round trip but doubles the DRAM traffic of the phase for
