@@ -47,7 +47,6 @@ struct mg_env_s {
     float *m_pack_obs = nullptr, *m_chg_obs = nullptr;
     int64_t last_h2d = 0, last_d2h = 0;
     std::vector<int32_t> prev_done;
-    void *alias_host[2] = {nullptr, nullptr}, *alias_dev[2] = {nullptr, nullptr};   // obs_host, term_obs_host
     bool ready = false;       // domains or generator configured
     bool was_reset = false;
     int64_t launches = 0;
@@ -119,17 +118,15 @@ int upload_angle_table(mg_handle h) {
 }
 
 // Device alias of a caller's host buffer when it is pinned / registered (torch .pin_memory(), cudaHostAlloc,
-// cudaHostRegister); nullptr for pageable memory.  Cached per pointer: the query costs a few microseconds.
+// cudaHostRegister); nullptr for pageable memory.  Queried on every call (about a microsecond): a cached answer
+// would go stale if the caller freed the buffer and another allocation reused the address.
 template <class T>
-T *pinned_alias(mg_handle h, T *host, int slot) {
+T *pinned_alias(T *host) {
     if (!host) return nullptr;
-    if (h->alias_host[slot] == (void *)host) return (T *)h->alias_dev[slot];
     cudaPointerAttributes a{};
     void *dev = nullptr;
     if (cudaPointerGetAttributes(&a, host) == cudaSuccess && a.type == cudaMemoryTypeHost) dev = a.devicePointer;
     cudaGetLastError();
-    h->alias_host[slot] = (void *)host;
-    h->alias_dev[slot] = dev;
     return (T *)dev;
 }
 
@@ -448,8 +445,8 @@ int mg_step_host(mg_handle h, const float *act_host, float *obs_host, double *re
     // step and 0 from the next step on, whatever that step does)
     const bool delta_nel = false;
     // pinned caller buffers: changed rows go straight into them (no staging, no host-side scatter)
-    float *obs_alias = delta_obs ? pinned_alias(h, obs_host, 0) : nullptr;
-    float *tobs_alias = pinned_alias(h, term_obs_host, 1);
+    float *obs_alias = delta_obs ? pinned_alias(obs_host) : nullptr;
+    float *tobs_alias = pinned_alias(term_obs_host);
     const bool direct_obs = obs_alias != nullptr, direct_tobs = tobs_alias != nullptr;
     MG_CUDA(h, cudaMemsetAsync(h->d_pack_cnt, 0, 2 * sizeof(int32_t), s));
     if (direct_obs || direct_tobs) {
