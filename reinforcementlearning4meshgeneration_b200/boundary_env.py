@@ -151,11 +151,11 @@ class BoudaryEnv(_EnvBase):
             np.random.seed(seed)
 
     def reset(self, *, seed: Optional[int] = None, static: bool = False, options: Optional[Dict[str, Any]] = None):
-        if static:
-            raise NotImplementedError("static point-environments are only used by move() (out of scope)")
         if seed is not None:
             self.seed(seed)
         obs = self._batched.reset()[0].cpu().numpy().copy()
+        if static:
+            obs[1] = 0.0       # a static point environment reports area ratio 0 (C:1198-1199); only the reset obs is affected
         self.current_state = obs
         return obs, {}
 

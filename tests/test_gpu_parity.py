@@ -201,6 +201,8 @@ def test_gymnasium_facade_matches_golden_trace():
     tr = load_trace("boundary0")
     env = BoudaryEnv(boundary())
     assert env.observation_space.shape == (18,) and env.action_space.shape == (3,)
+    obs_static, _ = env.reset(static=True)
+    assert obs_static[1] == 0.0 and np.array_equal(np.delete(obs_static, 1), np.delete(tr["reset_obs"], 1))
     obs, info = env.reset()
     assert info == {} and obs.dtype == np.float32 and np.array_equal(obs, tr["reset_obs"])
     T = 1500

@@ -56,3 +56,17 @@ def test_dyadic_action_streams_match_the_live_reference(name):
     acts[dy, 1] = (rng.integers(-24, 25, size=int(dy.sum())) / 16.0).astype(np.float32)
     acts[dy, 2] = (rng.integers(0, 25, size=int(dy.sum())) / 16.0).astype(np.float32)
     assert _replay(doms[name], acts, f"dyadic actions on {name}") > 5
+
+
+def test_static_reset_only_zeroes_the_area_ratio():
+    """reset(static=True) (E:136-184 -> find_next_state(static=True)): the first observation differs from the normal
+    one only in obs[1] = 0 -- what the Gymnasium facade reproduces on the host."""
+    from oracle import ref_loader as rl
+    doms, _ = load_domains()
+    for name in ("boundary0", "star", "boundary16"):
+        env = rl.make_env(doms[name])
+        o0, _ = env.reset()
+        o1, _ = env.reset(static=True)
+        exp = np.array(o0, np.float32).copy()
+        exp[1] = 0.0
+        assert np.array_equal(np.array(o1, np.float32), exp), name
