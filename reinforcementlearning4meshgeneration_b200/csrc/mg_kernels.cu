@@ -1123,11 +1123,24 @@ __device__ __forceinline__ void apply_successes(const Params &P, const StepIO &i
         __syncwarp();
         stage_issue(L.ring, L.mbar, P.xy + off, P.cap, lane);      // whole slab, overlaps the record load
         EnvState S = P.st[env];
+        const Pending Q = P.pend[env];                              // independent of the record: same round trip
         Warp w;
         w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = S.n;
+#ifndef MG_NO_ROW_PREFETCH
+        // the key / stamp / id rows are only touched on successes, so they come from DRAM: pull them into L2 now,
+        // behind the ring copy, instead of paying the round trips in the compaction and arg-min loops
+        {
+            const char *kp = reinterpret_cast<const char *>(P.key + off), *sp = reinterpret_cast<const char *>(P.stamp + off),
+                       *vp = reinterpret_cast<const char *>(P.vid + off);
+            for (int b = lane * 128; b < S.n * 8; b += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(kp + b));
+            for (int b = lane * 128; b < S.n * 4; b += 32 * 128) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + b));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(vp + b));
+            }
+        }
+#endif
         stage_wait(L.mbar, phase);
         phase ^= 1u;
-        const Pending Q = P.pend[env];
         const int n = S.n, idx = S.ref_index;
         const bool new_vertex = Q.new_vertex != 0;
         const P2 newp = mk(Q.newx, Q.newy);
