@@ -418,8 +418,8 @@ int mg_step(mg_handle h, const float *act_dev, float *obs_dev, double *rew_dev, 
     io.term_obs_out = term_obs_dev; io.n_elem_out = n_elem_dev;
     cudaStream_t s = (cudaStream_t)stream;
     const int full = grid_for(h->num_envs);
-    const int gb = full < h->sm_count * 16 ? full : h->sm_count * 16;
-    const int gc = full < h->sm_count * 4 ? full : h->sm_count * 4;
+    const int gb = full < h->sm_count * (32 / WPB) ? full : h->sm_count * (32 / WPB);     // 32 item slots per SM
+    const int gc = full < h->sm_count * (8 / WPB) ? full : h->sm_count * (8 / WPB);
     if (h->phase_mask & 1) mg_step_decide_kernel<<<(h->num_envs + WPB_A - 1) / WPB_A, WPB_A * 32, h->smem_a, s>>>(h->P, io);
     if (h->phase_mask & 2) mg_step_apply_reset_kernel<<<gb + gc, WPB * 32, h->smem, s>>>(h->P, io, gb);
     h->launches += 2;

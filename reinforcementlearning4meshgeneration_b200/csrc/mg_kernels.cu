@@ -19,7 +19,7 @@
 namespace mg {
 
 #ifndef MG_WPB
-#define MG_WPB 2     // apply / reset / template kernels: 2 warps (= environments in flight) per block, tuned on B200
+#define MG_WPB 1     // apply / reset / template kernels: one item per block, so a slot frees the moment its item ends
 #endif
 constexpr int WPB = MG_WPB;     // warps (= environments) per block
 #ifndef MG_MINB
@@ -1309,7 +1309,7 @@ __device__ __forceinline__ void apply_successes(const Params &P, const StepIO &i
 // ---- phases B + C in one launch: the last apply_blocks blocks apply the accepted elements, the first
 // blocks reset the envs that phase A finished (truncations, E:382-384); the two sets are disjoint.
 #ifndef MG_MINB_APPLY
-#define MG_MINB_APPLY 12    // tuned on B200: 80 registers, 24 warps per SM for the latency-bound apply phase
+#define MG_MINB_APPLY 21    // one-warp blocks: shared memory allows 21 per SM (ring + scratch + 1 KB reserved), 96 registers
 #endif
 __global__ void __launch_bounds__(WPB * 32, MG_MINB_APPLY) mg_step_apply_reset_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io, int apply_blocks) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
