@@ -23,7 +23,7 @@ namespace mg {
 #endif
 constexpr int WPB = MG_WPB;     // warps (= environments) per block
 #ifndef MG_MINB
-#define MG_MINB 20    // phase A blocks per SM (96 registers, no spills beyond 24 bytes; 18 / 22 measured slower)
+#define MG_MINB 20    // phase A blocks per SM (96 registers, no spills; 18 / 22 measured slower)
 #endif
 #ifndef MG_UNROLL_OBS
 #define MG_UNROLL_OBS 1

@@ -73,23 +73,25 @@ __device__ __forceinline__ double pdist(P2 a, P2 b) {
     return sqrt(dx * dx + dy * dy);
 }
 
-// pdist(a, b) < r decided from the squared distance: sqrt is monotonic and correctly rounded, so outside a 1e-12
-// relative band around r^2 the comparison is already decided; the exact sqrt only runs inside the band.
+// pdist(a, b) < r decided from the squared distance: sqrt is monotonic and correctly rounded, so outside a narrow
+// relative band around r^2 the comparison is already decided; the exact sqrt only runs inside the band.  The band
+// edges are kept as floats rounded outwards (1e-6 relative: two registers instead of four across the O(n) scans).
 struct DistBound {
-    double r, lo, hi;
+    double r;
+    float lo, hi;
 };
 __device__ __forceinline__ DistBound dist_bound(double r) {
     DistBound b;
     b.r = r;
-    b.lo = (r * r) * (1.0 - 1e-12);
-    b.hi = (r * r) * (1.0 + 1e-12);
+    b.lo = __double2float_rd((r * r) * (1.0 - 1e-6));
+    b.hi = __double2float_ru((r * r) * (1.0 + 1e-6));
     return b;
 }
 __device__ __forceinline__ bool dist_less(P2 a, P2 b, const DistBound &B) {
     double dx = a.x - b.x, dy = a.y - b.y;
     double s = dx * dx + dy * dy;
-    if (s < B.lo) return true;
-    if (s > B.hi) return false;
+    if (s < (double)B.lo) return true;
+    if (s > (double)B.hi) return false;
     return sqrt(s) < B.r;
 }
 
