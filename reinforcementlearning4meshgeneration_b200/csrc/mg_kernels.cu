@@ -280,25 +280,30 @@ __device__ __noinline__ ObsOut compute_obs(const Warp w, const double2 *sc, int 
 #pragma unroll
     for (int k = 0; k < 6; k++) dl[k] = shfl_d(val, k);
     double base = py_round4(py_sum<6>(dl) / 6);
-    double theta = shfl_d(val, 8), a_r1 = shfl_d(val, 9), a_r2 = shfl_d(val, 10), a_l1 = shfl_d(val, 11),
-           a_l2 = shfl_d(val, 12), rot = shfl_d(val, 13);
-    double d_r = shfl_d(val, 16), d_l = shfl_d(val, 17), d_r1 = shfl_d(val, 18), d_r2 = shfl_d(val, 19),
-           d_l1 = shfl_d(val, 20), d_l2 = shfl_d(val, 21);
+    const double theta = shfl_d(val, 8), rot = shfl_d(val, 13);
     const double T = base * 4;
     const double clip = theta + PI / 2;
 
-    // r_points float32[9][2]; lane-uniform copies in registers
-    float r0[9], r1[9];
+    // r_points float32[9][2] (C:1193): every lane that owns a distance / angle turns it into its float32 entry
+    // itself (one division for the six distances instead of six lane-uniform ones) and the entry is shuffled to the
+    // lane that outputs it; only the three sector entries, which the scan below updates, stay lane-uniform.
+    //   lanes 16..21 = d_r, d_l, d_r1, d_r2, d_l1, d_l2    lanes 9..12 = a_r1, a_r2, a_l1, a_l2    lane 8 = theta
+    float tv = 0.0f;
+    if (lane >= 16 && lane < 22) tv = (float)((val * inv_radius) / base);
+    else if (lane == 8) tv = (float)val;
+    else if (lane == 9 || lane == 10) tv = (float)(val < PI ? val : fmax(val, 1.5 * PI) - 2 * PI);
+    else if (lane == 11 || lane == 12) tv = (float)fmin(val, clip);
+    // output lane L = 2 i (+1) holds r[i][0] (r[i][1]): source lanes of r[0], r[1], r[2], -, -, -, r[6], r[7], r[8]
+    const int src_of[18] = {16, 0, 18, 9, 19, 10, 0, 0, 0, 0, 0, 0, 21, 12, 20, 11, 17, 8};
+    int src = 0;
 #pragma unroll
-    for (int i = 0; i < 9; i++) { r0[i] = 1.0f; r1[i] = 1.0f; }
-    r0[0] = (float)((d_r * inv_radius) / base);  r1[0] = (float)area_ratio;
-    r0[8] = (float)((d_l * inv_radius) / base);  r1[8] = (float)theta;
-    r0[1] = (float)((d_r1 * inv_radius) / base); r1[1] = (float)(a_r1 < PI ? a_r1 : fmax(a_r1, 1.5 * PI) - 2 * PI);
-    r0[2] = (float)((d_r2 * inv_radius) / base); r1[2] = (float)(a_r2 < PI ? a_r2 : fmax(a_r2, 1.5 * PI) - 2 * PI);
-    r0[7] = (float)((d_l1 * inv_radius) / base); r1[7] = (float)fmin(a_l1, clip);
-    r0[6] = (float)((d_l2 * inv_radius) / base); r1[6] = (float)fmin(a_l2, clip);
+    for (int i = 0; i < 18; i++)
+        if (lane == i) src = src_of[i];
+    float out = __shfl_sync(FULL, tv, src);
+    if (lane == 1) out = (float)area_ratio;
+    float s0[3], s1[3];          // sector entries r[3..5]
 #pragma unroll
-    for (int j = 0; j < 3; j++) r1[3 + j] = (float)fmin((2 * j + 1) * theta / 6, clip);
+    for (int j = 0; j < 3; j++) { s0[j] = 1.0f; s1[j] = (float)fmin((2 * j + 1) * theta / 6, clip); }
 
     // p_s = ref + rotate((T cos(theta/2), T sin(theta/2)), rot)                      (C:154-168, C:1243)
     double s_h, c_h, s_r, c_r;
@@ -313,7 +318,7 @@ __device__ __noinline__ ObsOut compute_obs(const Warp w, const double2 *sc, int 
     // --- scan of the other n-1 vertices in the reference's order o = 1 .. n-1  (m = idx - o) --
     const double sector = theta / 3;
     unsigned long long bs0 = ~0ull, bs1 = ~0ull, bs2 = ~0ull;  // per sector: (float bits of cand, order)
-    double ma0 = 0, ma1 = 0, ma2 = 0;
+    float ma0 = 0, ma1 = 0, ma2 = 0;                           // (float)min(angle, clip) of the lane's best candidate
     double best_ray = CUDART_INF;                             // f64 value of the nearest bisector hit
     int best_ray_o = 0x7fffffff;
     // Two passes (like rebuild_candidates): pass 1 is a light filter that keeps the few vertices that can matter --
@@ -341,9 +346,10 @@ __device__ __noinline__ ObsOut compute_obs(const Warp w, const double2 *sc, int 
             float cand = (float)((d * inv_radius) / base);
             if (cand < 1.0f) {
                 unsigned long long keyv = ((unsigned long long)__float_as_uint(cand) << 32) | (unsigned)o;
-                if (k == 0) { if (keyv < bs0) { bs0 = keyv; ma0 = angle; } }
-                else if (k == 1) { if (keyv < bs1) { bs1 = keyv; ma1 = angle; } }
-                else { if (keyv < bs2) { bs2 = keyv; ma2 = angle; } }
+                const float fa = (float)fmin(angle, clip);
+                if (k == 0) { if (keyv < bs0) { bs0 = keyv; ma0 = fa; } }
+                else if (k == 1) { if (keyv < bs1) { bs1 = keyv; ma1 = fa; } }
+                else { if (keyv < bs2) { bs2 = keyv; ma2 = fa; } }
             }
         }
         // C:657-676 ll.intersection_vertex(seg) with ll = (ref, p_s), seg = (B[m], B[m+1])
@@ -424,13 +430,12 @@ __device__ __noinline__ ObsOut compute_obs(const Warp w, const double2 *sc, int 
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         const unsigned long long mine = k == 0 ? bs0 : (k == 1 ? bs1 : bs2);
-        const double mine_ang = k == 0 ? ma0 : (k == 1 ? ma1 : ma2);
+        const float mine_ang = k == 0 ? ma0 : (k == 1 ? ma1 : ma2);
         unsigned long long m = warp_min_u64(mine);
         if (m != ~0ull) {
             unsigned src = __ffs(__ballot_sync(FULL, mine == m)) - 1;
-            double ang = shfl_d(mine_ang, src);
-            r0[3 + k] = __uint_as_float((unsigned)(m >> 32));
-            r1[3 + k] = (float)fmin(ang, clip);
+            s0[k] = __uint_as_float((unsigned)(m >> 32));
+            s1[k] = __shfl_sync(FULL, mine_ang, src);
         }
     }
     // nearest bisector hit (C:1266-1287)
@@ -443,29 +448,28 @@ __device__ __noinline__ ObsOut compute_obs(const Warp w, const double2 *sc, int 
             unsigned oo = (kv == m && best_ray < 1.0) ? (unsigned)best_ray_o : 0xffffffffu;
             unsigned omin = __reduce_min_sync(FULL, oo);
             double sv2 = shfl_d(best_ray, __ffs(cand_mask) - 1);
-            if ((float)sv2 < r0[4]) {                         // float32 comparison (NEP 50)
+            if ((float)sv2 < s0[1]) {                         // float32 comparison with r[4][0] (NEP 50)
                 int mi = idx - (int)omin;                      // _i (may be negative like in Python)
-                double v2 = 0;
+                float v2 = 0.0f;
                 if (lane < 3) {
                     int jj = wrapn(lane - 1 + mi, n);
-                    v2 = pdist(ref, w.at(jj));
+                    v2 = (float)((pdist(ref, w.at(jj)) * inv_radius) / base);
                 } else if (lane >= 4 && lane < 7) {
                     int jj = wrapn(lane - 4 - 1 + mi, n);
-                    v2 = cw_angle(ref, w.at(jj), right_p);
+                    v2 = (float)cw_angle(ref, w.at(jj), right_p);
                 }
 #pragma unroll
                 for (int j = 0; j < 3; j++) {
-                    r0[3 + j] = (float)((shfl_d(v2, j) * inv_radius) / base);
-                    r1[3 + j] = (float)shfl_d(v2, 4 + j);
+                    s0[j] = __shfl_sync(FULL, v2, j);
+                    s1[j] = __shfl_sync(FULL, v2, 4 + j);
                 }
             }
         }
     }
-    float out = 0.0f;
 #pragma unroll
-    for (int i = 0; i < 9; i++) {
-        if (lane == 2 * i) out = r0[i];
-        if (lane == 2 * i + 1) out = r1[i];
+    for (int j = 0; j < 3; j++) {
+        if (lane == 6 + 2 * j) out = s0[j];
+        if (lane == 7 + 2 * j) out = s1[j];
     }
     ObsOut R;
     R.base = base;
