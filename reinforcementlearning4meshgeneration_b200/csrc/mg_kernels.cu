@@ -1126,8 +1126,27 @@ __device__ __forceinline__ void apply_successes(const Params &P, const StepIO &i
         const size_t off = (size_t)env * P.cap;
         __syncwarp();
         stage_issue(L.ring, L.mbar, P.xy + off, P.cap, lane);      // whole slab, overlaps the record load
-        EnvState S = P.st[env];
+        // The 128-byte record is parked in this warp's shared scratch (words 128..159: compute_obs and the candidate
+        // queue use words 0..63) and only the fields this phase works on are kept in registers; everything else
+        // comes back from shared memory for the tail (carried in registers it was spilled to local memory).
+        int4 *rec_stash = reinterpret_cast<int4 *>(L.queue + 128);
+        {
+            const int4 *g = reinterpret_cast<const int4 *>(P.st + env);
+            if (lane < 8) rec_stash[lane] = g[lane];
+        }
         const Pending Q = P.pend[env];                              // independent of the record: same round trip
+        __syncwarp();
+        struct { int32_t n, ref_index, n_elements; double current_area; } S;     // what stays in registers
+        {
+            const int4 c0 = rec_stash[0];
+            S.n = c0.x; S.ref_index = c0.y; S.n_elements = c0.z;
+            S.current_area = reinterpret_cast<const double2 *>(rec_stash)[2].y;
+        }
+        // the rest is read from the stash where it is used: EnvState = {n, ref_index, n_elements, n0 | base_length,
+        // failed_num, ep_len | ep_return, current_area | original_area, area_min | area_crit, next_vid, stamp_ctr | ...}
+        auto st_i = [&](int word) { return reinterpret_cast<const int32_t *>(rec_stash)[word]; };
+        auto st_d = [&](int dword) { return reinterpret_cast<const double *>(rec_stash)[dword]; };
+        constexpr int W_N0 = 3, W_NEXT_VID = 18, W_STAMP_CTR = 19, D_ORIGINAL_AREA = 6, D_AREA_MIN = 7, D_AREA_CRIT = 8;
         Warp w;
         w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = S.n;
 #ifndef MG_NO_ROW_PREFETCH
@@ -1174,20 +1193,20 @@ __device__ __forceinline__ void apply_successes(const Params &P, const StepIO &i
         int nb[4];          // the four neighbours whose candidate keys are re-evaluated, in order
         int t0 = 0, t1 = 0; // surviving quad vertices (no-new-vertex case), new indices
         int elem_ids[4];
+        const int next_vid0 = st_i(W_NEXT_VID);
 #pragma unroll
-        for (int k = 0; k < 4; k++) elem_ids[k] = qi[k] < 0 ? S.next_vid : P.vid[off + qi[k]];
+        for (int k = 0; k < 4; k++) elem_ids[k] = qi[k] < 0 ? next_vid0 : P.vid[off + qi[k]];
         __syncwarp();
         if (new_vertex) {
             // insert P at index(ref) and remove ref: the slot is replaced in place
             if (lane == 0) {
                 w.ring[idx] = make_double2(newp.x, newp.y);
                 P.xy[off + idx] = make_double2(newp.x, newp.y);
-                P.vid[off + idx] = S.next_vid;
+                P.vid[off + idx] = next_vid0;
                 P.key[off + idx] = CUDART_INF;
-                if (P.ins_xy && S.next_vid - S.n0 < P.ins_cap)
-                    P.ins_xy[(size_t)env * P.ins_cap + (S.next_vid - S.n0)] = make_double2(newp.x, newp.y);
+                const int ins = next_vid0 - st_i(W_N0);
+                if (P.ins_xy && ins < P.ins_cap) P.ins_xy[(size_t)env * P.ins_cap + ins] = make_double2(newp.x, newp.y);
             }
-            S.next_vid++;
             __syncwarp();
             nb[0] = ip1; nb[1] = im1; nb[2] = wrapn(idx + 2, n); nb[3] = wrapn(idx - 2, n);
         } else {
@@ -1244,10 +1263,9 @@ __device__ __forceinline__ void apply_successes(const Params &P, const StepIO &i
             for (int k2 = k + 1; k2 < 4; k2++) later_dup |= nb[k2] == nb[k];
             if (lane == k && !later_dup) {
                 P.key[off + nb[k]] = kv;
-                P.stamp[off + nb[k]] = S.stamp_ctr - 1 - k;
+                P.stamp[off + nb[k]] = st_i(W_STAMP_CTR) - 1 - k;
             }
         }
-        S.stamp_ctr -= 4;
         // ---- element log ----------------------------------------------------------------------
         if (P.elem && lane < 4 && S.n_elements < P.elem_cap)
             P.elem[((size_t)env * P.elem_cap + S.n_elements) * 4 + lane] =
@@ -1280,7 +1298,8 @@ __device__ __forceinline__ void apply_successes(const Params &P, const StepIO &i
         }
         double quality = e_reward + 1 * (b_reward - 1);              // M:1754-1766
         // ---- speed penalty (E:590-607) ------------------------------------------------------
-        double min_area = S.area_min * S.area_min, crit = S.area_crit * S.area_crit, pen;
+        const double a_min = st_d(D_AREA_MIN), a_crit = st_d(D_AREA_CRIT);
+        double min_area = a_min * a_min, crit = a_crit * a_crit, pen;
         if (min_area <= mesh_area && mesh_area < crit) pen = (mesh_area - crit) / (crit - min_area);
         else if (mesh_area < min_area) pen = -1;
         else pen = 0;
@@ -1298,12 +1317,32 @@ __device__ __forceinline__ void apply_successes(const Params &P, const StepIO &i
         bool obs_none = false;
         __syncwarp();
         S.ref_index = find_reference_index(w, P.key + off, P.stamp + off);
+        double new_base = 0;
         if (S.ref_index >= 0) {
-            const ObsOut R = compute_obs(w, P.sc_full, S.ref_index, S.current_area / S.original_area);
-            obs = R.obs; S.base_length = R.base;
+            const ObsOut R = compute_obs(w, P.sc_full, S.ref_index, S.current_area / st_d(D_ORIGINAL_AREA));
+            obs = R.obs; new_base = R.base;
         } else obs_none = true;
-        S.failed_num = 0;
-        if (finish_step(P, io, env, lane, S, n, reward, done, false, true, obs_none, obs)) {
+        // back to the full record for the tail of the step
+        EnvState F;
+        {
+            const int4 c1 = rec_stash[1], c5 = rec_stash[5];
+            const double2 c2 = reinterpret_cast<const double2 *>(rec_stash)[2];
+            const int4 c4 = rec_stash[4];
+            const double2 c3 = reinterpret_cast<const double2 *>(rec_stash)[3];
+            F.n0 = st_i(W_N0);
+            F.ep_len = c1.w; F.ep_return = c2.x;
+            F.original_area = c3.x; F.area_min = c3.y; F.area_crit = __hiloint2double(c4.y, c4.x);
+            F.next_vid = c4.z + (new_vertex ? 1 : 0); F.stamp_ctr = c4.w - 4;
+            F.domain = c5.x; F.episode = c5.y;
+            F.base_length = __hiloint2double(c1.y, c1.x);
+#pragma unroll
+            for (int k = 0; k < 5; k++) F.pad[k] = 0;
+        }
+        F.n = S.n; F.ref_index = S.ref_index; F.n_elements = S.n_elements;
+        F.current_area = S.current_area;
+        if (S.ref_index >= 0) F.base_length = new_base;
+        F.failed_num = 0;
+        if (finish_step(P, io, env, lane, F, n, reward, done, false, true, obs_none, obs)) {
             __syncwarp();                        // lane 0's record store is visible to the warp
             reset_in_place(P, io, env, w);
         }
