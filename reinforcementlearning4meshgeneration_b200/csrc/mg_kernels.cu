@@ -1196,6 +1196,24 @@ __device__ __forceinline__ void apply_successes(const Params &P, const StepIO &i
         const int next_vid0 = st_i(W_NEXT_VID);
 #pragma unroll
         for (int k = 0; k < 4; k++) elem_ids[k] = qi[k] < 0 ? next_vid0 : P.vid[off + qi[k]];
+        // ---- element log, area and robust quality first: they only need the quad (old ring + new vertex), and doing
+        // them here ends the live ranges of the quad, its corner angles and the vertex ids before the boundary update
+        if (P.elem && lane < 4 && S.n_elements < P.elem_cap)
+            P.elem[((size_t)env * P.elem_cap + S.n_elements) * 4 + lane] =
+                lane == 0 ? elem_ids[0] : (lane == 1 ? elem_ids[1] : (lane == 2 ? elem_ids[2] : elem_ids[3]));
+        S.n_elements++;
+        // ---- area (C:943-958), robust quality (C:881-892) -----------------------------------
+        double e0 = pdist(m[0], m[3]), e1 = pdist(m[1], m[0]), e2 = pdist(m[2], m[1]), e3 = pdist(m[3], m[2]);
+        double sn0, sn2, cs_unused;
+        sincos_quantised(P.sc_full, corner[0], false, sn0, cs_unused);
+        sincos_quantised(P.sc_full, corner[2], false, sn2, cs_unused);
+        double mesh_area = 0.5 * e0 * e1 * sn0 + 0.5 * e2 * e3 * sn2;
+        S.current_area -= mesh_area;
+        double mn = fmin(fmin(e0, e1), fmin(e2, e3));
+        double q1 = sqrt(2.0) * mn / fmax(pdist(m[0], m[2]), pdist(m[1], m[3]));
+        double amin = fmin(fmin(corner[0], corner[1]), fmin(corner[2], corner[3]));
+        double amax = fmax(fmax(corner[0], corner[1]), fmax(corner[2], corner[3]));
+        double e_reward = sqrt(q1 * (amin / amax));
         __syncwarp();
         if (new_vertex) {
             // insert P at index(ref) and remove ref: the slot is replaced in place
@@ -1266,23 +1284,6 @@ __device__ __forceinline__ void apply_successes(const Params &P, const StepIO &i
                 P.stamp[off + nb[k]] = st_i(W_STAMP_CTR) - 1 - k;
             }
         }
-        // ---- element log ----------------------------------------------------------------------
-        if (P.elem && lane < 4 && S.n_elements < P.elem_cap)
-            P.elem[((size_t)env * P.elem_cap + S.n_elements) * 4 + lane] =
-                lane == 0 ? elem_ids[0] : (lane == 1 ? elem_ids[1] : (lane == 2 ? elem_ids[2] : elem_ids[3]));
-        S.n_elements++;
-        // ---- area (C:943-958), robust quality (C:881-892) -----------------------------------
-        double e0 = pdist(m[0], m[3]), e1 = pdist(m[1], m[0]), e2 = pdist(m[2], m[1]), e3 = pdist(m[3], m[2]);
-        double sn0, sn2, cs_unused;
-        sincos_quantised(P.sc_full, corner[0], false, sn0, cs_unused);
-        sincos_quantised(P.sc_full, corner[2], false, sn2, cs_unused);
-        double mesh_area = 0.5 * e0 * e1 * sn0 + 0.5 * e2 * e3 * sn2;
-        S.current_area -= mesh_area;
-        double mn = fmin(fmin(e0, e1), fmin(e2, e3));
-        double q1 = sqrt(2.0) * mn / fmax(pdist(m[0], m[2]), pdist(m[1], m[3]));
-        double amin = fmin(fmin(corner[0], corner[1]), fmin(corner[2], corner[3]));
-        double amax = fmax(fmax(corner[0], corner[1]), fmax(corner[2], corner[3]));
-        double e_reward = sqrt(q1 * (amin / amax));
         // ---- boundary quality (M:410-452) ---------------------------------------------------
         double b_reward;
         __syncwarp();
