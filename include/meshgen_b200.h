@@ -159,6 +159,13 @@ int mg_get_state(mg_handle h, int env, mg_state_view *view);
 int mg_get_elements(mg_handle h, int env, int32_t *quads_host, int max_elements, int32_t *n_elements_out,
                     double *vertex_xy_host, int max_vertices, int32_t *n_vertices_out);
 
+/* Capacity of the per-env element log and inserted-vertex log (what mg_get_elements can return; the element COUNT is
+ * always exact).  Default: 8 x max_verts each -- the reference's evaluation runs report up to ~5 x n0 elements per
+ * episode (rl/baselines/evaluation.txt).  mg_set_log_capacity reallocates the logs (call it before mg_reset;
+ * contents are discarded). */
+int mg_set_log_capacity(mg_handle h, int max_elements_per_env, int max_inserted_per_env);
+int mg_log_capacity(mg_handle h, int32_t *max_elements_per_env, int32_t *max_inserted_per_env);
+
 /* Sum the per-env episode counters on the device, copy them to *out (synchronises);
  * reset != 0 zeroes the counters afterwards. */
 int mg_stats(mg_handle h, mg_episode_stats *out, int reset);

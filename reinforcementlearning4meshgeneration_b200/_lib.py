@@ -21,7 +21,7 @@ NVCC_FLAGS = [
 
 SYMBOLS = [
     "mg_create", "mg_set_domains", "mg_set_random", "mg_set_auto_reset", "mg_reset", "mg_step", "mg_step_host", "mg_set_host_delta", "mg_last_host_bytes", "mg_sample_actions",
-    "mg_get_state", "mg_get_elements", "mg_stats", "mg_replay_add", "mg_snapshot_bytes", "mg_snapshot_save", "mg_snapshot_load", "mg_set_phase_mask", "mg_num_envs", "mg_max_verts", "mg_launch_count", "mg_destroy",
+    "mg_get_state", "mg_get_elements", "mg_stats", "mg_set_log_capacity", "mg_log_capacity", "mg_replay_add", "mg_snapshot_bytes", "mg_snapshot_save", "mg_snapshot_load", "mg_set_phase_mask", "mg_num_envs", "mg_max_verts", "mg_launch_count", "mg_destroy",
     "mg_last_error", "mg_version",
 ]
 
@@ -88,6 +88,8 @@ def load():
     L.mg_get_state.argtypes = [vp, i32, C.POINTER(StateView)]
     L.mg_get_elements.argtypes = [vp, i32, vp, i32, C.POINTER(C.c_int32), vp, i32, C.POINTER(C.c_int32)]
     L.mg_stats.argtypes = [vp, C.POINTER(EpisodeStats), i32]
+    L.mg_set_log_capacity.argtypes = [vp, i32, i32]
+    L.mg_log_capacity.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.mg_replay_add.argtypes = [vp, i64, i64] + [vp] * 14
     L.mg_snapshot_bytes.argtypes = [vp]
     L.mg_snapshot_bytes.restype = i64

@@ -239,13 +239,20 @@ class BatchedBoudaryEnv:
 
     def get_elements(self, env: int):
         """(quads[m,4] int32 vertex ids, vertex_xy[nv,2]) of env's current episode (generated_meshes)."""
-        cap = self.max_verts + 2
-        quads = np.zeros((cap, 4), np.int32)
-        vxy = np.zeros((2 * cap, 2), np.float64)
+        ce, ci = C.c_int32(), C.c_int32()
+        check(self._L.mg_log_capacity(self._h, C.byref(ce), C.byref(ci)), self._h, "mg_log_capacity")
+        cap_e, cap_v = ce.value, self.max_verts + 2 + ci.value
+        quads = np.zeros((cap_e, 4), np.int32)
+        vxy = np.zeros((cap_v, 2), np.float64)
         ne, nv = C.c_int32(), C.c_int32()
-        check(self._L.mg_get_elements(self._h, int(env), quads.ctypes.data, cap, C.byref(ne), vxy.ctypes.data, 2 * cap,
+        check(self._L.mg_get_elements(self._h, int(env), quads.ctypes.data, cap_e, C.byref(ne), vxy.ctypes.data, cap_v,
                                       C.byref(nv)), self._h, "mg_get_elements")
-        return quads[:min(ne.value, cap)].copy(), vxy[:min(nv.value, 2 * cap)].copy(), ne.value
+        return quads[:min(ne.value, cap_e)].copy(), vxy[:min(nv.value, cap_v)].copy(), ne.value
+
+    def set_log_capacity(self, max_elements: int, max_inserted: Optional[int] = None) -> None:
+        """Capacity of the per-env element / inserted-vertex logs (default 8 x max_verts each); reset afterwards."""
+        check(self._L.mg_set_log_capacity(self._h, int(max_elements), int(max_inserted or max_elements)), self._h,
+              "mg_set_log_capacity")
 
     def stats(self, reset: bool = False) -> dict:
         s = EpisodeStats()

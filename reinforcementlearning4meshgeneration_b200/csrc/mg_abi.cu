@@ -161,8 +161,8 @@ int mg_create(mg_handle *out, int device, int num_envs, int max_verts) {
     P.auto_reset = 1;
     P.cap = (max_verts + 1) & ~1;
     const size_t NC = (size_t)num_envs * P.cap;
-    P.elem_cap = P.cap;           // an episode creates at most ~n0/2 + inserted elements; capped
-    P.ins_cap = P.cap;
+    P.elem_cap = 8 * P.cap;       // element count per episode scales with the domain's area, not its boundary: the
+    P.ins_cap = 8 * P.cap;        // reference's evaluation runs report up to ~5 n0 elements (mg_set_log_capacity to change)
     int rc = MG_OK;
     auto A = [&](cudaError_t er, const char *what) {
         if (er != cudaSuccess && rc == MG_OK) rc = fail(h, MG_ERR_CUDA, std::string("cudaMalloc ") + what + ": " + cudaGetErrorString(er));
@@ -585,6 +585,27 @@ int mg_get_elements(mg_handle h, int env, int32_t *quads_host, int max_elements,
             MG_CUDA(h, cudaMemcpy(vertex_xy_host + 2 * (size_t)S.n0, h->P.ins_xy + (size_t)env * h->P.ins_cap, sizeof(double2) * ni,
                                   cudaMemcpyDeviceToHost));
     }
+    return MG_OK;
+}
+
+int mg_set_log_capacity(mg_handle h, int max_elements_per_env, int max_inserted_per_env) {
+    if (!h || max_elements_per_env < 1 || max_inserted_per_env < 1) return fail(h, MG_ERR_ARG, "mg_set_log_capacity: bad argument");
+    MG_CUDA(h, cudaSetDevice(h->device));
+    MG_CUDA(h, cudaDeviceSynchronize());
+    Params &P = h->P;
+    cudaFree(P.elem); cudaFree(P.ins_xy);
+    P.elem = nullptr; P.ins_xy = nullptr;
+    P.elem_cap = max_elements_per_env; P.ins_cap = max_inserted_per_env;
+    MG_CUDA(h, dalloc(&P.elem, (size_t)h->num_envs * P.elem_cap * 4));
+    MG_CUDA(h, dalloc(&P.ins_xy, (size_t)h->num_envs * P.ins_cap));
+    h->was_reset = false;            // logs were discarded: the caller resets before stepping again
+    return MG_OK;
+}
+
+int mg_log_capacity(mg_handle h, int32_t *max_elements_per_env, int32_t *max_inserted_per_env) {
+    if (!h) return fail(h, MG_ERR_ARG, "mg_log_capacity: null handle");
+    if (max_elements_per_env) *max_elements_per_env = h->P.elem_cap;
+    if (max_inserted_per_env) *max_inserted_per_env = h->P.ins_cap;
     return MG_OK;
 }
 

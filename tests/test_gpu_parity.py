@@ -629,3 +629,40 @@ def test_snapshot_restore_reproduces_the_rollout():
     c = _mk(None, N // 2, **kw)
     with pytest.raises(Exception):
         c.restore(blob)
+
+
+def test_batched_evaluation_loop_against_the_oracle(tmp_path):
+    """evaluation.evaluate_models (the batched form of eval_loop.py:48-113): one env per domain, one episode each,
+    summary {completed, n_elements} equal to single-env oracle rollouts under the same action streams; meshes saved."""
+    import json
+    import torch
+    from oracle.c_oracle import OracleEnv
+    from reinforcementlearning4meshgeneration_b200.evaluation import evaluate_models
+    doms, areas = load_domains()
+    names = ["boundary0", "star", "half_wheel"]
+    T = 3000
+    streams = np.stack([action_stream(700 + k, T) for k in range(len(names))], axis=1)      # [T, N, 3]
+    t = {"i": 0}
+
+    def predict(obs):
+        a = torch.from_numpy(streams[t["i"]]).to(obs.device)
+        t["i"] += 1
+        return a
+
+    out = evaluate_models(lambda: _mk([doms[k] for k in names], len(names), env_domain=np.arange(len(names)), auto_reset=False),
+                          {"m0": predict}, max_steps=T, save_summary=str(tmp_path / "s.json"), mesh_dir=str(tmp_path / "meshes"),
+                          domain_names=names)
+    exp_c, exp_n = [], []
+    for k, name in enumerate(names):
+        o = OracleEnv(doms[name], original_area=areas[name])
+        te = tr = False
+        for i in range(T):
+            _, _, te, tr, _ = o.step(streams[i, k])
+            if te or tr:
+                break
+        assert te or tr, "the action stream should finish the episode"
+        exp_c.append(int(te)); exp_n.append(o.n_elements)
+        d = json.load(open(tmp_path / "meshes" / f"m0_{name}.json"))
+        assert len(d["elements"]) == o.n_elements
+    assert out == {"m0": {"completed": exp_c, "n_elements": exp_n}}
+    assert json.load(open(tmp_path / "s.json")) == out
