@@ -1,16 +1,23 @@
 #!/usr/bin/env python
 """Benchmark of the batched BoudaryEnv hot path (env-steps/s, whole job).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c1] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c4|c2|c1] [--impl reference]
 
 One "step" = one pass of the hot path over the whole batch: the synthetic policy kernel
-(uniform actions in the action box) + the step kernel (every env advances
-one transition, auto-reset included).  Workloads (BASELINE.json configs):
+(uniform actions in the action box) + mg_step (screen, decide, update and observe kernels:
+every env advances one transition, auto-reset included) + every 64 steps the all-reduce of the episode statistics.
+Workloads (BASELINE.json configs):
   c3 (default): random star polygons, 64..512 vertices, 65536 envs per GPU, in-kernel auto-reset
+  c4          : the same with 131072 envs per GPU (1 M envs on 8 GPUs)
   c2          : paper domains d1/d2/d3 (120/196/272 vertices), 4096 envs per GPU
   c1          : BoudaryEnv(boundary()), 30 vertices, 4096 envs per GPU
-Multi-GPU: launched by torchrun, one rank per GPU, envs sharded by global env id (weak scaling),
-the only collective is the all-reduce of the 10-element episode-statistics vector.
+Multi-GPU: launched by torchrun, one rank per GPU, envs sharded by global env id (weak scaling); the only
+collective is the all-reduce of the 12-element episode-statistics vector, enqueued every 64 steps inside the
+timed loop (NCCL, no host synchronisation).
+`--impl reference` times the reference's CPU implementation of the same path on the host cores: the C port of
+the reference env (oracle/, kind "port") and, when the reference tree itself is importable (this build
+container; it is not on the GPU box), the reference's own Python env on os.cpu_count() processes.  That arm never
+imports the product package.
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -30,9 +37,26 @@ sys.path.insert(0, ROOT)
 
 METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
-ENVS_PER_GPU = {"c3": 65536, "c2": 4096, "c1": 4096}
+ENVS_PER_GPU = {"c3": 65536, "c4": 131072, "c2": 4096, "c1": 4096}
 GEN = dict(min_verts=64, max_verts=512)
 SEED = 2026
+STATS_INTERVAL = 64
+WORKLOAD_TEXT = {
+    "c3": "c3: random star polygons 64..512 vertices, in-kernel auto-reset",
+    "c4": "c4: random star polygons 64..512 vertices, in-kernel auto-reset, 131072 envs per GPU",
+    "c2": "c2: paper domains d1/d2/d3 (boundary16/boundary15/test1)",
+    "c1": "c1: BoudaryEnv(boundary()) 30 vertices",
+}
+
+
+def make_config(args, world):
+    """The workload description both arms print (so that the driver can check they ran the same thing)."""
+    N = args.envs or ENVS_PER_GPU[args.workload]
+    state_bytes = N * (GEN["max_verts"] if args.workload in ("c3", "c4") else 272) * 32
+    return {"workload": WORKLOAD_TEXT[args.workload], "envs_per_gpu": N, "global_envs": N * world,
+            "policy": "uniform actions in the action box (Philox)", "parallelism": f"env-sharded x{world}",
+            "burn_in_steps": args.burn_in, "stats_allreduce_every": STATS_INTERVAL,
+            "l2": "L2 flushed between timed steps" if state_bytes < 256 * 1024 * 1024 else f"state {state_bytes >> 20} MiB > L2"}
 
 
 def load_peaks():
@@ -108,8 +132,24 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------
-# CPU arm: the oracle port (C restatement of the reference env) on the host cores
+# CPU arm: the reference env on the host cores (C port always; the Python reference when importable)
 # --------------------------------------------------------------------------------------------
+def sample_polygons(workload):
+    """Polygons for the CPU arm: the fixed domains, or (c3 / c4) the committed sample of the device generator's
+    polygons, tests/golden/c3_polys.npz (recorded once by oracle/record_c3_polys.py: seed 2026, global env ids
+    0..63, first episode).  Never touches the product package."""
+    doms = workload_domains(workload)
+    if doms is not None:
+        return doms, f"{workload}: {len(doms)} domain(s)"
+    p = os.path.join(ROOT, "tests", "golden", "c3_polys.npz")
+    if os.path.exists(p):
+        z = np.load(p)
+        polys = [z[k] for k in sorted(z.files, key=lambda s: int(s[1:]))]
+        return polys, f"{workload}: {len(polys)} polygons of the device generator (seed {SEED}, tests/golden/c3_polys.npz)"
+    d = golden_domains()
+    return [d["boundary16"], d["boundary15"], d["test1"], d["test3"]], f"{workload} stand-in: d1/d2/d3/test3 (fixture missing)"
+
+
 def cpu_port_throughput(polys, seconds_budget=12.0, threads=None):
     """Steps/s of oracle/liboracle.so (kind "port") with one env per host thread (ctypes releases
     the GIL), uniform random actions, auto-reset, on the given sample of polygons."""
@@ -136,54 +176,89 @@ def cpu_port_throughput(polys, seconds_budget=12.0, threads=None):
     return sum(done) / dt, threads, steps, dt
 
 
-def sample_polygons(workload, n_sample=32):
-    """Polygons for the CPU arm: the fixed domains, or a sample of generated random polygons copied
-    from the device generator (c3) -- falls back to the committed domains when no GPU is present."""
-    doms = workload_domains(workload)
-    if doms is not None:
-        return doms, f"{workload}: {len(doms)} domain(s)"
-    try:
-        import torch
-        if torch.cuda.is_available():
-            from reinforcementlearning4meshgeneration_b200 import BatchedBoudaryEnv
-            env = BatchedBoudaryEnv(None, num_envs=n_sample, random_polygons=GEN, seed=SEED)
-            env.reset()
-            polys = [env.get_state(e)["xy"] for e in range(n_sample)]
-            env.close()
-            return polys, f"c3: {n_sample} random polygons copied from the device generator (seed {SEED})"
-    except Exception:
-        pass
-    d = golden_domains()
-    return [d["boundary16"], d["boundary15"], d["test1"], d["test3"]], "c3 stand-in: d1/d2/d3/test3 (no GPU for the generator)"
+def reference_root():
+    """Where the reference's own Python tree is importable from, or None (it is not on the GPU box)."""
+    for r in (os.environ.get("MESHGEN_REFERENCE_ROOT"), os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if r and os.path.isfile(os.path.join(r, "v2", "src", "mesh_rl", "envs", "boundary_env.py")):
+            return r
+    return None
+
+
+def _python_ref_worker(args):
+    """One worker process: the unmodified reference BoudaryEnv (v2) on one polygon, uniform random float32
+    actions, reset on done, for `seconds` of wall time after a short warm-up."""
+    root, xy, seed, seconds = args
+    os.environ["MESHGEN_REFERENCE_ROOT"] = root
+    sys.path.insert(0, ROOT)
+    from oracle import ref_loader
+    env = ref_loader.make_env(np.asarray(xy))
+    env.reset()
+    rng = np.random.default_rng(seed)
+    lo, hi = ref_loader.LOW, ref_loader.HIGH
+
+    def run(budget):
+        n = 0
+        t_end = time.perf_counter() + budget
+        while time.perf_counter() < t_end:
+            for _ in range(20):
+                obs, _, te, tr, _ = env.step(rng.uniform(lo, hi).astype(np.float32))
+                n += 1
+                if te or tr or obs is None:
+                    env.reset()
+        return n
+
+    run(min(1.0, seconds / 5))
+    t0 = time.perf_counter()
+    n = run(seconds)
+    return n, time.perf_counter() - t0
+
+
+def python_reference_throughput(polys, seconds=10.0, procs=None):
+    """Steps/s of the reference's own Python env on `procs` worker processes."""
+    import multiprocessing as mp
+    root = reference_root()
+    if root is None:
+        return None
+    procs = procs or os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        res = pool.map(_python_ref_worker, [(root, np.asarray(polys[i % len(polys)]), 1000 + i, seconds) for i in range(procs)])
+    rate = sum(n / dt for n, dt in res)
+    return {"value": rate, "unit": UNIT, "cores": procs, "kind": "reference",
+            "sample": f"unmodified reference v2 BoudaryEnv under the stub loader (oracle/ref_loader.py), {procs} processes x "
+                      f"{seconds:.0f} s, {sum(n for n, _ in res)} steps", "per_core": rate / procs}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path.  The reference is pure
-    Python and is not present on the GPU box, so this arm times its C restatement (oracle port)
-    on all host cores; each step of this arm is one bounded sample of the same workload."""
+    """--impl reference: the reference's CPU implementation of the path on all host cores; each step of this arm is
+    one bounded sample of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     polys, sample = sample_polygons(args.workload)
     vals = []
-    total_steps = 0
     t_all = time.perf_counter()
     budget = max(1.0, min(8.0, 100.0 / max(1, args.steps + args.warmup)))
+    threads = steps = 0
     for i in range(args.warmup + args.steps):
         v, threads, steps, dt = cpu_port_throughput(polys, seconds_budget=budget)
         if i >= args.warmup:
             vals.append(v)
-            total_steps += steps * threads
     value = float(np.mean(vals))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * (time.perf_counter() - t_all) / max(1, args.steps + args.warmup),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "note": "CPU arm: C port of the reference env (oracle/), all host threads"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "config": make_config(args, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"C port of the reference env (oracle/liboracle.so); {sample}; {steps} steps x {threads} threads per timed step"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    py = python_reference_throughput(polys, seconds=args.python_ref_seconds) if not args.no_python_reference else None
+    line["cpu_baseline_python"] = py if py is not None else {
+        "unavailable": "the reference's Python tree is not importable on this box (it exists only in the build container)"}
     emit(line)
 
 
@@ -203,7 +278,7 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     from reinforcementlearning4meshgeneration_b200 import BatchedBoudaryEnv
-    from reinforcementlearning4meshgeneration_b200.distributed import allreduce_stats
+    from reinforcementlearning4meshgeneration_b200.distributed import allreduce_stats, allreduce_stats_device, stats_from_tensor
 
     N = args.envs or ENVS_PER_GPU[args.workload]
     doms = workload_domains(args.workload)
@@ -212,8 +287,8 @@ def run_gpu(args):
     else:
         env = BatchedBoudaryEnv(doms, num_envs=N, device=dev)
     env.reset()
-    state_bytes = N * env.max_verts * 32
-    need_flush = state_bytes < 256 * 1024 * 1024           # L2 is ~126 MB
+    config = make_config(args, world)
+    need_flush = config["l2"].startswith("L2 flushed")
     flush_buf = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev) if need_flush else None
 
     def barrier():
@@ -225,6 +300,7 @@ def run_gpu(args):
     if rank == 0:
         sampler.start()          # sampled under the same load from burn-in to the end of the timed region
     step_idx = 0
+    stats_dev = torch.zeros(12, dtype=torch.int64, device=dev)
     # burn-in (setup, untimed): all envs start their first episode together; run until resets are
     # spread over the steps so that the timed region sees the steady-state mix of episode phases
     for _ in range(args.burn_in):
@@ -233,60 +309,51 @@ def run_gpu(args):
     for _ in range(args.warmup):
         env.step(env.sample_actions(SEED, step_idx))
         step_idx += 1
+    if world > 1:                                            # warm the collective up (communicator set-up is not a step)
+        allreduce_stats_device(env.stats_async(stats_dev))
     env.stats(reset=True)
     launches0 = env.launch_count
 
     K = args.steps
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(K)]
+    n_reduces = 0
     barrier()
     t_wall0 = time.perf_counter()
-    if need_flush:
-        for k in range(K):
+    for k in range(K):
+        if need_flush:
             flush_buf.fill_(k & 0xFF)                       # evict the env state from L2 (not timed)
-            ev[k][0].record()
-            a = env.sample_actions(SEED, step_idx)
-            ev[k][1].record()
-            env.step(a)
-            ev[k][2].record()
-            step_idx += 1
-    else:
-        for k in range(K):
-            ev[k][0].record()
-            a = env.sample_actions(SEED, step_idx)
-            ev[k][1].record()
-            env.step(a)
-            ev[k][2].record()
-            step_idx += 1
+        ev[k][0].record()
+        a = env.sample_actions(SEED, step_idx)
+        ev[k][1].record()
+        env.step(a)
+        if (k + 1) % STATS_INTERVAL == 0:                   # the job's one collective, inside the timed loop
+            allreduce_stats_device(env.stats_async(stats_dev))
+            n_reduces += 1
+        ev[k][2].record()
+        step_idx += 1
     barrier()
     t_wall = time.perf_counter() - t_wall0
     if need_flush:
         total_ms = sum(e[0].elapsed_time(e[2]) for e in ev)
     else:
         total_ms = ev[0][0].elapsed_time(ev[-1][2])
-    kern_ms = sum(e[1].elapsed_time(e[2]) for e in ev)      # step kernel only
+    kern_ms = sum(e[1].elapsed_time(e[2]) for e in ev)      # mg_step (+ the statistics reduce on its steps) only
     clocks = sampler.stop() if rank == 0 else None
     launches = env.launch_count - launches0
     stats = env.stats(reset=True)
 
-    # ---- optional: device time of phase A alone (state frozen at steady state), B+C by difference ----
-    phase_times = None
-    if args.phase_times:
-        from reinforcementlearning4meshgeneration_b200._lib import check
-        check(env._L.mg_set_phase_mask(env._h, 1), env._h, "mg_set_phase_mask")
-        a = env.sample_actions(SEED, step_idx)
-        for _ in range(5):
-            env.step(a)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(50):
-            env.step(a)
-        e1.record()
-        torch.cuda.synchronize(dev)
-        check(env._L.mg_set_phase_mask(env._h, 3), env._h, "mg_set_phase_mask")
-        ta = e0.elapsed_time(e1) / 50
-        phase_times = {"decide_ms": ta, "apply_reset_ms": kern_ms / K - ta}
-        env.stats(reset=True)
+    # ---- per-kernel device times (CUDA events inside mg_step, a separate short pass on the same steady state) ----
+    env.set_kernel_timing(True)
+    Kt = max(8, min(K, 200))
+    for _ in range(Kt):
+        if need_flush:
+            flush_buf.fill_(1)
+        env.step(env.sample_actions(SEED, step_idx))
+        step_idx += 1
+    ktimes = env.kernel_times()
+    env.set_kernel_timing(False)
+    kstats = env.stats(reset=True)
 
     # ---- e2e: host buffers through the C ABI (mg_step_host), H2D + D2H inside the timed region ----
     Ke = max(3, min(K, 100))
@@ -300,8 +367,7 @@ def run_gpu(args):
     host_actions = [torch.from_numpy(rng.uniform(lo, hi, size=(N, 3)).astype(np.float32)) for _ in range(4)]
     out = {k: v for k, v in pinned.items() if k != "act"}
     reward_view = out["reward"].numpy()                       # host view the caller reads its results through
-    env.set_host_delta(True)      # persistent pinned result buffers: only the rows that changed cross PCIe
-    for k in range(2):
+    for k in range(3):
         pinned["act"].copy_(host_actions[k % 4])
         env.step_host(pinned["act"], out)
     barrier()
@@ -313,18 +379,16 @@ def run_gpu(args):
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     h2d_meas, d2h_meas = env.last_host_bytes()
-    h2d = N * 3 * 4
-    # obs + reward + flags + element counts for every env; terminal observations only for finished envs
-    # (mg_step_host ships them compacted: ~0.3 % of the envs per step in steady state)
-    d2h = N * (18 * 4 + 8 + 1 + 1 + 4)
     env.stats(reset=True)
 
     # ---- reductions over ranks --------------------------------------------------------------
-    t = torch.tensor([total_ms, kern_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, kern_ms, e2e_s * 1e3, ktimes["screen_ms"], ktimes["decide_ms"], ktimes["update_ms"], ktimes["observe_ms"]],
+                     dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max, kern_ms_max, e2e_ms_max = [float(x) for x in t.tolist()]
+    total_ms_max, kern_ms_max, e2e_ms_max, screen_ms, decide_ms, update_ms, observe_ms = [float(x) for x in t.tolist()]
     gstats = allreduce_stats(stats, dev) if world > 1 else stats
+    gk = allreduce_stats(kstats, dev) if world > 1 else kstats
     total_env_steps = N * K * world
     value = total_env_steps / (total_ms_max * 1e-3)
     e2e_value = N * Ke * world / (e2e_ms_max * 1e-3)
@@ -336,43 +400,84 @@ def run_gpu(args):
         alg_bytes_per_launch_per_gpu = alg_bytes / max(1, K) / world
         kern_s_per_launch = kern_ms_max * 1e-3 / K
         achieved = alg_bytes_per_launch_per_gpu / kern_s_per_launch / 1e9
-        traffic = None
+        # bytes the memoised two-kernel design has to move: every env's 128-byte record + action + outputs + the 32
+        # record bytes a failed step changes (screen kernel); ring, keys and stamps only for the steps that reach the
+        # ring kernel
+        per_env_screen = 128 + 12 + 14 + 32
+        ksteps = max(1, gk["steps"])
+        per = 1.0 / Kt / world
+        screen_bytes = per_env_screen * ksteps * per
+        # decide: ring (16 n) + records per item; update: ring + keys + stamps + ids (32 n) read, shifted tail (16 n on
+        # average) written per accepted element; observe: ring + keys + stamps (28 n) per changed env
+        decide_items = gk["ring_items"] - (gk["successes"] - 0)          # upper bound on the decide list: every ring item
+        decide_bytes = (16.0 * gk["sum_n_ring"] + 226.0 * gk["ring_items"]) * per
+        update_bytes = (48.0 * gk["sum_n_success"] + 226.0 * gk["successes"]) * per
+        observe_bytes = (28.0 * gk["sum_n_success"] + 226.0 * gk["successes"]) * per
+
+        def entry(name, ms, b, units, **extra):
+            d = {"name": name, "ms": ms, "alg_bytes": b, "frac": b / (ms * 1e-3) / 1e9 / peak if ms > 0 else None, "units": units}
+            d.update(extra)
+            return d
+        per_kernel = [
+            entry("mg_step_screen_kernel", screen_ms, screen_bytes, "every env: 128 B record + 12 B action read, 14 B results + 32 B record written"),
+            entry("mg_step_decide_kernel", decide_ms, decide_bytes, "per item that needs the boundary: 16 n (ring) + 226 (upper bound: counts every ring item)",
+                  items_per_launch=gk["ring_items"] * per),
+            entry("mg_step_update_kernel", update_ms, update_bytes, "per accepted element: 32 n read (ring, keys, stamps, ids) + ~16 n written (shifted tail) + 226",
+                  items_per_launch=gk["successes"] * per),
+            entry("mg_step_observe_kernel", observe_ms, observe_bytes, "per changed env: 28 n (ring, keys, stamps) + 226; resets on top",
+                  items_per_launch=gk["successes"] * per),
+        ]
+        ring_bytes = decide_bytes + update_bytes + observe_bytes
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get(args.workload)
+                tj = json.load(open(tp))
+                traffic = tj.get(args.workload)
+                traffic_src = tj.get("source")
             except Exception:
                 traffic = None
+        memo_bytes = screen_bytes + ring_bytes
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
-            "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": {"c3": "c3: random star polygons 64..512 vertices, in-kernel auto-reset",
-                                    "c2": "c2: paper domains d1/d2/d3 (boundary16/boundary15/test1)",
-                                    "c1": "c1: BoudaryEnv(boundary()) 30 vertices"}[args.workload],
-                       "envs_per_gpu": N, "global_envs": N * world, "policy": "uniform actions in the action box (Philox)",
-                       "parallelism": f"env-sharded x{world}", "burn_in_steps": args.burn_in,
-                       "l2": "L2 flushed between timed steps" if need_flush else f"state {state_bytes >> 20} MiB > L2"},
+            "ms_per_step": total_ms_max / K, "timed_ms": total_ms_max, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_meas, "d2h_bytes_per_step": d2h_meas, "steps": Ke,
-                    "note": "mg_step_host, delta rows (observations of changed envs, terminal observations of finished envs)"},
+                    "pcie_gbs_per_rank": (h2d_meas + d2h_meas) / (e2e_ms_max * 1e-3 / Ke) / 1e9,
+                    "note": "mg_step_host with pinned host buffers: H2D actions; rewards, flags, element counts, changed "
+                            "observation rows and terminal rows written by the step kernels into the caller's arrays; one sync"},
             "gpu_launches": int(launches),
+            "collective": {"op": "all_reduce(sum) of mg_episode_stats (10 x int64 + 2 x float64)", "backend": "nccl" if world > 1 else "none (1 rank: device-side sum only)",
+                           "every_steps": STATS_INTERVAL, "inside_timed_loop": n_reduces},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "mg_step_kernel",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "kernel": max(per_kernel, key=lambda k: k["ms"])["name"],
                          "kernel_ms_per_launch": kern_ms_max / K,
-                         "alg_bytes_per_launch": alg_bytes_per_launch_per_gpu},
+                         "alg_bytes_per_launch": alg_bytes_per_launch_per_gpu,
+                         "model": "SURVEY 8d: sum(28 n + 14 n s + 226) per env-step, i.e. every env's boundary crossing HBM once per "
+                                  "step.  The kernels memoise the state-only predicates, so ~93 % of the steps never read their "
+                                  "boundary: `frac` can exceed 1; `memo_frac` uses the bytes this design must move (per_kernel)",
+                         "memo_alg_bytes_per_launch": memo_bytes,
+                         "memo_frac": memo_bytes / kern_s_per_launch / 1e9 / peak,
+                         "per_kernel": per_kernel,
+                         "per_kernel_note": f"CUDA events around each kernel inside mg_step, {ktimes['steps']} steps after the timed region"},
             "episode_stats": {k: (float(v) if isinstance(v, float) else int(v)) for k, v in gstats.items()},
             "mean_boundary_n": gstats["sum_n"] / max(1, gstats["steps"]),
             "success_rate": gstats["successes"] / max(1, gstats["steps"]),
+            "ring_fraction": gstats["ring_items"] / max(1, gstats["steps"]),
             "wall_s_timed_region": t_wall,
         }
-        if phase_times:
-            line["phase_times"] = phase_times
         if world == 1 and not args.no_cpu_baseline:
             polys, sample = sample_polygons(args.workload)
             v, threads, steps, dt = cpu_port_throughput(polys, seconds_budget=10.0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"{sample}; {steps} steps x {threads} threads, {dt:.1f} s"}
+                                    "sample": f"C port of the reference env (oracle/liboracle.so); {sample}; {steps} steps x {threads} threads, {dt:.1f} s"}
+            py = python_reference_throughput(polys, seconds=args.python_ref_seconds) if not args.no_python_reference else None
+            line["cpu_baseline_python"] = py if py is not None else {
+                "unavailable": "the reference's Python tree is not importable on this box (it exists only in the build container); "
+                               "measured there: profiles/r2_bench_reference_container.json"}
         else:
             line["cpu_baseline"] = None
         emit(line)
@@ -406,11 +511,12 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=50)
-    ap.add_argument("--workload", choices=["c1", "c2", "c3"], default="c3")
+    ap.add_argument("--workload", choices=["c1", "c2", "c3", "c4"], default="c3")
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's BASELINE size)")
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--phase-times", action="store_true", help="also time phase A alone (profiling aid)")
+    ap.add_argument("--no-python-reference", action="store_true", help="skip the Python reference even when its tree is importable")
+    ap.add_argument("--python-ref-seconds", type=float, default=10.0)
     ap.add_argument("--burn-in", type=int, default=1500, help="untimed setup steps that de-synchronise the episodes")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":

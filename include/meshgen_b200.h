@@ -56,7 +56,7 @@ typedef struct mg_polygen_cfg {
 } mg_polygen_cfg;
 
 /* Episode statistics summed over all envs of the handle since the last mg_stats(reset=1).
- * This 10-element vector is the only thing the multi-GPU driver all-reduces. */
+ * This 12-element vector (10 int64 counters, 2 float64 sums) is the only thing the multi-GPU driver all-reduces. */
 typedef struct mg_episode_stats {
     int64_t episodes;      /* finished episodes */
     int64_t completed;     /* ... that ended with is_complete (terminated) */
@@ -66,6 +66,8 @@ typedef struct mg_episode_stats {
     int64_t elements;      /* elements in finished episodes */
     int64_t sum_n;         /* sum over steps of the live boundary size (roofline accounting) */
     int64_t sum_n_success; /* same, restricted to successful steps */
+    int64_t ring_items;    /* steps that needed the whole boundary (work items of the ring kernel) */
+    int64_t sum_n_ring;    /* sum of the live boundary size over those steps */
     double sum_return;     /* sum of finished-episode returns */
     double sum_length;     /* sum of finished-episode lengths */
 } mg_episode_stats;
@@ -77,7 +79,8 @@ typedef struct mg_state_view {
     int32_t n_elements;     /* len(generated_meshes) */
     int32_t failed_num;     /* E:378-384 */
     int32_t n0;             /* original polygon size */
-    int32_t reserved;
+    int32_t memo_flags;     /* memoised verdict of the rule -1 / +1 elements in this state: bit 0 / 1 accepted, bit 2 / 3
+                             * valid with the boundary-intersection test still pending (see mg_step) */
     double base_length;     /* C:1089-1090 */
     double current_area;    /* E:336 */
     double original_area;   /* E:72 */
@@ -118,7 +121,11 @@ int mg_set_auto_reset(mg_handle h, int enabled);
 int mg_reset(mg_handle h, const uint8_t *mask_dev, float *obs_dev, void *stream);
 
 /* Replaces BoudaryEnv.step (E:388-457) followed by the VecEnv auto-reset (V:40-52 with the
- * stock SB3 behaviour): one transition for every env.
+ * stock SB3 behaviour): one transition for every env.  Four launches: a screen kernel (one thread per env) that
+ * settles every step whose outcome follows from the env's 128-byte record -- the verdict of the rule -1 / +1
+ * elements depends on the state only and is memoised, and a new-vertex element that fails Mesh.is_valid
+ * (C:738-757) fails whatever the point-in-polygon test says -- and three warp-per-item kernels (decide, update,
+ * observe) for the steps that need the whole boundary.  Results are the reference's for every step.
  *   act_dev      in  num_envs*3 float32
  *   obs_dev      out num_envs*18 float32   next observation (after auto-reset when done)
  *   rew_dev      out num_envs float64      reward (the reference returns np.float64)
@@ -132,15 +139,20 @@ int mg_step(mg_handle h, const float *act_dev, float *obs_dev, double *rew_dev, 
             uint8_t *trunc_dev, float *term_obs_dev, int32_t *n_elem_dev, void *stream);
 
 /* Same transition through HOST buffers (what a numpy-facing caller such as SB3's VecEnv pays):
- * H2D of the actions, the step, D2H of all outputs, one stream synchronise. */
+ * H2D of the actions, the step, D2H of all outputs, one stream synchronise.  Output buffers that are pinned
+ * (cudaHostAlloc / cudaHostRegister / torch .pin_memory()) are written by the step kernels directly; pageable ones
+ * are copied from staging buffers after the step.  term_obs_host rows are defined only where the episode ended.
+ * Runs on a private stream after everything the caller enqueued through mg_reset / mg_step / mg_snapshot_* has
+ * finished, and returns after its own work has finished. */
 int mg_step_host(mg_handle h, const float *act_host, float *obs_host, double *rew_host,
                  uint8_t *term_host, uint8_t *trunc_host, float *term_obs_host, int32_t *n_elem_host);
 
-/* Delta transfers for mg_step_host: enabled != 0 lets the library ship observations
- * only for the envs whose state changed in the step (an element was created or the env was reset -- on a
- * failed step the reference itself returns a bit-identical observation).  Requires the caller to pass the
- * same, unmodified obs_host buffer on every call (the first call, a pointer change or an
- * mg_reset fall back to a full copy). */
+/* Observation delta.  A failed step leaves the env untouched and the reference itself returns a bit-identical
+ * observation, so with enabled != 0 mg_step / mg_step_host write only the observation rows that changed (accepted
+ * element or reset) when they are handed the SAME obs buffer as the previous call (or the preceding mg_reset) --
+ * the caller promises not to modify that buffer in between.  A different pointer, mg_reset without an obs buffer or
+ * mg_snapshot_load fall back to one full write.  Off by default.  mg_set_host_delta is the round-1 name. */
+int mg_set_obs_delta(mg_handle h, int enabled);
 int mg_set_host_delta(mg_handle h, int enabled);
 
 /* Bytes moved host->device and device->host by the last mg_step_host call. */
@@ -154,21 +166,38 @@ int mg_sample_actions(mg_handle h, uint64_t seed, uint64_t step_index, float *ac
 int mg_get_state(mg_handle h, int env, mg_state_view *view);
 
 /* Element log of env `env` (generated_meshes, E:331,351): up to max_elements quads as 4 vertex
- * ids each, and the coordinates of every vertex id < n_vertices.  Synchronises.  Returns the
- * number of elements through *n_elements_out and of vertices through *n_vertices_out. */
+ * ids each, and the coordinates of every vertex id < n_vertices (original polygon first; in random-polygon mode it
+ * is regenerated from the episode's counter).  Synchronises.  Returns the number of elements through
+ * *n_elements_out and of vertices through *n_vertices_out.  MG_ERR_CAPACITY when the episode outgrew the log (the
+ * counts and the returned prefix are still valid). */
 int mg_get_elements(mg_handle h, int env, int32_t *quads_host, int max_elements, int32_t *n_elements_out,
                     double *vertex_xy_host, int max_vertices, int32_t *n_vertices_out);
 
+/* Parity / debug read-back of the workload generator (random-polygon mode; synchronises): the polygon of episode
+ * `episode` of env `env` (episode < 0: the env's current episode) regenerated from its Philox counter.
+ *   xy_host        out, up to max_vertices (x, y) pairs of the densified clockwise ring (env units); *n_out its size
+ *   area_out       out, the shoelace area the in-kernel reset computes for it (original_area)
+ *   coarse_px_host out, 64 int32: the coarse star polygon in pixels, clockwise (ui/GenerateRandomPolygon.py:5-49 reversed);
+ *                  *k_out its vertex count;  *spacing_out the densifier spacing A in pixels (ui/tk-ui.py:252-276)
+ * Any output pointer may be NULL. */
+int mg_debug_polygon(mg_handle h, int env, int episode, double *xy_host, int max_vertices, int32_t *n_out, double *area_out,
+                     int32_t *coarse_px_host, int32_t *k_out, double *spacing_out);
+
 /* Capacity of the per-env element log and inserted-vertex log (what mg_get_elements can return; the element COUNT is
- * always exact).  Default: 8 x max_verts each -- the reference's evaluation runs report up to ~5 x n0 elements per
- * episode (rl/baselines/evaluation.txt).  mg_set_log_capacity reallocates the logs (call it before mg_reset;
- * contents are discarded). */
+ * always exact).  Default: 2 x max_verts each (at least 64).  Element counts scale with the domain's area: the
+ * reference's evaluation runs report up to ~5 x n0 elements per episode (rl/baselines/evaluation.txt), so an
+ * evaluator raises it (the Python BoudaryEnv facade and evaluation loop use 8 x).  mg_set_log_capacity reallocates
+ * the logs (call it before mg_reset; contents are discarded). */
 int mg_set_log_capacity(mg_handle h, int max_elements_per_env, int max_inserted_per_env);
 int mg_log_capacity(mg_handle h, int32_t *max_elements_per_env, int32_t *max_inserted_per_env);
 
 /* Sum the per-env episode counters on the device, copy them to *out (synchronises);
  * reset != 0 zeroes the counters afterwards. */
 int mg_stats(mg_handle h, mg_episode_stats *out, int reset);
+
+/* Same sum written to a DEVICE mg_episode_stats on `stream`, no synchronisation: what a multi-GPU job all-reduces
+ * every few steps (10 int64 counters followed by 2 float64 sums) without stalling the step stream. */
+int mg_stats_async(mg_handle h, mg_episode_stats *stats_dev, int reset, void *stream);
 
 /* Device-resident replay buffer write (replaces, for a batched env, what SB3's
  * OffPolicyAlgorithm._store_transition + ReplayBuffer.add do on the host -- the callers named in
@@ -189,14 +218,19 @@ int mg_replay_add(mg_handle h, int64_t capacity_steps, int64_t slot, float *buf_
  * log, statistics, cached observations) -- the reference never checkpoints its env; with a
  * batched env this is what makes long rollouts resumable and lets a caller branch from a state.  The blob is
  * mg_snapshot_bytes(h) bytes of DEVICE memory owned by the caller; copies are enqueued on `stream`.  A blob can be
- * loaded into any handle created with the same num_envs / max_verts and the same domains or generator settings. */
+ * loaded into any handle created with the same num_envs / max_verts and the same domains or generator settings; the header of the blob
+ * records num_envs, max_verts, mode, log capacities, domain count, generator seed and env id offset, and
+ * mg_snapshot_load rejects a blob that disagrees with the handle or is shorter than mg_snapshot_bytes. */
 int64_t mg_snapshot_bytes(mg_handle h);
 int mg_snapshot_save(mg_handle h, void *blob_dev, void *stream);
-int mg_snapshot_load(mg_handle h, const void *blob_dev, void *stream);
+int mg_snapshot_load(mg_handle h, const void *blob_dev, int64_t blob_bytes, void *stream);
 
-/* Profiling aid (bench.py --phase-times): restrict mg_step to phase A (bit 0) and/or phases B+C
- * (bit 1).  With a partial mask the environments do not advance correctly; restore 3 afterwards. */
-int mg_set_phase_mask(mg_handle h, int mask);
+/* Profiling aid (bench.py roofline.per_kernel): with enabled != 0 every mg_step / mg_step_host records CUDA events
+ * around its four kernels; mg_kernel_times synchronises, returns the mean device time in ms of the screen, decide,
+ * update and observe kernels (ms4[0..3]) over the (at most 256 most recent) steps since the last call, and starts a
+ * new window. */
+int mg_set_kernel_timing(mg_handle h, int enabled);
+int mg_kernel_times(mg_handle h, double *ms4, int64_t *steps);
 
 int mg_num_envs(mg_handle h);
 int mg_max_verts(mg_handle h);

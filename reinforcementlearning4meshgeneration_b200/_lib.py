@@ -20,9 +20,11 @@ NVCC_FLAGS = [
 ]
 
 SYMBOLS = [
-    "mg_create", "mg_set_domains", "mg_set_random", "mg_set_auto_reset", "mg_reset", "mg_step", "mg_step_host", "mg_set_host_delta", "mg_last_host_bytes", "mg_sample_actions",
-    "mg_get_state", "mg_get_elements", "mg_stats", "mg_set_log_capacity", "mg_log_capacity", "mg_replay_add", "mg_snapshot_bytes", "mg_snapshot_save", "mg_snapshot_load", "mg_set_phase_mask", "mg_num_envs", "mg_max_verts", "mg_launch_count", "mg_destroy",
-    "mg_last_error", "mg_version",
+    "mg_create", "mg_set_domains", "mg_set_random", "mg_set_auto_reset", "mg_reset", "mg_step", "mg_step_host",
+    "mg_set_obs_delta", "mg_set_host_delta", "mg_last_host_bytes", "mg_sample_actions", "mg_get_state", "mg_get_elements", "mg_debug_polygon",
+    "mg_stats", "mg_stats_async", "mg_set_log_capacity", "mg_log_capacity", "mg_replay_add", "mg_snapshot_bytes",
+    "mg_snapshot_save", "mg_snapshot_load", "mg_set_kernel_timing", "mg_kernel_times", "mg_num_envs", "mg_max_verts",
+    "mg_launch_count", "mg_destroy", "mg_last_error", "mg_version",
 ]
 
 
@@ -35,6 +37,7 @@ class PolygenCfg(C.Structure):
 class EpisodeStats(C.Structure):
     _fields_ = [("episodes", C.c_int64), ("completed", C.c_int64), ("truncated", C.c_int64), ("steps", C.c_int64),
                 ("successes", C.c_int64), ("elements", C.c_int64), ("sum_n", C.c_int64), ("sum_n_success", C.c_int64),
+                ("ring_items", C.c_int64), ("sum_n_ring", C.c_int64),
                 ("sum_return", C.c_double), ("sum_length", C.c_double)]
 
     def as_dict(self):
@@ -43,7 +46,7 @@ class EpisodeStats(C.Structure):
 
 class StateView(C.Structure):
     _fields_ = [("n", C.c_int32), ("ref_index", C.c_int32), ("n_elements", C.c_int32), ("failed_num", C.c_int32),
-                ("n0", C.c_int32), ("reserved", C.c_int32), ("base_length", C.c_double), ("current_area", C.c_double),
+                ("n0", C.c_int32), ("memo_flags", C.c_int32), ("base_length", C.c_double), ("current_area", C.c_double),
                 ("original_area", C.c_double), ("area_min", C.c_double), ("area_crit", C.c_double),
                 ("xy_host", C.c_void_p), ("vertex_id_host", C.c_void_p), ("cand_key_host", C.c_void_p),
                 ("cand_stamp_host", C.c_void_p)]
@@ -82,20 +85,25 @@ def load():
     L.mg_reset.argtypes = [vp, vp, vp, vp]
     L.mg_step.argtypes = [vp] + [vp] * 7 + [vp]
     L.mg_step_host.argtypes = [vp] + [vp] * 7
+    L.mg_set_obs_delta.argtypes = [vp, i32]
     L.mg_set_host_delta.argtypes = [vp, i32]
     L.mg_last_host_bytes.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.mg_sample_actions.argtypes = [vp, u64, u64, vp, vp]
     L.mg_get_state.argtypes = [vp, i32, C.POINTER(StateView)]
     L.mg_get_elements.argtypes = [vp, i32, vp, i32, C.POINTER(C.c_int32), vp, i32, C.POINTER(C.c_int32)]
+    L.mg_debug_polygon.argtypes = [vp, i32, i32, vp, i32, C.POINTER(C.c_int32), C.POINTER(C.c_double), vp, C.POINTER(C.c_int32),
+                                   C.POINTER(C.c_double)]
     L.mg_stats.argtypes = [vp, C.POINTER(EpisodeStats), i32]
+    L.mg_stats_async.argtypes = [vp, vp, i32, vp]
     L.mg_set_log_capacity.argtypes = [vp, i32, i32]
     L.mg_log_capacity.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.mg_replay_add.argtypes = [vp, i64, i64] + [vp] * 14
     L.mg_snapshot_bytes.argtypes = [vp]
     L.mg_snapshot_bytes.restype = i64
     L.mg_snapshot_save.argtypes = [vp, vp, vp]
-    L.mg_snapshot_load.argtypes = [vp, vp, vp]
-    L.mg_set_phase_mask.argtypes = [vp, i32]
+    L.mg_snapshot_load.argtypes = [vp, vp, i64, vp]
+    L.mg_set_kernel_timing.argtypes = [vp, i32]
+    L.mg_kernel_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.mg_num_envs.argtypes = [vp]
     L.mg_max_verts.argtypes = [vp]
     L.mg_launch_count.argtypes = [vp]

@@ -63,12 +63,18 @@ class BatchedBoudaryEnv:
     env_domain: per-env index into ``domains`` (default: round-robin blocks, env e -> e*D//N).
     random_polygons: dict of generator settings (see ``PolygenCfg``) -> every reset draws a fresh
                 random star polygon in-kernel (BASELINE configs 3/4).
+    obs_delta : the observation tensor returned by ``reset`` / ``step`` is one persistent buffer; with
+                ``obs_delta`` (default) a step only rewrites the rows whose env changed (a failed step returns a
+                bit-identical observation in the reference too), so do not modify that tensor in place -- copy it,
+                or pass ``obs_delta=False``.
+    log_capacity: entries of the per-env element / inserted-vertex logs (default 2 x max_verts; element counts are
+                exact either way, ``get_elements`` raises when an episode outgrew the log).
     """
 
     def __init__(self, domains=None, num_envs: int = 1, device: Optional[int | str | torch.device] = None,
                  env_domain: Optional[Sequence[int]] = None, max_verts: Optional[int] = None,
                  random_polygons: Optional[dict] = None, seed: int = 0, env_id_offset: int = 0,
-                 auto_reset: bool = True):
+                 auto_reset: bool = True, obs_delta: bool = True, log_capacity: Optional[int] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedBoudaryEnv needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self._L = _lib.load()
@@ -110,6 +116,9 @@ class BatchedBoudaryEnv:
                                          areas.ctypes.data), self._h, "mg_set_domains")
         self.auto_reset = bool(auto_reset)
         check(self._L.mg_set_auto_reset(self._h, int(self.auto_reset)), self._h, "mg_set_auto_reset")
+        check(self._L.mg_set_obs_delta(self._h, int(bool(obs_delta))), self._h, "mg_set_obs_delta")
+        if log_capacity is not None:
+            check(self._L.mg_set_log_capacity(self._h, int(log_capacity), int(log_capacity)), self._h, "mg_set_log_capacity")
         N = self.num_envs
         with torch.cuda.device(self.device):
             self.obs = torch.zeros((N, OBS_DIM), dtype=torch.float32, device=self.device)
@@ -119,6 +128,7 @@ class BatchedBoudaryEnv:
             self.terminal_obs = torch.zeros((N, OBS_DIM), dtype=torch.float32, device=self.device)
             self.n_elements = torch.zeros(N, dtype=torch.int32, device=self.device)
             self._act = torch.zeros((N, ACT_DIM), dtype=torch.float32, device=self.device)
+            self._stats_dev = torch.zeros(12, dtype=torch.int64, device=self.device)
 
     # ------------------------------------------------------------------
     def _stream(self):
@@ -161,8 +171,8 @@ class BatchedBoudaryEnv:
     def step_host(self, actions: np.ndarray, out: Optional[dict] = None) -> dict:
         """Same transition through host (numpy / pinned) buffers: H2D + step + D2H + sync inside the
         library (mg_step_host) -- the path a numpy-facing caller such as SB3 pays.  With pinned ``out`` buffers
-        (torch ``.pin_memory()``) and ``set_host_delta(True)`` the rows that changed are written by the GPU straight
-        into them."""
+        (torch ``.pin_memory()``) the GPU writes the results straight into them (only the observation rows that
+        changed when ``obs_delta`` is on: keep passing the same, unmodified ``out['obs']``)."""
         is_t = isinstance(actions, torch.Tensor)
         if is_t:
             if actions.dtype != torch.float32 or not actions.is_contiguous() or actions.device.type != "cpu":
@@ -197,13 +207,16 @@ class BatchedBoudaryEnv:
     def restore(self, blob: torch.Tensor) -> torch.Tensor:
         """Load a ``snapshot()`` (same num_envs / max_verts / domains or generator); returns the current obs."""
         blob = blob.to(device=self.device, dtype=torch.uint8).contiguous()
-        check(self._L.mg_snapshot_load(self._h, C.c_void_p(blob.data_ptr()), self._stream()), self._h, "mg_snapshot_load")
+        check(self._L.mg_snapshot_load(self._h, C.c_void_p(blob.data_ptr()), int(blob.numel()), self._stream()), self._h,
+              "mg_snapshot_load")
         return self.reset(torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device))   # empty mask: reads the cached obs
 
-    def set_host_delta(self, enabled: bool = True) -> None:
-        """step_host ships only the observation rows that changed (see mg_set_host_delta); the caller
-        must then pass the same, unmodified ``out`` buffers on every call."""
-        check(self._L.mg_set_host_delta(self._h, int(enabled)), self._h, "mg_set_host_delta")
+    def set_obs_delta(self, enabled: bool = True) -> None:
+        """step / step_host write only the observation rows that changed (see mg_set_obs_delta); the caller
+        must then pass the same, unmodified observation buffer on every call."""
+        check(self._L.mg_set_obs_delta(self._h, int(enabled)), self._h, "mg_set_obs_delta")
+
+    set_host_delta = set_obs_delta      # round-1 name
 
     def last_host_bytes(self):
         h2d, d2h = C.c_int64(), C.c_int64()
@@ -233,31 +246,70 @@ class BatchedBoudaryEnv:
         cand.sort(key=lambda t: (t[1], t[2]))
         return dict(n=n, ref_index=v.ref_index, n_elements=v.n_elements, failed_num=v.failed_num, n0=v.n0,
                     base_length=v.base_length, current_area=v.current_area, original_area=v.original_area,
-                    area_range=(v.area_min, v.area_crit), xy=xy[:n].copy(), ids=vid[:n].copy(),
+                    area_range=(v.area_min, v.area_crit), memo_flags=int(v.memo_flags), xy=xy[:n].copy(), ids=vid[:n].copy(),
                     cand_key=key[:n].copy(), cand_stamp=stamp[:n].copy(),
                     candidates=[(c[0], c[1]) for c in cand])
 
-    def get_elements(self, env: int):
-        """(quads[m,4] int32 vertex ids, vertex_xy[nv,2]) of env's current episode (generated_meshes)."""
+    def get_elements(self, env: int, allow_truncated: bool = False):
+        """(quads[m,4] int32 vertex ids, vertex_xy[nv,2], element count) of env's current episode
+        (generated_meshes).  Raises when the episode outgrew the element / inserted-vertex log unless
+        ``allow_truncated`` (the count is exact either way)."""
         ce, ci = C.c_int32(), C.c_int32()
         check(self._L.mg_log_capacity(self._h, C.byref(ce), C.byref(ci)), self._h, "mg_log_capacity")
         cap_e, cap_v = ce.value, self.max_verts + 2 + ci.value
         quads = np.zeros((cap_e, 4), np.int32)
         vxy = np.zeros((cap_v, 2), np.float64)
         ne, nv = C.c_int32(), C.c_int32()
-        check(self._L.mg_get_elements(self._h, int(env), quads.ctypes.data, cap_e, C.byref(ne), vxy.ctypes.data, cap_v,
-                                      C.byref(nv)), self._h, "mg_get_elements")
+        rc = self._L.mg_get_elements(self._h, int(env), quads.ctypes.data, cap_e, C.byref(ne), vxy.ctypes.data, cap_v, C.byref(nv))
+        if not (rc == -4 and allow_truncated):      # MG_ERR_CAPACITY: counts and the returned prefix are valid
+            check(rc, self._h, "mg_get_elements")
         return quads[:min(ne.value, cap_e)].copy(), vxy[:min(nv.value, cap_v)].copy(), ne.value
+
+    def debug_polygon(self, env: int, episode: int = -1) -> dict:
+        """Random-polygon mode: the polygon of ``episode`` of ``env`` (default: its current episode) regenerated
+        from its counter, with the generator's coarse polygon (pixels, clockwise) and densifier spacing."""
+        xy = np.zeros((self.max_verts + 2, 2), np.float64)
+        coarse = np.zeros(64, np.int32)
+        n, k, area, spacing = C.c_int32(), C.c_int32(), C.c_double(), C.c_double()
+        check(self._L.mg_debug_polygon(self._h, int(env), int(episode), xy.ctypes.data, self.max_verts + 2, C.byref(n), C.byref(area),
+                                       coarse.ctypes.data, C.byref(k), C.byref(spacing)), self._h, "mg_debug_polygon")
+        return dict(xy=xy[:n.value].copy(), n=n.value, original_area=area.value,
+                    coarse_px=coarse[:2 * k.value].reshape(-1, 2).copy(), spacing_px=spacing.value)
 
     def set_log_capacity(self, max_elements: int, max_inserted: Optional[int] = None) -> None:
         """Capacity of the per-env element / inserted-vertex logs (default 8 x max_verts each); reset afterwards."""
         check(self._L.mg_set_log_capacity(self._h, int(max_elements), int(max_inserted or max_elements)), self._h,
               "mg_set_log_capacity")
 
+    def n_elements_of(self, env: int) -> int:
+        """len(generated_meshes) of one env (a 128-byte read-back, not the whole log)."""
+        v = StateView()
+        check(self._L.mg_get_state(self._h, int(env), C.byref(v)), self._h, "mg_get_state")
+        return int(v.n_elements)
+
     def stats(self, reset: bool = False) -> dict:
         s = EpisodeStats()
         check(self._L.mg_stats(self._h, C.byref(s), int(reset)), self._h, "mg_stats")
         return s.as_dict()
+
+    def stats_async(self, out: Optional[torch.Tensor] = None, reset: bool = False) -> torch.Tensor:
+        """Episode statistics summed on the device into a 12 x int64 tensor laid out like ``mg_episode_stats``
+        (entries 0..9 int64 counters, entries 10..11 the bit patterns of two float64 sums: ``out[10:].view(torch.float64)``),
+        enqueued on the current stream without any host synchronisation (mg_stats_async)."""
+        out = self._stats_dev if out is None else out
+        if out.numel() != 12 or out.dtype != torch.int64 or out.device != self.device or not out.is_contiguous():
+            raise ValueError("stats buffer must be a contiguous 12 x int64 tensor on the env's device")
+        check(self._L.mg_stats_async(self._h, C.c_void_p(out.data_ptr()), int(reset), self._stream()), self._h, "mg_stats_async")
+        return out
+
+    def set_kernel_timing(self, enabled: bool = True) -> None:
+        check(self._L.mg_set_kernel_timing(self._h, int(enabled)), self._h, "mg_set_kernel_timing")
+
+    def kernel_times(self) -> dict:
+        """Mean device time (ms) of the four step kernels over the steps since the last call."""
+        ms, n = (C.c_double * 4)(), C.c_int64()
+        check(self._L.mg_kernel_times(self._h, ms, C.byref(n)), self._h, "mg_kernel_times")
+        return {"screen_ms": ms[0], "decide_ms": ms[1], "update_ms": ms[2], "observe_ms": ms[3], "steps": n.value}
 
     @property
     def launch_count(self) -> int:

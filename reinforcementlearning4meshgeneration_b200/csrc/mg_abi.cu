@@ -21,38 +21,36 @@ struct mg_env_s {
     double2 *t_xy = nullptr;
     double *t_key = nullptr;
     int32_t *t_stamp = nullptr;
-    DomainScalars *t_sc = nullptr;
+    DomainProto *t_proto = nullptr;
     float *t_obs = nullptr;
     mg_episode_stats *d_stats_out = nullptr;
     double2 *sc_tab = nullptr;      // [2][ANGLE_TAB_N] host-libm {sin, cos} of the quantised angles and their halves
-    // staging buffers for mg_step_host
+    // staging buffers for mg_step_host (used for every caller buffer that is not pinned)
     float *d_act = nullptr, *d_obs = nullptr, *d_term_obs = nullptr;
     double *d_rew = nullptr;
     uint8_t *d_term = nullptr, *d_trunc = nullptr;
     int32_t *d_nel = nullptr;
     cudaStream_t host_stream = nullptr;
-    // mg_step_host: terminal observations travel compacted (only finished envs)
-    int32_t *d_pack_cnt = nullptr, *h_pack_idx = nullptr, *h_pack_cnt = nullptr;
-    float *h_pack_obs = nullptr;
-    int32_t *h_cnt_all = nullptr;
-    float *last_term_obs_host = nullptr;
-    // delta mode (mg_set_host_delta): observations / element counts travel only for the envs whose state changed
-    bool host_delta = false;
-    float *last_obs_host = nullptr;
-    int32_t *last_nel_host = nullptr;
-    int32_t *h_chg_idx = nullptr, *h_chg_nel = nullptr;
-    float *h_chg_obs = nullptr;
-    // device-side aliases of the mapped pinned buffers above
-    int32_t *m_pack_idx = nullptr, *m_chg_idx = nullptr, *m_chg_nel = nullptr;
-    float *m_pack_obs = nullptr, *m_chg_obs = nullptr;
+    int32_t *h_cnt = nullptr;       // pinned copy of the step counters (byte accounting of mg_step_host)
+    // observation delta (mg_set_obs_delta / mg_set_host_delta): the buffer that is known to hold every env's current
+    // observation (written in full by mg_reset or by the previous mg_step with the same pointer)
+    bool obs_delta = false;
+    const float *obs_bound = nullptr;
     int64_t last_h2d = 0, last_d2h = 0;
-    std::vector<int32_t> prev_done;
+    // ordering between the caller's stream (mg_reset / mg_step / mg_snapshot_*) and the private stream of mg_step_host
+    cudaStream_t last_user_stream = nullptr;
+    bool user_work_pending = false;
     bool ready = false;       // domains or generator configured
     bool was_reset = false;
     int64_t launches = 0;
-    int phase_mask = 3;       // profiling aid: bit 0 = phase A launch, bit 1 = phase B+C launch
+    // per-kernel timing (mg_set_kernel_timing): CUDA events around the two step kernels
+    bool timing = false;
+    static constexpr int TIMING_SLOTS = 256;
+    cudaEvent_t ev[TIMING_SLOTS][5] = {};
+    int64_t timing_steps = 0;
     int sm_count = 148;
-    size_t smem = 0, smem_a = 0;
+    size_t smem = 0, smem_nq = 0;      // one-warp block with / without the integer scratch queue
+    int blocks_decide = 16, blocks_update = 16, blocks_observe = 16;
     std::string err;
 };
 
@@ -73,6 +71,26 @@ int fail(mg_handle h, int code, const std::string &msg) {
             return fail(h, MG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
     } while (0)
 
+// Every entry point works on the handle's device and leaves the caller's current device as it found it.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t status = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) {
+            status = cudaSetDevice(device);
+            switched = status == cudaSuccess;
+        }
+    }
+    ~DeviceGuard() {
+        if (switched && prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define MG_DEVICE(h)                \
+    DeviceGuard guard_((h)->device); \
+    MG_CUDA(h, guard_.status)
+
 template <class T>
 cudaError_t dalloc(T **p, size_t count) {
     cudaError_t e = cudaMalloc((void **)p, count * sizeof(T));
@@ -80,22 +98,35 @@ cudaError_t dalloc(T **p, size_t count) {
     return e;
 }
 
-int grid_for(int n) { return (n + WPB - 1) / WPB; }
-
 int configure_kernels(mg_handle h) {
-    h->smem = smem_bytes(h->P.cap);
-    h->smem_a = smem_bytes_a(h->P.cap);
-    if (h->smem_a > 48 * 1024)
-        MG_CUDA(h, cudaFuncSetAttribute(mg_step_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_a));
+    h->smem = smem_bytes(h->P.cap, true);
+    h->smem_nq = smem_bytes(h->P.cap, false);
     if (h->smem > 48 * 1024) {
-        MG_CUDA(h, cudaFuncSetAttribute(mg_step_apply_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        MG_CUDA(h, cudaFuncSetAttribute(mg_step_observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         MG_CUDA(h, cudaFuncSetAttribute(mg_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         MG_CUDA(h, cudaFuncSetAttribute(mg_template_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        MG_CUDA(h, cudaFuncSetAttribute(mg_regen_polygon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    }
+    if (h->smem_nq > 48 * 1024) {
+        MG_CUDA(h, cudaFuncSetAttribute(mg_step_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_nq));
+        MG_CUDA(h, cudaFuncSetAttribute(mg_step_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_nq));
     }
     // the vertex rings want shared memory, not L1: ask for the largest carve-out so that the number of
     // resident warps is set by registers, not by the driver's default split
     MG_CUDA(h, cudaFuncSetAttribute(mg_step_decide_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    MG_CUDA(h, cudaFuncSetAttribute(mg_step_apply_reset_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    MG_CUDA(h, cudaFuncSetAttribute(mg_step_update_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    MG_CUDA(h, cudaFuncSetAttribute(mg_step_observe_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    // the screen kernel has 128 bytes of shared memory and reads one 128-byte record per thread: all L1
+    MG_CUDA(h, cudaFuncSetAttribute(mg_step_screen_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
+    // resident one-warp blocks per SM of each item kernel (grid = that many blocks: items beyond the first wave are
+    // handed out by ticket)
+    int nb = 0;
+    MG_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mg_step_decide_kernel, 32, h->smem_nq));
+    h->blocks_decide = nb > 0 ? nb : 16;
+    MG_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mg_step_update_kernel, 32, h->smem_nq));
+    h->blocks_update = nb > 0 ? nb : 16;
+    MG_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mg_step_observe_kernel, 32, h->smem));
+    h->blocks_observe = nb > 0 ? nb : 16;
     return MG_OK;
 }
 
@@ -131,15 +162,73 @@ T *pinned_alias(T *host) {
 }
 
 void free_templates(mg_handle h) {
-    cudaFree(h->t_xy); cudaFree(h->t_key); cudaFree(h->t_stamp); cudaFree(h->t_sc); cudaFree(h->t_obs);
-    h->t_xy = nullptr; h->t_key = nullptr; h->t_stamp = nullptr; h->t_sc = nullptr; h->t_obs = nullptr;
+    cudaFree(h->t_xy); cudaFree(h->t_key); cudaFree(h->t_stamp); cudaFree(h->t_proto); cudaFree(h->t_obs);
+    h->t_xy = nullptr; h->t_key = nullptr; h->t_stamp = nullptr; h->t_proto = nullptr; h->t_obs = nullptr;
+    h->P.t_xy = nullptr; h->P.t_key = nullptr; h->P.t_stamp = nullptr; h->P.t_proto = nullptr; h->P.t_obs = nullptr;
+    h->P.n_domains = 0;
+}
+
+void note_user_stream(mg_handle h, cudaStream_t s) {
+    h->last_user_stream = s;
+    h->user_work_pending = true;
+}
+
+// The four launches of one step on stream s.
+int launch_step(mg_handle h, const StepIO &io, cudaStream_t s) {
+    const int N = h->num_envs;
+    auto grid = [&](int per_sm) { const int r = h->sm_count * per_sm; return N < r ? N : r; };
+    cudaEvent_t *ev = h->timing ? h->ev[h->timing_steps % mg_env_s::TIMING_SLOTS] : nullptr;
+    if (ev) cudaEventRecord(ev[0], s);
+    mg_step_screen_kernel<<<(N + SCREEN_THREADS - 1) / SCREEN_THREADS, SCREEN_THREADS, 0, s>>>(h->P, io);
+    if (ev) cudaEventRecord(ev[1], s);
+    mg_step_decide_kernel<<<grid(h->blocks_decide), 32, h->smem_nq, s>>>(h->P, io);
+    if (ev) cudaEventRecord(ev[2], s);
+    mg_step_update_kernel<<<grid(h->blocks_update), 32, h->smem_nq, s>>>(h->P, io);
+    if (ev) cudaEventRecord(ev[3], s);
+    mg_step_observe_kernel<<<grid(h->blocks_observe), 32, h->smem, s>>>(h->P, io);
+    if (ev) { cudaEventRecord(ev[4], s); h->timing_steps++; }
+    h->launches += 4;
+    MG_CUDA(h, cudaGetLastError());
+    return MG_OK;
+}
+
+// Random-polygon mode: regenerate the polygon of (env, episode) -- episode < 0 = the env's current one -- and copy up
+// to max_vertices of it to the host (see mg_regen_polygon_kernel).  Synchronises.
+int regen_polygon(mg_handle h, int env, int episode, double *xy_host, int max_vertices, int32_t *n_out, double *area_out,
+                  int32_t *coarse_px_host, int32_t *k_out, double *spacing_out) {
+    const int cap = h->P.cap;
+    char *buf = nullptr;
+    const size_t off_n = sizeof(double2) * cap, off_dbg = off_n + 16, off_area = off_dbg + sizeof(double) * 66;
+    MG_CUDA(h, cudaMalloc((void **)&buf, off_area + 16));
+    mg_regen_polygon_kernel<<<1, 32, h->smem>>>(h->P, env, episode, (double2 *)buf, (int32_t *)(buf + off_n), (double *)(buf + off_dbg),
+                                                (double *)(buf + off_area));
+    h->launches++;
+    int32_t n = 0;
+    double dbg[66], area = 0;
+    cudaError_t e = cudaMemcpy(&n, buf + off_n, sizeof(n), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(dbg, buf + off_dbg, sizeof(dbg), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(&area, buf + off_area, sizeof(area), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && xy_host && n > 0 && n <= cap) {
+        const int c = n < max_vertices ? n : max_vertices;
+        if (c > 0) e = cudaMemcpy(xy_host, buf, sizeof(double2) * c, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(buf);
+    if (e != cudaSuccess) return fail(h, MG_ERR_CUDA, std::string("mg_regen_polygon_kernel: ") + cudaGetErrorString(e));
+    if (n_out) *n_out = n;
+    if (area_out) *area_out = area;
+    const int K = (int)dbg[0];
+    if (k_out) *k_out = K;
+    if (spacing_out) *spacing_out = dbg[1];
+    if (coarse_px_host)
+        for (int i = 0; i < 2 * K && i < 64; i++) coarse_px_host[i] = (int32_t)dbg[2 + i];
+    return MG_OK;
 }
 
 }  // namespace
 
 extern "C" {
 
-const char *mg_version(void) { return "meshgen_b200 0.1 (sm_100a)"; }
+const char *mg_version(void) { return "meshgen_b200 0.2 (sm_100a)"; }
 
 const char *mg_last_error(mg_handle h) { return h ? h->err.c_str() : g_err.c_str(); }
 
@@ -154,24 +243,33 @@ int mg_create(mg_handle *out, int device, int num_envs, int max_verts) {
     mg_handle h = new (std::nothrow) mg_env_s();
     if (!h) return fail(nullptr, MG_ERR_ARG, "mg_create: out of host memory");
     h->device = device; h->num_envs = num_envs; h->max_verts = max_verts;
-    MG_CUDA(h, cudaSetDevice(device));
+    DeviceGuard guard(device);
+    if (guard.status != cudaSuccess) {
+        fail(nullptr, MG_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(guard.status));
+        delete h;
+        return MG_ERR_CUDA;
+    }
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     Params &P = h->P;
     P.num_envs = num_envs;
     P.auto_reset = 1;
     P.cap = (max_verts + 1) & ~1;
     const size_t NC = (size_t)num_envs * P.cap;
-    P.elem_cap = 8 * P.cap;       // element count per episode scales with the domain's area, not its boundary: the
-    P.ins_cap = 8 * P.cap;        // reference's evaluation runs report up to ~5 n0 elements (mg_set_log_capacity to change)
+    // per-env element / inserted-vertex logs: 2 x max_verts entries each by default (what a random or half-trained
+    // policy produces before it is truncated); evaluation of a trained policy on a large domain needs more
+    // (element counts scale with the domain's area: mg_set_log_capacity).  The element COUNT is always exact.
+    P.elem_cap = 2 * P.cap < 64 ? 64 : 2 * P.cap;
+    P.ins_cap = P.elem_cap;
     int rc = MG_OK;
     auto A = [&](cudaError_t er, const char *what) {
         if (er != cudaSuccess && rc == MG_OK) rc = fail(h, MG_ERR_CUDA, std::string("cudaMalloc ") + what + ": " + cudaGetErrorString(er));
     };
     A(dalloc(&P.xy, NC), "xy"); A(dalloc(&P.key, NC), "key"); A(dalloc(&P.stamp, NC), "stamp"); A(dalloc(&P.vid, NC), "vid");
-    A(dalloc(&P.st, (size_t)num_envs), "state"); A(dalloc(&P.stats, (size_t)STAT_SLOTS), "stats");
+    A(dalloc(&P.hot, (size_t)num_envs), "hot"); A(dalloc(&P.cold, (size_t)num_envs), "cold");
+    A(dalloc(&P.stats, (size_t)STAT_SLOTS), "stats");
     A(dalloc(&P.obs_cache, (size_t)num_envs * MG_OBS_DIM), "obs");
-    A(dalloc(&P.pend, (size_t)num_envs), "pend"); A(dalloc(&P.succ_list, (size_t)num_envs), "succ_list");
-    A(dalloc(&P.reset_list, (size_t)num_envs), "reset_list"); A(dalloc(&P.counters, (size_t)CNT_N), "counters");
+    A(dalloc(&P.decide_list, (size_t)num_envs), "decide_list"); A(dalloc(&P.accept_list, (size_t)num_envs), "accept_list");
+    A(dalloc(&P.observe_list, (size_t)num_envs), "observe_list"); A(dalloc(&P.counters, (size_t)CNT_N), "counters");
     A(dalloc(&P.elem, (size_t)num_envs * P.elem_cap * 4), "elem"); A(dalloc(&P.ins_xy, (size_t)num_envs * P.ins_cap), "ins_xy");
     A(dalloc(&h->d_stats_out, 1), "stats_out");
     A(dalloc(&h->sc_tab, (size_t)2 * ANGLE_TAB_N), "angle table");
@@ -179,23 +277,7 @@ int mg_create(mg_handle *out, int device, int num_envs, int max_verts) {
     A(dalloc(&h->d_term_obs, (size_t)num_envs * MG_OBS_DIM), "term_obs"); A(dalloc(&h->d_rew, (size_t)num_envs), "rew");
     A(dalloc(&h->d_term, (size_t)num_envs), "term"); A(dalloc(&h->d_trunc, (size_t)num_envs), "trunc");
     A(dalloc(&h->d_nel, (size_t)num_envs), "nel");
-    A(dalloc(&h->d_pack_cnt, (size_t)2), "pack_cnt");
-    // packed rows are written by the pack kernels straight into mapped pinned host memory (coalesced rows over
-    // PCIe): no second copy + synchronise round once the counts are known
-    A(cudaHostAlloc((void **)&h->h_pack_idx, sizeof(int32_t) * num_envs, cudaHostAllocMapped), "h_pack_idx");
-    A(cudaMallocHost((void **)&h->h_pack_cnt, 4 * sizeof(int32_t)), "h_pack_cnt");
-    A(cudaMallocHost((void **)&h->h_cnt_all, CNT_N * sizeof(int32_t)), "h_cnt_all");
-    A(cudaHostAlloc((void **)&h->h_pack_obs, sizeof(float) * MG_OBS_DIM * num_envs, cudaHostAllocMapped), "h_pack_obs");
-    A(cudaHostAlloc((void **)&h->h_chg_idx, sizeof(int32_t) * num_envs, cudaHostAllocMapped), "h_chg_idx");
-    A(cudaHostAlloc((void **)&h->h_chg_nel, sizeof(int32_t) * num_envs, cudaHostAllocMapped), "h_chg_nel");
-    A(cudaHostAlloc((void **)&h->h_chg_obs, sizeof(float) * MG_OBS_DIM * num_envs, cudaHostAllocMapped), "h_chg_obs");
-    if (rc == MG_OK) {
-        A(cudaHostGetDevicePointer((void **)&h->m_pack_idx, h->h_pack_idx, 0), "map pack_idx");
-        A(cudaHostGetDevicePointer((void **)&h->m_pack_obs, h->h_pack_obs, 0), "map pack_obs");
-        A(cudaHostGetDevicePointer((void **)&h->m_chg_idx, h->h_chg_idx, 0), "map chg_idx");
-        A(cudaHostGetDevicePointer((void **)&h->m_chg_nel, h->h_chg_nel, 0), "map chg_nel");
-        A(cudaHostGetDevicePointer((void **)&h->m_chg_obs, h->h_chg_obs, 0), "map chg_obs");
-    }
+    A(cudaMallocHost((void **)&h->h_cnt, CNT_N * sizeof(int32_t)), "h_cnt");
     if (rc == MG_OK && cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking) != cudaSuccess)
         rc = fail(h, MG_ERR_CUDA, "cudaStreamCreate");
     if (rc == MG_OK) rc = configure_kernels(h);
@@ -207,18 +289,19 @@ int mg_create(mg_handle *out, int device, int num_envs, int max_verts) {
 
 int mg_destroy(mg_handle h) {
     if (!h) return MG_OK;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     Params &P = h->P;
-    cudaFree(P.xy); cudaFree(P.key); cudaFree(P.stamp); cudaFree(P.vid); cudaFree(P.st); cudaFree(P.stats);
+    cudaFree(P.xy); cudaFree(P.key); cudaFree(P.stamp); cudaFree(P.vid); cudaFree(P.hot); cudaFree(P.cold); cudaFree(P.stats);
     cudaFree(P.obs_cache); cudaFree(P.elem); cudaFree(P.ins_xy);
-    cudaFree(P.pend); cudaFree(P.succ_list); cudaFree(P.reset_list); cudaFree(P.counters);
+    cudaFree(P.decide_list); cudaFree(P.accept_list); cudaFree(P.observe_list); cudaFree(P.counters);
     free_templates(h);
     cudaFree(h->sc_tab);
     cudaFree(h->d_stats_out); cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_term_obs); cudaFree(h->d_rew);
     cudaFree(h->d_term); cudaFree(h->d_trunc); cudaFree(h->d_nel);
-    cudaFree(h->d_pack_cnt);
-    cudaFreeHost(h->h_pack_idx); cudaFreeHost(h->h_pack_cnt); cudaFreeHost(h->h_pack_obs); cudaFreeHost(h->h_cnt_all);
-    cudaFreeHost(h->h_chg_idx); cudaFreeHost(h->h_chg_nel); cudaFreeHost(h->h_chg_obs);
+    cudaFreeHost(h->h_cnt);
+    for (auto &tr : h->ev)
+        for (cudaEvent_t e : tr)
+            if (e) cudaEventDestroy(e);
     if (h->host_stream) cudaStreamDestroy(h->host_stream);
     delete h;
     return MG_OK;
@@ -238,7 +321,7 @@ int mg_replay_add(mg_handle h, int64_t capacity_steps, int64_t slot, float *buf_
         !rew || !term || !trunc || !term_obs)
         return fail(h, MG_ERR_ARG, "mg_replay_add: null pointer");
     if (capacity_steps <= 0 || slot < 0 || slot >= capacity_steps) return fail(h, MG_ERR_ARG, "mg_replay_add: slot out of range");
-    MG_CUDA(h, cudaSetDevice(h->device));
+    MG_DEVICE(h);
     const size_t N = (size_t)h->num_envs, s = (size_t)slot;
     const int total = h->num_envs * MG_OBS_DIM;
     mg_replay_add_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
@@ -249,6 +332,7 @@ int mg_replay_add(mg_handle h, int64_t capacity_steps, int64_t slot, float *buf_
     return MG_OK;
 }
 
+// ---- snapshot / restore --------------------------------------------------------------------------
 namespace {
 struct Piece { void *ptr; size_t bytes; };
 std::vector<Piece> snapshot_pieces(mg_handle h) {
@@ -256,18 +340,36 @@ std::vector<Piece> snapshot_pieces(mg_handle h) {
     const size_t N = (size_t)h->num_envs, NC = N * P.cap;
     return {
         {P.xy, NC * sizeof(double2)}, {P.key, NC * sizeof(double)}, {P.stamp, NC * sizeof(int32_t)}, {P.vid, NC * sizeof(int32_t)},
-        {P.st, N * sizeof(EnvState)}, {P.stats, STAT_SLOTS * sizeof(StatsAcc)}, {P.obs_cache, N * MG_OBS_DIM * sizeof(float)},
+        {P.hot, N * sizeof(EnvHot)}, {P.cold, N * sizeof(EnvCold)}, {P.stats, STAT_SLOTS * sizeof(StatsAcc)},
+        {P.obs_cache, N * MG_OBS_DIM * sizeof(float)},
         {P.elem, N * P.elem_cap * 4 * sizeof(int32_t)}, {P.ins_xy, N * P.ins_cap * sizeof(double2)},
         {P.counters, CNT_N * sizeof(int)},
     };
 }
 constexpr size_t SNAP_ALIGN = 256;
 size_t snap_round(size_t b) { return (b + SNAP_ALIGN - 1) / SNAP_ALIGN * SNAP_ALIGN; }
+// everything a blob must agree on with the handle it is loaded into
+struct SnapHeader {
+    int64_t magic, version, total_bytes;
+    int64_t num_envs, cap, random_mode, elem_cap, ins_cap, n_domains;
+    uint64_t seed;
+    int64_t env_id_offset;
+};
+static_assert(sizeof(SnapHeader) <= SNAP_ALIGN, "snapshot header");
+constexpr int64_t SNAP_MAGIC = 0x4d4753324e415053ll, SNAP_VERSION = 2;
+SnapHeader snap_header(mg_handle h, int64_t total) {
+    SnapHeader H{};
+    H.magic = SNAP_MAGIC; H.version = SNAP_VERSION; H.total_bytes = total;
+    H.num_envs = h->num_envs; H.cap = h->P.cap; H.random_mode = h->P.random_mode; H.elem_cap = h->P.elem_cap;
+    H.ins_cap = h->P.ins_cap; H.n_domains = h->P.random_mode ? 0 : h->P.n_domains;
+    H.seed = h->P.random_mode ? h->P.seed : 0; H.env_id_offset = h->P.random_mode ? h->P.env_id_offset : 0;
+    return H;
+}
 }  // namespace
 
 int64_t mg_snapshot_bytes(mg_handle h) {
     if (!h) return 0;
-    size_t total = SNAP_ALIGN;                       // header: num_envs, cap, was_reset
+    size_t total = SNAP_ALIGN;                       // header
     for (const Piece &p : snapshot_pieces(h)) total += snap_round(p.bytes);
     return (int64_t)total;
 }
@@ -275,47 +377,46 @@ int64_t mg_snapshot_bytes(mg_handle h) {
 int mg_snapshot_save(mg_handle h, void *blob_dev, void *stream) {
     if (!h || !blob_dev) return fail(h, MG_ERR_ARG, "mg_snapshot_save: null pointer");
     if (!h->was_reset) return fail(h, MG_ERR_STATE, "mg_snapshot_save: call mg_reset first");
-    MG_CUDA(h, cudaSetDevice(h->device));
+    MG_DEVICE(h);
     cudaStream_t s = (cudaStream_t)stream;
-    const int32_t hdr[4] = {0x4d475331, h->num_envs, h->P.cap, h->P.random_mode};
-    MG_CUDA(h, cudaMemcpyAsync(blob_dev, hdr, sizeof(hdr), cudaMemcpyHostToDevice, s));
+    const SnapHeader hdr = snap_header(h, mg_snapshot_bytes(h));
+    MG_CUDA(h, cudaMemcpyAsync(blob_dev, &hdr, sizeof(hdr), cudaMemcpyHostToDevice, s));
     MG_CUDA(h, cudaStreamSynchronize(s));            // hdr is a stack object
     char *dst = (char *)blob_dev + SNAP_ALIGN;
     for (const Piece &p : snapshot_pieces(h)) {
         MG_CUDA(h, cudaMemcpyAsync(dst, p.ptr, p.bytes, cudaMemcpyDeviceToDevice, s));
         dst += snap_round(p.bytes);
     }
+    note_user_stream(h, s);
     return MG_OK;
 }
 
-int mg_snapshot_load(mg_handle h, const void *blob_dev, void *stream) {
+int mg_snapshot_load(mg_handle h, const void *blob_dev, int64_t blob_bytes, void *stream) {
     if (!h || !blob_dev) return fail(h, MG_ERR_ARG, "mg_snapshot_load: null pointer");
     if (!h->ready) return fail(h, MG_ERR_STATE, "mg_snapshot_load: configure domains or the generator first");
-    MG_CUDA(h, cudaSetDevice(h->device));
+    if (blob_bytes < (int64_t)SNAP_ALIGN) return fail(h, MG_ERR_ARG, "mg_snapshot_load: blob shorter than its header");
+    MG_DEVICE(h);
     cudaStream_t s = (cudaStream_t)stream;
-    int32_t hdr[4] = {0, 0, 0, 0};
-    MG_CUDA(h, cudaMemcpyAsync(hdr, blob_dev, sizeof(hdr), cudaMemcpyDeviceToHost, s));
+    SnapHeader got{};
+    MG_CUDA(h, cudaMemcpyAsync(&got, blob_dev, sizeof(got), cudaMemcpyDeviceToHost, s));
     MG_CUDA(h, cudaStreamSynchronize(s));
-    if (hdr[0] != 0x4d475331 || hdr[1] != h->num_envs || hdr[2] != h->P.cap || hdr[3] != h->P.random_mode)
-        return fail(h, MG_ERR_ARG, "mg_snapshot_load: blob does not match this handle (num_envs / max_verts / mode)");
+    const SnapHeader want = snap_header(h, mg_snapshot_bytes(h));
+    if (got.magic != want.magic || got.version != want.version)
+        return fail(h, MG_ERR_ARG, "mg_snapshot_load: not a snapshot of this library version");
+    if (got.total_bytes != want.total_bytes || blob_bytes < want.total_bytes)
+        return fail(h, MG_ERR_ARG, "mg_snapshot_load: blob size does not match this handle (truncated blob or different capacities)");
+    if (got.num_envs != want.num_envs || got.cap != want.cap || got.random_mode != want.random_mode || got.elem_cap != want.elem_cap ||
+        got.ins_cap != want.ins_cap || got.n_domains != want.n_domains || got.seed != want.seed || got.env_id_offset != want.env_id_offset)
+        return fail(h, MG_ERR_ARG, "mg_snapshot_load: blob does not match this handle (num_envs / max_verts / mode / log capacity / "
+                                   "domains / generator seed / env id offset)");
     const char *src = (const char *)blob_dev + SNAP_ALIGN;
     for (const Piece &p : snapshot_pieces(h)) {
         MG_CUDA(h, cudaMemcpyAsync(p.ptr, src, p.bytes, cudaMemcpyDeviceToDevice, s));
         src += snap_round(p.bytes);
     }
     h->was_reset = true;
-    h->last_obs_host = nullptr;          // host-side delta copies are stale
-    h->last_nel_host = nullptr;
-    return MG_OK;
-}
-
-int mg_set_phase_mask(mg_handle h, int mask) {
-    if (!h) return fail(h, MG_ERR_ARG, "mg_set_phase_mask: null handle");
-    h->phase_mask = mask & 3;
-    // masked steps leave entries in the work lists: start clean on every change of the mask
-    MG_CUDA(h, cudaSetDevice(h->device));
-    MG_CUDA(h, cudaDeviceSynchronize());
-    MG_CUDA(h, cudaMemset(h->P.counters, 0, 4 * sizeof(int)));
+    h->obs_bound = nullptr;              // no caller buffer holds the restored observations yet
+    note_user_stream(h, s);
     return MG_OK;
 }
 
@@ -326,11 +427,11 @@ int64_t mg_launch_count(mg_handle h) { return h ? h->launches : 0; }
 int mg_set_domains(mg_handle h, const double *xy_host, const int32_t *offsets_host, int n_domains,
                    const int32_t *env_domain_host, const double *areas_host) {
     if (!h || !xy_host || !offsets_host || !env_domain_host || n_domains <= 0) return fail(h, MG_ERR_ARG, "mg_set_domains: bad argument");
-    MG_CUDA(h, cudaSetDevice(h->device));
+    MG_DEVICE(h);
     Params &P = h->P;
     const int cap = P.cap;
     std::vector<double2> txy((size_t)n_domains * cap, make_double2(0, 0));
-    std::vector<DomainScalars> tsc(n_domains);
+    std::vector<int32_t> n0s(n_domains);
     for (int d = 0; d < n_domains; d++) {
         int n = offsets_host[d + 1] - offsets_host[d];
         if (n < 3) return fail(h, MG_ERR_ARG, "mg_set_domains: polygon with fewer than 3 vertices");
@@ -339,39 +440,44 @@ int mg_set_domains(mg_handle h, const double *xy_host, const int32_t *offsets_ho
             const double *p = xy_host + 2 * ((size_t)offsets_host[d] + j);
             txy[(size_t)d * cap + j] = make_double2(p[0], p[1]);
         }
-        std::memset(&tsc[d], 0, sizeof(DomainScalars));
-        tsc[d].n0 = n;
+        n0s[d] = n;
     }
-    std::vector<EnvState> st(h->num_envs);
-    std::memset(st.data(), 0, sizeof(EnvState) * st.size());
+    std::vector<EnvCold> cold(h->num_envs);
+    std::memset(cold.data(), 0, sizeof(EnvCold) * cold.size());
     for (int e = 0; e < h->num_envs; e++) {
         int d = env_domain_host[e];
         if (d < 0 || d >= n_domains) return fail(h, MG_ERR_ARG, "mg_set_domains: env_domain out of range");
-        st[e].domain = d;
+        cold[e].domain = d;
     }
+    MG_CUDA(h, cudaDeviceSynchronize());
+    h->ready = false; h->was_reset = false;          // a failure below leaves the handle unconfigured, not half configured
     free_templates(h);
     MG_CUDA(h, dalloc(&h->t_xy, (size_t)n_domains * cap));
     MG_CUDA(h, dalloc(&h->t_key, (size_t)n_domains * cap));
     MG_CUDA(h, dalloc(&h->t_stamp, (size_t)n_domains * cap));
-    MG_CUDA(h, dalloc(&h->t_sc, (size_t)n_domains));
+    MG_CUDA(h, dalloc(&h->t_proto, (size_t)n_domains));
     MG_CUDA(h, dalloc(&h->t_obs, (size_t)n_domains * MG_OBS_DIM));
     MG_CUDA(h, cudaMemcpy(h->t_xy, txy.data(), sizeof(double2) * txy.size(), cudaMemcpyHostToDevice));
-    MG_CUDA(h, cudaMemcpy(h->t_sc, tsc.data(), sizeof(DomainScalars) * tsc.size(), cudaMemcpyHostToDevice));
-    MG_CUDA(h, cudaMemcpy(P.st, st.data(), sizeof(EnvState) * st.size(), cudaMemcpyHostToDevice));
+    MG_CUDA(h, cudaMemcpy(P.cold, cold.data(), sizeof(EnvCold) * cold.size(), cudaMemcpyHostToDevice));
+    MG_CUDA(h, cudaMemset(P.hot, 0, sizeof(EnvHot) * h->num_envs));
     double *d_areas = nullptr;
+    int32_t *d_n0 = nullptr;
+    MG_CUDA(h, cudaMalloc((void **)&d_n0, sizeof(int32_t) * n_domains));
+    MG_CUDA(h, cudaMemcpy(d_n0, n0s.data(), sizeof(int32_t) * n_domains, cudaMemcpyHostToDevice));
     if (areas_host) {
         MG_CUDA(h, cudaMalloc((void **)&d_areas, sizeof(double) * n_domains));
         MG_CUDA(h, cudaMemcpy(d_areas, areas_host, sizeof(double) * n_domains, cudaMemcpyHostToDevice));
     }
     P.n_domains = n_domains; P.random_mode = 0;
-    P.t_xy = h->t_xy; P.t_key = h->t_key; P.t_stamp = h->t_stamp; P.t_sc = h->t_sc; P.t_obs = h->t_obs;
-    mg_template_kernel<<<grid_for(n_domains), WPB * 32, h->smem>>>(P, h->t_xy, h->t_key, h->t_stamp, h->t_sc, h->t_obs, d_areas);
+    P.t_xy = h->t_xy; P.t_key = h->t_key; P.t_stamp = h->t_stamp; P.t_proto = h->t_proto; P.t_obs = h->t_obs;
+    mg_template_kernel<<<n_domains, 32, h->smem>>>(P, h->t_xy, h->t_key, h->t_stamp, h->t_proto, h->t_obs, d_n0, d_areas);
     h->launches++;
     cudaError_t e = cudaDeviceSynchronize();
     if (d_areas) cudaFree(d_areas);
+    cudaFree(d_n0);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, MG_ERR_CUDA, std::string("mg_template_kernel: ") + cudaGetErrorString(e));
-    h->ready = true; h->was_reset = false;
+    h->ready = true;
     return MG_OK;
 }
 
@@ -387,8 +493,10 @@ int mg_set_random(mg_handle h, uint64_t seed, const mg_polygen_cfg *cfg, int64_t
         c.max_verts > h->max_verts || c.min_verts < c.max_coarse)
         return fail(h, MG_ERR_ARG, "mg_set_random: bad generator configuration (need 3<=min_coarse<=max_coarse<=32, "
                                    "max_coarse<=min_verts<=max_verts<=handle max_verts)");
-    MG_CUDA(h, cudaSetDevice(h->device));
-    MG_CUDA(h, cudaMemset(h->P.st, 0, sizeof(EnvState) * h->num_envs));
+    MG_DEVICE(h);
+    MG_CUDA(h, cudaDeviceSynchronize());
+    MG_CUDA(h, cudaMemset(h->P.hot, 0, sizeof(EnvHot) * h->num_envs));
+    MG_CUDA(h, cudaMemset(h->P.cold, 0, sizeof(EnvCold) * h->num_envs));
     h->P.random_mode = 1; h->P.seed = seed; h->P.gen = c; h->P.env_id_offset = env_id_offset;
     h->ready = true; h->was_reset = false;
     return MG_OK;
@@ -398,13 +506,13 @@ int mg_reset(mg_handle h, const uint8_t *mask_dev, float *obs_dev, void *stream)
     if (!h) return fail(h, MG_ERR_ARG, "mg_reset: null handle");
     if (!h->ready) return fail(h, MG_ERR_STATE, "mg_reset: call mg_set_domains or mg_set_random first");
     if (mask_dev && !h->was_reset) return fail(h, MG_ERR_STATE, "mg_reset: the first reset must cover all envs (mask = NULL)");
-    MG_CUDA(h, cudaSetDevice(h->device));
-    mg_reset_kernel<<<grid_for(h->num_envs), WPB * 32, h->smem, (cudaStream_t)stream>>>(h->P, mask_dev, obs_dev);
+    MG_DEVICE(h);
+    mg_reset_kernel<<<h->num_envs, 32, h->smem, (cudaStream_t)stream>>>(h->P, mask_dev, obs_dev);
     h->launches++;
     MG_CUDA(h, cudaGetLastError());
     h->was_reset = true;
-    h->last_obs_host = nullptr;          // host-side delta copies are stale after a reset
-    h->last_nel_host = nullptr;
+    h->obs_bound = obs_dev;              // every row was written (NULL: no caller buffer holds the observations)
+    note_user_stream(h, (cudaStream_t)stream);
     return MG_OK;
 }
 
@@ -412,18 +520,15 @@ int mg_step(mg_handle h, const float *act_dev, float *obs_dev, double *rew_dev, 
             float *term_obs_dev, int32_t *n_elem_dev, void *stream) {
     if (!h || !act_dev || !obs_dev || !rew_dev || !term_dev || !trunc_dev) return fail(h, MG_ERR_ARG, "mg_step: null pointer");
     if (!h->was_reset) return fail(h, MG_ERR_STATE, "mg_step: call mg_reset first");
-    MG_CUDA(h, cudaSetDevice(h->device));
+    MG_DEVICE(h);
     StepIO io;
     io.act = act_dev; io.obs_out = obs_dev; io.rew_out = rew_dev; io.term_out = term_dev; io.trunc_out = trunc_dev;
     io.term_obs_out = term_obs_dev; io.n_elem_out = n_elem_dev;
-    cudaStream_t s = (cudaStream_t)stream;
-    const int full = grid_for(h->num_envs);
-    const int gb = full < h->sm_count * (32 / WPB) ? full : h->sm_count * (32 / WPB);     // 32 item slots per SM
-    const int gc = full < h->sm_count * (8 / WPB) ? full : h->sm_count * (8 / WPB);
-    if (h->phase_mask & 1) mg_step_decide_kernel<<<(h->num_envs + WPB_A - 1) / WPB_A, WPB_A * 32, h->smem_a, s>>>(h->P, io);
-    if (h->phase_mask & 2) mg_step_apply_reset_kernel<<<gb + gc, WPB * 32, h->smem, s>>>(h->P, io, gb);
-    h->launches += 2;
-    MG_CUDA(h, cudaGetLastError());
+    io.obs_full = (h->obs_delta && h->obs_bound == obs_dev) ? 0 : 1;
+    const int rc = launch_step(h, io, (cudaStream_t)stream);
+    if (rc != MG_OK) return rc;
+    h->obs_bound = obs_dev;
+    note_user_stream(h, (cudaStream_t)stream);
     return MG_OK;
 }
 
@@ -431,95 +536,65 @@ int mg_step_host(mg_handle h, const float *act_host, float *obs_host, double *re
                  uint8_t *trunc_host, float *term_obs_host, int32_t *n_elem_host) {
     if (!h || !act_host || !obs_host || !rew_host || !term_host || !trunc_host) return fail(h, MG_ERR_ARG, "mg_step_host: null pointer");
     if (!h->was_reset) return fail(h, MG_ERR_STATE, "mg_step_host: call mg_reset first");
-    MG_CUDA(h, cudaSetDevice(h->device));
+    MG_DEVICE(h);
     const size_t N = h->num_envs;
     cudaStream_t s = h->host_stream;
+    // work the caller enqueued on its own stream (mg_reset, mg_step, mg_snapshot_*) must finish before this step
+    // touches the env state on the library's private stream
+    if (h->user_work_pending) {
+        MG_CUDA(h, cudaStreamSynchronize(h->last_user_stream));
+        h->user_work_pending = false;
+    }
     MG_CUDA(h, cudaMemcpyAsync(h->d_act, act_host, N * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
-    int rc = mg_step(h, h->d_act, h->d_obs, h->d_rew, h->d_term, h->d_trunc, h->d_term_obs, h->d_nel, s);
+    // Pinned caller buffers are written by the step kernels themselves through their device aliases (posted PCIe
+    // writes that overlap the later kernels: no staging copy, no copy-engine round after the step); pageable ones go
+    // through the handle's staging buffers and one cudaMemcpyAsync each.
+    float *obs_a = pinned_alias(obs_host), *tobs_a = pinned_alias(term_obs_host);
+    double *rew_a = pinned_alias(rew_host);
+    uint8_t *term_a = pinned_alias(term_host), *trunc_a = pinned_alias(trunc_host);
+    int32_t *nel_a = pinned_alias(n_elem_host);
+    StepIO io;
+    io.act = h->d_act;
+    io.obs_out = obs_a ? obs_a : h->d_obs;
+    io.rew_out = rew_a ? rew_a : h->d_rew;
+    io.term_out = term_a ? term_a : h->d_term;
+    io.trunc_out = trunc_a ? trunc_a : h->d_trunc;
+    io.term_obs_out = term_obs_host ? (tobs_a ? tobs_a : h->d_term_obs) : nullptr;
+    io.n_elem_out = n_elem_host ? (nel_a ? nel_a : h->d_nel) : nullptr;
+    io.obs_full = (h->obs_delta && h->obs_bound == io.obs_out) ? 0 : 1;
+    const int rc = launch_step(h, io, s);
     if (rc != MG_OK) return rc;
-    int64_t d2h = 0;
-    // observations (and element counts) only change for envs that created an element or were reset: in delta
-    // mode, with the caller's buffers unchanged since the previous call, only those rows cross PCIe
-    const bool delta_obs = h->host_delta && h->last_obs_host == obs_host;
-    // (element counts are not delta-coded: a reset env reports the finished episode's count in the reset
-    // step and 0 from the next step on, whatever that step does)
-    const bool delta_nel = false;
-    // pinned caller buffers: changed rows go straight into them (no staging, no host-side scatter)
-    float *obs_alias = delta_obs ? pinned_alias(obs_host) : nullptr;
-    float *tobs_alias = pinned_alias(term_obs_host);
-    const bool direct_obs = obs_alias != nullptr, direct_tobs = tobs_alias != nullptr;
-    MG_CUDA(h, cudaMemsetAsync(h->d_pack_cnt, 0, 2 * sizeof(int32_t), s));
-    if (direct_obs || direct_tobs) {
-        mg_scatter_rows_host_kernel<<<h->sm_count * 2, 256, 0, s>>>(h->P, h->d_obs, direct_obs ? obs_alias : nullptr, h->d_term,
-                                                                   h->d_trunc, h->d_term_obs, direct_tobs ? tobs_alias : nullptr,
-                                                                   h->d_pack_cnt);
-        h->launches++;
-    }
-    if (term_obs_host && !direct_tobs) {
-        mg_pack_terminal_kernel<<<(h->num_envs + 255) / 256, 256, 0, s>>>(h->num_envs, h->d_term, h->d_trunc, h->d_term_obs,
-                                                                           h->m_pack_idx, h->m_pack_obs, h->d_pack_cnt);
-        h->launches++;
-    }
-    if (delta_obs && !direct_obs) {
-        mg_pack_changed_kernel<<<h->sm_count * 2, 256, 0, s>>>(h->P, h->d_obs, h->d_nel, h->m_chg_idx, h->m_chg_obs,
-                                                              h->m_chg_nel, h->d_pack_cnt + 1);
-        h->launches++;
-    } else if (!delta_obs) {
-        MG_CUDA(h, cudaMemcpyAsync(obs_host, h->d_obs, N * MG_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
-        d2h += N * MG_OBS_DIM * sizeof(float);
-    }
-    if (direct_obs || direct_tobs) {      // row counts for the byte accounting (both counter sets + the current set)
-        MG_CUDA(h, cudaMemcpyAsync(h->h_cnt_all, h->P.counters, CNT_N * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    }
-    MG_CUDA(h, cudaMemcpyAsync(h->h_pack_cnt, h->d_pack_cnt, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    MG_CUDA(h, cudaMemcpyAsync(rew_host, h->d_rew, N * sizeof(double), cudaMemcpyDeviceToHost, s));
-    MG_CUDA(h, cudaMemcpyAsync(term_host, h->d_term, N, cudaMemcpyDeviceToHost, s));
-    MG_CUDA(h, cudaMemcpyAsync(trunc_host, h->d_trunc, N, cudaMemcpyDeviceToHost, s));
-    d2h += N * (sizeof(double) + 2) + 2 * sizeof(int32_t);
-    if (n_elem_host && !delta_nel) {
-        MG_CUDA(h, cudaMemcpyAsync(n_elem_host, h->d_nel, N * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-        d2h += N * sizeof(int32_t);
-    }
+    h->obs_bound = io.obs_out;
+    int64_t d2h = N * (sizeof(double) + 2) + (n_elem_host ? N * sizeof(int32_t) : 0);
+    if (!obs_a) MG_CUDA(h, cudaMemcpyAsync(obs_host, h->d_obs, N * MG_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (!rew_a) MG_CUDA(h, cudaMemcpyAsync(rew_host, h->d_rew, N * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (!term_a) MG_CUDA(h, cudaMemcpyAsync(term_host, h->d_term, N, cudaMemcpyDeviceToHost, s));
+    if (!trunc_a) MG_CUDA(h, cudaMemcpyAsync(trunc_host, h->d_trunc, N, cudaMemcpyDeviceToHost, s));
+    if (term_obs_host && !tobs_a)
+        MG_CUDA(h, cudaMemcpyAsync(term_obs_host, h->d_term_obs, N * MG_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (n_elem_host && !nel_a) MG_CUDA(h, cudaMemcpyAsync(n_elem_host, h->d_nel, N * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    MG_CUDA(h, cudaMemcpyAsync(h->h_cnt, h->P.counters, CNT_N * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     MG_CUDA(h, cudaStreamSynchronize(s));
-    const int c_term = (term_obs_host && !direct_tobs) ? h->h_pack_cnt[0] : 0, c_chg = (delta_obs && !direct_obs) ? h->h_pack_cnt[1] : 0;
-    d2h += (int64_t)c_term * (4 + 4 * MG_OBS_DIM) + (int64_t)c_chg * (4 + 4 * MG_OBS_DIM + 4);    // written by the pack kernels
-    if (direct_obs) {
-        const int cur = h->h_cnt_all[CNT_CUR] & 1;
-        d2h += (int64_t)(h->h_cnt_all[2 * cur] + h->h_cnt_all[2 * cur + 1]) * 4 * MG_OBS_DIM;
-    }
-    if (direct_tobs) d2h += (int64_t)h->h_pack_cnt[0] * 4 * MG_OBS_DIM;
-    for (int i = 0; i < c_chg; i++) {
-        const size_t e = (size_t)h->h_chg_idx[i];
-        std::memcpy(obs_host + e * MG_OBS_DIM, h->h_chg_obs + (size_t)i * MG_OBS_DIM, sizeof(float) * MG_OBS_DIM);
-        if (delta_nel) n_elem_host[e] = h->h_chg_nel[i];
-    }
-    if (term_obs_host && !direct_tobs) {
-        // terminal observations are only defined where done: those rows travel compacted instead of N*72 bytes
-        if (h->last_term_obs_host != term_obs_host) {
-            std::memset(term_obs_host, 0, sizeof(float) * MG_OBS_DIM * N);
-            h->last_term_obs_host = term_obs_host;
-        } else {
-            for (int32_t e : h->prev_done) std::memset(term_obs_host + (size_t)e * MG_OBS_DIM, 0, sizeof(float) * MG_OBS_DIM);
-        }
-        h->prev_done.assign(h->h_pack_idx, h->h_pack_idx + c_term);
-        for (int i = 0; i < c_term; i++)
-            std::memcpy(term_obs_host + (size_t)h->h_pack_idx[i] * MG_OBS_DIM, h->h_pack_obs + (size_t)i * MG_OBS_DIM,
-                        sizeof(float) * MG_OBS_DIM);
-    }
-    h->last_obs_host = obs_host;
-    h->last_nel_host = n_elem_host;
+    // bytes that crossed PCIe towards the host: rewards, flags, element counts for every env; observation rows of the
+    // envs that changed (all rows without delta mode or through staging); terminal rows of finished envs (all rows
+    // through staging)
+    const int cur = h->h_cnt[CNT_CUR] & 1;
+    const int64_t row = sizeof(float) * MG_OBS_DIM;
+    d2h += (obs_a && !io.obs_full) ? (int64_t)h->h_cnt[CNT_SET * cur + CNT_OBSERVE] * row : (int64_t)N * row;
+    if (term_obs_host) d2h += tobs_a ? (int64_t)h->h_cnt[CNT_SET * cur + CNT_DONE] * row : (int64_t)N * row;
     h->last_h2d = (int64_t)(N * 3 * sizeof(float));
     h->last_d2h = d2h;
     return MG_OK;
 }
 
-int mg_set_host_delta(mg_handle h, int enabled) {
-    if (!h) return fail(h, MG_ERR_ARG, "mg_set_host_delta: null handle");
-    h->host_delta = enabled != 0;
-    h->last_obs_host = nullptr;
-    h->last_nel_host = nullptr;
+int mg_set_obs_delta(mg_handle h, int enabled) {
+    if (!h) return fail(h, MG_ERR_ARG, "mg_set_obs_delta: null handle");
+    h->obs_delta = enabled != 0;
+    h->obs_bound = nullptr;
     return MG_OK;
 }
+
+int mg_set_host_delta(mg_handle h, int enabled) { return mg_set_obs_delta(h, enabled); }
 
 int mg_last_host_bytes(mg_handle h, int64_t *h2d, int64_t *d2h) {
     if (!h) return fail(h, MG_ERR_ARG, "mg_last_host_bytes: null handle");
@@ -530,7 +605,7 @@ int mg_last_host_bytes(mg_handle h, int64_t *h2d, int64_t *d2h) {
 
 int mg_sample_actions(mg_handle h, uint64_t seed, uint64_t step_index, float *act_dev, void *stream) {
     if (!h || !act_dev) return fail(h, MG_ERR_ARG, "mg_sample_actions: null pointer");
-    MG_CUDA(h, cudaSetDevice(h->device));
+    MG_DEVICE(h);
     mg_sample_actions_kernel<<<(h->num_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->num_envs, seed, step_index,
                                                                                          h->P.env_id_offset, act_dev);
     h->launches++;
@@ -540,13 +615,16 @@ int mg_sample_actions(mg_handle h, uint64_t seed, uint64_t step_index, float *ac
 
 int mg_get_state(mg_handle h, int env, mg_state_view *v) {
     if (!h || !v || env < 0 || env >= h->num_envs) return fail(h, MG_ERR_ARG, "mg_get_state: bad argument");
-    MG_CUDA(h, cudaSetDevice(h->device));
+    MG_DEVICE(h);
     MG_CUDA(h, cudaDeviceSynchronize());
-    EnvState S;
-    MG_CUDA(h, cudaMemcpy(&S, h->P.st + env, sizeof(S), cudaMemcpyDeviceToHost));
-    v->n = S.n; v->ref_index = S.ref_index; v->n_elements = S.n_elements; v->failed_num = S.failed_num; v->n0 = S.n0;
-    v->base_length = S.base_length; v->current_area = S.current_area; v->original_area = S.original_area;
-    v->area_min = S.area_min; v->area_crit = S.area_crit;
+    EnvHot S;
+    EnvCold C;
+    MG_CUDA(h, cudaMemcpy(&S, h->P.hot + env, sizeof(S), cudaMemcpyDeviceToHost));
+    MG_CUDA(h, cudaMemcpy(&C, h->P.cold + env, sizeof(C), cudaMemcpyDeviceToHost));
+    v->n = S.n; v->ref_index = S.ref_index; v->n_elements = S.n_elements; v->failed_num = S.failed_num; v->n0 = C.n0;
+    v->memo_flags = S.flags;
+    v->base_length = S.base_length; v->current_area = S.current_area; v->original_area = C.original_area;
+    v->area_min = C.area_min; v->area_crit = C.area_crit;
     const size_t off = (size_t)env * h->P.cap;
     const int n = S.n;
     if (n < 0 || n > h->P.cap) return fail(h, MG_ERR_STATE, "mg_get_state: corrupt env state");
@@ -560,45 +638,68 @@ int mg_get_state(mg_handle h, int env, mg_state_view *v) {
 int mg_get_elements(mg_handle h, int env, int32_t *quads_host, int max_elements, int32_t *n_elements_out,
                     double *vertex_xy_host, int max_vertices, int32_t *n_vertices_out) {
     if (!h || env < 0 || env >= h->num_envs) return fail(h, MG_ERR_ARG, "mg_get_elements: bad argument");
-    MG_CUDA(h, cudaSetDevice(h->device));
+    if (!h->was_reset) return fail(h, MG_ERR_STATE, "mg_get_elements: call mg_reset first");
+    MG_DEVICE(h);
     MG_CUDA(h, cudaDeviceSynchronize());
-    EnvState S;
-    MG_CUDA(h, cudaMemcpy(&S, h->P.st + env, sizeof(S), cudaMemcpyDeviceToHost));
-    int ne = S.n_elements < h->P.elem_cap ? S.n_elements : h->P.elem_cap;
+    EnvHot S;
+    EnvCold C;
+    MG_CUDA(h, cudaMemcpy(&S, h->P.hot + env, sizeof(S), cudaMemcpyDeviceToHost));
+    MG_CUDA(h, cudaMemcpy(&C, h->P.cold + env, sizeof(C), cudaMemcpyDeviceToHost));
+    bool overflow = false;
+    int ne = S.n_elements;
+    if (ne > h->P.elem_cap) { ne = h->P.elem_cap; overflow = quads_host != nullptr; }
     if (n_elements_out) *n_elements_out = S.n_elements;
     if (quads_host && max_elements > 0) {
         int c = ne < max_elements ? ne : max_elements;
         MG_CUDA(h, cudaMemcpy(quads_host, h->P.elem + (size_t)env * h->P.elem_cap * 4, sizeof(int32_t) * 4 * c, cudaMemcpyDeviceToHost));
     }
-    int nv = S.next_vid;
+    int nv = C.next_vid;
     if (n_vertices_out) *n_vertices_out = nv;
     if (vertex_xy_host && max_vertices > 0) {
-        // original vertices come from the template (domain mode); inserted ones from the log
-        int n0 = S.n0 < max_vertices ? S.n0 : max_vertices;
-        if (!h->P.random_mode)
-            MG_CUDA(h, cudaMemcpy(vertex_xy_host, h->t_xy + (size_t)S.domain * h->P.cap, sizeof(double2) * n0, cudaMemcpyDeviceToHost));
-        else std::memset(vertex_xy_host, 0, sizeof(double) * 2 * n0);
-        int ni = nv - S.n0;
-        if (ni > h->P.ins_cap) ni = h->P.ins_cap;
-        if (S.n0 + ni > max_vertices) ni = max_vertices - S.n0;
+        // original vertices: the domain's template, or (random-polygon mode) the episode's polygon regenerated from
+        // its counter; inserted ones from the log
+        int n0 = C.n0 < max_vertices ? C.n0 : max_vertices;
+        if (!h->P.random_mode) {
+            MG_CUDA(h, cudaMemcpy(vertex_xy_host, h->t_xy + (size_t)C.domain * h->P.cap, sizeof(double2) * n0, cudaMemcpyDeviceToHost));
+        } else {
+            int32_t n_gen = 0;
+            const int rc = regen_polygon(h, env, -1, vertex_xy_host, n0, &n_gen, nullptr, nullptr, nullptr, nullptr);
+            if (rc != MG_OK) return rc;
+            if (n_gen != C.n0) return fail(h, MG_ERR_STATE, "mg_get_elements: regenerated polygon does not match the episode");
+        }
+        int ni = nv - C.n0;
+        if (ni > h->P.ins_cap) { ni = h->P.ins_cap; overflow = true; }
+        if (C.n0 + ni > max_vertices) ni = max_vertices - C.n0;
         if (ni > 0)
-            MG_CUDA(h, cudaMemcpy(vertex_xy_host + 2 * (size_t)S.n0, h->P.ins_xy + (size_t)env * h->P.ins_cap, sizeof(double2) * ni,
+            MG_CUDA(h, cudaMemcpy(vertex_xy_host + 2 * (size_t)C.n0, h->P.ins_xy + (size_t)env * h->P.ins_cap, sizeof(double2) * ni,
                                   cudaMemcpyDeviceToHost));
     }
+    if (overflow)
+        return fail(h, MG_ERR_CAPACITY, "mg_get_elements: the episode outgrew the element / inserted-vertex log (the returned "
+                                        "prefix and the counts are valid); raise it with mg_set_log_capacity");
     return MG_OK;
+}
+
+int mg_debug_polygon(mg_handle h, int env, int episode, double *xy_host, int max_vertices, int32_t *n_out, double *area_out,
+                     int32_t *coarse_px_host, int32_t *k_out, double *spacing_out) {
+    if (!h || env < 0 || env >= h->num_envs) return fail(h, MG_ERR_ARG, "mg_debug_polygon: bad argument");
+    if (!h->P.random_mode) return fail(h, MG_ERR_STATE, "mg_debug_polygon: the handle is not in random-polygon mode");
+    MG_DEVICE(h);
+    MG_CUDA(h, cudaDeviceSynchronize());
+    return regen_polygon(h, env, episode, xy_host, max_vertices, n_out, area_out, coarse_px_host, k_out, spacing_out);
 }
 
 int mg_set_log_capacity(mg_handle h, int max_elements_per_env, int max_inserted_per_env) {
     if (!h || max_elements_per_env < 1 || max_inserted_per_env < 1) return fail(h, MG_ERR_ARG, "mg_set_log_capacity: bad argument");
-    MG_CUDA(h, cudaSetDevice(h->device));
+    MG_DEVICE(h);
     MG_CUDA(h, cudaDeviceSynchronize());
     Params &P = h->P;
     cudaFree(P.elem); cudaFree(P.ins_xy);
     P.elem = nullptr; P.ins_xy = nullptr;
+    h->was_reset = false;            // logs were discarded: the caller resets before stepping again
     P.elem_cap = max_elements_per_env; P.ins_cap = max_inserted_per_env;
     MG_CUDA(h, dalloc(&P.elem, (size_t)h->num_envs * P.elem_cap * 4));
     MG_CUDA(h, dalloc(&P.ins_xy, (size_t)h->num_envs * P.ins_cap));
-    h->was_reset = false;            // logs were discarded: the caller resets before stepping again
     return MG_OK;
 }
 
@@ -609,14 +710,55 @@ int mg_log_capacity(mg_handle h, int32_t *max_elements_per_env, int32_t *max_ins
     return MG_OK;
 }
 
+int mg_stats_async(mg_handle h, mg_episode_stats *stats_dev, int reset, void *stream) {
+    if (!h || !stats_dev) return fail(h, MG_ERR_ARG, "mg_stats_async: null pointer");
+    MG_DEVICE(h);
+    mg_stats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->P.stats, stats_dev, reset);
+    h->launches++;
+    MG_CUDA(h, cudaGetLastError());
+    note_user_stream(h, (cudaStream_t)stream);
+    return MG_OK;
+}
+
 int mg_stats(mg_handle h, mg_episode_stats *out, int reset) {
     if (!h || !out) return fail(h, MG_ERR_ARG, "mg_stats: null pointer");
-    MG_CUDA(h, cudaSetDevice(h->device));
+    MG_DEVICE(h);
     MG_CUDA(h, cudaDeviceSynchronize());
     mg_stats_kernel<<<1, 32>>>(h->P.stats, h->d_stats_out, reset);
     h->launches++;
     MG_CUDA(h, cudaGetLastError());
     MG_CUDA(h, cudaMemcpy(out, h->d_stats_out, sizeof(*out), cudaMemcpyDeviceToHost));
+    return MG_OK;
+}
+
+int mg_set_kernel_timing(mg_handle h, int enabled) {
+    if (!h) return fail(h, MG_ERR_ARG, "mg_set_kernel_timing: null handle");
+    MG_DEVICE(h);
+    MG_CUDA(h, cudaDeviceSynchronize());
+    if (enabled && !h->ev[0][0])
+        for (auto &tr : h->ev)
+            for (cudaEvent_t &e : tr) MG_CUDA(h, cudaEventCreate(&e));
+    h->timing = enabled != 0;
+    h->timing_steps = 0;
+    return MG_OK;
+}
+
+int mg_kernel_times(mg_handle h, double *ms4, int64_t *steps) {
+    if (!h) return fail(h, MG_ERR_ARG, "mg_kernel_times: null handle");
+    MG_DEVICE(h);
+    MG_CUDA(h, cudaDeviceSynchronize());
+    const int64_t n = h->timing_steps < mg_env_s::TIMING_SLOTS ? h->timing_steps : mg_env_s::TIMING_SLOTS;
+    double acc[4] = {0, 0, 0, 0};
+    for (int64_t i = 0; i < n; i++)
+        for (int k = 0; k < 4; k++) {
+            float t = 0;
+            MG_CUDA(h, cudaEventElapsedTime(&t, h->ev[i][k], h->ev[i][k + 1]));
+            acc[k] += t;
+        }
+    if (ms4)
+        for (int k = 0; k < 4; k++) ms4[k] = n ? acc[k] / n : 0;
+    if (steps) *steps = n;
+    h->timing_steps = 0;
     return MG_OK;
 }
 

@@ -1,11 +1,13 @@
-// Batched BoudaryEnv reset/step for sm_100a: one warp per environment.
+// Batched BoudaryEnv reset/step for sm_100a.
 //
-// The active boundary (updated_boundary.vertices) of the warp's environment is staged once per
-// phase from HBM into a per-warp shared-memory ring with a single 1-D bulk async copy
-// (cp.async.bulk + mbarrier, UBLKCP in SASS); every O(n) predicate then strides the ring with
-// 32 lanes (double2 loads) and is resolved with ballots / shuffle reductions.  Angle
-// classifications use the exact-safe filters of mg_math.cuh, so atan2 only runs where the
-// quantised value itself is needed (candidate keys, observation, element quality).
+// A step is two kernels (see the block comment above mg_step_screen_kernel): a screen over all envs, one thread per
+// env, that settles every step whose outcome follows from the env's 128-byte record (memoised rule -1 / +1
+// verdicts, Mesh.is_valid of the new-vertex quad from the neighbour fan), and a ring kernel, one warp per item,
+// for the steps that need the whole boundary.  There the active boundary (updated_boundary.vertices) is staged
+// once per item from HBM into a per-warp shared-memory ring with a single 1-D bulk async copy (cp.async.bulk +
+// mbarrier, UBLKCP in SASS); every O(n) predicate then strides the ring with 32 lanes (double2 loads) and is
+// resolved with ballots / shuffle reductions.  Angle classifications use the exact-safe filters of mg_math.cuh, so
+// atan2 only runs where the quantised value itself is needed (candidate keys, observation, element quality).
 //
 // Citations: E = v2/src/mesh_rl/envs/boundary_env.py, M = v2/src/mesh_rl/mesh_core.py,
 // C = v2/src/mesh_rl/components_core.py, D = v2/src/mesh_rl/data_core.py (reference tree).
@@ -18,13 +20,6 @@
 
 namespace mg {
 
-#ifndef MG_WPB
-#define MG_WPB 1     // apply / reset / template kernels: one item per block, so a slot frees the moment its item ends
-#endif
-constexpr int WPB = MG_WPB;     // warps (= environments) per block
-#ifndef MG_MINB
-#define MG_MINB 20    // phase A blocks per SM (96 registers, no spills; 18 / 22 measured slower)
-#endif
 #ifndef MG_UNROLL_OBS
 #define MG_UNROLL_OBS 1
 #endif
@@ -35,11 +30,6 @@ constexpr int WPB = MG_WPB;     // warps (= environments) per block
 #define MG_UNROLL_PIP 1
 #endif
 constexpr int UNROLL_OBS = MG_UNROLL_OBS, UNROLL_BQ = MG_UNROLL_BQ, UNROLL_PIP = MG_UNROLL_PIP;   // tuning knobs (profiles/README.md)
-#ifndef MG_WPB_A
-#define MG_WPB_A 1   // phase A (decide): one env per block (no slot held by the slower of two envs), 128-byte scratch
-#endif
-constexpr int WPB_A = MG_WPB_A;
-constexpr int QCAP_A = 32;       // phase A scratch: the parked record chunks + cached observation (26 words)
 constexpr int QCAP = 128 + 256;  // per-warp scratch: 4x32 ints + 32x4 doubles (coarse polygon of the generator)
 
 // ---------------------------------------------------------------------------------------------
@@ -743,218 +733,42 @@ __device__ __forceinline__ double u01(unsigned a, unsigned b) {   // 53-bit unif
 // random star polygon (ui/GenerateRandomPolygon.py:5-49) + densifier (ui/tk-ui.py:252-276)
 // Written by the warp into ring[0..n); returns n (even, min_verts <= n <= max_verts).
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ int generate_polygon(const Params &P, const Warp w, long long global_env, int episode);
+__device__ __noinline__ int generate_polygon(const Params &P, const Warp w, long long global_env, int episode, double *dbg = nullptr);
 
 // ---------------------------------------------------------------------------------------------
-// reset of one env (E:136-184): restore the polygon, rebuild candidates, first observation
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float reset_env(const Params &P, Warp &w, int env, EnvState &S) {
-    const int lane = w.lane;
-    const size_t off = (size_t)env * P.cap;
-    float obs;
-    if (!P.random_mode) {
-        const DomainScalars D = P.t_sc[S.domain];
-        const size_t toff = (size_t)S.domain * P.cap;
-#pragma unroll 1
-        for (int j = lane; j < D.n0; j += 32) {
-            P.xy[off + j] = P.t_xy[toff + j];
-            P.key[off + j] = P.t_key[toff + j];
-            P.stamp[off + j] = P.t_stamp[toff + j];
-            P.vid[off + j] = j;
-        }
-        S.n = D.n0; S.n0 = D.n0; S.ref_index = D.ref_index;
-        S.base_length = D.base_length; S.original_area = D.original_area; S.current_area = D.original_area;
-        S.area_min = D.area_min; S.area_crit = D.area_crit;
-        obs = lane < MG_OBS_DIM ? P.t_obs[S.domain * MG_OBS_DIM + lane] : 0.0f;
-    } else {
-        int n = generate_polygon(P, w, P.env_id_offset + env, S.episode);
-        w.n = n;
-        __syncwarp();
-#pragma unroll 1
-        for (int j = lane; j < n; j += 32) {
-            P.xy[off + j] = w.ring[j];
-            P.vid[off + j] = j;
-        }
-        rebuild_candidates(w, P.key + off, P.stamp + off);
-        __syncwarp();
-        S.n = n; S.n0 = n;
-        S.original_area = shoelace_area(w);
-        S.current_area = S.original_area;
-        { const double2 ar = estimate_area_range(w); S.area_min = ar.x; S.area_crit = ar.y; }
-        S.ref_index = find_reference_index(w, P.key + off, P.stamp + off);
-        obs = 0.0f;
-        if (S.ref_index >= 0) {
-            const ObsOut R = compute_obs(w, P.sc_full, S.ref_index, S.current_area / S.original_area);
-            obs = R.obs; S.base_length = R.base;
-        }
-    }
-    S.n_elements = 0; S.failed_num = 0; S.next_vid = S.n0; S.stamp_ctr = 0; S.ep_len = 0; S.ep_return = 0;
-    return obs;
-}
-
-// ---------------------------------------------------------------------------------------------
-// kernels
+// shared-memory layout of the one-warp blocks (decide / update / observe / reset / template kernels)
 // ---------------------------------------------------------------------------------------------
 struct SmemLayout {
     double2 *ring;
     int *queue;
+    int4 *stash;                 // 12 x 16 B: the env's EnvHot (chunks 0..7) and EnvCold (chunks 8..11)
     unsigned long long *mbar;
 };
-__device__ __forceinline__ SmemLayout carve(unsigned char *raw, int cap, int warp) {
+constexpr int STASH_BYTES = 256;
+// with_queue = false: kernels that never touch Warp::queue (decide, update)
+__device__ __forceinline__ SmemLayout carve(unsigned char *raw, int cap, bool with_queue = true) {
     SmemLayout L;
-    L.ring = reinterpret_cast<double2 *>(raw) + (size_t)warp * cap;
-    int *q = reinterpret_cast<int *>(reinterpret_cast<double2 *>(raw) + (size_t)WPB * cap);
-    L.queue = q + warp * QCAP;
-    L.mbar = reinterpret_cast<unsigned long long *>(q + WPB * QCAP) + warp;
+    L.ring = reinterpret_cast<double2 *>(raw);
+    L.queue = reinterpret_cast<int *>(L.ring + cap);
+    L.stash = reinterpret_cast<int4 *>(L.queue + (with_queue ? QCAP : 0));
+    L.mbar = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(L.stash) + STASH_BYTES);
     return L;
 }
-size_t smem_bytes(int cap) { return (size_t)WPB * cap * 16 + (size_t)WPB * QCAP * 4 + WPB * 8; }
-__device__ __forceinline__ SmemLayout carve_a(unsigned char *raw, int cap, int warp) {
-    SmemLayout L;
-    L.ring = reinterpret_cast<double2 *>(raw) + (size_t)warp * cap;
-    int *q = reinterpret_cast<int *>(reinterpret_cast<double2 *>(raw) + (size_t)WPB_A * cap);
-    L.queue = q + warp * QCAP_A;
-    L.mbar = reinterpret_cast<unsigned long long *>(q + WPB_A * QCAP_A) + warp;
-    return L;
-}
-size_t smem_bytes_a(int cap) { return (size_t)WPB_A * cap * 16 + (size_t)WPB_A * QCAP_A * 4 + WPB_A * 8; }
+size_t smem_bytes(int cap, bool with_queue = true) { return (size_t)cap * 16 + (with_queue ? (size_t)QCAP * 4 : 0) + STASH_BYTES + 16; }
 
-// Per-domain reset template: one warp per domain.
-__global__ void __launch_bounds__(WPB * 32) mg_template_kernel(const __grid_constant__ Params P, double2 *t_xy, double *t_key, int32_t *t_stamp,
-                                                              DomainScalars *t_sc, float *t_obs, const double *areas) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int d = blockIdx.x * WPB + warp;
-    if (d >= P.n_domains) return;
-    SmemLayout L = carve(smem_raw, P.cap, warp);
-    Warp w;
-    w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = t_sc[d].n0;
-    const size_t toff = (size_t)d * P.cap;
-#pragma unroll 1
-    for (int j = lane; j < w.n; j += 32) w.ring[j] = t_xy[toff + j];
-    __syncwarp();
-    rebuild_candidates(w, t_key + toff, t_stamp + toff);
-    __syncwarp();
-    DomainScalars D = t_sc[d];
-    D.original_area = areas ? areas[d] : shoelace_area(w);
-    { const double2 ar = estimate_area_range(w); D.area_min = ar.x; D.area_crit = ar.y; }
-    D.ref_index = find_reference_index(w, t_key + toff, t_stamp + toff);
-    float obs = 0.0f;
-    D.base_length = 0;
-    if (D.ref_index >= 0) {
-        const ObsOut R = compute_obs(w, P.sc_full, D.ref_index, D.original_area / D.original_area);
-        obs = R.obs; D.base_length = R.base;
-    }
-    if (lane < MG_OBS_DIM) t_obs[d * MG_OBS_DIM + lane] = obs;
-    if (lane == 0) t_sc[d] = D;
-}
-
-__global__ void __launch_bounds__(WPB * 32) mg_reset_kernel(const __grid_constant__ Params P, const uint8_t *mask, float *obs_out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.x * WPB + warp;
-    if (env >= P.num_envs) return;
-    SmemLayout L = carve(smem_raw, P.cap, warp);
-    Warp w;
-    w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = 0;
-    float obs;
-    if (mask == nullptr || mask[env]) {
-        EnvState S = P.st[env];
-        obs = reset_env(P, w, env, S);
-        if (lane == 0) P.st[env] = S;
-        if (lane < MG_OBS_DIM) P.obs_cache[(size_t)env * MG_OBS_DIM + lane] = obs;
-    } else {
-        obs = lane < MG_OBS_DIM ? P.obs_cache[(size_t)env * MG_OBS_DIM + lane] : 0.0f;
-    }
-    if (obs_out && lane < MG_OBS_DIM) obs_out[(size_t)env * MG_OBS_DIM + lane] = obs;
+// words / doubles of the stash: EnvHot = {n, ref_index, n_elements, flags | base_length(d1), failed_num(w6), ep_len(w7) |
+// ep_return(d4), current_area(d5) | fan d6..15}; EnvCold at byte 128 = {original_area(d16), area_min(d17) | area_crit(d18),
+// n0(w38), next_vid(w39) | stamp_ctr(w40), domain(w41), episode(w42)}
+enum { W_N = 0, W_REF = 1, W_NEL = 2, W_FLAGS = 3, W_FAILED = 6, W_EP_LEN = 7, W_N0 = 38, W_NEXT_VID = 39, W_STAMP_CTR = 40 };
+enum { D_BASE = 1, D_EP_RETURN = 4, D_CUR_AREA = 5, D_ORIGINAL_AREA = 16, D_AREA_MIN = 17, D_AREA_CRIT = 18 };
+__device__ __forceinline__ void stash_records(const Params &P, int4 *stash, int env, int lane) {
+    if (lane < 8) stash[lane] = reinterpret_cast<const int4 *>(P.hot + env)[lane];
+    else if (lane < 12) stash[lane] = reinterpret_cast<const int4 *>(P.cold + env)[lane - 8];
 }
 
 // ---------------------------------------------------------------------------------------------
-// One environment transition (E:388-457) + VecEnv auto-reset, as three phase kernels over
-// compacted work lists.  Every warp of a phase runs the same small piece of code (the single
-// fused kernel was instruction-fetch bound: 65 % I-cache hit rate, see profiles/):
-//   A  mg_step_decide_kernel  all envs   action -> candidate quad -> validity decision; finishes the
-//                                        step of every env whose action failed (cached observation)
-//   B  apply blocks           successes  boundary update, candidate keys, reward, next observation
-//   C  reset blocks           done envs  in-place reset (template copy or fresh random polygon)
-//   (B and C share one launch, mg_step_apply_reset_kernel: their env sets are disjoint)
-// Work lists are appended with one atomicAdd per warp.  Two sets of list sizes alternate: phase A of step s uses
-// set (CNT_STEP & 1) and records it in CNT_CUR; the B/C launch reads CNT_CUR, and its first thread clears the
-// other (idle) set and advances CNT_STEP for the next step.  The parity lives in device memory, so no memset sits
-// between launches and any sequence of mg_step calls can be captured in a CUDA graph (a ticket that lets the last
-// block clear one set cost 5 us per step, an 8-byte memset node 2 us).
+// candidate quads (E:236-283) and the memoised verdicts of the rule -1 / +1 quads
 // ---------------------------------------------------------------------------------------------
-struct StepIO {
-    const float *act;
-    float *obs_out;
-    double *rew_out;
-    uint8_t *term_out;
-    uint8_t *trunc_out;
-    float *term_obs_out;
-    int32_t *n_elem_out;
-};
-
-__device__ __forceinline__ void push_list(int *list, int *counter, int env, int lane, int cap) {
-    if (lane == 0) {
-        const int i = atomicAdd(counter, 1);
-        if (i < cap) list[i] = env;          // (only a profiling run with phase B masked off can overrun the list)
-    }
-}
-
-__device__ __forceinline__ void store_state(const Params &P, int env, const EnvState &S) { P.st[env] = S; }
-// phase A only changes failed_num, ep_len, ep_return: chunks 1 and 2 of the record.  Packed from registers (taking
-// the address of the record would force it into local memory).
-__device__ __forceinline__ void store_state(const Params &P, int env, const EnvHot &S) {
-    int4 *dst = reinterpret_cast<int4 *>(P.st + env);
-    dst[1] = make_int4(__double2loint(S.base_length), __double2hiint(S.base_length), S.failed_num, S.ep_len);
-    dst[2] = make_int4(__double2loint(S.ep_return), __double2hiint(S.ep_return), __double2loint(S.current_area),
-                       __double2hiint(S.current_area));
-}
-__device__ __forceinline__ EnvHot unpack_hot(int4 c0, int4 c1, int4 c2) {
-    EnvHot S;
-    S.n = c0.x; S.ref_index = c0.y; S.n_elements = c0.z; S.n0 = c0.w;
-    S.base_length = __hiloint2double(c1.y, c1.x); S.failed_num = c1.z; S.ep_len = c1.w;
-    S.ep_return = __hiloint2double(c2.y, c2.x); S.current_area = __hiloint2double(c2.w, c2.z);
-    return S;
-}
-
-// Tail of step() shared by phases A and B (E:361-386 + outputs + statistics).
-template <class State>
-__device__ __forceinline__ bool finish_step(const Params &P, const StepIO &io, int env, int lane, State &S, int n_before,
-                                            double reward, bool done, bool failed, bool success, bool force_trunc,
-                                            float obs) {
-    bool is_complete = true;
-    if (failed && S.failed_num >= 100) { done = true; is_complete = false; }
-    bool terminated = done && is_complete, truncated = done && !is_complete;
-    if (force_trunc && !done) { done = true; truncated = true; }          // sentinel, see DESIGN.md
-    S.ep_return += reward; S.ep_len++;
-    if (lane == 0) {
-        StatsAcc *T = P.stats + ((env >> 1) & (STAT_SLOTS - 1));
-        atomicAdd(&T->steps, 1ull);
-        atomicAdd(&T->sum_n, (unsigned long long)n_before);
-        if (success) { atomicAdd(&T->successes, 1ull); atomicAdd(&T->sum_n_success, (unsigned long long)n_before); }
-        if (done) {
-            atomicAdd(&T->episodes, 1ull);
-            atomicAdd(&T->completed, (unsigned long long)terminated);
-            atomicAdd(&T->truncated, (unsigned long long)truncated);
-            atomicAdd(&T->elements, (unsigned long long)S.n_elements);
-            atomicAdd(&T->sum_return, S.ep_return);
-            atomicAdd(&T->sum_length, (double)S.ep_len);
-        }
-        io.rew_out[env] = reward;
-        io.term_out[env] = terminated;
-        io.trunc_out[env] = truncated;
-        if (io.n_elem_out) io.n_elem_out[env] = S.n_elements;
-        store_state(P, env, S);
-    }
-    if (lane < MG_OBS_DIM) {
-        if (io.term_obs_out && done) io.term_obs_out[(size_t)env * MG_OBS_DIM + lane] = obs;
-        if (success) P.obs_cache[(size_t)env * MG_OBS_DIM + lane] = obs;
-        io.obs_out[(size_t)env * MG_OBS_DIM + lane] = obs;
-    }
-    return done && P.auto_reset;
-}
-
 __device__ __forceinline__ void quad_indices(int rule, bool new_vertex, int idx, int n, int (&qi)[4], int &ri) {
     const int ip1 = idx + 1 >= n ? idx + 1 - n : idx + 1, im1 = idx - 1 < 0 ? idx - 1 + n : idx - 1;
     if (new_vertex) {
@@ -965,6 +779,219 @@ __device__ __forceinline__ void quad_indices(int rule, bool new_vertex, int idx,
         qi[0] = wrapn(idx - 2, n); qi[1] = im1; qi[2] = idx; qi[3] = ip1; ri = 2;
     }
 }
+
+// EnvHot::flags of the state in the ring.  A rule -1 / rule +1 element consists of boundary vertices only, so whether
+// such a step is accepted (E:319-323: Mesh.is_valid(0) and not check_intersection_with_boundary) is a function of
+// the state.  The O(1) half (Mesh.is_valid) is evaluated here, when the state changes; a valid quad is marked
+// pending and the O(n) half runs in the decide kernel the first time a rule action actually asks for it.
+__device__ __noinline__ int memo_flags(const Warp w, int idx) {
+    const int n = w.n;
+    if (idx < 0 || n < 6) return 0;
+    int flags = 0;
+#pragma unroll 1
+    for (int r = 0; r < 2; r++) {
+        int qi[4], ri;
+        quad_indices(r == 0 ? -1 : 1, false, idx, n, qi, ri);
+        Quad Q;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const P2 p = w.at(qi[k]); Q.x[k] = p.x; Q.y[k] = p.y; }
+        if (mesh_is_valid(w, Q)) flags |= (r == 0 ? HOT_PEND_M1 : HOT_PEND_P1);
+    }
+    return flags;
+}
+
+// Mesh.is_valid(0) (C:738-757, C:814-826) of one quad by one thread (the screen kernel): same predicates as
+// mesh_is_valid, evaluated in sequence; the conjunction does not depend on the order.
+__device__ __forceinline__ bool quad_valid_serial(P2 m0, P2 m1, P2 m2, P2 m3) {
+    double cr, dt;
+    cross_dot(m0, m1, m3, cr, dt);
+    if (corner_angle_invalid(cr, dt)) return false;
+    cross_dot(m1, m2, m0, cr, dt);
+    if (corner_angle_invalid(cr, dt)) return false;
+    cross_dot(m2, m3, m1, cr, dt);
+    if (corner_angle_invalid(cr, dt)) return false;
+    cross_dot(m3, m0, m2, cr, dt);
+    if (corner_angle_invalid(cr, dt)) return false;
+    if (is_cross(m0, m1, m2, m3)) return false;
+    if (is_cross(m0, m3, m1, m2)) return false;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// record stores (by the env's warp; the ring holds the env's current boundary)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_hot(EnvHot *dst_rec, const Warp &w, int ref_index, int n_elements, int flags,
+                                          double base_length, int failed_num, int ep_len, double ep_return, double current_area) {
+    int4 *dst = reinterpret_cast<int4 *>(dst_rec);
+    if (w.lane == 0) {
+        dst[0] = make_int4(w.n, ref_index, n_elements, flags);
+        dst[1] = make_int4(__double2loint(base_length), __double2hiint(base_length), failed_num, ep_len);
+        dst[2] = make_int4(__double2loint(ep_return), __double2hiint(ep_return), __double2loint(current_area),
+                           __double2hiint(current_area));
+    }
+    if (w.lane < 5) {                       // fan = B[i-2 .. i+2]
+        const int j = w.n > 0 ? wrapn((ref_index < 0 ? 0 : ref_index) - 2 + w.lane, w.n) : 0;
+        reinterpret_cast<double2 *>(dst)[3 + w.lane] = w.ring[j];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// reset of one env (E:136-184): restore the polygon, rebuild candidates, first observation.  Writes the env's
+// rings and records; returns the observation (lane < 18).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float reset_env(const Params &P, Warp &w, int env, int domain, int episode) {
+    const int lane = w.lane;
+    const size_t off = (size_t)env * P.cap;
+    float obs;
+    __syncwarp();
+    if (!P.random_mode) {
+        const DomainProto *T = P.t_proto + domain;
+        const int n0 = T->cold.n0;
+        const size_t toff = (size_t)domain * P.cap;
+#pragma unroll 1
+        for (int j = lane; j < n0; j += 32) {
+            P.xy[off + j] = P.t_xy[toff + j];
+            P.key[off + j] = P.t_key[toff + j];
+            P.stamp[off + j] = P.t_stamp[toff + j];
+            P.vid[off + j] = j;
+        }
+        if (lane < 8) reinterpret_cast<int4 *>(P.hot + env)[lane] = reinterpret_cast<const int4 *>(&T->hot)[lane];
+        if (lane == 8) {
+            EnvCold C = T->cold;
+            C.domain = domain; C.episode = episode;
+            P.cold[env] = C;
+        }
+        obs = lane < MG_OBS_DIM ? P.t_obs[domain * MG_OBS_DIM + lane] : 0.0f;
+    } else {
+        const int n = generate_polygon(P, w, P.env_id_offset + env, episode);
+        w.n = n;
+        __syncwarp();
+#pragma unroll 1
+        for (int j = lane; j < n; j += 32) {
+            P.xy[off + j] = w.ring[j];
+            P.vid[off + j] = j;
+        }
+        rebuild_candidates(w, P.key + off, P.stamp + off);
+        __syncwarp();
+        EnvCold C;
+        C.original_area = shoelace_area(w);
+        { const double2 ar = estimate_area_range(w); C.area_min = ar.x; C.area_crit = ar.y; }
+        C.n0 = n; C.next_vid = n; C.stamp_ctr = 0; C.domain = domain; C.episode = episode;
+#pragma unroll
+        for (int k = 0; k < 5; k++) C.pad[k] = 0;
+        const int ref_index = find_reference_index(w, P.key + off, P.stamp + off);
+        obs = 0.0f;
+        double base = 0;
+        if (ref_index >= 0) {
+            const ObsOut R = compute_obs(w, P.sc_full, ref_index, C.original_area / C.original_area);
+            obs = R.obs; base = R.base;
+        }
+        const int flags = memo_flags(w, ref_index);
+        store_hot(P.hot + env, w, ref_index, 0, flags, base, 0, 0, 0.0, C.original_area);
+        if (lane == 0) P.cold[env] = C;
+    }
+    return obs;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+// Per-domain reset template: one warp per domain.
+__global__ void __launch_bounds__(32) mg_template_kernel(const __grid_constant__ Params P, double2 *t_xy, double *t_key, int32_t *t_stamp,
+                                                       DomainProto *t_proto, float *t_obs, const int32_t *n0s, const double *areas) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    const int d = blockIdx.x;
+    if (d >= P.n_domains) return;
+    SmemLayout L = carve(smem_raw, P.cap);
+    Warp w;
+    w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = n0s[d];
+    const size_t toff = (size_t)d * P.cap;
+#pragma unroll 1
+    for (int j = lane; j < w.n; j += 32) w.ring[j] = t_xy[toff + j];
+    __syncwarp();
+    rebuild_candidates(w, t_key + toff, t_stamp + toff);
+    __syncwarp();
+    EnvCold C;
+    C.original_area = areas ? areas[d] : shoelace_area(w);
+    { const double2 ar = estimate_area_range(w); C.area_min = ar.x; C.area_crit = ar.y; }
+    C.n0 = w.n; C.next_vid = w.n; C.stamp_ctr = 0; C.domain = d; C.episode = 0;
+#pragma unroll
+    for (int k = 0; k < 5; k++) C.pad[k] = 0;
+    const int ref_index = find_reference_index(w, t_key + toff, t_stamp + toff);
+    float obs = 0.0f;
+    double base = 0;
+    if (ref_index >= 0) {
+        const ObsOut R = compute_obs(w, P.sc_full, ref_index, C.original_area / C.original_area);
+        obs = R.obs; base = R.base;
+    }
+    const int flags = memo_flags(w, ref_index);
+    store_hot(&t_proto[d].hot, w, ref_index, 0, flags, base, 0, 0, 0.0, C.original_area);
+    if (lane == 0) t_proto[d].cold = C;
+    if (lane < MG_OBS_DIM) t_obs[d * MG_OBS_DIM + lane] = obs;
+}
+
+__global__ void __launch_bounds__(32) mg_reset_kernel(const __grid_constant__ Params P, const uint8_t *mask, float *obs_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    const int env = blockIdx.x;
+    if (env >= P.num_envs) return;
+    SmemLayout L = carve(smem_raw, P.cap);
+    Warp w;
+    w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = 0;
+    float obs;
+    if (mask == nullptr || mask[env]) {
+        const int domain = P.cold[env].domain, episode = P.cold[env].episode;
+        obs = reset_env(P, w, env, domain, episode);
+        if (lane < MG_OBS_DIM) P.obs_cache[(size_t)env * MG_OBS_DIM + lane] = obs;
+    } else {
+        obs = lane < MG_OBS_DIM ? P.obs_cache[(size_t)env * MG_OBS_DIM + lane] : 0.0f;
+    }
+    if (obs_out && lane < MG_OBS_DIM) obs_out[(size_t)env * MG_OBS_DIM + lane] = obs;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One environment transition (E:388-457) + VecEnv auto-reset, as four kernels with SMALL code images.
+//
+//   1  mg_step_screen_kernel   all envs, ONE THREAD per env.  Reads the 128-byte EnvHot record and the action and
+//      settles every step whose outcome follows from them: a rule -1 / +1 action against the memoised verdict
+//      (flags), a rule-0 action whose new-vertex quad [P, B[i-1], B[i], B[i+1]] is not a valid element (Mesh.is_valid
+//      needs only the neighbour fan) while the rule -1 fallback (E:258-262) is known to fail too.  A failed step
+//      leaves the state untouched and returns the cached observation (verified bit-identical), so
+//      these envs never touch their boundary ring: reward, flags, counters and the 32 changed bytes of the record
+//      are all that moves.  Under a uniform random policy ~91 % of the steps end here.
+//   The other three run ONE WARP per work item over compacted lists; the boundary is staged once per item into a
+//   shared-memory ring with one cp.async.bulk:
+//   2  mg_step_decide_kernel   rule-0 candidates whose new vertex still needs the whole boundary (point-in-polygon
+//      M:74-128, find_same_point E:766-769, boundary intersection M:536-556) and rule -1 / +1 actions whose verdict
+//      is still pending (valid quad, intersection test not done yet: evaluated once per state, then memoised).
+//      Failed steps end here; accepted elements go to the next list.
+//   3  mg_step_update_kernel   accepted elements: element log, boundary update, candidate keys, area, quality,
+//      reward, termination (M:601-674, C:943-958, C:881-892, M:355-452, E:590-607, E:345-351).
+//   4  mg_step_observe_kernel  every env whose state changed: reference point (M:295-316), next observation
+//      (C:1192-1290), new memo; and the in-place resets of finished envs (template copy or fresh random polygon).
+//
+// Why four launches: a warp-per-item kernel is bound by instruction fetch as soon as its image outgrows the SM's
+// instruction cache -- every warp walks its own path through the image (profiles/r2a_*: one 248 KB ring kernel
+// spent 57 % of its issue slots in stall_no_instruction; round 1's 186 KB apply kernel 25 %).  Each image here is
+// well under 100 KB on its common path.  Kernels hand items over through 32-byte work records.
+//
+// Work lists are appended with one atomicAdd per warp.  Two sets of counters alternate: the screen kernel of step s
+// uses set (CNT_STEP & 1) and records it in CNT_CUR; the later kernels read CNT_CUR, and the first thread of the
+// observe kernel clears the other (idle) set and advances CNT_STEP for the next step.  The parity lives in device
+// memory, so no memset sits between launches and any sequence of mg_step calls can be captured in a CUDA graph.
+// ---------------------------------------------------------------------------------------------
+struct StepIO {
+    const float *act;
+    float *obs_out;
+    double *rew_out;
+    uint8_t *term_out;
+    uint8_t *trunc_out;
+    float *term_obs_out;
+    int32_t *n_elem_out;
+    int obs_full;     // 1: every row of obs_out is written.  0: obs_out still holds the previous step's observations
+                      // (same unmodified buffer, mg_set_obs_delta): only the rows that change are written
+};
 
 // |x * 1e4 - (k + 0.5)| < tol for some integer k: np_round4(x) could flip under a perturbation of x
 __device__ __forceinline__ bool near_round4_tie(double x, double tol) {
@@ -983,192 +1010,376 @@ __device__ __noinline__ double2 action_frame_exact(double ax, double ay, double 
     return make_double2(ox, oy);
 }
 
-// ---- phase A ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(WPB_A * 32, MG_MINB) mg_step_decide_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.x * WPB_A + warp;
-    if (env >= P.num_envs) return;
-    SmemLayout L = carve_a(smem_raw, P.cap, warp);
-    init_mbar(L.mbar, lane);
-    // the record first (kept L2-resident by its evict_last hint), then exactly n vertices: copying the whole
-    // `cap` slab before the record arrives hides one L2 round trip but doubles the DRAM traffic of the phase for
-    // the same time (profiles/README.md, A/B v1)
-    const int4 *rec = reinterpret_cast<const int4 *>(P.st + env);
-    const int4 rec0 = ldg_keep(rec), rec1 = ldg_keep(rec + 1), rec2 = ldg_keep(rec + 2);
-    if (env == 0 && lane == 0) P.counters[CNT_CUR] = P.counters[CNT_STEP] & 1;    // the set this step's lists use
-    // requested now so that the tail of a failed step does not pay another DRAM round trip
-    const float obs_cached = lane < MG_OBS_DIM ? P.obs_cache[(size_t)env * MG_OBS_DIM + lane] : 0.0f;
-    EnvHot S = unpack_hot(rec0, rec1, rec1);
-    stage_issue(L.ring, L.mbar, P.xy + (size_t)env * P.cap, S.n > 0 ? S.n : 2, lane);
-    // Everything only the tail of the step needs (failed_num, ep_len, ep_return, current_area, the cached
-    // observation) is parked in this warp's shared scratch instead of being carried -- and spilled to local
-    // memory -- across the predicate calls: with the shared-memory carve-out at its maximum L1 is tiny and every
-    // spill reload was an L2 round trip (profiles/r1_ncu_step_v9.txt).
-    int4 *stash = reinterpret_cast<int4 *>(L.queue);
-    float *stash_obs = reinterpret_cast<float *>(L.queue) + 8;
-    if (lane == 0) { stash[0] = rec1; stash[1] = rec2; }
-    if (lane < MG_OBS_DIM) stash_obs[lane] = obs_cached;
-    const float a0 = io.act[(size_t)env * 3 + 0], a1 = io.act[(size_t)env * 3 + 1], a2 = io.act[(size_t)env * 3 + 2];
-    Warp w;
-    w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = S.n;
-    // An env without a reference point (empty candidate list, E:736-738 returns None) has no
-    // defined continuation in the reference (its next step raises): it is reported truncated.
-    const bool dead = S.ref_index < 0 || S.n < 3;
-    stage_wait(L.mbar, 0);
-
-    const int n = S.n, idx = dead ? 0 : S.ref_index;
-    const P2 ref = dead ? mk(0, 0) : w.at(idx), right_p = dead ? mk(1, 0) : w.at(idx - 1);
-
-    // ---- action -> candidate vertex (E:783-792, E:202-210, D:112-137) ------------------------
-    // theta = 2 pi - atan2(dy, dx)  =>  cos(theta) ~ dx / r, sin(theta) ~ -dy / r.  The frame is first
-    // evaluated from the edge vector (no atan2 / sincos); that value is within ~1e-14 of the reference's,
-    // so both round to the same 4-decimal vertex unless a coordinate sits next to a rounding tie.  Ties
-    // are NOT rare on axis-aligned domains (dyadic action components times a short base length land
-    // exactly on k + 0.5, and the reference's sin(fl(2 pi)) = -2.4e-16 then decides): in that band the
-    // reference's own expression is evaluated (exact-safe filter, like the angle classes of mg_math.cuh).
-    P2 newp;
-    {
-        double ax = (double)np_round4f(a1), ay = (double)np_round4f(a2);
-        double dx = right_p.x - ref.x, dy = right_p.y - ref.y;
-        double r2 = dx * dx + dy * dy;
-        double rinv = rsqrt(r2);                        // estimate only: the tie band below is > 1000x wider than its error
-        double c = r2 > 0 ? dx * rinv : 1.0, s = r2 > 0 ? -(dy * rinv) : 0.0;
-        double ox = c * ax + s * ay;
-        double oy = -s * ax + c * ay;
-        ox *= S.base_length; oy *= S.base_length;
-        ox += ref.x; oy += ref.y;
-        const double tol = 1e-8 * (3 * fabs(S.base_length) + fabs(ref.x) + fabs(ref.y) + 1);   // in units of 1e-4
-        if (near_round4_tie(ox, tol) || near_round4_tie(oy, tol)) {
-            const double2 o = action_frame_exact(ax, ay, dx, dy, S.base_length, ref);
-            ox = o.x; oy = o.y;
-        }
-        newp = mk(np_round4(ox), np_round4(oy));
+// action -> candidate vertex (E:783-792, E:202-210, D:112-137).
+// theta = 2 pi - atan2(dy, dx)  =>  cos(theta) ~ dx / r, sin(theta) ~ -dy / r.  The frame is first evaluated from
+// the edge vector (no atan2 / sincos); that value is within ~1e-14 of the reference's, so both round to the same
+// 4-decimal vertex unless a coordinate sits next to a rounding tie.  Ties are NOT rare on axis-aligned domains
+// (dyadic action components times a short base length land exactly on k + 0.5, and the reference's
+// sin(fl(2 pi)) = -2.4e-16 then decides): in that band the reference's own expression is evaluated (exact-safe
+// filter, like the angle classes of mg_math.cuh).
+__device__ __forceinline__ P2 action_to_point(float a1, float a2, P2 ref, P2 right_p, double base_length) {
+    double ax = (double)np_round4f(a1), ay = (double)np_round4f(a2);
+    double dx = right_p.x - ref.x, dy = right_p.y - ref.y;
+    double r2 = dx * dx + dy * dy;
+    double rinv = rsqrt(r2);                        // estimate only: the tie band below is > 1000x wider than its error
+    double c = r2 > 0 ? dx * rinv : 1.0, s = r2 > 0 ? -(dy * rinv) : 0.0;
+    double ox = c * ax + s * ay;
+    double oy = -s * ax + c * ay;
+    ox *= base_length; oy *= base_length;
+    ox += ref.x; oy += ref.y;
+    const double tol = 1e-8 * (3 * fabs(base_length) + fabs(ref.x) + fabs(ref.y) + 1);   // in units of 1e-4
+    if (near_round4_tie(ox, tol) || near_round4_tie(oy, tol)) {
+        const double2 o = action_frame_exact(ax, ay, dx, dy, base_length, ref);
+        ox = o.x; oy = o.y;
     }
+    return mk(np_round4(ox), np_round4(oy));
+}
 
-    bool done = false;
-    double reward = 0;
-    bool have_mesh = true, new_vertex = false;
-    int rule = 0;   // -1, +1, 0
-    if (dead) {
-        have_mesh = false;
-    } else if (n <= 5) {                            // E:428-430
-        reward = 10; done = true; have_mesh = false;
-    } else if (a0 <= -0.5f) rule = -1;
-    else if (a0 >= 0.5f) rule = 1;
-    else {
-        if (point_inside(w, newp, P.vid + (size_t)env * P.cap, S.n0)) {
-            if (find_same_point(w, newp)) rule = -1;
-            else new_vertex = true;
+// one work record appended by one warp (lane 0)
+__device__ __forceinline__ void push_item(WorkItem *list, int *counter, int cap, const WorkItem &W, int lane) {
+    if (lane == 0) {
+        const int i = atomicAdd(counter, 1);
+        if (i < cap) list[i] = W;
+    }
+}
+__device__ __forceinline__ WorkItem make_item(int env, int n, int kind, int rule, int flag, int done, double x, double y) {
+    WorkItem W;
+    W.newx = x; W.newy = y; W.env = env; W.n = n;
+    W.kind = (int8_t)kind; W.rule = (int8_t)rule; W.flag = (int8_t)flag; W.done = (int8_t)done; W.pad = 0;
+    return W;
+}
+
+// ---- kernel 1: screen ------------------------------------------------------------------------
+constexpr int SCREEN_THREADS = 128;
+__global__ void __launch_bounds__(SCREEN_THREADS) mg_step_screen_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io) {
+    __shared__ uint8_t s_copy[SCREEN_THREADS];     // bit 0: cached observation -> obs_out, bit 1: -> term_obs_out
+    const int env = blockIdx.x * SCREEN_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool active = env < P.num_envs;
+    const int set = P.counters[CNT_STEP] & 1;
+    if (env == 0) P.counters[CNT_CUR] = set;          // the set this step's lists use
+    int *cnt = P.counters + CNT_SET * set;
+
+    // where the step goes: 0 = settled here, 1 = decide list, 2 = accept list
+    int route = 0;
+    bool settled_done = false, trunc_flag = false, term_flag = false;
+    WorkItem W = make_item(env, 0, WORK_APPLY, 0, 0, 0, 0.0, 0.0);
+    int n = 0, n_elements = 0, ep_len = 0;
+    double ep_return = 0;
+    uint8_t copy_code = 0;
+    if (active) {
+        const int4 *rec = reinterpret_cast<const int4 *>(P.hot + env);
+        const int4 c0 = rec[0], c1 = rec[1], c2 = rec[2];
+        n = c0.x;
+        const int ref_index = c0.y, flags = c0.w;
+        n_elements = c0.z;
+        const double base_length = __hiloint2double(c1.y, c1.x);
+        int failed_num = c1.z;
+        ep_len = c1.w;
+        ep_return = __hiloint2double(c2.y, c2.x);
+        const float a0 = io.act[(size_t)env * 3 + 0], a1 = io.act[(size_t)env * 3 + 1], a2 = io.act[(size_t)env * 3 + 2];
+        W.n = n;
+        // An env without a reference point (empty candidate list, E:736-738 returns None) has no defined
+        // continuation in the reference (its next step raises): it is reported truncated.
+        const bool dead = ref_index < 0 || n < 3;
+        double reward = 0;
+        bool done = false, fail_penalty = false;
+        if (dead) {
+        } else if (n <= 5) {                              // E:428-430
+            reward = 10; done = true;
+        } else if (a0 <= -0.5f || a0 >= 0.5f) {           // rule -1 / +1: memoised verdict
+            const bool m1 = a0 <= -0.5f;
+            W.rule = m1 ? -1 : 1;
+            if (flags & (m1 ? HOT_OK_M1 : HOT_OK_P1)) route = 2;
+            else if (flags & (m1 ? HOT_PEND_M1 : HOT_PEND_P1)) { route = 1; W.kind = WORK_DECIDE_RULE; }
+            else fail_penalty = true;
         } else {
-            reward += S.n_elements ? -1.0 / S.n_elements : -1;      // E:279
-            have_mesh = false;
+            const double2 *fan = reinterpret_cast<const double2 *>(rec) + 3;
+            const double2 f1 = fan[1], f2 = fan[2], f3 = fan[3];
+            const P2 ref = mk(f2.x, f2.y), right_p = mk(f1.x, f1.y), left_p = mk(f3.x, f3.y);
+            const P2 newp = action_to_point(a1, a2, ref, right_p, base_length);
+            // the new-vertex element (E:264-270) must pass Mesh.is_valid (E:319); if the candidate vertex coincides
+            // with a boundary vertex the rule -1 element is used instead (E:258-262).  When neither can be accepted
+            // the step fails whatever the point-in-polygon test says (same reward, E:279 / E:357).
+            const bool qvalid = quad_valid_serial(newp, right_p, ref, left_p);
+            if (qvalid || (flags & (HOT_OK_M1 | HOT_PEND_M1))) {
+                route = 1;
+                W.kind = WORK_DECIDE_NEW; W.flag = qvalid ? 1 : 0; W.newx = newp.x; W.newy = newp.y;
+            } else fail_penalty = true;
+        }
+        if (route == 0) {
+            // failed step (or the n <= 5 sentinel): nothing changed, the observation is the cached one
+            if (fail_penalty) reward += n_elements ? -1.0 / n_elements : -1;          // E:279 / E:357
+            failed_num++;
+            bool is_complete = true;
+            if (failed_num >= 100) { done = true; is_complete = false; }              // E:382-384
+            term_flag = done && is_complete;
+            trunc_flag = done && !is_complete;
+            if (dead && !done) { done = true; trunc_flag = true; }                    // sentinel, see DESIGN.md
+            ep_return += reward;
+            ep_len++;
+            settled_done = done;
+            io.rew_out[env] = reward;
+            io.term_out[env] = term_flag;
+            io.trunc_out[env] = trunc_flag;
+            if (io.n_elem_out) io.n_elem_out[env] = n_elements;
+            int4 *dst = reinterpret_cast<int4 *>(P.hot + env);
+            dst[1] = make_int4(c1.x, c1.y, failed_num, ep_len);
+            dst[2] = make_int4(__double2loint(ep_return), __double2hiint(ep_return), c2.z, c2.w);
+            copy_code = (io.obs_full ? 1 : 0) | ((done && io.term_obs_out) ? 2 : 0);
         }
     }
-    if (have_mesh) {
-        P2 m[4]; int qi[4]; int ri;
-        quad_indices(rule, new_vertex, idx, n, qi, ri);
-#pragma unroll
-        for (int k = 0; k < 4; k++) m[k] = qi[k] < 0 ? newp : w.at(qi[k]);
-        Quad Q;
-#pragma unroll
-        for (int k = 0; k < 4; k++) { Q.x[k] = m[k].x; Q.y[k] = m[k].y; }
-        bool valid = mesh_is_valid(w, Q);
-        if (valid) valid = !intersects_boundary(w, Q, make_int4(qi[0], qi[1], qi[2], qi[3]), ri, ref);
-        if (valid) {
-            // hand the element over to phase B
-            if (lane == 0) {
-                Pending Q;
-                Q.newx = newp.x; Q.newy = newp.y;
-                Q.rule = rule; Q.new_vertex = new_vertex ? 1 : 0;
-                P.pend[env] = Q;
-            }
-            push_list(P.succ_list, P.counters + 2 * (P.counters[CNT_STEP] & 1) + 0, env, lane, P.num_envs);
-            return;
-        }
-        reward += S.n_elements ? -1.0 / S.n_elements : -1;          // E:357
-    }
-    // failed step: nothing changed, the reference recomputes a bit-identical observation
-    __syncwarp();
-    const float obs = lane < MG_OBS_DIM ? stash_obs[lane] : 0.0f;
+    // ---- work lists: one atomicAdd per warp and list ------------------------------------------
     {
-        const int4 r1 = stash[0], r2 = stash[1];
-        S.base_length = __hiloint2double(r1.y, r1.x); S.failed_num = r1.z; S.ep_len = r1.w;
-        S.ep_return = __hiloint2double(r2.y, r2.x); S.current_area = __hiloint2double(r2.w, r2.z);
+        const unsigned md = __ballot_sync(FULL, route == 1);
+        if (md) {
+            int base = 0;
+            if (lane == __ffs(md) - 1) base = atomicAdd(&cnt[CNT_DECIDE], __popc(md));
+            base = __shfl_sync(FULL, base, __ffs(md) - 1);
+            if (route == 1) P.decide_list[base + __popc(md & ((1u << lane) - 1))] = W;
+        }
+        const unsigned ma = __ballot_sync(FULL, route == 2);
+        if (ma) {
+            int base = 0;
+            if (lane == __ffs(ma) - 1) base = atomicAdd(&cnt[CNT_ACCEPT], __popc(ma));
+            base = __shfl_sync(FULL, base, __ffs(ma) - 1);
+            if (route == 2) P.accept_list[base + __popc(ma & ((1u << lane) - 1))] = W;
+        }
+        const bool to_reset = settled_done && P.auto_reset;
+        const unsigned r = __ballot_sync(FULL, to_reset);
+        if (r) {
+            int base = 0;
+            if (lane == __ffs(r) - 1) base = atomicAdd(&cnt[CNT_OBSERVE], __popc(r));
+            base = __shfl_sync(FULL, base, __ffs(r) - 1);
+            if (to_reset) P.observe_list[base + __popc(r & ((1u << lane) - 1))] = make_item(env, 0, WORK_RESET, 0, 0, 0, 0.0, 0.0);
+        }
     }
-    S.failed_num++;
-    if (finish_step(P, io, env, lane, S, n, reward, done, true, false, dead, obs))
-        push_list(P.reset_list, P.counters + 2 * (P.counters[CNT_STEP] & 1) + 1, env, lane, P.num_envs);
+    // ---- statistics: one set of atomics per warp --------------------------------------------
+    {
+        const unsigned steps = __popc(__ballot_sync(FULL, active));
+        const unsigned sum_n = __reduce_add_sync(FULL, active ? (unsigned)n : 0u);
+        const unsigned dm = __ballot_sync(FULL, settled_done);
+        StatsAcc *T = P.stats + ((blockIdx.x * (SCREEN_THREADS / 32) + (threadIdx.x >> 5)) & (STAT_SLOTS - 1));
+        const unsigned rm = __ballot_sync(FULL, route != 0);
+        const unsigned ring_n = __reduce_add_sync(FULL, route != 0 ? (unsigned)n : 0u);
+        if (lane == 0 && steps) {
+            atomicAdd(&T->steps, (unsigned long long)steps);
+            atomicAdd(&T->sum_n, (unsigned long long)sum_n);
+            if (rm) {
+                atomicAdd(&T->ring_items, (unsigned long long)__popc(rm));
+                atomicAdd(&T->sum_n_ring, (unsigned long long)ring_n);
+            }
+        }
+        if (dm) {
+            const unsigned n_term = __popc(__ballot_sync(FULL, settled_done && term_flag));
+            const unsigned n_trunc = __popc(__ballot_sync(FULL, settled_done && trunc_flag));
+            const unsigned elems = __reduce_add_sync(FULL, settled_done ? (unsigned)n_elements : 0u);
+            const double ret = warp_sum_d(settled_done ? ep_return : 0.0);
+            const unsigned len = __reduce_add_sync(FULL, settled_done ? (unsigned)ep_len : 0u);
+            if (lane == 0) {
+                atomicAdd(&cnt[CNT_DONE], __popc(dm));
+                atomicAdd(&T->episodes, (unsigned long long)__popc(dm));
+                atomicAdd(&T->completed, (unsigned long long)n_term);
+                atomicAdd(&T->truncated, (unsigned long long)n_trunc);
+                atomicAdd(&T->elements, (unsigned long long)elems);
+                atomicAdd(&T->sum_return, ret);
+                atomicAdd(&T->sum_length, (double)len);
+            }
+        }
+    }
+    // ---- observation rows of the settled envs (cached: nothing changed) ------------------------
+    s_copy[threadIdx.x] = copy_code;
+    if (__syncthreads_or(copy_code != 0)) {
+        const size_t row0 = (size_t)blockIdx.x * SCREEN_THREADS * MG_OBS_DIM;
+        for (int e = threadIdx.x; e < SCREEN_THREADS * MG_OBS_DIM; e += SCREEN_THREADS) {
+            const uint8_t code = s_copy[e / MG_OBS_DIM];
+            if (code) {
+                const float v = P.obs_cache[row0 + e];
+                if (code & 1) io.obs_out[row0 + e] = v;
+                if (code & 2) io.term_obs_out[row0 + e] = v;
+            }
+        }
+    }
 }
 
-// ---- phase B ---------------------------------------------------------------------------------
-// in-place reset of one finished env (V:40-52): new episode, first observation to the caller
-__device__ __noinline__ void reset_in_place(const Params &P, const StepIO &io, int env, Warp w) {
-    EnvState S = P.st[env];                      // reloaded here: the caller's copy stays in registers
-    S.episode++;
-    float obs = reset_env(P, w, env, S);
-    if (w.lane == 0) P.st[env] = S;
-    if (w.lane < MG_OBS_DIM) {
-        P.obs_cache[(size_t)env * MG_OBS_DIM + w.lane] = obs;
-        io.obs_out[(size_t)env * MG_OBS_DIM + w.lane] = obs;
+// ---- the three warp-per-item kernels -----------------------------------------------------------
+// Item loop shared by them: the first item of a block is its block index, later ones come from a ticket counter (an
+// early finisher takes the next item; the ticket is requested at the start of the previous item, so its latency is
+// hidden).
+#define MG_ITEM_LOOP_BEGIN(total, ticket)                                                   \
+    int t_ = blockIdx.x;                                                                    \
+    if (t_ >= (total)) return;                                                              \
+    init_mbar(L.mbar, lane);                                                                \
+    unsigned phase = 0;                                                                     \
+    _Pragma("unroll 1") while (t_ < (total)) {                                              \
+        int next_t_ = 0;                                                                    \
+        if (lane == 0) next_t_ = gridDim.x + atomicAdd((ticket), 1);
+#define MG_ITEM_LOOP_END                          \
+        t_ = __shfl_sync(FULL, next_t_, 0);       \
     }
-    __syncwarp();
+
+// E:319-323 for a quad whose Mesh.is_valid(0) is already known to hold: not check_intersection_with_boundary
+__device__ __noinline__ bool quad_clear_of_boundary(const Warp w, const Quad Q, const int4 qv, int ri, P2 ref) {
+    return !intersects_boundary(w, Q, qv, ri, ref);
+}
+// the pending half of a memoised rule -1 / +1 verdict (see memo_flags)
+__device__ __forceinline__ bool rule_quad_clear(const Warp w, int rule, int idx) {
+    int qi[4], ri;
+    quad_indices(rule, false, idx, w.n, qi, ri);
+    Quad Q;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const P2 p = w.at(qi[k]); Q.x[k] = p.x; Q.y[k] = p.y; }
+    return quad_clear_of_boundary(w, Q, make_int4(qi[0], qi[1], qi[2], qi[3]), ri, w.at(idx));
 }
 
-__device__ __forceinline__ void apply_successes(const Params &P, const StepIO &io, int set, const SmemLayout &L, int first,
-                                                int stride, int lane) {
-    init_mbar(L.mbar, lane);
-    const int count = min(P.counters[2 * set + 0], P.num_envs);
-    unsigned phase = 0;
-#pragma unroll 1
-    for (int item = first; item < count; item += stride) {
-        const int env = P.succ_list[item];
+// ---- kernel 2: decide ---------------------------------------------------------------------------
+#ifndef MG_MINB_DECIDE
+#define MG_MINB_DECIDE 24
+#endif
+__global__ void __launch_bounds__(32, MG_MINB_DECIDE) mg_step_decide_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    const SmemLayout L = carve(smem_raw, P.cap, false);
+    int *cnt = P.counters + CNT_SET * P.counters[CNT_CUR];
+    const int total = min(cnt[CNT_DECIDE], P.num_envs);
+    int4 *const rec_stash = L.stash;
+    auto st_i = [&](int word) { return reinterpret_cast<const int32_t *>(rec_stash)[word]; };
+    auto st_d = [&](int dword) { return reinterpret_cast<const double *>(rec_stash)[dword]; };
+    MG_ITEM_LOOP_BEGIN(total, &cnt[CNT_TICKET_DECIDE])
+        const WorkItem W = P.decide_list[t_];
+        const int env = W.env;
         const size_t off = (size_t)env * P.cap;
         __syncwarp();
-        stage_issue(L.ring, L.mbar, P.xy + off, P.cap, lane);      // whole slab, overlaps the record load
-        // The 128-byte record is parked in this warp's shared scratch (words 128..159: compute_obs and the candidate
-        // queue use words 0..63) and only the fields this phase works on are kept in registers; everything else
-        // comes back from shared memory for the tail (carried in registers it was spilled to local memory).
-        int4 *rec_stash = reinterpret_cast<int4 *>(L.queue + 128);
-        {
-            const int4 *g = reinterpret_cast<const int4 *>(P.st + env);
-            if (lane < 8) rec_stash[lane] = g[lane];
-        }
-        const Pending Q = P.pend[env];                              // independent of the record: same round trip
+        stage_issue(L.ring, L.mbar, P.xy + off, W.n, lane);
+        stash_records(P, rec_stash, env, lane);
         __syncwarp();
-        struct { int32_t n, ref_index, n_elements; double current_area; } S;     // what stays in registers
-        {
-            const int4 c0 = rec_stash[0];
-            S.n = c0.x; S.ref_index = c0.y; S.n_elements = c0.z;
-            S.current_area = reinterpret_cast<const double2 *>(rec_stash)[2].y;
-        }
-        // the rest is read from the stash where it is used: EnvState = {n, ref_index, n_elements, n0 | base_length,
-        // failed_num, ep_len | ep_return, current_area | original_area, area_min | area_crit, next_vid, stamp_ctr | ...}
-        auto st_i = [&](int word) { return reinterpret_cast<const int32_t *>(rec_stash)[word]; };
-        auto st_d = [&](int dword) { return reinterpret_cast<const double *>(rec_stash)[dword]; };
-        constexpr int W_N0 = 3, W_NEXT_VID = 18, W_STAMP_CTR = 19, D_ORIGINAL_AREA = 6, D_AREA_MIN = 7, D_AREA_CRIT = 8;
         Warp w;
-        w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = S.n;
+        w.ring = L.ring; w.queue = nullptr; w.lane = lane; w.n = W.n;
+        const int idx = st_i(W_REF);
+        int flags = st_i(W_FLAGS);
+        stage_wait(L.mbar, phase);
+        phase ^= 1u;
+        // ---- the verdict (E:236-283, E:319-323) ------------------------------------------------
+        int rule = W.rule;
+        bool accepted = false, new_vertex = false, flags_changed = false;
+        const P2 newp = mk(W.newx, W.newy);
+        auto rule_verdict = [&](int r) {          // memoised verdict of the rule r element, resolving a pending one
+            const int ok_bit = r == -1 ? HOT_OK_M1 : HOT_OK_P1, pend_bit = r == -1 ? HOT_PEND_M1 : HOT_PEND_P1;
+            if (flags & ok_bit) return true;
+            if (!(flags & pend_bit)) return false;
+            const bool ok = rule_quad_clear(w, r, idx);
+            flags = (flags & ~pend_bit) | (ok ? ok_bit : 0);
+            flags_changed = true;
+            return ok;
+        };
+        if (W.kind == WORK_DECIDE_RULE) {
+            accepted = rule_verdict(rule);
+        } else if (point_inside(w, newp, P.vid + off, st_i(W_N0))) {
+            if (find_same_point(w, newp)) {                    // E:258-262: an existing vertex: the rule -1 element
+                rule = -1;
+                accepted = rule_verdict(-1);
+            } else if (W.flag) {                               // Mesh.is_valid of the new-vertex quad (screen kernel)
+                int qi[4], ri;
+                quad_indices(0, true, idx, w.n, qi, ri);
+                Quad Q;
+                Q.x[0] = newp.x; Q.y[0] = newp.y;
+#pragma unroll
+                for (int k = 1; k < 4; k++) { const P2 p = w.at(qi[k]); Q.x[k] = p.x; Q.y[k] = p.y; }
+                accepted = quad_clear_of_boundary(w, Q, make_int4(qi[0], qi[1], qi[2], qi[3]), ri, w.at(idx));
+                new_vertex = accepted;
+            }
+        }
+        if (flags_changed && lane == 0) P.hot[env].flags = flags;
+        if (accepted) {
+            push_item(P.accept_list, &cnt[CNT_ACCEPT], P.num_envs,
+                      make_item(env, W.n, WORK_APPLY, rule, new_vertex ? 1 : 0, 0, W.newx, W.newy), lane);
+        } else {
+            // ---- failed step: nothing changed, cached observation (same tail as the screen kernel) ----
+            const int n_el = st_i(W_NEL);
+            const double reward = n_el ? -1.0 / n_el : -1;                      // E:279 / E:357
+            const int failed_num = st_i(W_FAILED) + 1;
+            const bool done = failed_num >= 100;                                 // E:382-384
+            const double ep_return = st_d(D_EP_RETURN) + reward;
+            const int ep_len = st_i(W_EP_LEN) + 1;
+            if (lane == 0) {
+                io.rew_out[env] = reward;
+                io.term_out[env] = 0;
+                io.trunc_out[env] = done;
+                if (io.n_elem_out) io.n_elem_out[env] = n_el;
+                int4 *dst = reinterpret_cast<int4 *>(P.hot + env);
+                const int4 c1 = rec_stash[1], c2 = rec_stash[2];
+                dst[1] = make_int4(c1.x, c1.y, failed_num, ep_len);
+                dst[2] = make_int4(__double2loint(ep_return), __double2hiint(ep_return), c2.z, c2.w);
+                if (done) {
+                    StatsAcc *T = P.stats + (env & (STAT_SLOTS - 1));
+                    atomicAdd(&cnt[CNT_DONE], 1);
+                    atomicAdd(&T->episodes, 1ull);
+                    atomicAdd(&T->truncated, 1ull);
+                    atomicAdd(&T->elements, (unsigned long long)n_el);
+                    atomicAdd(&T->sum_return, ep_return);
+                    atomicAdd(&T->sum_length, (double)ep_len);
+                }
+            }
+            if ((io.obs_full || (done && io.term_obs_out)) && lane < MG_OBS_DIM) {
+                const float o = P.obs_cache[(size_t)env * MG_OBS_DIM + lane];
+                if (io.obs_full) io.obs_out[(size_t)env * MG_OBS_DIM + lane] = o;
+                if (done && io.term_obs_out) io.term_obs_out[(size_t)env * MG_OBS_DIM + lane] = o;
+            }
+            if (done && P.auto_reset)
+                push_item(P.observe_list, &cnt[CNT_OBSERVE], P.num_envs, make_item(env, 0, WORK_RESET, 0, 0, 0, 0.0, 0.0), lane);
+        }
+    MG_ITEM_LOOP_END
+}
+
+// ---- kernel 3: update ---------------------------------------------------------------------------
+#ifndef MG_MINB_UPDATE
+#define MG_MINB_UPDATE 22
+#endif
+__global__ void __launch_bounds__(32, MG_MINB_UPDATE) mg_step_update_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    const SmemLayout L = carve(smem_raw, P.cap, false);
+    int *cnt = P.counters + CNT_SET * P.counters[CNT_CUR];
+    const int total = min(cnt[CNT_ACCEPT], P.num_envs);
+    int4 *const rec_stash = L.stash;
+    auto st_i = [&](int word) { return reinterpret_cast<const int32_t *>(rec_stash)[word]; };
+    auto st_d = [&](int dword) { return reinterpret_cast<const double *>(rec_stash)[dword]; };
+    MG_ITEM_LOOP_BEGIN(total, &cnt[CNT_TICKET_UPDATE])
+        const WorkItem W = P.accept_list[t_];
+        const int env = W.env;
+        const size_t off = (size_t)env * P.cap;
+        __syncwarp();
+        stage_issue(L.ring, L.mbar, P.xy + off, W.n, lane);
+        // Both records are parked in this warp's shared stash and only the fields the item works on are kept in
+        // registers; everything else comes back from shared memory where it is used (carried in registers it was
+        // spilled to local memory, an L2 round trip with the shared-memory carve-out at its maximum).
+        stash_records(P, rec_stash, env, lane);
 #ifndef MG_NO_ROW_PREFETCH
-        // the key / stamp / id rows are only touched on successes, so they come from DRAM: pull them into L2 now,
-        // behind the ring copy, instead of paying the round trips in the compaction and arg-min loops
+        // the key / stamp / id rows are only touched on accepted elements, so they come from DRAM: pull them into L2
+        // now, behind the ring copy, instead of paying the round trips in the compaction loop
         {
             const char *kp = reinterpret_cast<const char *>(P.key + off), *sp = reinterpret_cast<const char *>(P.stamp + off),
                        *vp = reinterpret_cast<const char *>(P.vid + off);
-            for (int b = lane * 128; b < S.n * 8; b += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(kp + b));
-            for (int b = lane * 128; b < S.n * 4; b += 32 * 128) {
+            for (int b = lane * 128; b < W.n * 8; b += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(kp + b));
+            for (int b = lane * 128; b < W.n * 4; b += 32 * 128) {
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + b));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(vp + b));
             }
         }
 #endif
+        __syncwarp();
+        Warp w;
+        w.ring = L.ring; w.queue = nullptr; w.lane = lane; w.n = W.n;
+        const int n = W.n, idx = st_i(W_REF);
+        int n_elements = st_i(W_NEL);
+        double current_area = st_d(D_CUR_AREA);
         stage_wait(L.mbar, phase);
         phase ^= 1u;
-        const int n = S.n, idx = S.ref_index;
-        const bool new_vertex = Q.new_vertex != 0;
-        const P2 newp = mk(Q.newx, Q.newy);
+        const int rule = W.rule;
+        const bool new_vertex = W.flag != 0;
+        const P2 newp = mk(W.newx, W.newy);
         P2 m[4]; int qi[4]; int ri;
-        quad_indices(Q.rule, new_vertex, idx, n, qi, ri);
+        quad_indices(rule, new_vertex, idx, n, qi, ri);
 #pragma unroll
         for (int k = 0; k < 4; k++) m[k] = qi[k] < 0 ? newp : w.at(qi[k]);
         // the quad's four quantised corner angles (C:752, C:888, C:946-947), one per lane
@@ -1185,7 +1396,7 @@ __device__ __forceinline__ void apply_successes(const Params &P, const StepIO &i
 #pragma unroll
             for (int k = 0; k < 4; k++) corner[k] = shfl_d(ca, k);
         }
-        const int ip1 = qi[3] , im1 = new_vertex ? qi[1] : (Q.rule == -1 ? qi[0] : qi[1]);
+        const int ip1 = qi[3], im1 = new_vertex ? qi[1] : (rule == -1 ? qi[0] : qi[1]);
         double reward = 0;
         bool done = false;
 
@@ -1198,17 +1409,17 @@ __device__ __forceinline__ void apply_successes(const Params &P, const StepIO &i
         for (int k = 0; k < 4; k++) elem_ids[k] = qi[k] < 0 ? next_vid0 : P.vid[off + qi[k]];
         // ---- element log, area and robust quality first: they only need the quad (old ring + new vertex), and doing
         // them here ends the live ranges of the quad, its corner angles and the vertex ids before the boundary update
-        if (P.elem && lane < 4 && S.n_elements < P.elem_cap)
-            P.elem[((size_t)env * P.elem_cap + S.n_elements) * 4 + lane] =
+        if (P.elem && lane < 4 && n_elements < P.elem_cap)
+            P.elem[((size_t)env * P.elem_cap + n_elements) * 4 + lane] =
                 lane == 0 ? elem_ids[0] : (lane == 1 ? elem_ids[1] : (lane == 2 ? elem_ids[2] : elem_ids[3]));
-        S.n_elements++;
+        n_elements++;
         // ---- area (C:943-958), robust quality (C:881-892) -----------------------------------
         double e0 = pdist(m[0], m[3]), e1 = pdist(m[1], m[0]), e2 = pdist(m[2], m[1]), e3 = pdist(m[3], m[2]);
         double sn0, sn2, cs_unused;
         sincos_quantised(P.sc_full, corner[0], false, sn0, cs_unused);
         sincos_quantised(P.sc_full, corner[2], false, sn2, cs_unused);
         double mesh_area = 0.5 * e0 * e1 * sn0 + 0.5 * e2 * e3 * sn2;
-        S.current_area -= mesh_area;
+        current_area -= mesh_area;
         double mn = fmin(fmin(e0, e1), fmin(e2, e3));
         double q1 = sqrt(2.0) * mn / fmax(pdist(m[0], m[2]), pdist(m[1], m[3]));
         double amin = fmin(fmin(corner[0], corner[1]), fmin(corner[2], corner[3]));
@@ -1262,7 +1473,6 @@ __device__ __forceinline__ void apply_successes(const Params &P, const StepIO &i
             nb[0] = id; nb[1] = id - 1 < 0 ? id - 1 + nn : id - 1; nb[2] = wrapn(id + 1, nn);
             nb[3] = wrapn(id - 2, nn);
         }
-        S.n = w.n;
         const int nn = w.n;
         // ---- candidate keys of the four neighbours (lanes 2k, 2k+1 -> angles a0, a1 of nb[k]) ----
         double ang = 0;
@@ -1308,77 +1518,127 @@ __device__ __forceinline__ void apply_successes(const Params &P, const StepIO &i
         if (nn <= 5) {                                       // E:345-351
             reward += 10; done = true;
             if (nn == 4) {
-                if (P.elem && lane < 4 && S.n_elements < P.elem_cap)
-                    P.elem[((size_t)env * P.elem_cap + S.n_elements) * 4 + lane] = P.vid[off + lane];
-                S.n_elements++;
+                if (P.elem && lane < 4 && n_elements < P.elem_cap)
+                    P.elem[((size_t)env * P.elem_cap + n_elements) * 4 + lane] = P.vid[off + lane];
+                n_elements++;
             }
         }
-        // ---- next state (E:361-386) ---------------------------------------------------------
-        float obs = 0.0f;
-        bool obs_none = false;
-        __syncwarp();
-        S.ref_index = find_reference_index(w, P.key + off, P.stamp + off);
-        double new_base = 0;
-        if (S.ref_index >= 0) {
-            const ObsOut R = compute_obs(w, P.sc_full, S.ref_index, S.current_area / st_d(D_ORIGINAL_AREA));
-            obs = R.obs; new_base = R.base;
-        } else obs_none = true;
-        // back to the full record for the tail of the step
-        EnvState F;
-        {
-            const int4 c1 = rec_stash[1], c5 = rec_stash[5];
-            const double2 c2 = reinterpret_cast<const double2 *>(rec_stash)[2];
-            const int4 c4 = rec_stash[4];
-            const double2 c3 = reinterpret_cast<const double2 *>(rec_stash)[3];
-            F.n0 = st_i(W_N0);
-            F.ep_len = c1.w; F.ep_return = c2.x;
-            F.original_area = c3.x; F.area_min = c3.y; F.area_crit = __hiloint2double(c4.y, c4.x);
-            F.next_vid = c4.z + (new_vertex ? 1 : 0); F.stamp_ctr = c4.w - 4;
-            F.domain = c5.x; F.episode = c5.y;
-            F.base_length = __hiloint2double(c1.y, c1.x);
-#pragma unroll
-            for (int k = 0; k < 5; k++) F.pad[k] = 0;
+        // ---- results of the step; the next observation follows in the observe kernel -----------------------
+        const double ep_return = st_d(D_EP_RETURN) + reward;
+        const int ep_len = st_i(W_EP_LEN) + 1;
+        if (lane == 0) {
+            StatsAcc *T = P.stats + (env & (STAT_SLOTS - 1));
+            atomicAdd(&T->successes, 1ull);
+            atomicAdd(&T->sum_n_success, (unsigned long long)n);
+            if (done) {
+                atomicAdd(&cnt[CNT_DONE], 1);
+                atomicAdd(&T->episodes, 1ull);
+                atomicAdd(&T->completed, 1ull);
+                atomicAdd(&T->elements, (unsigned long long)n_elements);
+                atomicAdd(&T->sum_return, ep_return);
+                atomicAdd(&T->sum_length, (double)ep_len);
+            }
+            io.rew_out[env] = reward;
+            io.term_out[env] = done;
+            io.trunc_out[env] = 0;
+            if (io.n_elem_out) io.n_elem_out[env] = n_elements;
+            // the part of the records this kernel owns (reference index, base length, flags and fan follow in observe)
+            int4 *dst = reinterpret_cast<int4 *>(P.hot + env);
+            const int4 c1 = rec_stash[1];
+            dst[0] = make_int4(nn, -1, n_elements, 0);
+            dst[1] = make_int4(c1.x, c1.y, 0, ep_len);
+            dst[2] = make_int4(__double2loint(ep_return), __double2hiint(ep_return), __double2loint(current_area),
+                               __double2hiint(current_area));
+            P.cold[env].next_vid = next_vid0 + (new_vertex ? 1 : 0);
+            P.cold[env].stamp_ctr = st_i(W_STAMP_CTR) - 4;
         }
-        F.n = S.n; F.ref_index = S.ref_index; F.n_elements = S.n_elements;
-        F.current_area = S.current_area;
-        if (S.ref_index >= 0) F.base_length = new_base;
-        F.failed_num = 0;
-        if (finish_step(P, io, env, lane, F, n, reward, done, false, true, obs_none, obs)) {
-            __syncwarp();                        // lane 0's record store is visible to the warp
-            reset_in_place(P, io, env, w);
-        }
-    }
+        push_item(P.observe_list, &cnt[CNT_OBSERVE], P.num_envs, make_item(env, nn, WORK_OBSERVE, 0, 0, done ? 1 : 0, 0.0, 0.0), lane);
+    MG_ITEM_LOOP_END
 }
 
-// ---- phases B + C in one launch: the last apply_blocks blocks apply the accepted elements, the first
-// blocks reset the envs that phase A finished (truncations, E:382-384); the two sets are disjoint.
-#ifndef MG_MINB_APPLY
-#define MG_MINB_APPLY 21    // one-warp blocks: shared memory allows 21 per SM (ring + scratch + 1 KB reserved), 96 registers
-#endif
-__global__ void __launch_bounds__(WPB * 32, MG_MINB_APPLY) mg_step_apply_reset_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io, int apply_blocks) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    SmemLayout L = carve(smem_raw, P.cap, warp);
-    const int reset_blocks = gridDim.x - apply_blocks;     // scheduled first: one reset is the longest item
-    const int set = P.counters[CNT_CUR];                   // written by phase A of this step
-    if ((int)blockIdx.x >= reset_blocks) {
-        apply_successes(P, io, set, L, (blockIdx.x - reset_blocks) * WPB + warp, apply_blocks * WPB, lane);
-    } else {
-        const int rb = blockIdx.x, nrb = reset_blocks;
-        if (rb == 0 && threadIdx.x == 0) {               // the other counter set is idle during this step
-            P.counters[2 * (set ^ 1) + 0] = 0;
-            P.counters[2 * (set ^ 1) + 1] = 0;
-            P.counters[CNT_STEP] = (set ^ 1);            // parity of the next step; only phase A reads it
-        }
-        const int count = min(P.counters[2 * set + 1], P.num_envs);
-#pragma unroll 1
-        for (int item = rb * WPB + warp; item < count; item += nrb * WPB) {
-            const int env = P.reset_list[item];
-            Warp w;
-            w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = 0;
-            reset_in_place(P, io, env, w);
-        }
+// ---- kernel 4: observe (+ resets) ---------------------------------------------------------------
+// in-place reset of one finished env (V:40-52): new episode, first observation to the caller
+__device__ __noinline__ void reset_in_place(const Params &P, const StepIO &io, int env, Warp w) {
+    const int domain = P.cold[env].domain, episode = P.cold[env].episode + 1;
+    const float obs = reset_env(P, w, env, domain, episode);
+    if (w.lane < MG_OBS_DIM) {
+        P.obs_cache[(size_t)env * MG_OBS_DIM + w.lane] = obs;
+        io.obs_out[(size_t)env * MG_OBS_DIM + w.lane] = obs;
     }
+    __syncwarp();
+}
+
+#ifndef MG_MINB_OBSERVE
+#define MG_MINB_OBSERVE 21
+#endif
+__global__ void __launch_bounds__(32, MG_MINB_OBSERVE) mg_step_observe_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    const SmemLayout L = carve(smem_raw, P.cap, true);
+    const int set = P.counters[CNT_CUR];                   // written by the screen kernel of this step
+    int *cnt = P.counters + CNT_SET * set;
+    if (blockIdx.x == 0 && lane == 0) {                    // the other counter set is idle during this step
+        int *idle = P.counters + CNT_SET * (set ^ 1);
+#pragma unroll
+        for (int k = 0; k < CNT_SET; k++) idle[k] = 0;
+        P.counters[CNT_STEP] = (set ^ 1);                  // parity of the next step; only the screen kernel reads it
+    }
+    const int total = min(cnt[CNT_OBSERVE], P.num_envs);
+    int4 *const rec_stash = L.stash;
+    auto st_i = [&](int word) { return reinterpret_cast<const int32_t *>(rec_stash)[word]; };
+    auto st_d = [&](int dword) { return reinterpret_cast<const double *>(rec_stash)[dword]; };
+    MG_ITEM_LOOP_BEGIN(total, &cnt[CNT_TICKET_OBSERVE])
+        const WorkItem W = P.observe_list[t_];
+        const int env = W.env;
+        Warp w;
+        w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = 0;
+        if (W.kind == WORK_RESET) {
+            reset_in_place(P, io, env, w);
+        } else {
+            const size_t off = (size_t)env * P.cap;
+            __syncwarp();
+            stage_issue(L.ring, L.mbar, P.xy + off, W.n, lane);
+            stash_records(P, rec_stash, env, lane);
+            __syncwarp();
+            w.n = W.n;
+            stage_wait(L.mbar, phase);
+            phase ^= 1u;
+            // ---- next state (E:361-386) -----------------------------------------------------
+            const int ref_index = find_reference_index(w, P.key + off, P.stamp + off);
+            float obs = 0.0f;
+            double base = st_d(D_BASE);
+            if (ref_index >= 0) {
+                const ObsOut R = compute_obs(w, P.sc_full, ref_index, st_d(D_CUR_AREA) / st_d(D_ORIGINAL_AREA));
+                obs = R.obs; base = R.base;
+            }
+            // An env without a reference point (empty candidate list, E:736-738) is reported truncated (sentinel)
+            const bool truncated = !W.done && ref_index < 0;
+            const bool done = W.done || truncated;
+            if (truncated && lane == 0) {
+                io.trunc_out[env] = 1;
+                StatsAcc *T = P.stats + (env & (STAT_SLOTS - 1));
+                atomicAdd(&cnt[CNT_DONE], 1);
+                atomicAdd(&T->episodes, 1ull);
+                atomicAdd(&T->truncated, 1ull);
+                atomicAdd(&T->elements, (unsigned long long)st_i(W_NEL));
+                atomicAdd(&T->sum_return, st_d(D_EP_RETURN));
+                atomicAdd(&T->sum_length, (double)st_i(W_EP_LEN));
+            }
+            if (lane < MG_OBS_DIM) {
+                if (io.term_obs_out && done) io.term_obs_out[(size_t)env * MG_OBS_DIM + lane] = obs;
+                P.obs_cache[(size_t)env * MG_OBS_DIM + lane] = obs;
+                io.obs_out[(size_t)env * MG_OBS_DIM + lane] = obs;
+            }
+            if (done && P.auto_reset) {
+                __syncwarp();
+                reset_in_place(P, io, env, w);
+            } else {
+                // the state changed: new memo (rule -1 / +1 verdicts, neighbour fan) and the rest of the record
+                const int flags = done ? 0 : memo_flags(w, ref_index);
+                store_hot(P.hot + env, w, ref_index, st_i(W_NEL), flags, base, 0, st_i(W_EP_LEN), st_d(D_EP_RETURN), st_d(D_CUR_AREA));
+            }
+        }
+    MG_ITEM_LOOP_END
 }
 
 // Uniform actions in Box([-1,-1.5,0],[1,1.5,1.5]) -- the synthetic policy of the benchmarks.
@@ -1395,33 +1655,6 @@ __global__ void mg_sample_actions_kernel(int num_envs, uint64_t seed, uint64_t s
         float u = (float)(rr[k] >> 8) * (1.0f / 16777216.0f);
         act[(size_t)e * 3 + k] = lo[k] + (hi[k] - lo[k]) * u;
     }
-}
-
-// mg_step_host: gather the terminal observations of the envs that finished this step.
-__global__ void mg_pack_terminal_kernel(int num_envs, const uint8_t *term, const uint8_t *trunc, const float *term_obs,
-                                        int32_t *idx, float *packed, int32_t *count) {
-    int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= num_envs || !(term[e] | trunc[e])) return;
-    int i = atomicAdd(count, 1);
-    idx[i] = e;
-#pragma unroll
-    for (int k = 0; k < MG_OBS_DIM; k++) packed[(size_t)i * MG_OBS_DIM + k] = term_obs[(size_t)e * MG_OBS_DIM + k];
-}
-
-// mg_step_host, delta mode: gather observation + element count of every env that changed in this step
-// (accepted elements and resets: exactly the two work lists of the step), one warp per entry.
-__global__ void mg_pack_changed_kernel(const __grid_constant__ Params P, const float *obs, const int32_t *nel, int32_t *idx, float *pobs,
-                                       int32_t *pnel, int32_t *count) {
-    const int set = P.counters[CNT_CUR];
-    const int cs = min(P.counters[2 * set + 0], P.num_envs), cr = min(P.counters[2 * set + 1], P.num_envs);
-    const int lane = threadIdx.x & 31;
-    const int warps = gridDim.x * (blockDim.x >> 5);
-    for (int it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < cs + cr; it += warps) {
-        const int env = it < cs ? P.succ_list[it] : P.reset_list[it - cs];
-        if (lane == 0) { idx[it] = env; pnel[it] = nel[env]; }
-        if (lane < MG_OBS_DIM) pobs[(size_t)it * MG_OBS_DIM + lane] = obs[(size_t)env * MG_OBS_DIM + lane];
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) *count = cs + cr;
 }
 
 // mg_replay_add: the N transitions of one step into slot `slot` of the replay ring (coalesced: one thread per
@@ -1444,55 +1677,26 @@ __global__ void mg_replay_add_kernel(int num_envs, float *__restrict__ b_obs, fl
     if (k == 5) b_to[e] = tr ? 1 : 0;
 }
 
-// mg_step_host with PINNED caller buffers: the rows that changed are written straight into the caller's host arrays
-// through their device aliases (one 72-byte row per warp: coalesced PCIe writes, no staging copy, no host-side
-// scatter).  `obs_host` rows for the step's two work lists, `term_obs_host` rows for the envs that finished.
-__global__ void mg_scatter_rows_host_kernel(const __grid_constant__ Params P, const float *obs, float *obs_host,
-                                            const uint8_t *term, const uint8_t *trunc, const float *term_obs, float *term_obs_host,
-                                            int32_t *n_done_rows) {
-    const int lane = threadIdx.x & 31;
-    const int warps = gridDim.x * (blockDim.x >> 5), w0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (obs_host) {
-        const int set = P.counters[CNT_CUR];
-    const int cs = min(P.counters[2 * set + 0], P.num_envs), cr = min(P.counters[2 * set + 1], P.num_envs);
-        for (int it = w0; it < cs + cr; it += warps) {
-            const int env = it < cs ? P.succ_list[it] : P.reset_list[it - cs];
-            if (lane < MG_OBS_DIM) obs_host[(size_t)env * MG_OBS_DIM + lane] = obs[(size_t)env * MG_OBS_DIM + lane];
-        }
-    }
-    if (term_obs_host) {
-        // finished envs: one flag byte per lane, then one row per set bit
-        for (int base = w0 * 32; base < P.num_envs; base += warps * 32) {
-            const int e = base + lane;
-            unsigned m = __ballot_sync(FULL, e < P.num_envs && (term[e] | trunc[e]));
-            if (m && lane == 0) atomicAdd(n_done_rows, __popc(m));      // byte accounting of mg_last_host_bytes
-            while (m) {
-                const int env = base + __ffs(m) - 1;
-                m &= m - 1;
-                if (lane < MG_OBS_DIM) term_obs_host[(size_t)env * MG_OBS_DIM + lane] = term_obs[(size_t)env * MG_OBS_DIM + lane];
-            }
-        }
-    }
-}
-
 // Sum of the accumulator slots -> one mg_episode_stats (one warp).
 __global__ void mg_stats_kernel(StatsAcc *stats, mg_episode_stats *out, int reset) {
-    unsigned long long a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long a[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     double r = 0, l = 0;
     for (int e = threadIdx.x; e < STAT_SLOTS; e += 32) {
         StatsAcc T = stats[e];
         a[0] += T.episodes; a[1] += T.completed; a[2] += T.truncated; a[3] += T.steps; a[4] += T.successes;
-        a[5] += T.elements; a[6] += T.sum_n; a[7] += T.sum_n_success; r += T.sum_return; l += T.sum_length;
+        a[5] += T.elements; a[6] += T.sum_n; a[7] += T.sum_n_success; a[8] += T.ring_items; a[9] += T.sum_n_ring;
+        r += T.sum_return; l += T.sum_length;
         if (reset) { StatsAcc Z = {}; stats[e] = Z; }
     }
 #pragma unroll
-    for (int k = 0; k < 8; k++)
+    for (int k = 0; k < 10; k++)
         for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_xor_sync(FULL, a[k], o);
     r = warp_sum_d(r); l = warp_sum_d(l);
     if (threadIdx.x == 0) {
         out->episodes = (long long)a[0]; out->completed = (long long)a[1]; out->truncated = (long long)a[2];
         out->steps = (long long)a[3]; out->successes = (long long)a[4]; out->elements = (long long)a[5];
         out->sum_n = (long long)a[6]; out->sum_n_success = (long long)a[7];
+        out->ring_items = (long long)a[8]; out->sum_n_ring = (long long)a[9];
         out->sum_return = r; out->sum_length = l;
     }
 }
@@ -1512,7 +1716,7 @@ __global__ void mg_stats_kernel(StatsAcc *stats, mg_episode_stats *out, int rese
 //   prev + A (j+1) dir, j < x, followed by cur; if the total is odd the middle point of the last
 //   edge is dropped (tk-ui.py:267-269).  Coordinates / 100 (geometry.py:46).
 // One coarse vertex per lane (max_coarse <= 32).  The ring is written to w.ring[0..n).
-__device__ __noinline__ int generate_polygon(const Params &P, const Warp w, long long global_env, int episode) {
+__device__ __noinline__ int generate_polygon(const Params &P, const Warp w, long long global_env, int episode, double *dbg) {
     const mg_polygen_cfg &G = P.gen;
     const int lane = w.lane;
     int *cx = w.queue, *cy = w.queue + 32, *cnt = w.queue + 64, *offs = w.queue + 96;
@@ -1596,6 +1800,10 @@ __device__ __noinline__ int generate_polygon(const Params &P, const Warp w, long
     }
     if (lane < K) { cnt[lane] = c; offs[lane] = incl_c - c; }
     __syncwarp();
+    if (dbg != nullptr) {                              // parity read-back (mg_debug_polygon): K, spacing, clockwise coarse polygon in pixels
+        if (lane == 0) { dbg[0] = K; dbg[1] = A; }
+        if (lane < K) { dbg[2 + 2 * lane] = cx[K - 1 - lane]; dbg[3 + 2 * lane] = cy[K - 1 - lane]; }
+    }
     const bool odd = (total & 1) != 0;
     const int c_last = cnt[K - 1];
     const int drop = odd ? offs[K - 1] + c_last / 2 : -1;   // flat index popped from the last edge (tk-ui.py:267-269)
@@ -1630,6 +1838,28 @@ __device__ __noinline__ int generate_polygon(const Params &P, const Warp w, long
     __syncwarp();
     int n = odd ? total - 1 : total;
     return n <= P.cap ? n : (P.cap & ~1);
+}
+
+// The polygon of episode `episode` of env `env` in random-polygon mode, regenerated from (seed, global env id,
+// episode): the generator is a pure function of its counter, so the original vertices of an episode need not be
+// kept (mg_get_elements), and the parity tests can read back any episode's polygon (mg_debug_polygon).
+// dbg (optional) = {K, spacing, coarse clockwise polygon in pixels (2 K values)}, area_out = the shoelace area the
+// reset computes for this ring.
+__global__ void __launch_bounds__(32) mg_regen_polygon_kernel(const __grid_constant__ Params P, int env, int episode, double2 *out_xy,
+                                                            int32_t *out_n, double *dbg, double *area_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const SmemLayout L = carve(smem_raw, P.cap);
+    Warp w;
+    w.ring = L.ring; w.queue = L.queue; w.lane = threadIdx.x; w.n = 0;
+    const int n = generate_polygon(P, w, P.env_id_offset + env, episode < 0 ? P.cold[env].episode : episode, dbg);
+    w.n = n;
+    __syncwarp();
+    for (int j = threadIdx.x; j < n; j += 32) out_xy[j] = w.ring[j];
+    const double area = shoelace_area(w);
+    if (threadIdx.x == 0) {
+        *out_n = n;
+        if (area_out) *area_out = area;
+    }
 }
 
 }  // namespace mg

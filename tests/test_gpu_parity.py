@@ -385,14 +385,19 @@ def test_full_size_config3_properties_and_spot_check():
 
 
 def test_host_step_delta_transfers_equal_full_copies():
-    """mg_step_host in delta mode (only changed observation rows cross PCIe) delivers exactly the same
-    host arrays as the full-copy mode, including across a mid-run reset."""
+    """mg_step_host with pinned caller buffers in delta mode (the step kernels write only the changed observation rows
+    straight into the caller's arrays) delivers exactly the same host arrays as the full-copy mode through pageable
+    buffers, including across a mid-run reset."""
     import torch
     doms, _ = load_domains()
     N, T = 96, 260
-    envs = [_mk([doms["star"], doms["half_wheel"], doms["boundary16"]], N) for _ in range(2)]
-    envs[1].set_host_delta(True)
-    outs = [None, None]
+    envs = [_mk([doms["star"], doms["half_wheel"], doms["boundary16"]], N, obs_delta=False),
+            _mk([doms["star"], doms["half_wheel"], doms["boundary16"]], N, obs_delta=True)]
+    pinned = dict(obs=torch.zeros((N, 18), dtype=torch.float32).pin_memory(), reward=torch.zeros(N, dtype=torch.float64).pin_memory(),
+                  terminated=torch.zeros(N, dtype=torch.uint8).pin_memory(), truncated=torch.zeros(N, dtype=torch.uint8).pin_memory(),
+                  terminal_obs=torch.zeros((N, 18), dtype=torch.float32).pin_memory(), n_elements=torch.zeros(N, dtype=torch.int32).pin_memory())
+    act_pinned = torch.zeros((N, 3), dtype=torch.float32).pin_memory()
+    outs = [None, pinned]
     for e in envs:
         e.reset()
     rng = np.random.default_rng(3)
@@ -400,12 +405,13 @@ def test_host_step_delta_transfers_equal_full_copies():
     for t in range(T):
         a = rng.uniform(LOW_A, HIGH_A, size=(N, 3)).astype(np.float32)
         outs[0] = envs[0].step_host(a, outs[0])
-        outs[1] = envs[1].step_host(a, outs[1])
+        act_pinned.copy_(torch.from_numpy(a))
+        envs[1].step_host(act_pinned, pinned)
         moved.append(envs[1].last_host_bytes()[1])
         for k in ("obs", "reward", "terminated", "truncated", "n_elements"):
-            assert np.array_equal(outs[0][k], outs[1][k]), f"{k} differs at step {t}"
+            assert np.array_equal(outs[0][k], pinned[k].numpy()), f"{k} differs at step {t}"
         d = (outs[0]["terminated"] | outs[0]["truncated"]).astype(bool)
-        assert np.array_equal(outs[0]["terminal_obs"][d], outs[1]["terminal_obs"][d])
+        assert np.array_equal(outs[0]["terminal_obs"][d], pinned["terminal_obs"].numpy()[d])
         if t == 100:
             m = torch.zeros(N, dtype=torch.uint8)
             m[::3] = 1

@@ -1,0 +1,349 @@
+"""GPU parity, round-2 hardening (pytest -m gpu): per-step internal state against the golden trace of the live
+reference, sentinel paths, the workload generator against the host densifier, random polygons across episode
+boundaries, the memoised verdicts, and the new ABI entry points (observation delta, snapshot header, stream
+ordering, device-side statistics, kernel timing)."""
+import numpy as np
+import pytest
+
+from helpers import action_stream, assert_rollout_matches, load_domains, load_trace
+
+pytestmark = pytest.mark.gpu
+
+REWARD_TOL = 1e-9
+LOW_A = np.array([-1.0, -1.5, 0.0], np.float32)
+HIGH_A = np.array([1.0, 1.5, 1.5], np.float32)
+
+
+def _mk(domains, n, **kw):
+    from reinforcementlearning4meshgeneration_b200 import BatchedBoudaryEnv
+    return BatchedBoudaryEnv(domains, num_envs=n, **kw)
+
+
+def test_boundary0_internal_state_at_every_step_of_the_golden_trace():
+    """BoudaryEnv(boundary()), seed 7, 4096 steps -- at EVERY step the boundary vertex ids, the
+    coordinates of the inserted vertex, the reference index, the boundary size, base length and remaining area of
+    the CUDA env equal what the live reference recorded (state before the reset on done steps)."""
+    import torch
+    tr = load_trace("boundary0")
+    T = len(tr["reward"])
+    env = _mk([tr["xy0"]], 1, auto_reset=False)
+    env.reset()
+    acts = torch.from_numpy(tr["actions"]).to(env.device)
+    for t in range(T):
+        r = env.step(acts[t:t + 1])
+        s = env.get_state(0)
+        n = int(tr["n_boundary"][t])
+        assert s["n"] == n, f"boundary size differs at step {t}"
+        assert np.array_equal(s["ids"], tr["ids"][t][:n].astype(np.int32)), f"boundary vertex ids differ at step {t}"
+        if not tr["obs_none"][t]:
+            assert s["ref_index"] == int(tr["ref_index"][t]), f"reference index differs at step {t}"
+            assert s["base_length"] == float(tr["base_length"][t]), f"base length differs at step {t}"
+        assert s["current_area"] == float(tr["current_area"][t]) or \
+            abs(s["current_area"] - float(tr["current_area"][t])) <= 1e-12 * abs(float(tr["current_area"][t])), f"area differs at step {t}"
+        assert s["n_elements"] == int(tr["n_elements"][t])
+        if not np.isnan(tr["new_xy"][t, 0]):
+            j = int(np.argmax(s["ids"]))
+            assert np.array_equal(s["xy"][j], tr["new_xy"][t]), f"inserted vertex differs at step {t}"
+        head = min((c[1] for c in s["candidates"]), default=np.inf)
+        assert head == float(tr["cand_head_key"][t]), f"head of the candidate list differs at step {t}"
+        te, tru = bool(r.terminated[0]), bool(r.truncated[0])
+        assert te == bool(tr["terminated"][t]) and tru == bool(tr["truncated"][t])
+        if te or tru:
+            env.reset()
+
+
+def test_memoised_verdicts_agree_with_a_fresh_evaluation():
+    """EnvHot::flags (would a rule -1 / +1 step be accepted?) is memoised when the state changes.  Replaying every
+    env through the oracle with actions forced to rule -1 / +1 shows the verdict the reference would reach: the
+    step creates an element exactly when the flag is set."""
+    import torch
+    from oracle.c_oracle import OracleEnv
+    doms, areas = load_domains()
+    names = ["boundary16", "dolphine3", "easy1_1", "star", "basic2", "half_wheel"]
+    per, T = 8, 150
+    N = per * len(names)
+    env_domain = np.repeat(np.arange(len(names)), per)
+    env = _mk([doms[k] for k in names], N, env_domain=env_domain, auto_reset=False)
+    env.reset()
+    streams = [action_stream(4000 + e, T) for e in range(N)]
+    oracles = [OracleEnv(doms[names[env_domain[e]]], original_area=areas[names[env_domain[e]]]) for e in range(N)]
+    checked = accepted = 0
+    for t in range(T):
+        a = np.stack([s[t] for s in streams])
+        env.step(torch.from_numpy(a).to(env.device))
+        for e in range(N):
+            oracles[e].step(streams[e][t])
+        if t % 10 == 9:
+            for e in range(0, N, 3):
+                o = oracles[e]
+                if o.n <= 5 or o.ref_index < 0:
+                    continue
+                flags = env.get_state(e)["memo_flags"]
+                for bit, rule in ((1 | 4, -1.0), (2 | 8, 1.0)):      # accepted, or valid with the intersection test pending
+                    # probe on a copy of the oracle's state: rebuild it by replaying the stream so far
+                    p = OracleEnv(doms[names[env_domain[e]]], original_area=areas[names[env_domain[e]]])
+                    for u in range(t + 1):
+                        p.step(streams[e][u])
+                    p.step(np.array([rule, 0.0, 0.5], np.float32))
+                    ok = bool(p.last_info()["success"])
+                    if flags & bit & 3:
+                        assert ok, f"memoised 'accepted' is wrong at step {t} env {e} rule {rule}"
+                    if not (flags & bit):
+                        assert not ok, f"memoised 'rejected' is wrong at step {t} env {e} rule {rule}"
+                    checked += 1
+                    accepted += ok
+    assert checked > 100 and accepted > 3
+
+
+def test_sentinel_paths():
+    """(a) stepping an env that already finished (n <= 5 on entry, E:428-430): reward 10, done, every step -- as the
+    reference does; (b) a polygon without any reference candidate (all interior angles >= 0.972 pi): the reference
+    returns None as observation and raises on the next step; here the env reports a zero observation and is
+    truncated by its first step; (c) a polygon with a zero-length edge (division by zero in the reference,
+    C:664): IEEE semantics, finite outputs, no hang."""
+    import torch
+    from oracle.c_oracle import OracleEnv
+    # (a) auto-reset off on both sides: finished envs keep being stepped, like a careless caller of the reference would
+    doms, areas = load_domains()
+    xy, area = doms["tool"], areas["tool"]
+    N, T = 32, 300
+    env = _mk([xy], N, auto_reset=False)
+    env.reset()
+    oracles = [OracleEnv(xy, original_area=area) for _ in range(N)]
+    streams = [action_stream(600 + e, T) for e in range(N)]
+    n_after = 0
+    for t in range(T):
+        a = np.stack([s[t] for s in streams])
+        r = env.step(torch.from_numpy(a).to(env.device))
+        rew, te, tru = r.reward.cpu().numpy(), r.terminated.cpu().numpy(), r.truncated.cpu().numpy()
+        for e in range(N):
+            if oracles[e].crashed:
+                continue
+            finished = oracles[e].n <= 5
+            o, er, ete, etr, _ = oracles[e].step(streams[e][t])
+            if oracles[e].crashed:
+                continue
+            assert bool(te[e]) == ete and bool(tru[e]) == etr, f"flags differ t={t} env={e}"
+            assert abs(rew[e] - er) <= REWARD_TOL * max(1.0, abs(er)), f"reward differs t={t} env={e}"
+            if finished:
+                assert er == 10.0 and (ete or etr)
+                n_after += 1
+    assert n_after > 100, "no env finished with n <= 5 in this run"
+    # (b)
+    k = 240
+    ang = -2 * np.pi * np.arange(k) / k          # clockwise regular polygon: interior angle pi - 2 pi / k > 0.972 pi
+    env = _mk([np.stack([5 + 3 * np.cos(ang), 5 + 3 * np.sin(ang)], axis=1)], 2)
+    obs = env.reset().cpu().numpy()
+    assert env.get_state(0)["ref_index"] == -1 and not obs.any()
+    r = env.step(torch.zeros((2, 3), device=env.device))
+    assert r.truncated.cpu().numpy().all() and not r.terminated.cpu().numpy().any() and (r.reward.cpu().numpy() == 0).all()
+    # (c)
+    sq = [(0, 0), (0, 1), (0, 2), (0, 3), (1, 3), (2, 3), (3, 3), (3, 2), (3, 1), (3, 0), (2, 0), (2, 0), (1, 0)]
+    env = _mk([np.array(sq, np.float64)], 8)
+    env.reset()
+    for t in range(60):
+        r = env.step(env.sample_actions(5, t))
+    assert torch.isfinite(r.obs).all() and torch.isfinite(r.reward).all()
+
+
+def test_device_generator_against_the_host_densifier():
+    """the in-kernel workload generator densifies its coarse star polygon like ui/tk-ui.py:252-276.
+    The coarse polygon (pixels, clockwise) and the spacing are read back and pushed through the host densifier
+    (domains.densify, a restatement of calculate_density checked against the reference's own output in
+    tests/test_domain_tools_cpu.py): same vertex count, coordinates within 1e-12 (the kernel emits
+    prev + A (j+1) (cur - prev) / L, the reference prev + A (j+1) (cos, sin)(atan2(...)): ~1e-16 relative apart)."""
+    from reinforcementlearning4meshgeneration_b200.domains import densify
+    N = 64
+    env = _mk(None, N, random_polygons=dict(min_verts=64, max_verts=512), seed=31)
+    env.reset()
+    worst = 0.0
+    for e in range(N):
+        for ep in (0, 3):
+            d = env.debug_polygon(e, ep)
+            pts = [(float(x), float(y)) for x, y in d["coarse_px"]]
+            assert len(pts) >= 8 and len({p for p in pts}) >= 8
+            dense = np.array(densify(pts, [1.0] * len(pts), d["spacing_px"]), np.float64) / 100.0
+            assert len(dense) == d["n"], f"env {e} episode {ep}: {len(dense)} vertices on the host, {d['n']} on the device"
+            worst = max(worst, float(np.abs(dense - d["xy"]).max()))
+        assert np.array_equal(env.debug_polygon(e, 0)["xy"], env.get_state(e)["xy"])
+    assert worst <= 1e-12, worst
+
+
+def test_random_polygons_with_auto_reset_across_episode_boundaries():
+    """Config-3 soak in the test suite: random polygons, in-kernel auto-reset, device Philox actions; every picked
+    env is replayed through the CPU oracle across ALL its episodes (each episode's polygon and area are read back
+    from the generator's counter)."""
+    import torch
+    from oracle.c_oracle import OracleEnv
+    N, T = 512, 420
+    env = _mk(None, N, random_polygons=dict(min_verts=64, max_verts=512), seed=77)
+    env.reset()
+    dev = env.device
+    pick = list(range(0, N, 8))
+    idx = torch.tensor(pick, device=dev, dtype=torch.long)
+    K = len(pick)
+    rec = dict(act=torch.zeros((T, K, 3), device=dev), obs=torch.zeros((T, K, 18), device=dev),
+               tobs=torch.zeros((T, K, 18), device=dev), rew=torch.zeros((T, K), dtype=torch.float64, device=dev),
+               te=torch.zeros((T, K), dtype=torch.uint8, device=dev), tr=torch.zeros((T, K), dtype=torch.uint8, device=dev),
+               ne=torch.zeros((T, K), dtype=torch.int32, device=dev))
+    for t in range(T):
+        a = env.sample_actions(4242, t)
+        rec["act"][t] = a[idx]
+        r = env.step(a)
+        rec["obs"][t] = r.obs[idx]; rec["tobs"][t] = r.terminal_obs[idx]; rec["rew"][t] = r.reward[idx]
+        rec["te"][t] = r.terminated[idx]; rec["tr"][t] = r.truncated[idx]; rec["ne"][t] = r.n_elements[idx]
+    rec = {k: v.cpu().numpy() for k, v in rec.items()}
+    episodes = 0
+    for k, e in enumerate(pick):
+        ep = 0
+        poly = env.debug_polygon(e, ep)
+        o = OracleEnv(poly["xy"], original_area=poly["original_area"])
+        for t in range(T):
+            obs, r, te, tru, _ = o.step(rec["act"][t, k])
+            assert bool(rec["te"][t, k]) == te and bool(rec["tr"][t, k]) == tru, f"flags differ env {e} step {t}"
+            assert abs(rec["rew"][t, k] - r) <= REWARD_TOL * max(1.0, abs(r)), f"reward differs env {e} step {t}"
+            assert int(rec["ne"][t, k]) == o.n_elements
+            if te or tru:
+                exp_t = np.zeros(18, np.float32) if obs is None else obs
+                assert np.array_equal(rec["tobs"][t, k], exp_t), f"terminal obs differs env {e} step {t}"
+                ep += 1
+                episodes += 1
+                poly = env.debug_polygon(e, ep)
+                o = OracleEnv(poly["xy"], original_area=poly["original_area"])
+                obs = o.obs()
+            assert np.array_equal(rec["obs"][t, k], obs), f"obs differs env {e} step {t} (episode {ep})"
+    assert episodes >= K // 2
+
+
+def test_random_mode_element_log_returns_the_episode_polygon():
+    """mg_get_elements in random-polygon mode: original vertex coordinates are the episode's generated polygon
+    (round 1 returned zeros), inserted vertices follow, quads index into them."""
+    import torch
+    N = 16
+    env = _mk(None, N, random_polygons=dict(min_verts=64, max_verts=256), seed=5, auto_reset=False)
+    env.reset()
+    polys = [env.get_state(e)["xy"].copy() for e in range(N)]
+    for t in range(120):
+        env.step(env.sample_actions(8, t))
+    some = 0
+    for e in range(N):
+        quads, vxy, ne = env.get_elements(e)
+        n0 = len(polys[e])
+        assert np.array_equal(vxy[:n0], polys[e])
+        assert len(quads) == ne and (quads < len(vxy)).all() and (quads >= 0).all()
+        s = env.get_state(e)
+        for j, vid in enumerate(s["ids"]):
+            assert np.array_equal(vxy[vid], s["xy"][j])
+        some += ne
+    assert some > 10
+
+
+def test_observation_delta_equals_full_writes():
+    """mg_set_obs_delta: only the rows that changed are written, into the same persistent buffer -- identical to
+    the full-write mode at every step, across a masked reset and a snapshot restore."""
+    import torch
+    doms, _ = load_domains()
+    N, T = 192, 200
+    a = _mk([doms["star"], doms["boundary16"]], N, obs_delta=True)
+    b = _mk([doms["star"], doms["boundary16"]], N, obs_delta=False)
+    assert torch.equal(a.reset(), b.reset())
+    snap = None
+    for t in range(T):
+        act = a.sample_actions(3, t)
+        ra, rb = a.step(act), b.step(act.clone())
+        assert torch.equal(ra.obs, rb.obs), f"obs differ at step {t}"
+        assert torch.equal(ra.reward, rb.reward) and torch.equal(ra.terminated, rb.terminated)
+        d = (rb.terminated | rb.truncated).bool()
+        assert torch.equal(ra.terminal_obs[d], rb.terminal_obs[d])
+        if t == 70:
+            m = torch.zeros(N, dtype=torch.uint8)
+            m[::5] = 1
+            assert torch.equal(a.reset(m), b.reset(m))
+        if t == 100:
+            snap = a.snapshot()
+        if t == 140:
+            oa = a.restore(snap)
+            ob = b.restore(snap)
+            assert torch.equal(oa, ob)
+
+
+def test_snapshot_header_rejects_mismatched_handles():
+    import torch
+    from reinforcementlearning4meshgeneration_b200 import MeshgenError
+    doms, _ = load_domains()
+    a = _mk([doms["star"]], 8)
+    a.reset()
+    blob = a.snapshot()
+    b = _mk([doms["star"]], 8, log_capacity=77)
+    b.reset()
+    with pytest.raises(MeshgenError):
+        b.restore(blob)
+    with pytest.raises(MeshgenError):
+        a.restore(blob[: blob.numel() // 2])
+    c = _mk([doms["star"], doms["boundary16"]], 8)
+    c.reset()
+    with pytest.raises(MeshgenError):
+        c.restore(blob)
+    r1 = _mk(None, 8, random_polygons=dict(min_verts=64, max_verts=128), seed=1)
+    r2 = _mk(None, 8, random_polygons=dict(min_verts=64, max_verts=128), seed=2)
+    r1.reset(); r2.reset()
+    with pytest.raises(MeshgenError):
+        r2.restore(r1.snapshot())
+    a.restore(blob)          # the matching handle still loads it
+
+
+def test_reset_then_host_step_is_ordered():
+    """mg_reset / mg_step run on the caller's stream, mg_step_host on the library's private stream: a reset of a large
+    random-polygon batch (about a millisecond of kernel time) directly followed by step_host must see the reset
+    state (round-1 advisory: there was no ordering between the two streams)."""
+    N = 16384
+    kw = dict(random_polygons=dict(min_verts=64, max_verts=512), seed=9)
+    rng = np.random.default_rng(0)
+    act = rng.uniform(LOW_A, HIGH_A, size=(N, 3)).astype(np.float32)
+    import torch
+    ref = _mk(None, N, **kw)
+    ref.reset()
+    torch.cuda.synchronize()
+    exp = ref.step_host(act)
+    for _ in range(3):
+        env = _mk(None, N, **kw)
+        env.reset()                       # no synchronisation here
+        got = env.step_host(act)
+        for k in ("obs", "reward", "terminated", "truncated", "n_elements"):
+            assert np.array_equal(got[k], exp[k]), k
+        env.close()
+
+
+def test_device_side_statistics_and_kernel_timing():
+    import torch
+    from reinforcementlearning4meshgeneration_b200.distributed import stats_from_tensor
+    doms, _ = load_domains()
+    env = _mk([doms["boundary16"]], 4096)
+    env.reset()
+    env.set_kernel_timing(True)
+    for t in range(64):
+        env.step(env.sample_actions(1, t))
+    kt = env.kernel_times()
+    env.set_kernel_timing(False)
+    assert kt["steps"] == 64 and all(0 < kt[k] < 50 for k in ("screen_ms", "decide_ms", "update_ms", "observe_ms"))
+    dev_stats = stats_from_tensor(env.stats_async())
+    host_stats = env.stats()
+    assert dev_stats == host_stats and host_stats["steps"] == 64 * 4096
+    assert 0 < host_stats["ring_items"] < host_stats["steps"] and host_stats["successes"] <= host_stats["ring_items"]
+    assert host_stats["sum_n_success"] <= host_stats["sum_n_ring"] <= host_stats["sum_n"]
+
+
+def test_current_device_is_left_alone():
+    """Every ABI call works on the handle's device and restores the caller's current device."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    doms, _ = load_domains()
+    torch.cuda.set_device(0)
+    env = _mk([doms["star"]], 4, device="cuda:1")
+    env.reset()
+    env.step(env.sample_actions(0, 0))
+    env.stats()
+    assert torch.cuda.current_device() == 0
+    x = torch.zeros(4, device="cuda")
+    assert x.device.index == 0
