@@ -225,9 +225,14 @@ int64_t mg_snapshot_bytes(mg_handle h);
 int mg_snapshot_save(mg_handle h, void *blob_dev, void *stream);
 int mg_snapshot_load(mg_handle h, const void *blob_dev, int64_t blob_bytes, void *stream);
 
+/* Tuning switches (results never depend on them).  "fuse_decide" (default 1): the decide and update work of a step
+ * share one launch -- a warp that accepts an element applies it with the boundary it has already staged; 0 = two
+ * launches with smaller code images. */
+int mg_set_option(mg_handle h, const char *name, int value);
+
 /* Profiling aid (bench.py roofline.per_kernel): with enabled != 0 every mg_step / mg_step_host records CUDA events
  * around its four kernels; mg_kernel_times synchronises, returns the mean device time in ms of the screen, decide,
- * update and observe kernels (ms4[0..3]) over the (at most 256 most recent) steps since the last call, and starts a
+ * update and observe kernels (ms4[0..3]; decide is 0 when it is fused into update) over the (at most 256 most recent) steps since the last call, and starts a
  * new window. */
 int mg_set_kernel_timing(mg_handle h, int enabled);
 int mg_kernel_times(mg_handle h, double *ms4, int64_t *steps);

@@ -23,7 +23,7 @@ SYMBOLS = [
     "mg_create", "mg_set_domains", "mg_set_random", "mg_set_auto_reset", "mg_reset", "mg_step", "mg_step_host",
     "mg_set_obs_delta", "mg_set_host_delta", "mg_last_host_bytes", "mg_sample_actions", "mg_get_state", "mg_get_elements", "mg_debug_polygon",
     "mg_stats", "mg_stats_async", "mg_set_log_capacity", "mg_log_capacity", "mg_replay_add", "mg_snapshot_bytes",
-    "mg_snapshot_save", "mg_snapshot_load", "mg_set_kernel_timing", "mg_kernel_times", "mg_num_envs", "mg_max_verts",
+    "mg_snapshot_save", "mg_snapshot_load", "mg_set_option", "mg_set_kernel_timing", "mg_kernel_times", "mg_num_envs", "mg_max_verts",
     "mg_launch_count", "mg_destroy", "mg_last_error", "mg_version",
 ]
 
@@ -102,6 +102,7 @@ def load():
     L.mg_snapshot_bytes.restype = i64
     L.mg_snapshot_save.argtypes = [vp, vp, vp]
     L.mg_snapshot_load.argtypes = [vp, vp, i64, vp]
+    L.mg_set_option.argtypes = [vp, C.c_char_p, i32]
     L.mg_set_kernel_timing.argtypes = [vp, i32]
     L.mg_kernel_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.mg_num_envs.argtypes = [vp]

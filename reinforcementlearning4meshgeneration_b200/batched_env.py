@@ -9,6 +9,7 @@ step :388-457; auto-reset follows the stock SB3 VecEnv convention
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import numpy as np
@@ -117,6 +118,9 @@ class BatchedBoudaryEnv:
         self.auto_reset = bool(auto_reset)
         check(self._L.mg_set_auto_reset(self._h, int(self.auto_reset)), self._h, "mg_set_auto_reset")
         check(self._L.mg_set_obs_delta(self._h, int(bool(obs_delta))), self._h, "mg_set_obs_delta")
+        for kv in filter(None, os.environ.get("MESHGEN_OPTIONS", "").split(",")):     # tuning aid: "fuse_decide=0,..."
+            k, v = kv.split("=")
+            check(self._L.mg_set_option(self._h, k.strip().encode(), int(v)), self._h, "mg_set_option")
         if log_capacity is not None:
             check(self._L.mg_set_log_capacity(self._h, int(log_capacity), int(log_capacity)), self._h, "mg_set_log_capacity")
         N = self.num_envs
@@ -301,6 +305,10 @@ class BatchedBoudaryEnv:
             raise ValueError("stats buffer must be a contiguous 12 x int64 tensor on the env's device")
         check(self._L.mg_stats_async(self._h, C.c_void_p(out.data_ptr()), int(reset), self._stream()), self._h, "mg_stats_async")
         return out
+
+    def set_option(self, name: str, value: int) -> None:
+        """Tuning switch of the library (mg_set_option); results never depend on it."""
+        check(self._L.mg_set_option(self._h, name.encode(), int(value)), self._h, "mg_set_option")
 
     def set_kernel_timing(self, enabled: bool = True) -> None:
         check(self._L.mg_set_kernel_timing(self._h, int(enabled)), self._h, "mg_set_kernel_timing")

@@ -51,6 +51,7 @@ struct mg_env_s {
     int sm_count = 148;
     size_t smem = 0, smem_nq = 0;      // one-warp block with / without the integer scratch queue
     int blocks_decide = 16, blocks_update = 16, blocks_observe = 16;
+    bool fuse_decide = true;           // one launch for the decide and update work (mg_set_option "fuse_decide")
     std::string err;
 };
 
@@ -181,13 +182,13 @@ int launch_step(mg_handle h, const StepIO &io, cudaStream_t s) {
     if (ev) cudaEventRecord(ev[0], s);
     mg_step_screen_kernel<<<(N + SCREEN_THREADS - 1) / SCREEN_THREADS, SCREEN_THREADS, 0, s>>>(h->P, io);
     if (ev) cudaEventRecord(ev[1], s);
-    mg_step_decide_kernel<<<grid(h->blocks_decide), 32, h->smem_nq, s>>>(h->P, io);
+    if (!h->fuse_decide) mg_step_decide_kernel<<<grid(h->blocks_decide), 32, h->smem_nq, s>>>(h->P, io);
     if (ev) cudaEventRecord(ev[2], s);
-    mg_step_update_kernel<<<grid(h->blocks_update), 32, h->smem_nq, s>>>(h->P, io);
+    mg_step_update_kernel<<<grid(h->blocks_update), 32, h->smem_nq, s>>>(h->P, io, h->fuse_decide ? 1 : 0);
     if (ev) cudaEventRecord(ev[3], s);
     mg_step_observe_kernel<<<grid(h->blocks_observe), 32, h->smem, s>>>(h->P, io);
     if (ev) { cudaEventRecord(ev[4], s); h->timing_steps++; }
-    h->launches += 4;
+    h->launches += h->fuse_decide ? 3 : 4;
     MG_CUDA(h, cudaGetLastError());
     return MG_OK;
 }
@@ -268,8 +269,8 @@ int mg_create(mg_handle *out, int device, int num_envs, int max_verts) {
     A(dalloc(&P.hot, (size_t)num_envs), "hot"); A(dalloc(&P.cold, (size_t)num_envs), "cold");
     A(dalloc(&P.stats, (size_t)STAT_SLOTS), "stats");
     A(dalloc(&P.obs_cache, (size_t)num_envs * MG_OBS_DIM), "obs");
-    A(dalloc(&P.decide_list, (size_t)num_envs), "decide_list"); A(dalloc(&P.accept_list, (size_t)num_envs), "accept_list");
-    A(dalloc(&P.observe_list, (size_t)num_envs), "observe_list"); A(dalloc(&P.counters, (size_t)CNT_N), "counters");
+    A(dalloc(&P.decide_list, (size_t)NBINS * num_envs), "decide_list"); A(dalloc(&P.accept_list, (size_t)NBINS * num_envs), "accept_list");
+    A(dalloc(&P.observe_list, (size_t)NBINS * num_envs), "observe_list"); A(dalloc(&P.counters, (size_t)CNT_N), "counters");
     A(dalloc(&P.elem, (size_t)num_envs * P.elem_cap * 4), "elem"); A(dalloc(&P.ins_xy, (size_t)num_envs * P.ins_cap), "ins_xy");
     A(dalloc(&h->d_stats_out, 1), "stats_out");
     A(dalloc(&h->sc_tab, (size_t)2 * ANGLE_TAB_N), "angle table");
@@ -580,7 +581,8 @@ int mg_step_host(mg_handle h, const float *act_host, float *obs_host, double *re
     // through staging)
     const int cur = h->h_cnt[CNT_CUR] & 1;
     const int64_t row = sizeof(float) * MG_OBS_DIM;
-    d2h += (obs_a && !io.obs_full) ? (int64_t)h->h_cnt[CNT_SET * cur + CNT_OBSERVE] * row : (int64_t)N * row;
+    d2h += (obs_a && !io.obs_full) ? (int64_t)(h->h_cnt[CNT_SET * cur + CNT_OBSERVE] + h->h_cnt[CNT_SET * cur + CNT_OBSERVE + 1] + h->h_cnt[CNT_SET * cur + CNT_OBSERVE + 2] +
+                                             h->h_cnt[CNT_SET * cur + CNT_OBSERVE + 3]) * row : (int64_t)N * row;
     if (term_obs_host) d2h += tobs_a ? (int64_t)h->h_cnt[CNT_SET * cur + CNT_DONE] * row : (int64_t)N * row;
     h->last_h2d = (int64_t)(N * 3 * sizeof(float));
     h->last_d2h = d2h;
@@ -729,6 +731,12 @@ int mg_stats(mg_handle h, mg_episode_stats *out, int reset) {
     MG_CUDA(h, cudaGetLastError());
     MG_CUDA(h, cudaMemcpy(out, h->d_stats_out, sizeof(*out), cudaMemcpyDeviceToHost));
     return MG_OK;
+}
+
+int mg_set_option(mg_handle h, const char *name, int value) {
+    if (!h || !name) return fail(h, MG_ERR_ARG, "mg_set_option: null pointer");
+    if (std::strcmp(name, "fuse_decide") == 0) { h->fuse_decide = value != 0; return MG_OK; }
+    return fail(h, MG_ERR_ARG, std::string("mg_set_option: unknown option ") + name);
 }
 
 int mg_set_kernel_timing(mg_handle h, int enabled) {

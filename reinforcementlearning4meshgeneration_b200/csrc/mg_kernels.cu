@@ -380,6 +380,7 @@ __device__ __noinline__ ObsOut compute_obs(const Warp w, const double2 *sc, int 
     };
     {
         const double T2_far = (T * T) * (1.0 + 1e-12);
+        const double T2_beyond = 2.0 * (T * T) * (1.0 + 1e-6);
         const double ur = 1e-6 * (fabs(ux) + fabs(uy));
         int qn = 0, base_o = 1;
 #pragma unroll 1
@@ -387,24 +388,41 @@ __device__ __noinline__ ObsOut compute_obs(const Warp w, const double2 *sc, int 
             if (base_o < n) {
                 const int o = base_o + lane;
                 bool keep = false;
-                if (o < n && o != 1 && o != n - 1) {              // right_p / left_p (C:1249)
+                const bool valid = o < n && o != 1 && o != n - 1;   // right_p / left_p (C:1249)
+                double ax = 0, ay = 0, wx = 0, wy = 0, d2 = 0;
+                P2 q2 = ref;
+                bool conditioned = false, open = false;
+                if (valid) {
                     int j = idx - o;
                     if (j < 0) j += n;
-                    const P2 q = w.at(j), q2 = w.at(j + 1 >= n ? j + 1 - n : j + 1);
-                    const double ax = q.x - ref.x, ay = q.y - ref.y, wx = q2.x - q.x, wy = q2.y - q.y;
-                    const bool far = ax * ax + ay * ay > T2_far;
-                    const double sa = ux * ay - uy * ax;
-                    const double sb = ux * (q2.y - ref.y) - uy * (q2.x - ref.x);
-                    const double tol = ur * (fabs(ax) + fabs(ay) + fabs(wx) + fabs(wy));
-                    const bool conditioned = (wx == 0 || fabs(wx) > 1e-6 * fabs(wy)) && (wy == 0 || fabs(wy) > 1e-6 * fabs(wx));
-                    const bool off_line = conditioned && ((sa > tol && sb > tol) || (sa < -tol && sb < -tol));
-                    keep = !(far && off_line);
+                    const P2 q = w.at(j);
+                    q2 = w.at(j + 1 >= n ? j + 1 - n : j + 1);
+                    ax = q.x - ref.x; ay = q.y - ref.y; wx = q2.x - q.x; wy = q2.y - q.y;
+                    d2 = ax * ax + ay * ay;
+                    conditioned = (wx == 0 || fabs(wx) > 1e-6 * fabs(wy)) && (wy == 0 || fabs(wy) > 1e-6 * fabs(wx));
+                    // Cheap first cut: every point of the edge is within |w| of B[m], so with
+                    // |ref B[m]|^2 > 2 T^2 + 2 |w|^2 >= (T + |w|)^2 the whole edge is farther than T from ref.  The vertex
+                    // is then outside the radius and its edge cannot meet the bisector segment (length T) -- the body
+                    // would do nothing.  (Edges that are degenerate in x or y stay in: the reference's intersection
+                    // formulas are chaotic for them, C:657-676.)  Boundary vertices are spatially coherent, so most
+                    // 32-vertex chunks of a large polygon are cut as a whole and skip the orientation tests below.
+                    open = !(conditioned && d2 > T2_beyond + 2.0 * (1.0 + 1e-6) * (wx * wx + wy * wy));
                 }
-                const unsigned m = __ballot_sync(FULL, keep);
-                if (keep) w.queue[qn + __popc(m & ((1u << lane) - 1))] = o;
-                qn += __popc(m);
+                if (__any_sync(FULL, open)) {
+                    if (open) {
+                        const bool far = d2 > T2_far;
+                        const double sa = ux * ay - uy * ax;
+                        const double sb = ux * (q2.y - ref.y) - uy * (q2.x - ref.x);
+                        const double tol = ur * (fabs(ax) + fabs(ay) + fabs(wx) + fabs(wy));
+                        const bool off_line = conditioned && ((sa > tol && sb > tol) || (sa < -tol && sb < -tol));
+                        keep = !(far && off_line);
+                    }
+                    const unsigned m = __ballot_sync(FULL, keep);
+                    if (keep) w.queue[qn + __popc(m & ((1u << lane) - 1))] = o;
+                    qn += __popc(m);
+                    __syncwarp();
+                }
                 base_o += 32;
-                __syncwarp();
             }
             const bool scanning = base_o < n;
             if (qn >= 32 || (!scanning && qn > 0)) {          // one call site: the body is big
@@ -785,19 +803,27 @@ __device__ __forceinline__ void quad_indices(int rule, bool new_vertex, int idx,
 // the state.  The O(1) half (Mesh.is_valid) is evaluated here, when the state changes; a valid quad is marked
 // pending and the O(n) half runs in the decide kernel the first time a rule action actually asks for it.
 __device__ __noinline__ int memo_flags(const Warp w, int idx) {
-    const int n = w.n;
+    const int n = w.n, lane = w.lane;
     if (idx < 0 || n < 6) return 0;
-    int flags = 0;
-#pragma unroll 1
-    for (int r = 0; r < 2; r++) {
-        int qi[4], ri;
-        quad_indices(r == 0 ? -1 : 1, false, idx, n, qi, ri);
-        Quad Q;
-#pragma unroll
-        for (int k = 0; k < 4; k++) { const P2 p = w.at(qi[k]); Q.x[k] = p.x; Q.y[k] = p.y; }
-        if (mesh_is_valid(w, Q)) flags |= (r == 0 ? HOT_PEND_M1 : HOT_PEND_P1);
+    // lanes 0..5: the six tests of Mesh.is_valid (4 corners, 2 edge crossings; a pure conjunction, C:738-757 / C:814-826)
+    // on the rule -1 quad [B[i-1], B[i], B[i+1], B[i+2]]; lanes 8..13: the same on the rule +1 quad [B[i-2] .. B[i+1]]
+    const int g = (lane >> 3) & 1, t = lane & 7, first = idx - 1 - g;
+    const P2 m0 = w.at(wrapn(first, n)), m1 = w.at(wrapn(first + 1, n)), m2 = w.at(wrapn(first + 2, n)), m3 = w.at(wrapn(first + 3, n));
+    bool bad = false;
+    if (lane < 16) {
+        if (t < 4) {
+            P2 c = m0, p1 = m1, p2 = m3;
+            if (t == 1) { c = m1; p1 = m2; p2 = m0; }
+            if (t == 2) { c = m2; p1 = m3; p2 = m1; }
+            if (t == 3) { c = m3; p1 = m0; p2 = m2; }
+            double cr, dt;
+            cross_dot(c, p1, p2, cr, dt);
+            bad = corner_angle_invalid(cr, dt);
+        } else if (t == 4) bad = is_cross(m0, m1, m2, m3);
+        else if (t == 5) bad = is_cross(m0, m3, m1, m2);
     }
-    return flags;
+    const unsigned bm = __ballot_sync(FULL, bad);
+    return ((bm & 0x003Fu) == 0 ? HOT_PEND_M1 : 0) | ((bm & 0x3F00u) == 0 ? HOT_PEND_P1 : 0);
 }
 
 // Mesh.is_valid(0) (C:738-757, C:814-826) of one quad by one thread (the screen kernel): same predicates as
@@ -1035,11 +1061,16 @@ __device__ __forceinline__ P2 action_to_point(float a1, float a2, P2 ref, P2 rig
     return mk(np_round4(ox), np_round4(oy));
 }
 
+// Work lists are binned by boundary size (largest first): the item kernels hand out long items before short ones, so
+// that the tail of a launch is made of short items (longest-processing-time-first scheduling).
+__device__ __forceinline__ int size_bin(int n, int cap) {
+    return n > (3 * cap) / 4 ? 0 : (n > cap / 2 ? 1 : (n > cap / 4 ? 2 : 3));
+}
 // one work record appended by one warp (lane 0)
-__device__ __forceinline__ void push_item(WorkItem *list, int *counter, int cap, const WorkItem &W, int lane) {
+__device__ __forceinline__ void push_item(WorkItem *list, int *counters, const Params &P, int bin, const WorkItem &W, int lane) {
     if (lane == 0) {
-        const int i = atomicAdd(counter, 1);
-        if (i < cap) list[i] = W;
+        const int i = atomicAdd(&counters[bin], 1);
+        if (i < P.num_envs) list[(size_t)bin * P.num_envs + i] = W;
     }
 }
 __device__ __forceinline__ WorkItem make_item(int env, int n, int kind, int rule, int flag, int done, double x, double y) {
@@ -1047,6 +1078,14 @@ __device__ __forceinline__ WorkItem make_item(int env, int n, int kind, int rule
     W.newx = x; W.newy = y; W.env = env; W.n = n;
     W.kind = (int8_t)kind; W.rule = (int8_t)rule; W.flag = (int8_t)flag; W.done = (int8_t)done; W.pad = 0;
     return W;
+}
+// item t of a binned list (bins in order); counts[] = the list's NBINS counters, already clamped
+__device__ __forceinline__ WorkItem fetch_item(const WorkItem *list, const int (&counts)[NBINS], int num_envs, int t) {
+    int bin = 0;
+#pragma unroll
+    for (int b = 0; b < NBINS - 1; b++)
+        if (bin == b && t >= counts[b]) { t -= counts[b]; bin = b + 1; }
+    return list[(size_t)bin * num_envs + t];
 }
 
 // ---- kernel 1: screen ------------------------------------------------------------------------
@@ -1129,25 +1168,28 @@ __global__ void __launch_bounds__(SCREEN_THREADS) mg_step_screen_kernel(const __
             copy_code = (io.obs_full ? 1 : 0) | ((done && io.term_obs_out) ? 2 : 0);
         }
     }
-    // ---- work lists: one atomicAdd per warp and list ------------------------------------------
+    // ---- work lists: one atomicAdd per warp, list and size bin --------------------------------
     {
-        const unsigned md = __ballot_sync(FULL, route == 1);
-        if (md) {
-            int base = 0;
-            if (lane == __ffs(md) - 1) base = atomicAdd(&cnt[CNT_DECIDE], __popc(md));
-            base = __shfl_sync(FULL, base, __ffs(md) - 1);
-            if (route == 1) P.decide_list[base + __popc(md & ((1u << lane) - 1))] = W;
-        }
-        const unsigned ma = __ballot_sync(FULL, route == 2);
-        if (ma) {
-            int base = 0;
-            if (lane == __ffs(ma) - 1) base = atomicAdd(&cnt[CNT_ACCEPT], __popc(ma));
-            base = __shfl_sync(FULL, base, __ffs(ma) - 1);
-            if (route == 2) P.accept_list[base + __popc(ma & ((1u << lane) - 1))] = W;
+        const int bin = size_bin(n, P.cap);
+#pragma unroll 1
+        for (int r = 1; r <= 2; r++) {
+            const unsigned any = __ballot_sync(FULL, route == r);
+            if (!any) continue;
+            WorkItem *list = r == 1 ? P.decide_list : P.accept_list;
+            int *ctr = cnt + (r == 1 ? CNT_DECIDE : CNT_ACCEPT);
+#pragma unroll 1
+            for (int b = 0; b < NBINS; b++) {
+                const unsigned m = __ballot_sync(FULL, route == r && bin == b);
+                if (!m) continue;
+                int base = 0;
+                if (lane == __ffs(m) - 1) base = atomicAdd(&ctr[b], __popc(m));
+                base = __shfl_sync(FULL, base, __ffs(m) - 1);
+                if (route == r && bin == b) list[(size_t)b * P.num_envs + base + __popc(m & ((1u << lane) - 1))] = W;
+            }
         }
         const bool to_reset = settled_done && P.auto_reset;
         const unsigned r = __ballot_sync(FULL, to_reset);
-        if (r) {
+        if (r) {                                        // resets are the longest items: first bin
             int base = 0;
             if (lane == __ffs(r) - 1) base = atomicAdd(&cnt[CNT_OBSERVE], __popc(r));
             base = __shfl_sync(FULL, base, __ffs(r) - 1);
@@ -1202,7 +1244,7 @@ __global__ void __launch_bounds__(SCREEN_THREADS) mg_step_screen_kernel(const __
     }
 }
 
-// ---- the three warp-per-item kernels -----------------------------------------------------------
+// ---- the warp-per-item kernels ------------------------------------------------------------------
 // Item loop shared by them: the first item of a block is its block index, later ones come from a ticket counter (an
 // early finisher takes the next item; the ticket is requested at the start of the previous item, so its latency is
 // hidden).
@@ -1218,6 +1260,19 @@ __global__ void __launch_bounds__(SCREEN_THREADS) mg_step_screen_kernel(const __
         t_ = __shfl_sync(FULL, next_t_, 0);       \
     }
 
+__device__ __forceinline__ int load_counts(const int *ctr, int num_envs, int (&counts)[NBINS]) {
+    int total = 0;
+#pragma unroll
+    for (int b = 0; b < NBINS; b++) { counts[b] = min(ctr[b], num_envs); total += counts[b]; }
+    return total;
+}
+
+struct Stash {
+    int4 *p;
+    __device__ __forceinline__ int i(int word) const { return reinterpret_cast<const int32_t *>(p)[word]; }
+    __device__ __forceinline__ double d(int dword) const { return reinterpret_cast<const double *>(p)[dword]; }
+};
+
 // E:319-323 for a quad whose Mesh.is_valid(0) is already known to hold: not check_intersection_with_boundary
 __device__ __noinline__ bool quad_clear_of_boundary(const Warp w, const Quad Q, const int4 qv, int ri, P2 ref) {
     return !intersects_boundary(w, Q, qv, ri, ref);
@@ -1232,7 +1287,83 @@ __device__ __forceinline__ bool rule_quad_clear(const Warp w, int rule, int idx)
     return quad_clear_of_boundary(w, Q, make_int4(qi[0], qi[1], qi[2], qi[3]), ri, w.at(idx));
 }
 
-// ---- kernel 2: decide ---------------------------------------------------------------------------
+// The verdict on one decide item (E:236-283, E:319-323); the boundary is staged in w.ring and the records in the
+// stash.  Returns true when an element is accepted (rule / new_vertex say which); a failed step is finished here
+// (nothing changed: cached observation, same tail as the screen kernel).
+__device__ __forceinline__ bool decide_item(const Params &P, const StepIO &io, int *cnt, const Warp &w, const WorkItem &W,
+                                            const Stash S, int &rule, bool &new_vertex) {
+    const int lane = w.lane, env = W.env;
+    const size_t off = (size_t)env * P.cap;
+    const int idx = S.i(W_REF);
+    int flags = S.i(W_FLAGS);
+    rule = W.rule;
+    new_vertex = false;
+    bool accepted = false, flags_changed = false;
+    const P2 newp = mk(W.newx, W.newy);
+    auto rule_verdict = [&](int r) {          // memoised verdict of the rule r element, resolving a pending one
+        const int ok_bit = r == -1 ? HOT_OK_M1 : HOT_OK_P1, pend_bit = r == -1 ? HOT_PEND_M1 : HOT_PEND_P1;
+        if (flags & ok_bit) return true;
+        if (!(flags & pend_bit)) return false;
+        const bool ok = rule_quad_clear(w, r, idx);
+        flags = (flags & ~pend_bit) | (ok ? ok_bit : 0);
+        flags_changed = true;
+        return ok;
+    };
+    if (W.kind == WORK_DECIDE_RULE) {
+        accepted = rule_verdict(rule);
+    } else if (point_inside(w, newp, P.vid + off, S.i(W_N0))) {
+        if (find_same_point(w, newp)) {                    // E:258-262: an existing vertex: the rule -1 element
+            rule = -1;
+            accepted = rule_verdict(-1);
+        } else if (W.flag) {                               // Mesh.is_valid of the new-vertex quad (screen kernel)
+            int qi[4], ri;
+            quad_indices(0, true, idx, w.n, qi, ri);
+            Quad Q;
+            Q.x[0] = newp.x; Q.y[0] = newp.y;
+#pragma unroll
+            for (int k = 1; k < 4; k++) { const P2 p = w.at(qi[k]); Q.x[k] = p.x; Q.y[k] = p.y; }
+            accepted = quad_clear_of_boundary(w, Q, make_int4(qi[0], qi[1], qi[2], qi[3]), ri, w.at(idx));
+            new_vertex = accepted;
+        }
+    }
+    if (flags_changed && lane == 0) P.hot[env].flags = flags;
+    if (accepted) return true;
+    // ---- failed step ----------------------------------------------------------------------------
+    const int n_el = S.i(W_NEL);
+    const double reward = n_el ? -1.0 / n_el : -1;                      // E:279 / E:357
+    const int failed_num = S.i(W_FAILED) + 1;
+    const bool done = failed_num >= 100;                                 // E:382-384
+    const double ep_return = S.d(D_EP_RETURN) + reward;
+    const int ep_len = S.i(W_EP_LEN) + 1;
+    if (lane == 0) {
+        io.rew_out[env] = reward;
+        io.term_out[env] = 0;
+        io.trunc_out[env] = done;
+        if (io.n_elem_out) io.n_elem_out[env] = n_el;
+        int4 *dst = reinterpret_cast<int4 *>(P.hot + env);
+        const int4 c1 = S.p[1], c2 = S.p[2];
+        dst[1] = make_int4(c1.x, c1.y, failed_num, ep_len);
+        dst[2] = make_int4(__double2loint(ep_return), __double2hiint(ep_return), c2.z, c2.w);
+        if (done) {
+            StatsAcc *T = P.stats + (env & (STAT_SLOTS - 1));
+            atomicAdd(&cnt[CNT_DONE], 1);
+            atomicAdd(&T->episodes, 1ull);
+            atomicAdd(&T->truncated, 1ull);
+            atomicAdd(&T->elements, (unsigned long long)n_el);
+            atomicAdd(&T->sum_return, ep_return);
+            atomicAdd(&T->sum_length, (double)ep_len);
+        }
+    }
+    if ((io.obs_full || (done && io.term_obs_out)) && lane < MG_OBS_DIM) {
+        const float o = P.obs_cache[(size_t)env * MG_OBS_DIM + lane];
+        if (io.obs_full) io.obs_out[(size_t)env * MG_OBS_DIM + lane] = o;
+        if (done && io.term_obs_out) io.term_obs_out[(size_t)env * MG_OBS_DIM + lane] = o;
+    }
+    if (done && P.auto_reset) push_item(P.observe_list, cnt + CNT_OBSERVE, P, 0, make_item(env, 0, WORK_RESET, 0, 0, 0, 0.0, 0.0), lane);
+    return false;
+}
+
+// ---- kernel 2: decide (only launched when the decide and update kernels are not fused) ----------------------------
 #ifndef MG_MINB_DECIDE
 #define MG_MINB_DECIDE 24
 #endif
@@ -1241,111 +1372,60 @@ __global__ void __launch_bounds__(32, MG_MINB_DECIDE) mg_step_decide_kernel(cons
     const int lane = threadIdx.x;
     const SmemLayout L = carve(smem_raw, P.cap, false);
     int *cnt = P.counters + CNT_SET * P.counters[CNT_CUR];
-    const int total = min(cnt[CNT_DECIDE], P.num_envs);
-    int4 *const rec_stash = L.stash;
-    auto st_i = [&](int word) { return reinterpret_cast<const int32_t *>(rec_stash)[word]; };
-    auto st_d = [&](int dword) { return reinterpret_cast<const double *>(rec_stash)[dword]; };
+    int counts[NBINS];
+    const int total = load_counts(cnt + CNT_DECIDE, P.num_envs, counts);
+    const Stash S{L.stash};
     MG_ITEM_LOOP_BEGIN(total, &cnt[CNT_TICKET_DECIDE])
-        const WorkItem W = P.decide_list[t_];
-        const int env = W.env;
-        const size_t off = (size_t)env * P.cap;
+        const WorkItem W = fetch_item(P.decide_list, counts, P.num_envs, t_);
         __syncwarp();
-        stage_issue(L.ring, L.mbar, P.xy + off, W.n, lane);
-        stash_records(P, rec_stash, env, lane);
+        stage_issue(L.ring, L.mbar, P.xy + (size_t)W.env * P.cap, W.n, lane);
+        stash_records(P, L.stash, W.env, lane);
         __syncwarp();
         Warp w;
         w.ring = L.ring; w.queue = nullptr; w.lane = lane; w.n = W.n;
-        const int idx = st_i(W_REF);
-        int flags = st_i(W_FLAGS);
         stage_wait(L.mbar, phase);
         phase ^= 1u;
-        // ---- the verdict (E:236-283, E:319-323) ------------------------------------------------
-        int rule = W.rule;
-        bool accepted = false, new_vertex = false, flags_changed = false;
-        const P2 newp = mk(W.newx, W.newy);
-        auto rule_verdict = [&](int r) {          // memoised verdict of the rule r element, resolving a pending one
-            const int ok_bit = r == -1 ? HOT_OK_M1 : HOT_OK_P1, pend_bit = r == -1 ? HOT_PEND_M1 : HOT_PEND_P1;
-            if (flags & ok_bit) return true;
-            if (!(flags & pend_bit)) return false;
-            const bool ok = rule_quad_clear(w, r, idx);
-            flags = (flags & ~pend_bit) | (ok ? ok_bit : 0);
-            flags_changed = true;
-            return ok;
-        };
-        if (W.kind == WORK_DECIDE_RULE) {
-            accepted = rule_verdict(rule);
-        } else if (point_inside(w, newp, P.vid + off, st_i(W_N0))) {
-            if (find_same_point(w, newp)) {                    // E:258-262: an existing vertex: the rule -1 element
-                rule = -1;
-                accepted = rule_verdict(-1);
-            } else if (W.flag) {                               // Mesh.is_valid of the new-vertex quad (screen kernel)
-                int qi[4], ri;
-                quad_indices(0, true, idx, w.n, qi, ri);
-                Quad Q;
-                Q.x[0] = newp.x; Q.y[0] = newp.y;
-#pragma unroll
-                for (int k = 1; k < 4; k++) { const P2 p = w.at(qi[k]); Q.x[k] = p.x; Q.y[k] = p.y; }
-                accepted = quad_clear_of_boundary(w, Q, make_int4(qi[0], qi[1], qi[2], qi[3]), ri, w.at(idx));
-                new_vertex = accepted;
-            }
-        }
-        if (flags_changed && lane == 0) P.hot[env].flags = flags;
-        if (accepted) {
-            push_item(P.accept_list, &cnt[CNT_ACCEPT], P.num_envs,
-                      make_item(env, W.n, WORK_APPLY, rule, new_vertex ? 1 : 0, 0, W.newx, W.newy), lane);
-        } else {
-            // ---- failed step: nothing changed, cached observation (same tail as the screen kernel) ----
-            const int n_el = st_i(W_NEL);
-            const double reward = n_el ? -1.0 / n_el : -1;                      // E:279 / E:357
-            const int failed_num = st_i(W_FAILED) + 1;
-            const bool done = failed_num >= 100;                                 // E:382-384
-            const double ep_return = st_d(D_EP_RETURN) + reward;
-            const int ep_len = st_i(W_EP_LEN) + 1;
-            if (lane == 0) {
-                io.rew_out[env] = reward;
-                io.term_out[env] = 0;
-                io.trunc_out[env] = done;
-                if (io.n_elem_out) io.n_elem_out[env] = n_el;
-                int4 *dst = reinterpret_cast<int4 *>(P.hot + env);
-                const int4 c1 = rec_stash[1], c2 = rec_stash[2];
-                dst[1] = make_int4(c1.x, c1.y, failed_num, ep_len);
-                dst[2] = make_int4(__double2loint(ep_return), __double2hiint(ep_return), c2.z, c2.w);
-                if (done) {
-                    StatsAcc *T = P.stats + (env & (STAT_SLOTS - 1));
-                    atomicAdd(&cnt[CNT_DONE], 1);
-                    atomicAdd(&T->episodes, 1ull);
-                    atomicAdd(&T->truncated, 1ull);
-                    atomicAdd(&T->elements, (unsigned long long)n_el);
-                    atomicAdd(&T->sum_return, ep_return);
-                    atomicAdd(&T->sum_length, (double)ep_len);
-                }
-            }
-            if ((io.obs_full || (done && io.term_obs_out)) && lane < MG_OBS_DIM) {
-                const float o = P.obs_cache[(size_t)env * MG_OBS_DIM + lane];
-                if (io.obs_full) io.obs_out[(size_t)env * MG_OBS_DIM + lane] = o;
-                if (done && io.term_obs_out) io.term_obs_out[(size_t)env * MG_OBS_DIM + lane] = o;
-            }
-            if (done && P.auto_reset)
-                push_item(P.observe_list, &cnt[CNT_OBSERVE], P.num_envs, make_item(env, 0, WORK_RESET, 0, 0, 0, 0.0, 0.0), lane);
-        }
+        int rule; bool new_vertex;
+        if (decide_item(P, io, cnt, w, W, S, rule, new_vertex))
+            push_item(P.accept_list, cnt + CNT_ACCEPT, P, size_bin(W.n, P.cap),
+                      make_item(W.env, W.n, WORK_APPLY, rule, new_vertex ? 1 : 0, 0, W.newx, W.newy), lane);
     MG_ITEM_LOOP_END
 }
 
-// ---- kernel 3: update ---------------------------------------------------------------------------
+// ---- kernel 3: update (fused mode: decide + update) ---------------------------------------------
 #ifndef MG_MINB_UPDATE
-#define MG_MINB_UPDATE 22
+#define MG_MINB_UPDATE 20
 #endif
-__global__ void __launch_bounds__(32, MG_MINB_UPDATE) mg_step_update_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io) {
+__global__ void __launch_bounds__(32, MG_MINB_UPDATE) mg_step_update_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io, int fused) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
     const SmemLayout L = carve(smem_raw, P.cap, false);
     int *cnt = P.counters + CNT_SET * P.counters[CNT_CUR];
-    const int total = min(cnt[CNT_ACCEPT], P.num_envs);
-    int4 *const rec_stash = L.stash;
-    auto st_i = [&](int word) { return reinterpret_cast<const int32_t *>(rec_stash)[word]; };
-    auto st_d = [&](int dword) { return reinterpret_cast<const double *>(rec_stash)[dword]; };
+    // fused mode: the decide list is processed here too (a warp that accepts an element applies it with the boundary it
+    // has already staged); items are taken bin by bin, accepted elements before open decisions
+    int counts_a[NBINS], counts_d[NBINS];
+    const int total_a = load_counts(cnt + CNT_ACCEPT, P.num_envs, counts_a);
+    int total = total_a;
+#pragma unroll
+    for (int b = 0; b < NBINS; b++) counts_d[b] = 0;
+    if (fused) total += load_counts(cnt + CNT_DECIDE, P.num_envs, counts_d);
+    const Stash S{L.stash};
     MG_ITEM_LOOP_BEGIN(total, &cnt[CNT_TICKET_UPDATE])
-        const WorkItem W = P.accept_list[t_];
+        WorkItem W;
+        {
+            // bin b holds counts_a[b] accept items followed by counts_d[b] decide items
+            int t = t_, bin = 0;
+            bool from_decide = false;
+#pragma unroll
+            for (int b = 0; b < NBINS; b++) {
+                if (bin == b) {
+                    if (t < counts_a[b]) { from_decide = false; }
+                    else if (t < counts_a[b] + counts_d[b]) { t -= counts_a[b]; from_decide = true; }
+                    else if (b < NBINS - 1) { t -= counts_a[b] + counts_d[b]; bin = b + 1; }
+                }
+            }
+            W = (from_decide ? P.decide_list : P.accept_list)[(size_t)bin * P.num_envs + t];
+        }
         const int env = W.env;
         const size_t off = (size_t)env * P.cap;
         __syncwarp();
@@ -1353,7 +1433,7 @@ __global__ void __launch_bounds__(32, MG_MINB_UPDATE) mg_step_update_kernel(cons
         // Both records are parked in this warp's shared stash and only the fields the item works on are kept in
         // registers; everything else comes back from shared memory where it is used (carried in registers it was
         // spilled to local memory, an L2 round trip with the shared-memory carve-out at its maximum).
-        stash_records(P, rec_stash, env, lane);
+        stash_records(P, L.stash, env, lane);
 #ifndef MG_NO_ROW_PREFETCH
         // the key / stamp / id rows are only touched on accepted elements, so they come from DRAM: pull them into L2
         // now, behind the ring copy, instead of paying the round trips in the compaction loop
@@ -1370,13 +1450,19 @@ __global__ void __launch_bounds__(32, MG_MINB_UPDATE) mg_step_update_kernel(cons
         __syncwarp();
         Warp w;
         w.ring = L.ring; w.queue = nullptr; w.lane = lane; w.n = W.n;
-        const int n = W.n, idx = st_i(W_REF);
-        int n_elements = st_i(W_NEL);
-        double current_area = st_d(D_CUR_AREA);
+        const int n = W.n, idx = S.i(W_REF);
         stage_wait(L.mbar, phase);
         phase ^= 1u;
-        const int rule = W.rule;
-        const bool new_vertex = W.flag != 0;
+        int rule = W.rule;
+        bool new_vertex = W.flag != 0;
+        if (W.kind != WORK_APPLY) {
+            if (!decide_item(P, io, cnt, w, W, S, rule, new_vertex)) {
+                t_ = __shfl_sync(FULL, next_t_, 0);
+                continue;
+            }
+        }
+        int n_elements = S.i(W_NEL);
+        double current_area = S.d(D_CUR_AREA);
         const P2 newp = mk(W.newx, W.newy);
         P2 m[4]; int qi[4]; int ri;
         quad_indices(rule, new_vertex, idx, n, qi, ri);
@@ -1404,7 +1490,7 @@ __global__ void __launch_bounds__(32, MG_MINB_UPDATE) mg_step_update_kernel(cons
         int nb[4];          // the four neighbours whose candidate keys are re-evaluated, in order
         int t0 = 0, t1 = 0; // surviving quad vertices (no-new-vertex case), new indices
         int elem_ids[4];
-        const int next_vid0 = st_i(W_NEXT_VID);
+        const int next_vid0 = S.i(W_NEXT_VID);
 #pragma unroll
         for (int k = 0; k < 4; k++) elem_ids[k] = qi[k] < 0 ? next_vid0 : P.vid[off + qi[k]];
         // ---- element log, area and robust quality first: they only need the quad (old ring + new vertex), and doing
@@ -1433,7 +1519,7 @@ __global__ void __launch_bounds__(32, MG_MINB_UPDATE) mg_step_update_kernel(cons
                 P.xy[off + idx] = make_double2(newp.x, newp.y);
                 P.vid[off + idx] = next_vid0;
                 P.key[off + idx] = CUDART_INF;
-                const int ins = next_vid0 - st_i(W_N0);
+                const int ins = next_vid0 - S.i(W_N0);
                 if (P.ins_xy && ins < P.ins_cap) P.ins_xy[(size_t)env * P.ins_cap + ins] = make_double2(newp.x, newp.y);
             }
             __syncwarp();
@@ -1491,7 +1577,7 @@ __global__ void __launch_bounds__(32, MG_MINB_UPDATE) mg_step_update_kernel(cons
             for (int k2 = k + 1; k2 < 4; k2++) later_dup |= nb[k2] == nb[k];
             if (lane == k && !later_dup) {
                 P.key[off + nb[k]] = kv;
-                P.stamp[off + nb[k]] = st_i(W_STAMP_CTR) - 1 - k;
+                P.stamp[off + nb[k]] = S.i(W_STAMP_CTR) - 1 - k;
             }
         }
         // ---- boundary quality (M:410-452) ---------------------------------------------------
@@ -1509,7 +1595,7 @@ __global__ void __launch_bounds__(32, MG_MINB_UPDATE) mg_step_update_kernel(cons
         }
         double quality = e_reward + 1 * (b_reward - 1);              // M:1754-1766
         // ---- speed penalty (E:590-607) ------------------------------------------------------
-        const double a_min = st_d(D_AREA_MIN), a_crit = st_d(D_AREA_CRIT);
+        const double a_min = S.d(D_AREA_MIN), a_crit = S.d(D_AREA_CRIT);
         double min_area = a_min * a_min, crit = a_crit * a_crit, pen;
         if (min_area <= mesh_area && mesh_area < crit) pen = (mesh_area - crit) / (crit - min_area);
         else if (mesh_area < min_area) pen = -1;
@@ -1524,8 +1610,8 @@ __global__ void __launch_bounds__(32, MG_MINB_UPDATE) mg_step_update_kernel(cons
             }
         }
         // ---- results of the step; the next observation follows in the observe kernel -----------------------
-        const double ep_return = st_d(D_EP_RETURN) + reward;
-        const int ep_len = st_i(W_EP_LEN) + 1;
+        const double ep_return = S.d(D_EP_RETURN) + reward;
+        const int ep_len = S.i(W_EP_LEN) + 1;
         if (lane == 0) {
             StatsAcc *T = P.stats + (env & (STAT_SLOTS - 1));
             atomicAdd(&T->successes, 1ull);
@@ -1544,15 +1630,15 @@ __global__ void __launch_bounds__(32, MG_MINB_UPDATE) mg_step_update_kernel(cons
             if (io.n_elem_out) io.n_elem_out[env] = n_elements;
             // the part of the records this kernel owns (reference index, base length, flags and fan follow in observe)
             int4 *dst = reinterpret_cast<int4 *>(P.hot + env);
-            const int4 c1 = rec_stash[1];
+            const int4 c1 = S.p[1];
             dst[0] = make_int4(nn, -1, n_elements, 0);
             dst[1] = make_int4(c1.x, c1.y, 0, ep_len);
             dst[2] = make_int4(__double2loint(ep_return), __double2hiint(ep_return), __double2loint(current_area),
                                __double2hiint(current_area));
             P.cold[env].next_vid = next_vid0 + (new_vertex ? 1 : 0);
-            P.cold[env].stamp_ctr = st_i(W_STAMP_CTR) - 4;
+            P.cold[env].stamp_ctr = S.i(W_STAMP_CTR) - 4;
         }
-        push_item(P.observe_list, &cnt[CNT_OBSERVE], P.num_envs, make_item(env, nn, WORK_OBSERVE, 0, 0, done ? 1 : 0, 0.0, 0.0), lane);
+        push_item(P.observe_list, cnt + CNT_OBSERVE, P, size_bin(nn, P.cap), make_item(env, nn, WORK_OBSERVE, 0, 0, done ? 1 : 0, 0.0, 0.0), lane);
     MG_ITEM_LOOP_END
 }
 
@@ -1569,7 +1655,7 @@ __device__ __noinline__ void reset_in_place(const Params &P, const StepIO &io, i
 }
 
 #ifndef MG_MINB_OBSERVE
-#define MG_MINB_OBSERVE 21
+#define MG_MINB_OBSERVE 20
 #endif
 __global__ void __launch_bounds__(32, MG_MINB_OBSERVE) mg_step_observe_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1583,12 +1669,11 @@ __global__ void __launch_bounds__(32, MG_MINB_OBSERVE) mg_step_observe_kernel(co
         for (int k = 0; k < CNT_SET; k++) idle[k] = 0;
         P.counters[CNT_STEP] = (set ^ 1);                  // parity of the next step; only the screen kernel reads it
     }
-    const int total = min(cnt[CNT_OBSERVE], P.num_envs);
-    int4 *const rec_stash = L.stash;
-    auto st_i = [&](int word) { return reinterpret_cast<const int32_t *>(rec_stash)[word]; };
-    auto st_d = [&](int dword) { return reinterpret_cast<const double *>(rec_stash)[dword]; };
+    int counts[NBINS];
+    const int total = load_counts(cnt + CNT_OBSERVE, P.num_envs, counts);
+    const Stash S{L.stash};
     MG_ITEM_LOOP_BEGIN(total, &cnt[CNT_TICKET_OBSERVE])
-        const WorkItem W = P.observe_list[t_];
+        const WorkItem W = fetch_item(P.observe_list, counts, P.num_envs, t_);
         const int env = W.env;
         Warp w;
         w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = 0;
@@ -1598,7 +1683,7 @@ __global__ void __launch_bounds__(32, MG_MINB_OBSERVE) mg_step_observe_kernel(co
             const size_t off = (size_t)env * P.cap;
             __syncwarp();
             stage_issue(L.ring, L.mbar, P.xy + off, W.n, lane);
-            stash_records(P, rec_stash, env, lane);
+            stash_records(P, L.stash, env, lane);
             __syncwarp();
             w.n = W.n;
             stage_wait(L.mbar, phase);
@@ -1606,9 +1691,9 @@ __global__ void __launch_bounds__(32, MG_MINB_OBSERVE) mg_step_observe_kernel(co
             // ---- next state (E:361-386) -----------------------------------------------------
             const int ref_index = find_reference_index(w, P.key + off, P.stamp + off);
             float obs = 0.0f;
-            double base = st_d(D_BASE);
+            double base = S.d(D_BASE);
             if (ref_index >= 0) {
-                const ObsOut R = compute_obs(w, P.sc_full, ref_index, st_d(D_CUR_AREA) / st_d(D_ORIGINAL_AREA));
+                const ObsOut R = compute_obs(w, P.sc_full, ref_index, S.d(D_CUR_AREA) / S.d(D_ORIGINAL_AREA));
                 obs = R.obs; base = R.base;
             }
             // An env without a reference point (empty candidate list, E:736-738) is reported truncated (sentinel)
@@ -1620,9 +1705,9 @@ __global__ void __launch_bounds__(32, MG_MINB_OBSERVE) mg_step_observe_kernel(co
                 atomicAdd(&cnt[CNT_DONE], 1);
                 atomicAdd(&T->episodes, 1ull);
                 atomicAdd(&T->truncated, 1ull);
-                atomicAdd(&T->elements, (unsigned long long)st_i(W_NEL));
-                atomicAdd(&T->sum_return, st_d(D_EP_RETURN));
-                atomicAdd(&T->sum_length, (double)st_i(W_EP_LEN));
+                atomicAdd(&T->elements, (unsigned long long)S.i(W_NEL));
+                atomicAdd(&T->sum_return, S.d(D_EP_RETURN));
+                atomicAdd(&T->sum_length, (double)S.i(W_EP_LEN));
             }
             if (lane < MG_OBS_DIM) {
                 if (io.term_obs_out && done) io.term_obs_out[(size_t)env * MG_OBS_DIM + lane] = obs;
@@ -1635,7 +1720,7 @@ __global__ void __launch_bounds__(32, MG_MINB_OBSERVE) mg_step_observe_kernel(co
             } else {
                 // the state changed: new memo (rule -1 / +1 verdicts, neighbour fan) and the rest of the record
                 const int flags = done ? 0 : memo_flags(w, ref_index);
-                store_hot(P.hot + env, w, ref_index, st_i(W_NEL), flags, base, 0, st_i(W_EP_LEN), st_d(D_EP_RETURN), st_d(D_CUR_AREA));
+                store_hot(P.hot + env, w, ref_index, S.i(W_NEL), flags, base, 0, S.i(W_EP_LEN), S.d(D_EP_RETURN), S.d(D_CUR_AREA));
             }
         }
     MG_ITEM_LOOP_END

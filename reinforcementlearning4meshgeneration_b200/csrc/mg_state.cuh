@@ -89,12 +89,15 @@ struct __align__(16) WorkItem {
 static_assert(sizeof(WorkItem) == 32, "WorkItem size");
 enum { WORK_DECIDE_NEW = 0, WORK_DECIDE_RULE = 1, WORK_APPLY = 2, WORK_OBSERVE = 3, WORK_RESET = 4 };
 
-// counters[CNT_SET * set + ...]: sizes of the decide / accept / observe lists of counter set `set`, the item tickets of
-// the three warp-per-item kernels and the number of episodes that ended in the step; CNT_STEP = parity of the next
+// Every work list has NBINS segments of num_envs records, binned by boundary size (largest first), so that the item
+// kernels hand out long items before short ones.
+constexpr int NBINS = 4;
+// counters[CNT_SET * set + ...]: sizes of the decide / accept / observe list bins of counter set `set`, the item tickets
+// of the warp-per-item kernels and the number of episodes that ended in the step; CNT_STEP = parity of the next
 // step (the set its screen kernel will use); CNT_CUR = the set the current step uses.  Two sets alternate so that no
 // memset sits between the launches of a step and any sequence of steps can be captured in a CUDA graph.
-enum { CNT_DECIDE = 0, CNT_ACCEPT = 1, CNT_OBSERVE = 2, CNT_DONE = 3, CNT_TICKET_DECIDE = 4, CNT_TICKET_UPDATE = 5,
-       CNT_TICKET_OBSERVE = 6, CNT_SET = 8, CNT_STEP = 16, CNT_CUR = 17, CNT_N = 24 };
+enum { CNT_DECIDE = 0, CNT_ACCEPT = 4, CNT_OBSERVE = 8, CNT_DONE = 12, CNT_TICKET_DECIDE = 13, CNT_TICKET_UPDATE = 14,
+       CNT_TICKET_OBSERVE = 15, CNT_SET = 16, CNT_STEP = 32, CNT_CUR = 33, CNT_N = 40 };
 
 constexpr int ANGLE_TAB_N = 62833;      // round(2 pi, 4) = 6.2832
 
@@ -118,9 +121,9 @@ struct Params {
     StatsAcc *stats;     // [STAT_SLOTS]
     float *obs_cache;
     // per-step work lists
-    WorkItem *decide_list;   // [num_envs]  screen -> decide
-    WorkItem *accept_list;   // [num_envs]  screen / decide -> update
-    WorkItem *observe_list;  // [num_envs]  screen / decide (resets of truncated envs), update -> observe
+    WorkItem *decide_list;   // [NBINS][num_envs]  screen -> decide
+    WorkItem *accept_list;   // [NBINS][num_envs]  screen / decide -> update
+    WorkItem *observe_list;  // [NBINS][num_envs]  screen / decide (resets of truncated envs), update -> observe
     int *counters;           // [CNT_N]
     // element log: quads as 4 vertex ids, coordinates of inserted vertices
     int32_t *elem;       // [num_envs][elem_cap][4]
