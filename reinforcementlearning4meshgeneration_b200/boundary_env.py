@@ -98,9 +98,27 @@ def boundary(index: int = 0) -> Boundary2D:
     return Boundary2D([Vertex(x, y) for x, y in _BUILTIN[index]])
 
 
+class Mesh:
+    """One generated element: ``.vertices`` (4 ``Vertex``), ``.ids`` (vertex ids) -- what the reference's plotting /
+    quality helpers read from a ``Mesh`` (general/components.py:730-737)."""
+    __slots__ = ("vertices", "ids")
+
+    def __init__(self, xy, ids):
+        self.vertices = [Vertex(float(p[0]), float(p[1])) for p in xy]
+        self.ids = [int(i) for i in ids]
+
+    def __array__(self, dtype=None, copy=None):
+        a = np.array([[v.x, v.y] for v in self.vertices], dtype=np.float64)
+        return a if dtype is None else a.astype(dtype)
+
+    def __getitem__(self, k):
+        return np.asarray(self)[k]
+
+
 class _MeshList:
-    """``env.generated_meshes`` stand-in: evaluators only take ``len()`` (eval_loop.py:103) or
-    iterate quads; items are (4,2) coordinate arrays fetched from the device element log."""
+    """``env.generated_meshes`` stand-in.  ``len()`` (what the evaluators read, eval_loop.py:103, testbed.py:182) comes
+    from the element count the last step / reset reported -- no device synchronisation; iteration / indexing fetch the
+    element log and yield ``Mesh`` objects."""
 
     def __init__(self, env: "BoudaryEnv"):
         self._env = env
@@ -110,31 +128,56 @@ class _MeshList:
         return quads, vxy, ne
 
     def __len__(self):
-        return int(self._fetch()[2])
+        return int(self._env._n_elements)
 
     def __iter__(self):
         quads, vxy, _ = self._fetch()
         for q in quads:
-            yield vxy[q]
+            yield Mesh(vxy[q], q)
 
     def __getitem__(self, i):
         quads, vxy, _ = self._fetch()
-        return vxy[quads[i]]
+        if isinstance(i, slice):
+            return [Mesh(vxy[q], q) for q in quads[i]]
+        return Mesh(vxy[quads[i]], quads[i])
+
+
+# backend factory: (xy, device=..., auto_reset=..., log_capacity=...) -> object with the BatchedBoudaryEnv surface used
+# below (reset, step_host, get_elements, get_state, close).  The CPU-only tests swap in a fake here; the product
+# always uses the CUDA env.
+def _default_backend(xy, **kw):
+    return BatchedBoudaryEnv([xy], num_envs=1, **kw)
+
+
+_BACKEND_FACTORY = _default_backend
 
 
 class BoudaryEnv(_EnvBase):
-    """Single-environment Gymnasium facade (reference: envs/boundary_env.py:34-457)."""
+    """Single-environment facade (reference: envs/boundary_env.py:34-457; legacy rl/boundary_env.py:21-263).
+
+    ``api="gymnasium"`` (default): ``reset(*, seed, static, options) -> (obs, {})`` and the 5-tuple ``step`` of the v2
+    env.  ``api="gym"``: the legacy surface the v1 trainers use (rl/boundary_env.py:67-84, :263): ``reset() -> obs``
+    and ``step -> (obs, reward, done, info)``.  ``reinforcementlearning4meshgeneration_b200.legacy`` exports the
+    legacy flavour under the reference's names for mounting as ``rl.boundary_env``.
+    """
 
     metadata = {"render_modes": []}
     TYPE_THRESHOLD = 0.3
+    API = "gymnasium"
 
     @classmethod
     def from_domain_file(cls, filename, *, experiment_version: Optional[str] = None, env_name: Optional[int] = None):
         return cls(read_polygon(filename), experiment_version=experiment_version, env_name=env_name)
 
-    def __init__(self, boundary, experiment_version: Optional[str] = None, env_name: Optional[int] = None, device=None):
+    def __init__(self, boundary, experiment_version: Optional[str] = None, env_name: Optional[int] = None, device=None,
+                 api: Optional[str] = None):
         self._xy = as_xy(boundary)
-        self._batched = BatchedBoudaryEnv([self._xy], num_envs=1, device=device, auto_reset=False)
+        self.api = api or self.API
+        if self.api not in ("gymnasium", "gym"):
+            raise ValueError("api must be 'gymnasium' or 'gym'")
+        # element counts grow with the domain's area (the reference's evaluation runs report ~5 x n0): a single env can
+        # afford a deep log
+        self._batched = _BACKEND_FACTORY(self._xy, device=device, auto_reset=False, log_capacity=max(64 * len(self._xy), 1024))
         self.action_space = _spaces.Box(ACTION_LOW.copy(), ACTION_HIGH.copy(), dtype=np.float32)
         self.observation_space = _spaces.Box(low=np.full((OBS_DIM,), -999.0, np.float32),
                                              high=np.full((OBS_DIM,), 999.0, np.float32), dtype=np.float32)
@@ -142,10 +185,13 @@ class BoudaryEnv(_EnvBase):
         self.experiment_version = experiment_version if experiment_version else "test"
         self.env_name = env_name if env_name is not None else 1
         self.generated_meshes = _MeshList(self)
+        self._n_elements = 0
         self._out = None
         self.current_state = None
+        self.original_vertices = [Vertex(float(x), float(y)) for x, y in self._xy]      # rl/boundary_env.py:23
+        self.boundary = Boundary2D(self.original_vertices)                              # rl/boundary_env.py:22
 
-    # -- Gymnasium API ----------------------------------------------------------------------
+    # -- Gymnasium / gym API ------------------------------------------------------------------
     def seed(self, seed: Optional[int] = None) -> None:
         if seed is not None:
             np.random.seed(seed)
@@ -153,11 +199,12 @@ class BoudaryEnv(_EnvBase):
     def reset(self, *, seed: Optional[int] = None, static: bool = False, options: Optional[Dict[str, Any]] = None):
         if seed is not None:
             self.seed(seed)
-        obs = self._batched.reset()[0].cpu().numpy().copy()
+        obs = np.array(self._batched.reset()[0].cpu().numpy(), dtype=np.float32, copy=True)
         if static:
             obs[1] = 0.0       # a static point environment reports area ratio 0 (C:1198-1199); only the reset obs is affected
         self.current_state = obs
-        return obs, {}
+        self._n_elements = 0
+        return obs if self.api == "gym" else (obs, {})
 
     def step(self, action):
         a = np.asarray(action, dtype=np.float32).reshape(1, 3)
@@ -168,13 +215,33 @@ class BoudaryEnv(_EnvBase):
         terminated, truncated = bool(o["terminated"][0]), bool(o["truncated"][0])
         obs = o["obs"][0].copy()
         self.current_state = obs
-        return obs, np.float64(o["reward"][0]), terminated, truncated, {"is_complete": not truncated}
+        self._n_elements = int(o["n_elements"][0])
+        reward, info = np.float64(o["reward"][0]), {"is_complete": not truncated}
+        if self.api == "gym":
+            return obs, reward, terminated or truncated, info
+        return obs, reward, terminated, truncated, info
 
     def close(self) -> None:
         self._batched.close()
 
     def render(self, mode: str = "human") -> None:
         print(f"Generated elements: {len(self.generated_meshes)}")
+
+    # -- what the legacy evaluators touch besides reset / step (testbed.py:107-274, CustomizeCallback.py:131-133) ----
+    @property
+    def updated_boundary(self) -> Boundary2D:
+        """Current front as a ``Boundary2D`` (read-only view: ``.vertices[i].x/.y``; general/mesh.py:601-674)."""
+        st = self._batched.get_state(0)
+        return Boundary2D([Vertex(float(x), float(y)) for x, y in st["xy"]])
+
+    def save_meshes(self, name, meshes=None, quality: bool = False, indexing: bool = False, type: int = 0, dpi: int = 300,
+                    style: str = "k.-") -> str:
+        """general/mesh.py:1785-1792: draw the generated elements.  With matplotlib the figure is saved like the
+        reference does; without it (this image) an SVG with the same content is written next to ``name``.  Returns the
+        path written."""
+        from .export import save_meshes_figure
+        meshes = list(self.generated_meshes) if meshes is None else list(meshes)
+        return save_meshes_figure(name, meshes, self._xy, indexing=indexing, dpi=dpi, style=style)
 
     # -- element export (rl/boundary_env.py:648-669, general/mesh.py:1842-1864) ---------------
     def _mesh(self):
@@ -188,4 +255,3 @@ class BoudaryEnv(_EnvBase):
     def write_generated_elements_2_file(self, filename, format: str = "inp") -> None:
         from .export import write_inp
         write_inp(filename, *self._mesh())
-

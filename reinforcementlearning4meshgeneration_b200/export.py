@@ -76,3 +76,70 @@ def write_inp(filename, n0: int, quads: np.ndarray, vertex_xy: np.ndarray) -> No
         fw.write(f"*ELEMENT, TYPE=S4R, ELSET=EB{i+1} \n")
         for k, q in enumerate(quads):
             fw.write(f"{k+1}, {pos[int(q[0])]}, {pos[int(q[1])]}, {pos[int(q[2])]}, {pos[int(q[3])]}\n")
+
+
+def save_meshes_figure(name, meshes, boundary_xy, indexing: bool = False, dpi: int = 300, style: str = "k.-") -> str:
+    """``MeshGeneration.save_meshes`` (general/mesh.py:1785-1792 over generate_meshes_canvas :1761-1783): the original
+    boundary and every generated element as a closed polyline, element index at the centroid when ``indexing``.
+    With matplotlib the figure is written to ``name`` exactly like the reference; without it an SVG with the same
+    content is written to ``name`` with the suffix replaced by ``.svg``.  Returns the path written.
+
+    ``meshes``: iterable of (4, 2) arrays or objects with ``.vertices[i].x/.y``."""
+    import os
+
+    def xy_of(m):
+        if hasattr(m, "vertices"):
+            return np.array([[float(v.x), float(v.y)] for v in m.vertices], np.float64)
+        return np.asarray(m, np.float64).reshape(-1, 2)
+
+    polys = [xy_of(m) for m in meshes]
+    bxy = np.asarray(boundary_xy, np.float64).reshape(-1, 2)
+    try:
+        import matplotlib
+        if not isinstance(getattr(matplotlib, "__version__", None), str):     # an inert stand-in module, not matplotlib
+            raise ImportError("matplotlib is not installed")
+        matplotlib.use("Agg")
+        import matplotlib.pyplot as plt
+    except Exception:
+        plt = None
+    if plt is not None:
+        plt.clf()
+        closed = np.vstack([bxy, bxy[:1]])
+        plt.plot(closed[:, 0], closed[:, 1], style, linewidth=1)
+        for k, p in enumerate(polys):
+            c = np.vstack([p, p[:1]])
+            plt.plot(c[:, 0], c[:, 1], style, linewidth=1)
+            if indexing:
+                plt.text(p[:, 0].mean(), p[:, 1].mean(), k, fontsize=4)
+        plt.gca().set_aspect("equal", adjustable="box")
+        plt.subplots_adjust(top=1, bottom=0, right=1, left=-0, hspace=0, wspace=0)
+        plt.savefig(name, dpi=dpi)
+        plt.close("all")
+        return str(name)
+    pts = np.vstack([bxy] + polys) if polys else bxy
+    lo, hi = pts.min(axis=0), pts.max(axis=0)
+    span = max(hi[0] - lo[0], hi[1] - lo[1], 1e-9)
+    scale, pad = 1000.0 / span, 10.0
+
+    def tr(p):
+        return (pad + (p[0] - lo[0]) * scale, pad + (hi[1] - p[1]) * scale)          # y up
+
+    w, h = 2 * pad + (hi[0] - lo[0]) * scale, 2 * pad + (hi[1] - lo[1]) * scale
+    out = [f'<svg xmlns="http://www.w3.org/2000/svg" width="{w:.0f}" height="{h:.0f}" viewBox="0 0 {w:.1f} {h:.1f}">',
+           '<rect width="100%" height="100%" fill="white"/>']
+
+    def poly(p, width):
+        s = " ".join(f"{x:.2f},{y:.2f}" for x, y in (tr(q) for q in p))
+        out.append(f'<polygon points="{s}" fill="none" stroke="black" stroke-width="{width}"/>')
+
+    poly(bxy, 1.5)
+    for k, p in enumerate(polys):
+        poly(p, 0.8)
+        if indexing:
+            cx, cy = tr(p.mean(axis=0))
+            out.append(f'<text x="{cx:.1f}" y="{cy:.1f}" font-size="8" text-anchor="middle">{k}</text>')
+    out.append("</svg>")
+    path = os.path.splitext(str(name))[0] + ".svg"
+    with open(path, "w") as f:
+        f.write("\n".join(out))
+    return path

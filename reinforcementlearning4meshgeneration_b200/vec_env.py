@@ -41,6 +41,55 @@ def _pinned(shape, dtype):
         return t
 
 
+class _EnvView:
+    """``venv.envs[i]``: what the reference's callbacks / evaluators reach through a ``DummyVecEnv`` for one env
+    (rl/baselines/CustomizeCallback.py:131-133, rl/baselines/dummy_vec_env.py:21): ``generated_meshes``,
+    ``save_meshes``, ``boundary`` / ``original_vertices`` / ``updated_boundary``, ``write_2_file`` -- read-only views
+    fetched from the batched env on demand (``mg_get_elements`` / ``mg_get_state``)."""
+
+    def __init__(self, batched, index: int):
+        self._b, self._i = batched, int(index)
+
+    def _elements(self):
+        quads, vxy, ne = self._b.get_elements(self._i)
+        return quads, vxy, ne
+
+    @property
+    def generated_meshes(self):
+        from .boundary_env import Mesh
+        quads, vxy, _ = self._elements()
+        return [Mesh(vxy[q], q) for q in quads]
+
+    @property
+    def original_vertices(self):
+        from .boundary_env import Vertex
+        st = self._b.get_state(self._i)
+        _, vxy, _ = self._elements()
+        return [Vertex(float(x), float(y)) for x, y in vxy[: st["n0"]]]
+
+    @property
+    def boundary(self):
+        from .boundary_env import Boundary2D
+        return Boundary2D(self.original_vertices)
+
+    @property
+    def updated_boundary(self):
+        from .boundary_env import Boundary2D, Vertex
+        return Boundary2D([Vertex(float(x), float(y)) for x, y in self._b.get_state(self._i)["xy"]])
+
+    def save_meshes(self, name, meshes=None, quality=False, indexing=False, type=0, dpi=300, style="k.-"):
+        from .export import save_meshes_figure
+        _, vxy, _ = self._elements()
+        n0 = self._b.get_state(self._i)["n0"]
+        return save_meshes_figure(name, self.generated_meshes if meshes is None else list(meshes), vxy[:n0], indexing=indexing,
+                                  dpi=dpi, style=style)
+
+    def write_2_file(self, filename):
+        from .export import write_2_file
+        quads, vxy, _ = self._elements()
+        write_2_file(filename, self._b.get_state(self._i)["n0"], quads, vxy)
+
+
 class _VecEnvCore:
     """Backend-agnostic VecEnv logic (unit-tested on the CPU with a fake batched env)."""
 
@@ -57,8 +106,9 @@ class _VecEnvCore:
                          terminated=_pinned((N,), torch.uint8), truncated=_pinned((N,), torch.uint8),
                          terminal_obs=_pinned((N, OBS_DIM), torch.float32), n_elements=_pinned((N,), torch.int32))
         self._monitor = monitor
-        if hasattr(batched, "set_host_delta"):
-            batched.set_host_delta(True)      # the adapter owns its pinned buffers and hands out copies
+        self.envs = [_EnvView(batched, i) for i in range(N)]      # DummyVecEnv.envs (dummy_vec_env.py:21)
+        if hasattr(batched, "set_obs_delta"):
+            batched.set_obs_delta(True)       # the adapter owns its pinned buffers and hands out copies
         self._ep_ret = np.zeros(N, np.float64)
         self._ep_len = np.zeros(N, np.int64)
         self._t0 = time.time()
@@ -127,8 +177,11 @@ class _VecEnvCore:
         return indices
 
     def get_attr(self, attr_name: str, indices=None) -> List[Any]:
+        """Attribute of the individual envs (generated_meshes, boundary, ...) or, failing that, of the adapter."""
         if attr_name == "render_mode":
             return [None for _ in self._indices(indices)]
+        if hasattr(_EnvView, attr_name):
+            return [getattr(self.envs[i], attr_name) for i in self._indices(indices)]
         return [getattr(self, attr_name) for _ in self._indices(indices)]
 
     def set_attr(self, attr_name: str, value: Any, indices=None) -> None:
@@ -136,8 +189,10 @@ class _VecEnvCore:
 
     def env_method(self, method_name: str, *method_args, indices=None, **method_kwargs) -> List[Any]:
         if method_name == "generated_meshes_count":
-            st = [self._b.get_state(i) for i in self._indices(indices)]
-            return [s["n_elements"] for s in st]
+            return [self._b.n_elements_of(i) if hasattr(self._b, "n_elements_of") else self._b.get_state(i)["n_elements"]
+                    for i in self._indices(indices)]
+        if method_name in ("save_meshes", "write_2_file"):
+            return [getattr(self.envs[i], method_name)(*method_args, **method_kwargs) for i in self._indices(indices)]
         raise AttributeError(f"env_method {method_name!r} is not available on the batched CUDA env")
 
     def env_is_wrapped(self, wrapper_class, indices=None) -> List[bool]:

@@ -347,3 +347,36 @@ def test_current_device_is_left_alone():
     assert torch.cuda.current_device() == 0
     x = torch.zeros(4, device="cuda")
     assert x.device.index == 0
+
+
+def test_graph_captured_policy_and_env_rollout_equals_eager():
+    """BASELINE config 5: the actor MLP (18-128-128-128-(3+3), sb3_algos.py:56-62) consuming the env's device-resident
+    observation buffer and mg_step, captured together in ONE CUDA graph and replayed.  The env side must be bit for
+    bit what an eager env produces from the same actions, and the actions must be the policy's output for the
+    previous observation (cuBLAS may pick another GEMM algorithm under capture, so the policy is compared at float32
+    round-off, the env exactly)."""
+    import os
+    import sys
+    import torch
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples"))
+    import sac_rollout
+    torch.manual_seed(0)
+    actor = sac_rollout.Actor().cuda()
+    kw = dict(random_polygons=dict(min_verts=64, max_verts=256), seed=123)
+    N, T = 2048, 150
+    env = _mk(None, N, **kw)
+    obs0 = env.reset().clone()
+    rec = []
+    sac_rollout.rollout(env, actor, T, graph=True, stochastic=False, record=rec)
+    torch.cuda.synchronize()
+    assert env.stats()["successes"] > 100
+    eager = _mk(None, N, **kw)
+    prev = eager.reset().clone()
+    assert torch.equal(prev, obs0)
+    for t in range(T):
+        act, obs, rew, done = rec[t]
+        assert torch.allclose(act, actor(prev, False), rtol=1e-4, atol=1e-5), f"graph policy output differs at step {t}"
+        r = eager.step(act)
+        assert torch.equal(r.obs, obs), f"graph replay differs from the eager env at step {t}"
+        assert torch.equal(r.reward, rew) and torch.equal((r.terminated | r.truncated), done)
+        prev = r.obs.clone()
