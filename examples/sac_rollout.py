@@ -33,12 +33,19 @@ class Actor(torch.nn.Module):
         self.log_std = torch.nn.Linear(d, act_dim)
         self.register_buffer("low", torch.from_numpy(ACTION_LOW.copy()))
         self.register_buffer("high", torch.from_numpy(ACTION_HIGH.copy()))
+        self.register_buffer("tick", torch.zeros(1))          # forward-call counter of the deterministic exploration
+        self.register_buffer("phase", torch.tensor([0.0, 2.1, 4.2]))
 
     @torch.no_grad()
     def forward(self, obs, stochastic=True):
         h = self.body(obs)
         mu, log_std = self.mu(h), self.log_std(h).clamp(-20, 2)
-        a = torch.tanh(mu + log_std.exp() * torch.randn_like(mu) if stochastic else mu)
+        if stochastic:
+            eps = torch.randn_like(mu)
+        else:      # reproducible exploration (tests): a fixed function of the observation and of the call counter
+            eps = 1.5 * torch.sin(997.0 * obs.sum(dim=1, keepdim=True) + 0.7 * self.tick + self.phase)
+            self.tick += 1
+        a = torch.tanh(mu + log_std.exp() * eps)
         return (self.low + (a + 1) * 0.5 * (self.high - self.low)).contiguous()
 
 

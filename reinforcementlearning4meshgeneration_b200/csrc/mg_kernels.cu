@@ -91,8 +91,10 @@ __device__ __forceinline__ void stage_issue(double2 *ring, unsigned long long *m
     __syncwarp();
     if (lane == 0) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-#ifndef MG_NO_RING_EVICT_FIRST
-        // the rings are streamed once per phase (state >> L2): do not let them displace the small hot records
+#ifdef MG_RING_EVICT_FIRST
+        // (round 1 streamed every env's ring through L2 once per step and marked the copies evict-first; with the screen
+        // kernel only ~8 % of the rings are touched per step -- 25 MB -- and the observe kernel re-reads the ones the
+        // update kernel staged, so they are left to the normal L2 policy)
         unsigned long long pol;
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
         asm volatile(
@@ -1451,6 +1453,9 @@ __global__ void __launch_bounds__(32, MG_MINB_UPDATE) mg_step_update_kernel(cons
         Warp w;
         w.ring = L.ring; w.queue = nullptr; w.lane = lane; w.n = W.n;
         const int n = W.n, idx = S.i(W_REF);
+        // ids of the five vertices any of the three quads is made of (B[i-2..i+2]), requested now so that the DRAM
+        // round trip hides behind the ring copy and the decision instead of sitting in front of the element log
+        const int fan_vid = lane < 5 ? P.vid[off + wrapn(idx - 2 + lane, n)] : 0;
         stage_wait(L.mbar, phase);
         phase ^= 1u;
         int rule = W.rule;
@@ -1489,15 +1494,16 @@ __global__ void __launch_bounds__(32, MG_MINB_UPDATE) mg_step_update_kernel(cons
         // ---- update_boundary (M:601-674) ---------------------------------------------------
         int nb[4];          // the four neighbours whose candidate keys are re-evaluated, in order
         int t0 = 0, t1 = 0; // surviving quad vertices (no-new-vertex case), new indices
-        int elem_ids[4];
         const int next_vid0 = S.i(W_NEXT_VID);
-#pragma unroll
-        for (int k = 0; k < 4; k++) elem_ids[k] = qi[k] < 0 ? next_vid0 : P.vid[off + qi[k]];
         // ---- element log, area and robust quality first: they only need the quad (old ring + new vertex), and doing
         // them here ends the live ranges of the quad, its corner angles and the vertex ids before the boundary update
-        if (P.elem && lane < 4 && n_elements < P.elem_cap)
-            P.elem[((size_t)env * P.elem_cap + n_elements) * 4 + lane] =
-                lane == 0 ? elem_ids[0] : (lane == 1 ? elem_ids[1] : (lane == 2 ? elem_ids[2] : elem_ids[3]));
+        {
+            // quad vertex k is B[first + k] (the new vertex, id next_vid0, takes slot 0 of a new-vertex quad)
+            const int first = new_vertex ? -2 : (rule == -1 ? -1 : -2);       // offset of quad slot 0 from the reference point
+            const int my_id = __shfl_sync(FULL, fan_vid, (first + 2 + lane) & 7);
+            if (P.elem && lane < 4 && n_elements < P.elem_cap)
+                P.elem[((size_t)env * P.elem_cap + n_elements) * 4 + lane] = (new_vertex && lane == 0) ? next_vid0 : my_id;
+        }
         n_elements++;
         // ---- area (C:943-958), robust quality (C:881-892) -----------------------------------
         double e0 = pdist(m[0], m[3]), e1 = pdist(m[1], m[0]), e2 = pdist(m[2], m[1]), e3 = pdist(m[3], m[2]);
