@@ -60,6 +60,11 @@ typedef struct {
     double ep_return; int ep_len;
     int last_rule; int last_success; int last_inside; int last_existing;
     double dbg[8];                   /* last successful step: b_reward, e_reward, area, penalty, ... */
+    /* move() (E:459-594): not_valid_points as coordinates (the reference excludes candidates within 0.001 of one of
+     * them, M:428-433), static point environments (area-ratio slot of the observation = 0, C:1209-1214) */
+    double *excl; int nexcl, capexcl;
+    int static_obs;
+    int needs_smoothing;             /* move(): every candidate is excluded -> the reference calls smooth_pave (not restated) */
 } OEnv;
 
 /* ---------------------------------------------------------------- rounding ------------- */
@@ -315,6 +320,19 @@ static void find_next_state(OEnv *e) {
     if (e->cand_none) find_reference_candidates(e);          /* M:297-298 */
     if (e->ncand == 0) { e->ref_id = -1; e->obs_none = 1; return; }   /* returns None */
     int rid = e->cand_id[0];
+    if (e->nexcl > 0) {                                      /* M:310-314: first candidate that is not a not-valid point */
+        rid = -1;
+        for (int c = 0; c < e->ncand && rid < 0; c++) {
+            P2 v = VP(e, e->cand_id[c]);
+            int hit = 0;
+            for (int k = 0; k < e->nexcl && !hit; k++) {
+                P2 q = { e->excl[2 * k], e->excl[2 * k + 1] };
+                if (pdist(q, v) < 0.001) hit = 1;            /* M:428-433 is_vertex_inside_list */
+            }
+            if (!hit) rid = e->cand_id[c];
+        }
+        if (rid < 0) { e->ref_id = -1; e->obs_none = 1; return; }
+    }
     e->ref_id = rid;
     e->obs_none = 0;
     int n = e->n;
@@ -339,7 +357,7 @@ static void find_next_state(OEnv *e) {
     const double radius = 4;
     double T = base * radius;
     double theta = cw_angle(ref, left_p, right_p);
-    double area_ratio = e->current_area / e->original_area;
+    double area_ratio = e->static_obs ? 0.0 : e->current_area / e->original_area;     /* C:1209-1214 */
 
     r[0][0] = f32((pdist(ref, right_p) / radius) / base); r[0][1] = f32(area_ratio);
     r[8][0] = f32((pdist(ref, left_p) / radius) / base);  r[8][1] = f32(theta);
@@ -462,6 +480,7 @@ void oracle_reset(OEnv *e) {
     e->cand_none = 1; e->ncand = 0;
     e->failed_num = 0;
     e->ep_return = 0; e->ep_len = 0;
+    e->nexcl = 0; e->static_obs = 0; e->needs_smoothing = 0;
     find_next_state(e);
     estimate_area_range(e);
 }
@@ -490,6 +509,7 @@ OEnv *oracle_create(const double *xy, int n, double original_area) {
 }
 
 void oracle_destroy(OEnv *e) {
+    if (e) free(e->excl);
     if (!e) return;
     free_pool(e);
     free(e->v); free(e->B); free(e->xy0); free(e->cand_id); free(e->cand_key); free(e->elements);
@@ -832,6 +852,8 @@ void oracle_step(OEnv *e, const float *action, double *reward_out, int *terminat
     }
     /* E:361-386 */
     int is_complete = 1;
+    e->static_obs = 0;                        /* step() builds a non-static point environment (E:361); it passes
+                                               * self.not_valid_points, which only move() ever fills */
     find_next_state(e);
     if (!failed) e->failed_num = 0;
     else {
@@ -843,6 +865,103 @@ void oracle_step(OEnv *e, const float *action, double *reward_out, int *terminat
     *truncated = done && !is_complete;
     e->ep_return += reward; e->ep_len++;
 }
+
+
+/* CPython round(x, 6) on a float (same construction as py_round4) */
+static double py_round6(double x) {
+    double p = x * 1e6;
+    double r = nearbyint(p);
+    if (fabs(p - r) == 0.5) {
+        double err = fma(x, 1e6, -p);
+        if (err > 0) r = floor(p) + 1.0;
+        else if (err < 0) r = floor(p);
+    }
+    return r / 1e6;
+}
+
+static void excl_push(OEnv *e, double x, double y) {
+    if (e->nexcl == e->capexcl) {
+        e->capexcl = e->capexcl ? 2 * e->capexcl : 32;
+        e->excl = (double *)realloc(e->excl, sizeof(double) * 2 * e->capexcl);
+    }
+    e->excl[2 * e->nexcl] = x; e->excl[2 * e->nexcl + 1] = y; e->nexcl++;
+}
+
+/* E:459-594 move(new_point = (r, phi) polar in units of radius * base_length, type).  Returns through the pointers:
+ * done, is_complete, needs_smoothing (the reference would call smooth_pave here; that path is not restated: the
+ * caller stops comparing).  Reward is always 0.  new_point components are Python floats (CPython round). */
+void oracle_move(OEnv *e, const double *polar, double type, int *done_out, int *complete_out, int *smooth_out) {
+    int done = 0, not_valid_element = 1;
+    e->needs_smoothing = 0;
+    e->static_obs = 1;
+    int rid = e->ref_id;
+    int n = e->n;
+    e->last_rule = 2; e->last_success = 0; e->last_inside = -1; e->last_existing = 0;
+    if (rid < 0) { e->crashed = 1; *done_out = 1; *complete_out = 0; *smooth_out = 0; return; }
+    int index = B_index(e, rid);
+    P2 ref = VP(e, rid);
+    const double radius = 4;
+    double x = e->base_length * radius * polar[0] * cos(polar[1]);
+    double y = e->base_length * radius * polar[0] * sin(polar[1]);
+    double px = py_round6(x), py = py_round6(y);
+    /* E:202-210 detransformation(point, 1, v1, v2) + D:112-137 */
+    P2 p1 = BP(e, index - 1);
+    double theta = 2 * PI - atan2(p1.y - ref.y, p1.x - ref.x);
+    double ox = cos(theta) * px + sin(theta) * py;
+    double oy = -sin(theta) * px + cos(theta) * py;
+    ox *= 1; oy *= 1;
+    ox += ref.x; oy += ref.y;
+    P2 newp = { np_round4(ox), np_round4(oy) };
+
+    if (n <= 5) {
+        /* the reference leaves is_complete unbound here and raises; sentinel: done, complete iff n <= 4 */
+        *done_out = 1; *complete_out = n <= 4; *smooth_out = 0;
+        return;
+    }
+    int mid[4]; P2 m[4]; int have_mesh = 1; int n_new = 0, new_pos = -1;
+    if (type <= 0.3) {
+        e->last_rule = -1;
+        mid[0] = BI(e, index - 1); mid[1] = e->B[index]; mid[2] = e->B[(index + 1) % n]; mid[3] = e->B[(index + 2) % n];
+    } else if (type >= 1 - 0.3) {
+        e->last_rule = 1;
+        mid[0] = BI(e, index - 2); mid[1] = BI(e, index - 1); mid[2] = e->B[index]; mid[3] = e->B[(index + 1) % n];
+    } else {
+        e->last_rule = 0;
+        int inside = point_inside(e, newp);
+        e->last_inside = inside;
+        if (inside) {
+            mid[0] = -2; mid[1] = BI(e, index - 1); mid[2] = e->B[index]; mid[3] = e->B[(index + 1) % n];
+            n_new = 1; new_pos = 0;
+        } else have_mesh = 0;
+    }
+    if (have_mesh) {
+        for (int k = 0; k < 4; k++) m[k] = mid[k] == -2 ? newp : VP(e, mid[k]);
+        if (mesh_is_valid(m) && !check_intersection_with_boundary(e, mid, m, rid)) {
+            if (n_new) mid[new_pos] = new_vertex(e, newp.x, newp.y, 1);
+            connect_vertices(e, mid);
+            append_element(e, mid);
+            not_valid_element = 0;
+            e->last_success = 1;
+            update_boundary(e, mid, n_new, new_pos);
+            find_next_state(e);                               /* with the not-valid points collected so far */
+            if (e->n <= 5) {
+                done = 1;
+                if (e->n == 4) { int fm[4] = { e->B[0], e->B[1], e->B[2], e->B[3] }; append_element(e, fm); }
+            }
+        }
+    }
+    if (not_valid_element) {
+        excl_push(e, ref.x, ref.y);       /* `reference_point not in not_valid_points`: it cannot be selected twice */
+        find_next_state(e);
+    } else e->nexcl = 0;
+    int is_complete;
+    if (e->n > 4) {
+        is_complete = 0;
+        if (e->obs_none) { e->needs_smoothing = 1; done = 1; }
+    } else is_complete = 1;
+    *done_out = done; *complete_out = is_complete; *smooth_out = e->needs_smoothing;
+}
+int oracle_n_excluded(const OEnv *e) { return e->nexcl; }
 
 /* ---------------------------------------------------------------- accessors ------------ */
 

@@ -46,6 +46,9 @@ def lib():
         L.oracle_candidates.argtypes = [vp, vp, vp]
         L.oracle_elements.argtypes = [vp, vp]
         L.oracle_vertex_xy.argtypes = [vp, vp]
+        L.oracle_move.argtypes = [vp, vp, f64, vp, vp, vp]
+        L.oracle_n_excluded.restype = i32
+        L.oracle_n_excluded.argtypes = [vp]
         L.oracle_rollout.argtypes = [vp, vp, i32] + [vp] * 9
         L.oracle_run_random.restype = C.c_long
         L.oracle_run_random.argtypes = [vp, C.c_uint64, C.c_long, vp, vp, vp]
@@ -106,6 +109,19 @@ class OracleEnv:
         lib().oracle_step(self._h, _p(a), C.byref(r), C.byref(te), C.byref(tr))
         obs = None if lib().oracle_obs_none(self._h) else self.obs()
         return obs, r.value, bool(te.value), bool(tr.value), {"is_complete": not tr.value}
+
+    def move(self, new_point, type):
+        """E:459-594 move((r, phi), type) -> (obs | None, 0, done, {"is_complete": ...}, needs_smoothing).  When
+        needs_smoothing is set the reference would call smooth_pave (not restated): stop comparing there."""
+        p = np.ascontiguousarray(np.asarray(new_point, dtype=np.float64))
+        d, c, sm = C.c_int(), C.c_int(), C.c_int()
+        lib().oracle_move(self._h, _p(p), float(type), C.byref(d), C.byref(c), C.byref(sm))
+        obs = None if lib().oracle_obs_none(self._h) else self.obs()
+        return obs, 0, bool(d.value), {"is_complete": bool(c.value)}, bool(sm.value)
+
+    @property
+    def n_excluded(self):
+        return lib().oracle_n_excluded(self._h)
 
     # ---- state views --------------------------------------------------
     def obs(self):
