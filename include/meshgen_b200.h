@@ -138,6 +138,25 @@ int mg_reset(mg_handle h, const uint8_t *mask_dev, float *obs_dev, void *stream)
 int mg_step(mg_handle h, const float *act_dev, float *obs_dev, double *rew_dev, uint8_t *term_dev,
             uint8_t *trunc_dev, float *term_obs_dev, int32_t *n_elem_dev, void *stream);
 
+/* Replaces BoudaryEnv.move (E:459-594; legacy rl/boundary_env.py:265-432): the "apply this geometric move" entry point of
+ * the reference's data-generation utilities (general/EBRD.py, general/FNN_evaluation.py), one move for every env.
+ *   polar_dev     in  num_envs*2 float64  new_point = (r, phi), in units of radius (4) x base_length, Python floats in the
+ *                                         reference (rounded to 6 decimals by CPython's round, E:478)
+ *   type_dev      in  num_envs float64    <= 0.3: rule -1 element, >= 0.7: rule +1 element, otherwise a new vertex
+ *   obs_dev       out num_envs*18 float32 next observation of a STATIC point environment (area-ratio slot 0, C:1209-1214);
+ *                                         zeros where the reference returns None
+ *   done_dev / complete_dev out uint8     done and info["is_complete"] as the reference returns them (reward is always 0)
+ *   exhausted_dev out uint8               every reference candidate is on the not-valid list: the reference would smooth the
+ *                                         whole mesh here (smooth_pave, general/mesh.py:790-1067) and go on; that is NOT built,
+ *                                         the env reports done.  Reset it before the next move.
+ *   n_elem_dev    out num_envs int32      len(generated_meshes) (may be NULL)
+ * A failed move puts the reference point on the env's not-valid list (cleared by the next accepted element or by
+ * mg_reset), and the next reference point is the first candidate not within 0.001 of a listed point (M:310-314,
+ * M:428-433).  mg_step does not look at that list (in the reference, step() after failed move()s would): reset between
+ * the two APIs.  Entering with n <= 5 raises in the reference (unbound is_complete); here: done, complete iff n <= 4. */
+int mg_move(mg_handle h, const double *polar_dev, const double *type_dev, float *obs_dev, uint8_t *done_dev, uint8_t *complete_dev,
+            uint8_t *exhausted_dev, int32_t *n_elem_dev, void *stream);
+
 /* Same transition through HOST buffers (what a numpy-facing caller such as SB3's VecEnv pays):
  * H2D of the actions, the step, D2H of all outputs, one stream synchronise.  Output buffers that are pinned
  * (cudaHostAlloc / cudaHostRegister / torch .pin_memory()) are written by the step kernels directly; pageable ones

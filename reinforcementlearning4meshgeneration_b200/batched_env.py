@@ -172,6 +172,20 @@ class BatchedBoudaryEnv:
                               C.c_void_p(self.n_elements.data_ptr()), self._stream()), self._h, "mg_step")
         return StepResult(self.obs, self.reward, self.terminated, self.truncated, self.terminal_obs, self.n_elements)
 
+    def move(self, polar, type) -> dict:
+        """``BoudaryEnv.move`` (E:459-594) for every env: ``polar`` float64 [N,2] = (r, phi), ``type`` float64 [N].
+        Returns device tensors: obs (static point environment), done, is_complete, exhausted (the reference would call
+        smooth_pave here -- not built), n_elements.  Reward is always 0."""
+        polar = torch.as_tensor(polar, dtype=torch.float64).to(self.device).contiguous().reshape(self.num_envs, 2)
+        type = torch.as_tensor(type, dtype=torch.float64).to(self.device).contiguous().reshape(self.num_envs)
+        if not hasattr(self, "_move_flags"):
+            self._move_flags = torch.zeros((3, self.num_envs), dtype=torch.uint8, device=self.device)
+        f = self._move_flags
+        check(self._L.mg_move(self._h, C.c_void_p(polar.data_ptr()), C.c_void_p(type.data_ptr()), C.c_void_p(self.obs.data_ptr()),
+                              C.c_void_p(f[0].data_ptr()), C.c_void_p(f[1].data_ptr()), C.c_void_p(f[2].data_ptr()),
+                              C.c_void_p(self.n_elements.data_ptr()), self._stream()), self._h, "mg_move")
+        return dict(obs=self.obs, done=f[0], is_complete=f[1], exhausted=f[2], n_elements=self.n_elements)
+
     def step_host(self, actions: np.ndarray, out: Optional[dict] = None) -> dict:
         """Same transition through host (numpy / pinned) buffers: H2D + step + D2H + sync inside the
         library (mg_step_host) -- the path a numpy-facing caller such as SB3 pays.  With pinned ``out`` buffers

@@ -25,6 +25,7 @@ struct mg_env_s {
     float *t_obs = nullptr;
     mg_episode_stats *d_stats_out = nullptr;
     double2 *sc_tab = nullptr;      // [2][ANGLE_TAB_N] host-libm {sin, cos} of the quantised angles and their halves
+    double2 *excl = nullptr;        // [num_envs][cap] not-valid points of mg_move (allocated by its first call)
     // staging buffers for mg_step_host (used for every caller buffer that is not pinned)
     float *d_act = nullptr, *d_obs = nullptr, *d_term_obs = nullptr;
     double *d_rew = nullptr;
@@ -296,7 +297,7 @@ int mg_destroy(mg_handle h) {
     cudaFree(P.obs_cache); cudaFree(P.elem); cudaFree(P.ins_xy);
     cudaFree(P.decide_list); cudaFree(P.accept_list); cudaFree(P.observe_list); cudaFree(P.counters);
     free_templates(h);
-    cudaFree(h->sc_tab);
+    cudaFree(h->sc_tab); cudaFree(h->excl);
     cudaFree(h->d_stats_out); cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_term_obs); cudaFree(h->d_rew);
     cudaFree(h->d_term); cudaFree(h->d_trunc); cudaFree(h->d_nel);
     cudaFreeHost(h->h_cnt);
@@ -586,6 +587,27 @@ int mg_step_host(mg_handle h, const float *act_host, float *obs_host, double *re
     if (term_obs_host) d2h += tobs_a ? (int64_t)h->h_cnt[CNT_SET * cur + CNT_DONE] * row : (int64_t)N * row;
     h->last_h2d = (int64_t)(N * 3 * sizeof(float));
     h->last_d2h = d2h;
+    return MG_OK;
+}
+
+int mg_move(mg_handle h, const double *polar_dev, const double *type_dev, float *obs_dev, uint8_t *done_dev, uint8_t *complete_dev,
+            uint8_t *exhausted_dev, int32_t *n_elem_dev, void *stream) {
+    if (!h || !polar_dev || !type_dev || !obs_dev || !done_dev || !complete_dev || !exhausted_dev)
+        return fail(h, MG_ERR_ARG, "mg_move: null pointer");
+    if (!h->was_reset) return fail(h, MG_ERR_STATE, "mg_move: call mg_reset first");
+    MG_DEVICE(h);
+    if (!h->excl) {
+        MG_CUDA(h, dalloc(&h->excl, (size_t)h->num_envs * h->P.cap));
+        MG_CUDA(h, cudaFuncSetAttribute(mg_move_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    }
+    MoveIO io;
+    io.polar = polar_dev; io.type = type_dev; io.obs_out = obs_dev; io.done_out = done_dev; io.complete_out = complete_dev;
+    io.exhausted_out = exhausted_dev; io.n_elem_out = n_elem_dev;
+    mg_move_kernel<<<h->num_envs, 32, h->smem, (cudaStream_t)stream>>>(h->P, io, h->excl);
+    h->launches++;
+    MG_CUDA(h, cudaGetLastError());
+    h->obs_bound = obs_dev;              // every row was written
+    note_user_stream(h, (cudaStream_t)stream);
     return MG_OK;
 }
 

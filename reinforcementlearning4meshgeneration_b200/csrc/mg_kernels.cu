@@ -776,11 +776,11 @@ __device__ __forceinline__ SmemLayout carve(unsigned char *raw, int cap, bool wi
 }
 size_t smem_bytes(int cap, bool with_queue = true) { return (size_t)cap * 16 + (with_queue ? (size_t)QCAP * 4 : 0) + STASH_BYTES + 16; }
 
-// words / doubles of the stash: EnvHot = {n, ref_index, n_elements, flags | base_length(d1), failed_num(w6), ep_len(w7) |
-// ep_return(d4), current_area(d5) | fan d6..15}; EnvCold at byte 128 = {original_area(d16), area_min(d17) | area_crit(d18),
+// words / doubles of the stash: EnvHot = {n, ref_index, n_elements, flags | base_length(d2), failed_num(w6), ep_len(w7) |
+// ep_return(d4), current_area(d5) | fan d6..15} (base_length is double 2); EnvCold at byte 128 = {original_area(d16), area_min(d17) | area_crit(d18),
 // n0(w38), next_vid(w39) | stamp_ctr(w40), domain(w41), episode(w42)}
 enum { W_N = 0, W_REF = 1, W_NEL = 2, W_FLAGS = 3, W_FAILED = 6, W_EP_LEN = 7, W_N0 = 38, W_NEXT_VID = 39, W_STAMP_CTR = 40 };
-enum { D_BASE = 1, D_EP_RETURN = 4, D_CUR_AREA = 5, D_ORIGINAL_AREA = 16, D_AREA_MIN = 17, D_AREA_CRIT = 18 };
+enum { D_BASE = 2, D_EP_RETURN = 4, D_CUR_AREA = 5, D_ORIGINAL_AREA = 16, D_AREA_MIN = 17, D_AREA_CRIT = 18 };
 __device__ __forceinline__ void stash_records(const Params &P, int4 *stash, int env, int lane) {
     if (lane < 8) stash[lane] = reinterpret_cast<const int4 *>(P.hot + env)[lane];
     else if (lane < 12) stash[lane] = reinterpret_cast<const int4 *>(P.cold + env)[lane - 8];
@@ -1394,6 +1394,178 @@ __global__ void __launch_bounds__(32, MG_MINB_DECIDE) mg_step_decide_kernel(cons
     MG_ITEM_LOOP_END
 }
 
+// One accepted element (E:319-351 / move E:520-535): element log, update_boundary (M:601-674), candidate keys of the
+// four neighbours (M:206-226) and -- for step(), REWARD = true -- area (C:943-958), robust quality (C:881-892),
+// boundary quality (M:355-452), speed penalty (E:590-607).  The boundary is staged in w.ring (updated in place together
+// with the global rows), the records in the stash.
+struct ApplyOut {
+    int nn, n_elements, next_vid0;
+    double reward, current_area;
+    bool done;
+};
+template <bool REWARD>
+__device__ __forceinline__ ApplyOut apply_element(const Params &P, Warp &w, const Stash S, int env, int n, int idx, int rule,
+                                                  bool new_vertex, P2 newp, int fan_vid) {
+    const int lane = w.lane;
+    const size_t off = (size_t)env * P.cap;
+    int n_elements = S.i(W_NEL);
+    double current_area = S.d(D_CUR_AREA);
+    P2 m[4]; int qi[4]; int ri;
+    quad_indices(rule, new_vertex, idx, n, qi, ri);
+#pragma unroll
+    for (int k = 0; k < 4; k++) m[k] = qi[k] < 0 ? newp : w.at(qi[k]);
+    // the quad's four quantised corner angles (C:752, C:888, C:946-947), one per lane
+    double corner[4];
+    {
+        double ca = 0;
+        if (lane < 4) {
+            P2 c = m[0], p1 = m[1], p2 = m[3];
+            if (lane == 1) { c = m[1]; p1 = m[2]; p2 = m[0]; }
+            if (lane == 2) { c = m[2]; p1 = m[3]; p2 = m[1]; }
+            if (lane == 3) { c = m[3]; p1 = m[0]; p2 = m[2]; }
+            ca = cw_angle(c, p1, p2);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) corner[k] = shfl_d(ca, k);
+    }
+    const int ip1 = qi[3], im1 = new_vertex ? qi[1] : (rule == -1 ? qi[0] : qi[1]);
+    double reward = 0;
+    bool done = false;
+
+    // ---- update_boundary (M:601-674) ---------------------------------------------------
+    int nb[4];          // the four neighbours whose candidate keys are re-evaluated, in order
+    int t0 = 0, t1 = 0; // surviving quad vertices (no-new-vertex case), new indices
+    const int next_vid0 = S.i(W_NEXT_VID);
+    // ---- element log, area and robust quality first: they only need the quad (old ring + new vertex), and doing
+    // them here ends the live ranges of the quad, its corner angles and the vertex ids before the boundary update
+    {
+        // quad vertex k is B[first + k] (the new vertex, id next_vid0, takes slot 0 of a new-vertex quad)
+        const int first = new_vertex ? -2 : (rule == -1 ? -1 : -2);       // offset of quad slot 0 from the reference point
+        const int my_id = __shfl_sync(FULL, fan_vid, (first + 2 + lane) & 7);
+        if (P.elem && lane < 4 && n_elements < P.elem_cap)
+            P.elem[((size_t)env * P.elem_cap + n_elements) * 4 + lane] = (new_vertex && lane == 0) ? next_vid0 : my_id;
+    }
+    n_elements++;
+    // ---- area (C:943-958), robust quality (C:881-892) -----------------------------------
+    double mesh_area = 0, e_reward = 0;
+    if (REWARD) {
+        double e0 = pdist(m[0], m[3]), e1 = pdist(m[1], m[0]), e2 = pdist(m[2], m[1]), e3 = pdist(m[3], m[2]);
+        double sn0, sn2, cs_unused;
+        sincos_quantised(P.sc_full, corner[0], false, sn0, cs_unused);
+        sincos_quantised(P.sc_full, corner[2], false, sn2, cs_unused);
+        mesh_area = 0.5 * e0 * e1 * sn0 + 0.5 * e2 * e3 * sn2;
+        current_area -= mesh_area;
+        double mn = fmin(fmin(e0, e1), fmin(e2, e3));
+        double q1 = sqrt(2.0) * mn / fmax(pdist(m[0], m[2]), pdist(m[1], m[3]));
+        double amin = fmin(fmin(corner[0], corner[1]), fmin(corner[2], corner[3]));
+        double amax = fmax(fmax(corner[0], corner[1]), fmax(corner[2], corner[3]));
+        e_reward = sqrt(q1 * (amin / amax));
+    }
+    __syncwarp();
+    if (new_vertex) {
+        // insert P at index(ref) and remove ref: the slot is replaced in place
+        if (lane == 0) {
+            w.ring[idx] = make_double2(newp.x, newp.y);
+            P.xy[off + idx] = make_double2(newp.x, newp.y);
+            P.vid[off + idx] = next_vid0;
+            P.key[off + idx] = CUDART_INF;
+            const int ins = next_vid0 - S.i(W_N0);
+            if (P.ins_xy && ins < P.ins_cap) P.ins_xy[(size_t)env * P.ins_cap + ins] = make_double2(newp.x, newp.y);
+        }
+        __syncwarp();
+        nb[0] = ip1; nb[1] = im1; nb[2] = wrapn(idx + 2, n); nb[3] = wrapn(idx - 2, n);
+    } else {
+        // remove the two middle quad vertices; compact ring + key/stamp/vid
+        const int r0 = qi[1], r1 = qi[2];
+        const int lo = r0 < r1 ? r0 : r1, hi = r0 < r1 ? r1 : r0;
+        auto newpos = [&](int j) { return j - (j > lo ? 1 : 0) - (j > hi ? 1 : 0); };
+#pragma unroll 1
+        for (int base = lo; base < n; base += 128) {
+            // every element moves left by at most 2, so a group only overwrites slots that it (or an
+            // earlier group) has already read; 4 chunks of loads are in flight per DRAM round trip
+            double2 v[4]; double k[4]; int st[4], id[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                int j = base + 32 * c + lane;
+                bool mv = j < n && j != lo && j != hi;
+                v[c] = make_double2(0, 0); k[c] = 0; st[c] = 0; id[c] = 0;
+                if (mv) { v[c] = w.ring[j]; k[c] = P.key[off + j]; st[c] = P.stamp[off + j]; id[c] = P.vid[off + j]; }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                int j = base + 32 * c + lane;
+                if (j < n && j != lo && j != hi) {
+                    int q = newpos(j);
+                    w.ring[q] = v[c]; P.xy[off + q] = v[c]; P.key[off + q] = k[c]; P.stamp[off + q] = st[c]; P.vid[off + q] = id[c];
+                }
+            }
+            __syncwarp();
+        }
+        t0 = newpos(qi[0]); t1 = newpos(qi[3]);
+        w.n = n - 2;
+        const int nn = n - 2;
+        const int id = t0 > t1 ? t0 : t1;
+        nb[0] = id; nb[1] = id - 1 < 0 ? id - 1 + nn : id - 1; nb[2] = wrapn(id + 1, nn);
+        nb[3] = wrapn(id - 2, nn);
+    }
+    const int nn = w.n;
+    // ---- candidate keys of the four neighbours (lanes 2k, 2k+1 -> angles a0, a1 of nb[k]) ----
+    double ang = 0;
+    if (lane < 8) {
+        int k = lane >> 1, v = nb[k], d = 1 + (lane & 1);
+        ang = cw_angle(w.at(v), w.at(wrapn(v + d, nn)), w.at(wrapn(v - d, nn)));
+    }
+    double nb_a0[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        nb_a0[k] = shfl_d(ang, 2 * k);
+        double a1v = shfl_d(ang, 2 * k + 1);
+        double kv = cand_key_from_angles(nb_a0[k], a1v);
+        bool later_dup = false;
+#pragma unroll
+        for (int k2 = k + 1; k2 < 4; k2++) later_dup |= nb[k2] == nb[k];
+        if (lane == k && !later_dup) {
+            P.key[off + nb[k]] = kv;
+            P.stamp[off + nb[k]] = S.i(W_STAMP_CTR) - 1 - k;
+        }
+    }
+    __syncwarp();
+    if (REWARD) {
+        // ---- boundary quality (M:410-452) ---------------------------------------------------
+        double b_reward;
+        if (new_vertex) b_reward = boundary_quality_new_vertex(w, idx, nb_a0[0], nb_a0[1]);
+        else {
+            double g0 = 0, g1 = 0;            // interior angles at the two survivors
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (nb[k] == t0) g0 = nb_a0[k];
+                if (nb[k] == t1) g1 = nb_a0[k];
+            }
+            b_reward = boundary_quality_no_new(w, t0, t1, g0, g1);
+        }
+        double quality = e_reward + 1 * (b_reward - 1);              // M:1754-1766
+        // ---- speed penalty (E:590-607) ------------------------------------------------------
+        const double a_min = S.d(D_AREA_MIN), a_crit = S.d(D_AREA_CRIT);
+        double min_area = a_min * a_min, crit = a_crit * a_crit, pen;
+        if (min_area <= mesh_area && mesh_area < crit) pen = (mesh_area - crit) / (crit - min_area);
+        else if (mesh_area < min_area) pen = -1;
+        else pen = 0;
+        reward += quality + pen;
+    }
+    if (nn <= 5) {                                       // E:345-351
+        reward += 10; done = true;
+        if (nn == 4) {
+            if (P.elem && lane < 4 && n_elements < P.elem_cap)
+                P.elem[((size_t)env * P.elem_cap + n_elements) * 4 + lane] = P.vid[off + lane];
+            n_elements++;
+        }
+    }
+    ApplyOut R;
+    R.nn = nn; R.n_elements = n_elements; R.next_vid0 = next_vid0; R.reward = reward; R.current_area = current_area; R.done = done;
+    return R;
+}
+
 // ---- kernel 3: update (fused mode: decide + update) ---------------------------------------------
 #ifndef MG_MINB_UPDATE
 #define MG_MINB_UPDATE 20
@@ -1466,155 +1638,10 @@ __global__ void __launch_bounds__(32, MG_MINB_UPDATE) mg_step_update_kernel(cons
                 continue;
             }
         }
-        int n_elements = S.i(W_NEL);
-        double current_area = S.d(D_CUR_AREA);
-        const P2 newp = mk(W.newx, W.newy);
-        P2 m[4]; int qi[4]; int ri;
-        quad_indices(rule, new_vertex, idx, n, qi, ri);
-#pragma unroll
-        for (int k = 0; k < 4; k++) m[k] = qi[k] < 0 ? newp : w.at(qi[k]);
-        // the quad's four quantised corner angles (C:752, C:888, C:946-947), one per lane
-        double corner[4];
-        {
-            double ca = 0;
-            if (lane < 4) {
-                P2 c = m[0], p1 = m[1], p2 = m[3];
-                if (lane == 1) { c = m[1]; p1 = m[2]; p2 = m[0]; }
-                if (lane == 2) { c = m[2]; p1 = m[3]; p2 = m[1]; }
-                if (lane == 3) { c = m[3]; p1 = m[0]; p2 = m[2]; }
-                ca = cw_angle(c, p1, p2);
-            }
-#pragma unroll
-            for (int k = 0; k < 4; k++) corner[k] = shfl_d(ca, k);
-        }
-        const int ip1 = qi[3], im1 = new_vertex ? qi[1] : (rule == -1 ? qi[0] : qi[1]);
-        double reward = 0;
-        bool done = false;
-
-        // ---- update_boundary (M:601-674) ---------------------------------------------------
-        int nb[4];          // the four neighbours whose candidate keys are re-evaluated, in order
-        int t0 = 0, t1 = 0; // surviving quad vertices (no-new-vertex case), new indices
-        const int next_vid0 = S.i(W_NEXT_VID);
-        // ---- element log, area and robust quality first: they only need the quad (old ring + new vertex), and doing
-        // them here ends the live ranges of the quad, its corner angles and the vertex ids before the boundary update
-        {
-            // quad vertex k is B[first + k] (the new vertex, id next_vid0, takes slot 0 of a new-vertex quad)
-            const int first = new_vertex ? -2 : (rule == -1 ? -1 : -2);       // offset of quad slot 0 from the reference point
-            const int my_id = __shfl_sync(FULL, fan_vid, (first + 2 + lane) & 7);
-            if (P.elem && lane < 4 && n_elements < P.elem_cap)
-                P.elem[((size_t)env * P.elem_cap + n_elements) * 4 + lane] = (new_vertex && lane == 0) ? next_vid0 : my_id;
-        }
-        n_elements++;
-        // ---- area (C:943-958), robust quality (C:881-892) -----------------------------------
-        double e0 = pdist(m[0], m[3]), e1 = pdist(m[1], m[0]), e2 = pdist(m[2], m[1]), e3 = pdist(m[3], m[2]);
-        double sn0, sn2, cs_unused;
-        sincos_quantised(P.sc_full, corner[0], false, sn0, cs_unused);
-        sincos_quantised(P.sc_full, corner[2], false, sn2, cs_unused);
-        double mesh_area = 0.5 * e0 * e1 * sn0 + 0.5 * e2 * e3 * sn2;
-        current_area -= mesh_area;
-        double mn = fmin(fmin(e0, e1), fmin(e2, e3));
-        double q1 = sqrt(2.0) * mn / fmax(pdist(m[0], m[2]), pdist(m[1], m[3]));
-        double amin = fmin(fmin(corner[0], corner[1]), fmin(corner[2], corner[3]));
-        double amax = fmax(fmax(corner[0], corner[1]), fmax(corner[2], corner[3]));
-        double e_reward = sqrt(q1 * (amin / amax));
-        __syncwarp();
-        if (new_vertex) {
-            // insert P at index(ref) and remove ref: the slot is replaced in place
-            if (lane == 0) {
-                w.ring[idx] = make_double2(newp.x, newp.y);
-                P.xy[off + idx] = make_double2(newp.x, newp.y);
-                P.vid[off + idx] = next_vid0;
-                P.key[off + idx] = CUDART_INF;
-                const int ins = next_vid0 - S.i(W_N0);
-                if (P.ins_xy && ins < P.ins_cap) P.ins_xy[(size_t)env * P.ins_cap + ins] = make_double2(newp.x, newp.y);
-            }
-            __syncwarp();
-            nb[0] = ip1; nb[1] = im1; nb[2] = wrapn(idx + 2, n); nb[3] = wrapn(idx - 2, n);
-        } else {
-            // remove the two middle quad vertices; compact ring + key/stamp/vid
-            const int r0 = qi[1], r1 = qi[2];
-            const int lo = r0 < r1 ? r0 : r1, hi = r0 < r1 ? r1 : r0;
-            auto newpos = [&](int j) { return j - (j > lo ? 1 : 0) - (j > hi ? 1 : 0); };
-#pragma unroll 1
-            for (int base = lo; base < n; base += 128) {
-                // every element moves left by at most 2, so a group only overwrites slots that it (or an
-                // earlier group) has already read; 4 chunks of loads are in flight per DRAM round trip
-                double2 v[4]; double k[4]; int st[4], id[4];
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    int j = base + 32 * c + lane;
-                    bool mv = j < n && j != lo && j != hi;
-                    v[c] = make_double2(0, 0); k[c] = 0; st[c] = 0; id[c] = 0;
-                    if (mv) { v[c] = w.ring[j]; k[c] = P.key[off + j]; st[c] = P.stamp[off + j]; id[c] = P.vid[off + j]; }
-                }
-                __syncwarp();
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    int j = base + 32 * c + lane;
-                    if (j < n && j != lo && j != hi) {
-                        int q = newpos(j);
-                        w.ring[q] = v[c]; P.xy[off + q] = v[c]; P.key[off + q] = k[c]; P.stamp[off + q] = st[c]; P.vid[off + q] = id[c];
-                    }
-                }
-                __syncwarp();
-            }
-            t0 = newpos(qi[0]); t1 = newpos(qi[3]);
-            w.n = n - 2;
-            const int nn = n - 2;
-            const int id = t0 > t1 ? t0 : t1;
-            nb[0] = id; nb[1] = id - 1 < 0 ? id - 1 + nn : id - 1; nb[2] = wrapn(id + 1, nn);
-            nb[3] = wrapn(id - 2, nn);
-        }
-        const int nn = w.n;
-        // ---- candidate keys of the four neighbours (lanes 2k, 2k+1 -> angles a0, a1 of nb[k]) ----
-        double ang = 0;
-        if (lane < 8) {
-            int k = lane >> 1, v = nb[k], d = 1 + (lane & 1);
-            ang = cw_angle(w.at(v), w.at(wrapn(v + d, nn)), w.at(wrapn(v - d, nn)));
-        }
-        double nb_a0[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            nb_a0[k] = shfl_d(ang, 2 * k);
-            double a1v = shfl_d(ang, 2 * k + 1);
-            double kv = cand_key_from_angles(nb_a0[k], a1v);
-            bool later_dup = false;
-#pragma unroll
-            for (int k2 = k + 1; k2 < 4; k2++) later_dup |= nb[k2] == nb[k];
-            if (lane == k && !later_dup) {
-                P.key[off + nb[k]] = kv;
-                P.stamp[off + nb[k]] = S.i(W_STAMP_CTR) - 1 - k;
-            }
-        }
-        // ---- boundary quality (M:410-452) ---------------------------------------------------
-        double b_reward;
-        __syncwarp();
-        if (new_vertex) b_reward = boundary_quality_new_vertex(w, idx, nb_a0[0], nb_a0[1]);
-        else {
-            double g0 = 0, g1 = 0;            // interior angles at the two survivors
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (nb[k] == t0) g0 = nb_a0[k];
-                if (nb[k] == t1) g1 = nb_a0[k];
-            }
-            b_reward = boundary_quality_no_new(w, t0, t1, g0, g1);
-        }
-        double quality = e_reward + 1 * (b_reward - 1);              // M:1754-1766
-        // ---- speed penalty (E:590-607) ------------------------------------------------------
-        const double a_min = S.d(D_AREA_MIN), a_crit = S.d(D_AREA_CRIT);
-        double min_area = a_min * a_min, crit = a_crit * a_crit, pen;
-        if (min_area <= mesh_area && mesh_area < crit) pen = (mesh_area - crit) / (crit - min_area);
-        else if (mesh_area < min_area) pen = -1;
-        else pen = 0;
-        reward += quality + pen;
-        if (nn <= 5) {                                       // E:345-351
-            reward += 10; done = true;
-            if (nn == 4) {
-                if (P.elem && lane < 4 && n_elements < P.elem_cap)
-                    P.elem[((size_t)env * P.elem_cap + n_elements) * 4 + lane] = P.vid[off + lane];
-                n_elements++;
-            }
-        }
+        const ApplyOut A = apply_element<true>(P, w, S, env, n, idx, rule, new_vertex, mk(W.newx, W.newy), fan_vid);
+        const int nn = A.nn, n_elements = A.n_elements, next_vid0 = A.next_vid0;
+        const double reward = A.reward, current_area = A.current_area;
+        const bool done = A.done;
         // ---- results of the step; the next observation follows in the observe kernel -----------------------
         const double ep_return = S.d(D_EP_RETURN) + reward;
         const int ep_len = S.i(W_EP_LEN) + 1;
@@ -1730,6 +1757,166 @@ __global__ void __launch_bounds__(32, MG_MINB_OBSERVE) mg_step_observe_kernel(co
             }
         }
     MG_ITEM_LOOP_END
+}
+
+// ---------------------------------------------------------------------------------------------
+// BoudaryEnv.move() (E:459-594; legacy rl/boundary_env.py:265-432): the deterministic "apply this geometric move"
+// entry point of the data-generation utilities (general/EBRD.py, FNN_evaluation.py).  Differences from step():
+// polar action (r, phi) in units of radius * base_length rounded to 6 decimals by CPython's round, rule selection by
+// TYPE_THRESHOLD = 0.3, no find_same_point fallback, reward 0, no failed-step counter; a failed move puts the
+// reference point on the not-valid list and the next reference point is the first candidate that is not within 0.001
+// of a listed point (M:310-314, M:428-433); point environments are static (area-ratio slot of the observation = 0,
+// C:1209-1214).  One warp per env, one launch: this is not a throughput path.
+// When every candidate is excluded the reference smooths the whole mesh (smooth_pave, general/mesh.py:790-1067) and
+// goes on; that is not built: the env reports done with `exhausted` set.
+// ---------------------------------------------------------------------------------------------
+// rint(x * 1e6) / 1e6 as CPython's round(x, 6) picks it (see py_rint4)
+__device__ __forceinline__ double py_round6(double x) {
+    double p = x * 1e6;
+    double r = rint(p);
+    if (fabs(p - r) == 0.5) {
+        double e = __fma_rn(x, 1e6, -p);
+        if (e > 0) r = floor(p) + 1.0;
+        else if (e < 0) r = floor(p);
+    }
+    return r / 1e6;
+}
+
+// arg-min of (key, stamp) over the candidates that are not within 0.001 of a not-valid point; -1 when none is left
+__device__ __noinline__ int find_reference_index_excl(const Warp w, const double *key, const int32_t *stamp, const double2 *excl, int nexcl) {
+    double bk = CUDART_INF;
+    int bs = 0x7fffffff, bj = -1;
+#pragma unroll 1
+    for (int j = w.lane; j < w.n; j += 32) {
+        const double k = key[j];
+        if (k == CUDART_INF) continue;
+        const P2 v = w.at(j);
+        bool hit = false;
+#pragma unroll 1
+        for (int q = 0; q < nexcl && !hit; q++) {
+            const double2 e = excl[q];
+            hit = pdist(mk(e.x, e.y), v) < 0.001;
+        }
+        if (hit) continue;
+        const int s = stamp[j];
+        if (k < bk || (k == bk && s < bs)) { bk = k; bs = s; bj = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double ok = __shfl_xor_sync(FULL, bk, o);
+        int os = __shfl_xor_sync(FULL, bs, o);
+        int oj = __shfl_xor_sync(FULL, bj, o);
+        if (ok < bk || (ok == bk && ok != CUDART_INF && os < bs)) { bk = ok; bs = os; bj = oj; }
+    }
+    return bk == CUDART_INF ? -1 : bj;
+}
+
+struct MoveIO {
+    const double *polar;     // [N][2] (r, phi)
+    const double *type;      // [N]
+    float *obs_out;          // [N][18]
+    uint8_t *done_out, *complete_out, *exhausted_out;
+    int32_t *n_elem_out;
+};
+
+__global__ void __launch_bounds__(32) mg_move_kernel(const __grid_constant__ Params P, const __grid_constant__ MoveIO io, double2 *excl_all) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    const int env = blockIdx.x;
+    if (env >= P.num_envs) return;
+    const SmemLayout L = carve(smem_raw, P.cap, true);
+    const Stash S{L.stash};
+    const size_t off = (size_t)env * P.cap;
+    double2 *excl = excl_all + off;
+    stash_records(P, L.stash, env, lane);
+    __syncwarp();
+    Warp w;
+    w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = S.i(W_N);
+    const int n = w.n, idx = S.i(W_REF);
+    int nexcl = reinterpret_cast<const int32_t *>(L.stash)[43];          // EnvCold::pad[0]
+    int n_elements = S.i(W_NEL);
+    auto finish = [&](float obs, bool done, bool complete, bool exhausted) {
+        if (lane < MG_OBS_DIM) io.obs_out[(size_t)env * MG_OBS_DIM + lane] = obs;
+        if (lane == 0) {
+            io.done_out[env] = done; io.complete_out[env] = complete; io.exhausted_out[env] = exhausted;
+            if (io.n_elem_out) io.n_elem_out[env] = n_elements;
+        }
+    };
+    if (idx < 0 || n < 3) {                 // no reference point: the reference would have raised before this call
+        finish(0.0f, true, false, true);
+        return;
+    }
+    if (n <= 5) {                           // E:484-486 (the reference leaves is_complete unbound here and raises)
+        float o = lane < MG_OBS_DIM ? P.obs_cache[(size_t)env * MG_OBS_DIM + lane] : 0.0f;
+        if (lane == 1) o = 0.0f;
+        finish(o, true, n <= 4, false);
+        return;
+    }
+    for (int j = lane; j < n; j += 32) w.ring[j] = P.xy[off + j];
+    __syncwarp();
+    const P2 ref = w.at(idx), right_p = w.at(idx - 1);
+    // ---- polar action -> candidate vertex (E:467-478, E:202-210 with dist = 1, D:112-137) -------------------------
+    const double base_length = S.d(D_BASE);
+    const double pr = io.polar[2 * (size_t)env], phi = io.polar[2 * (size_t)env + 1], type = io.type[env];
+    P2 newp;
+    {
+        const double2 sc = mg_sincos(phi);
+        const double px = py_round6(base_length * 4 * pr * sc.y), py = py_round6(base_length * 4 * pr * sc.x);
+        const double2 o = action_frame_exact(px, py, right_p.x - ref.x, right_p.y - ref.y, 1.0, ref);
+        newp = mk(np_round4(o.x), np_round4(o.y));
+    }
+    // ---- the element (E:490-520) --------------------------------------------------------------------------------
+    int rule = 0;
+    bool new_vertex = false, have_mesh = true;
+    if (type <= 0.3) rule = -1;
+    else if (type >= 1 - 0.3) rule = 1;
+    else if (point_inside(w, newp, P.vid + off, S.i(W_N0))) new_vertex = true;
+    else have_mesh = false;
+    bool accepted = false;
+    if (have_mesh) {
+        int qi[4], ri;
+        quad_indices(rule, new_vertex, idx, n, qi, ri);
+        Quad Q;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const P2 p = qi[k] < 0 ? newp : w.at(qi[k]); Q.x[k] = p.x; Q.y[k] = p.y; }
+        accepted = mesh_is_valid(w, Q) && !intersects_boundary(w, Q, make_int4(qi[0], qi[1], qi[2], qi[3]), ri, ref);
+    }
+    bool done = false;
+    int next_vid = S.i(W_NEXT_VID), stamp_ctr = S.i(W_STAMP_CTR);
+    if (accepted) {
+        const int fan_vid = lane < 5 ? P.vid[off + wrapn(idx - 2 + lane, n)] : 0;
+        const ApplyOut A = apply_element<false>(P, w, S, env, n, idx, rule, new_vertex, newp, fan_vid);
+        n_elements = A.n_elements;
+        done = A.done;
+        next_vid += new_vertex ? 1 : 0;
+        stamp_ctr -= 4;
+    } else {
+        if (lane == 0 && nexcl < P.cap) excl[nexcl] = make_double2(ref.x, ref.y);       // E:538-540
+        nexcl++;
+    }
+    __syncwarp();
+    __threadfence_block();
+    // ---- next state with the not-valid points collected so far (E:527 / E:541), static point environment --------
+    const int ref_index = find_reference_index_excl(w, P.key + off, P.stamp + off, excl, nexcl < P.cap ? nexcl : P.cap);
+    if (accepted) nexcl = 0;                                                             // E:542-543
+    float obs = 0.0f, obs_cache = 0.0f;
+    double base = base_length;
+    if (ref_index >= 0) {
+        const ObsOut R = compute_obs(w, P.sc_full, ref_index, S.d(D_CUR_AREA) / S.d(D_ORIGINAL_AREA));
+        obs_cache = R.obs; base = R.base;
+        obs = lane == 1 ? 0.0f : R.obs;                                                  // static: area-ratio slot = 0
+    }
+    const bool exhausted = ref_index < 0 && w.n > 4;          // the reference would call smooth_pave here (E:548-575)
+    done = done || exhausted;
+    if (lane < MG_OBS_DIM) P.obs_cache[(size_t)env * MG_OBS_DIM + lane] = obs_cache;    // step() afterwards: non-static
+    const int flags = done ? 0 : memo_flags(w, ref_index);
+    store_hot(P.hot + env, w, ref_index, n_elements, flags, base, S.i(W_FAILED), S.i(W_EP_LEN), S.d(D_EP_RETURN), S.d(D_CUR_AREA));
+    if (lane == 0) {
+        P.cold[env].next_vid = next_vid;
+        P.cold[env].stamp_ctr = stamp_ctr;
+        P.cold[env].pad[0] = nexcl;
+    }
+    finish(obs, done, w.n <= 4, exhausted);
 }
 
 // Uniform actions in Box([-1,-1.5,0],[1,1.5,1.5]) -- the synthetic policy of the benchmarks.

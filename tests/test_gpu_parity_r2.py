@@ -383,3 +383,74 @@ def test_graph_captured_policy_and_env_rollout_equals_eager():
         assert torch.equal(r.obs, obs), f"graph replay differs from the eager env at step {t}"
         assert torch.equal(r.reward, rew) and torch.equal((r.terminated | r.truncated), done)
         prev = r.obs.clone()
+
+
+@pytest.mark.parametrize("name", ["boundary0", "dolphine3", "easy1_1"])
+def test_move_against_golden_trace_and_oracle(name):
+    """BoudaryEnv.move() (E:459-594) on the CUDA env -- env 0 replays the golden trace recorded from the live
+    reference, the other envs fresh action streams checked against the C oracle: observation (static point environment)
+    bit-exact, done / is_complete / element count / boundary ids and coordinates / reference index exact, up to the step
+    where the reference would call smooth_pave (reported as `exhausted`; not built), after which the env is reset."""
+    import os
+    import torch
+    from helpers import GOLDEN
+    from oracle.c_oracle import OracleEnv
+    z = np.load(os.path.join(GOLDEN, f"move_{name}.npz"))
+    tr = {k: z[k] for k in z.files}
+    T = min(len(tr["type"]), 600)
+    N = 4
+    env = _mk([tr["xy0"]], N, auto_reset=False)
+    env.reset()
+    rng = np.random.default_rng(17)
+    pol = np.stack([np.stack([rng.uniform(0.05, 0.5, T), rng.uniform(0.2, 2.9, T)], axis=1) for _ in range(N)], axis=1)   # [T, N, 2]
+    typ = np.stack([rng.choice([0.1, 0.5, 0.9], size=T, p=[0.15, 0.7, 0.15]) for _ in range(N)], axis=1)
+    pol[:, 0], typ[:, 0] = tr["polar"][:T], tr["type"][:T]
+    oracles = [OracleEnv(tr["xy0"], original_area=float(tr["original_area"])) for _ in range(N)]
+    n_acc = 0
+    for t in range(T):
+        r = env.move(pol[t], typ[t])
+        obs, done, comp, exh, nel = (r[k].cpu().numpy() for k in ("obs", "done", "is_complete", "exhausted", "n_elements"))
+        reset_mask = np.zeros(N, np.uint8)
+        for e in range(N):
+            oo, _, od, oinfo, osm = oracles[e].move(pol[t, e], typ[t, e])
+            assert bool(exh[e]) == osm and bool(done[e]) == od and bool(comp[e]) == oinfo["is_complete"], f"{name}: flags differ t={t} env={e}"
+            assert np.array_equal(obs[e], np.zeros(18, np.float32) if oo is None else oo), f"{name}: obs differs t={t} env={e}"
+            assert int(nel[e]) == oracles[e].n_elements
+            if e == 0:
+                assert bool(tr["smooth"][t]) == osm and bool(tr["done"][t]) == od and int(tr["n_elements"][t]) == int(nel[0])
+                assert np.array_equal(obs[0], tr["obs"][t])
+            if t % 7 == 0 or od:
+                s = env.get_state(e)
+                ids, xy = oracles[e].boundary()
+                assert s["n"] == oracles[e].n and np.array_equal(s["ids"], ids) and np.array_equal(s["xy"], xy), f"{name}: boundary differs t={t} env={e}"
+                if oo is not None:
+                    assert s["ref_index"] == oracles[e].ref_index
+            if od:
+                reset_mask[e] = 1
+                oracles[e].reset()
+        n_acc = max(n_acc, int(nel.max()))
+        if reset_mask.any():
+            env.reset(torch.from_numpy(reset_mask))
+    assert n_acc > 20
+
+
+def test_move_facade_like_the_data_generation_scripts():
+    """general/EBRD.py:544: ``state, reward, done, info = env.move(action, round(type_values, 2))`` on the single-env facade."""
+    from reinforcementlearning4meshgeneration_b200.boundary_env import BoudaryEnv
+    from oracle.c_oracle import OracleEnv
+    tr = load_trace("boundary0")
+    env = BoudaryEnv(tr["xy0"])
+    env.reset()
+    o = OracleEnv(tr["xy0"], original_area=float(tr["original_area"]))
+    rng = np.random.default_rng(4)
+    for t in range(200):
+        p, ty = [float(rng.uniform(0.05, 0.5)), float(rng.uniform(0.2, 2.9))], float(rng.choice([0.1, 0.5, 0.9], p=[0.15, 0.7, 0.15]))
+        state, reward, done, info = env.move(p, round(ty, 2))
+        oo, _, od, oinfo, osm = o.move(p, round(ty, 2))
+        assert reward == 0 and done == od and info["is_complete"] == oinfo["is_complete"] and info.get("needs_smoothing", False) == osm
+        assert (state is None) == (oo is None) and (state is None or np.array_equal(state, oo))
+        assert len(env.generated_meshes) == o.n_elements
+        if done:
+            env.reset()
+            o.reset()
+    env.close()
