@@ -158,9 +158,11 @@ int mg_move(mg_handle h, const double *polar_dev, const double *type_dev, float 
             uint8_t *exhausted_dev, int32_t *n_elem_dev, void *stream);
 
 /* Same transition through HOST buffers (what a numpy-facing caller such as SB3's VecEnv pays):
- * H2D of the actions, the step, D2H of all outputs, one stream synchronise.  Output buffers that are pinned
- * (cudaHostAlloc / cudaHostRegister / torch .pin_memory()) are written by the step kernels directly; pageable ones
- * are copied from staging buffers after the step.  term_obs_host rows are defined only where the episode ended.
+ * H2D of the actions, the step, D2H of all outputs, one stream synchronise.  Buffers that are pinned
+ * (cudaHostAlloc / cudaHostRegister / torch .pin_memory()) are used by the step kernels directly -- the actions are
+ * read over PCIe by the first kernel while it loads the env records, the outputs are written by the kernels that
+ * produce them; pageable ones go through staging buffers and one copy each.  term_obs_host rows are defined only
+ * where the episode ended.
  * Runs on a private stream after everything the caller enqueued through mg_reset / mg_step / mg_snapshot_* has
  * finished, and returns after its own work has finished. */
 int mg_step_host(mg_handle h, const float *act_host, float *obs_host, double *rew_host,
@@ -174,7 +176,8 @@ int mg_step_host(mg_handle h, const float *act_host, float *obs_host, double *re
 int mg_set_obs_delta(mg_handle h, int enabled);
 int mg_set_host_delta(mg_handle h, int enabled);
 
-/* Bytes moved host->device and device->host by the last mg_step_host call. */
+/* Bytes moved host->device and device->host by the last mg_step_host call (evaluated here, from the step counters of
+ * that call: synchronises). */
 int mg_last_host_bytes(mg_handle h, int64_t *h2d, int64_t *d2h);
 
 /* Uniform actions in the action box (E:78-80) from the handle's Philox stream -- the synthetic
@@ -246,7 +249,10 @@ int mg_snapshot_load(mg_handle h, const void *blob_dev, int64_t blob_bytes, void
 
 /* Tuning switches (results never depend on them).  "fuse_decide" (default 1): the decide and update work of a step
  * share one launch -- a warp that accepts an element applies it with the boundary it has already staged; 0 = two
- * launches with smaller code images. */
+ * launches with smaller code images.  "reset_side" (default 1): the in-place resets of the envs a step truncated run
+ * in their own kernel on a side stream next to the update kernel (0: in the caller's stream, before the observe
+ * kernel).  "update_blocks" / "observe_blocks" / "reset_blocks": resident one-warp blocks per SM of those kernels
+ * (default: what fits). */
 int mg_set_option(mg_handle h, const char *name, int value);
 
 /* Profiling aid (bench.py roofline.per_kernel): with enabled != 0 every mg_step / mg_step_host records CUDA events

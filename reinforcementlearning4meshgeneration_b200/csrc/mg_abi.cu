@@ -32,12 +32,16 @@ struct mg_env_s {
     uint8_t *d_term = nullptr, *d_trunc = nullptr;
     int32_t *d_nel = nullptr;
     cudaStream_t host_stream = nullptr;
+    cudaStream_t side_stream = nullptr;           // mg_step_reset_kernel runs here, next to the update kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int32_t *h_cnt = nullptr;       // pinned copy of the step counters (byte accounting of mg_step_host)
     // observation delta (mg_set_obs_delta / mg_set_host_delta): the buffer that is known to hold every env's current
     // observation (written in full by mg_reset or by the previous mg_step with the same pointer)
     bool obs_delta = false;
     const float *obs_bound = nullptr;
     int64_t last_h2d = 0, last_d2h = 0;
+    bool acct_valid = false, acct_obs_rows_delta = false, acct_n_elem = false;
+    int acct_term_obs = 0;             // 0 none, 1 pinned (finished rows only), 2 staged (all rows)
     // ordering between the caller's stream (mg_reset / mg_step / mg_snapshot_*) and the private stream of mg_step_host
     cudaStream_t last_user_stream = nullptr;
     bool user_work_pending = false;
@@ -51,8 +55,9 @@ struct mg_env_s {
     int64_t timing_steps = 0;
     int sm_count = 148;
     size_t smem = 0, smem_nq = 0;      // one-warp block with / without the integer scratch queue
-    int blocks_decide = 16, blocks_update = 16, blocks_observe = 16;
+    int blocks_decide = 16, blocks_update = 16, blocks_observe = 16, blocks_reset = 16;
     bool fuse_decide = true;           // one launch for the decide and update work (mg_set_option "fuse_decide")
+    bool reset_side = true;            // resets on the side stream, next to the update kernel (mg_set_option "reset_side")
     std::string err;
 };
 
@@ -105,6 +110,7 @@ int configure_kernels(mg_handle h) {
     h->smem_nq = smem_bytes(h->P.cap, false);
     if (h->smem > 48 * 1024) {
         MG_CUDA(h, cudaFuncSetAttribute(mg_step_observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        MG_CUDA(h, cudaFuncSetAttribute(mg_step_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         MG_CUDA(h, cudaFuncSetAttribute(mg_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         MG_CUDA(h, cudaFuncSetAttribute(mg_template_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         MG_CUDA(h, cudaFuncSetAttribute(mg_regen_polygon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
@@ -118,8 +124,9 @@ int configure_kernels(mg_handle h) {
     MG_CUDA(h, cudaFuncSetAttribute(mg_step_decide_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     MG_CUDA(h, cudaFuncSetAttribute(mg_step_update_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     MG_CUDA(h, cudaFuncSetAttribute(mg_step_observe_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    // the screen kernel has 128 bytes of shared memory and reads one 128-byte record per thread: all L1
-    MG_CUDA(h, cudaFuncSetAttribute(mg_step_screen_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
+    MG_CUDA(h, cudaFuncSetAttribute(mg_step_reset_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    // the screen kernel stages its block's records in 16.5 KB of shared memory, four blocks per SM (registers)
+    MG_CUDA(h, cudaFuncSetAttribute(mg_step_screen_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 40));
     // resident one-warp blocks per SM of each item kernel (grid = that many blocks: items beyond the first wave are
     // handed out by ticket)
     int nb = 0;
@@ -129,6 +136,7 @@ int configure_kernels(mg_handle h) {
     h->blocks_update = nb > 0 ? nb : 16;
     MG_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mg_step_observe_kernel, 32, h->smem));
     h->blocks_observe = nb > 0 ? nb : 16;
+    h->blocks_reset = 4;               // ~0.3 % of the envs are reset per step: a few one-warp blocks per SM, tickets beyond
     return MG_OK;
 }
 
@@ -175,21 +183,34 @@ void note_user_stream(mg_handle h, cudaStream_t s) {
     h->user_work_pending = true;
 }
 
-// The four launches of one step on stream s.
+// The launches of one step on stream s: screen, [decide,] update, observe -- and, with auto-reset, the reset kernel on
+// the side stream between the screen kernel and the end of the step (event fork / join: capturable in a CUDA graph).
+// The side stream has the default priority on purpose: with a higher one the resets take the first slots that free up
+// (the failed decisions, ~7 us into the update kernel) and slow the update kernel's busy phase down by 7 us; as it is
+// they start in its tail (profiles/README.md, round 2).
 int launch_step(mg_handle h, const StepIO &io, cudaStream_t s) {
     const int N = h->num_envs;
     auto grid = [&](int per_sm) { const int r = h->sm_count * per_sm; return N < r ? N : r; };
     cudaEvent_t *ev = h->timing ? h->ev[h->timing_steps % mg_env_s::TIMING_SLOTS] : nullptr;
+    const bool side = h->P.auto_reset != 0 && h->reset_side;
     if (ev) cudaEventRecord(ev[0], s);
     mg_step_screen_kernel<<<(N + SCREEN_THREADS - 1) / SCREEN_THREADS, SCREEN_THREADS, 0, s>>>(h->P, io);
     if (ev) cudaEventRecord(ev[1], s);
+    if (side) {
+        MG_CUDA(h, cudaEventRecord(h->ev_fork, s));
+        MG_CUDA(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+        mg_step_reset_kernel<<<grid(h->blocks_reset), 32, h->smem, h->side_stream>>>(h->P, io);
+        MG_CUDA(h, cudaEventRecord(h->ev_join, h->side_stream));
+    }
     if (!h->fuse_decide) mg_step_decide_kernel<<<grid(h->blocks_decide), 32, h->smem_nq, s>>>(h->P, io);
     if (ev) cudaEventRecord(ev[2], s);
     mg_step_update_kernel<<<grid(h->blocks_update), 32, h->smem_nq, s>>>(h->P, io, h->fuse_decide ? 1 : 0);
     if (ev) cudaEventRecord(ev[3], s);
+    if (h->P.auto_reset != 0 && !side) mg_step_reset_kernel<<<grid(h->blocks_reset), 32, h->smem, s>>>(h->P, io);
     mg_step_observe_kernel<<<grid(h->blocks_observe), 32, h->smem, s>>>(h->P, io);
+    if (side) MG_CUDA(h, cudaStreamWaitEvent(s, h->ev_join, 0));
     if (ev) { cudaEventRecord(ev[4], s); h->timing_steps++; }
-    h->launches += h->fuse_decide ? 3 : 4;
+    h->launches += (h->fuse_decide ? 3 : 4) + (h->P.auto_reset != 0 ? 1 : 0);
     MG_CUDA(h, cudaGetLastError());
     return MG_OK;
 }
@@ -272,6 +293,7 @@ int mg_create(mg_handle *out, int device, int num_envs, int max_verts) {
     A(dalloc(&P.obs_cache, (size_t)num_envs * MG_OBS_DIM), "obs");
     A(dalloc(&P.decide_list, (size_t)NBINS * num_envs), "decide_list"); A(dalloc(&P.accept_list, (size_t)NBINS * num_envs), "accept_list");
     A(dalloc(&P.observe_list, (size_t)NBINS * num_envs), "observe_list"); A(dalloc(&P.counters, (size_t)CNT_N), "counters");
+    A(dalloc(&P.reset_list, (size_t)num_envs), "reset_list");
     A(dalloc(&P.elem, (size_t)num_envs * P.elem_cap * 4), "elem"); A(dalloc(&P.ins_xy, (size_t)num_envs * P.ins_cap), "ins_xy");
     A(dalloc(&h->d_stats_out, 1), "stats_out");
     A(dalloc(&h->sc_tab, (size_t)2 * ANGLE_TAB_N), "angle table");
@@ -280,8 +302,11 @@ int mg_create(mg_handle *out, int device, int num_envs, int max_verts) {
     A(dalloc(&h->d_term, (size_t)num_envs), "term"); A(dalloc(&h->d_trunc, (size_t)num_envs), "trunc");
     A(dalloc(&h->d_nel, (size_t)num_envs), "nel");
     A(cudaMallocHost((void **)&h->h_cnt, CNT_N * sizeof(int32_t)), "h_cnt");
-    if (rc == MG_OK && cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking) != cudaSuccess)
-        rc = fail(h, MG_ERR_CUDA, "cudaStreamCreate");
+    if (rc == MG_OK && (cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking) != cudaSuccess ||
+                        cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+                        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess))
+        rc = fail(h, MG_ERR_CUDA, "cudaStreamCreate / cudaEventCreate");
     if (rc == MG_OK) rc = configure_kernels(h);
     if (rc == MG_OK) rc = upload_angle_table(h);
     if (rc != MG_OK) { g_err = h->err; mg_destroy(h); return rc; }
@@ -295,7 +320,7 @@ int mg_destroy(mg_handle h) {
     Params &P = h->P;
     cudaFree(P.xy); cudaFree(P.key); cudaFree(P.stamp); cudaFree(P.vid); cudaFree(P.hot); cudaFree(P.cold); cudaFree(P.stats);
     cudaFree(P.obs_cache); cudaFree(P.elem); cudaFree(P.ins_xy);
-    cudaFree(P.decide_list); cudaFree(P.accept_list); cudaFree(P.observe_list); cudaFree(P.counters);
+    cudaFree(P.decide_list); cudaFree(P.accept_list); cudaFree(P.observe_list); cudaFree(P.counters); cudaFree(P.reset_list);
     free_templates(h);
     cudaFree(h->sc_tab); cudaFree(h->excl);
     cudaFree(h->d_stats_out); cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_term_obs); cudaFree(h->d_rew);
@@ -305,6 +330,9 @@ int mg_destroy(mg_handle h) {
         for (cudaEvent_t e : tr)
             if (e) cudaEventDestroy(e);
     if (h->host_stream) cudaStreamDestroy(h->host_stream);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     delete h;
     return MG_OK;
 }
@@ -358,7 +386,7 @@ struct SnapHeader {
     int64_t env_id_offset;
 };
 static_assert(sizeof(SnapHeader) <= SNAP_ALIGN, "snapshot header");
-constexpr int64_t SNAP_MAGIC = 0x4d4753324e415053ll, SNAP_VERSION = 2;
+constexpr int64_t SNAP_MAGIC = 0x4d4753324e415053ll, SNAP_VERSION = 3;
 SnapHeader snap_header(mg_handle h, int64_t total) {
     SnapHeader H{};
     H.magic = SNAP_MAGIC; H.version = SNAP_VERSION; H.total_bytes = total;
@@ -547,16 +575,18 @@ int mg_step_host(mg_handle h, const float *act_host, float *obs_host, double *re
         MG_CUDA(h, cudaStreamSynchronize(h->last_user_stream));
         h->user_work_pending = false;
     }
-    MG_CUDA(h, cudaMemcpyAsync(h->d_act, act_host, N * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
-    // Pinned caller buffers are written by the step kernels themselves through their device aliases (posted PCIe
-    // writes that overlap the later kernels: no staging copy, no copy-engine round after the step); pageable ones go
-    // through the handle's staging buffers and one cudaMemcpyAsync each.
+    // Pinned caller buffers are used by the step kernels themselves through their device aliases: the screen kernel
+    // reads the actions over PCIe while it loads the env records (no copy in front of the step), results are posted
+    // PCIe writes that overlap the later kernels (no staging copy, no copy-engine round after the step).  Pageable
+    // buffers go through the handle's staging buffers and one cudaMemcpyAsync each.
+    const float *act_a = pinned_alias(act_host);
+    if (!act_a) MG_CUDA(h, cudaMemcpyAsync(h->d_act, act_host, N * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
     float *obs_a = pinned_alias(obs_host), *tobs_a = pinned_alias(term_obs_host);
     double *rew_a = pinned_alias(rew_host);
     uint8_t *term_a = pinned_alias(term_host), *trunc_a = pinned_alias(trunc_host);
     int32_t *nel_a = pinned_alias(n_elem_host);
     StepIO io;
-    io.act = h->d_act;
+    io.act = act_a ? act_a : h->d_act;
     io.obs_out = obs_a ? obs_a : h->d_obs;
     io.rew_out = rew_a ? rew_a : h->d_rew;
     io.term_out = term_a ? term_a : h->d_term;
@@ -567,7 +597,6 @@ int mg_step_host(mg_handle h, const float *act_host, float *obs_host, double *re
     const int rc = launch_step(h, io, s);
     if (rc != MG_OK) return rc;
     h->obs_bound = io.obs_out;
-    int64_t d2h = N * (sizeof(double) + 2) + (n_elem_host ? N * sizeof(int32_t) : 0);
     if (!obs_a) MG_CUDA(h, cudaMemcpyAsync(obs_host, h->d_obs, N * MG_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (!rew_a) MG_CUDA(h, cudaMemcpyAsync(rew_host, h->d_rew, N * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (!term_a) MG_CUDA(h, cudaMemcpyAsync(term_host, h->d_term, N, cudaMemcpyDeviceToHost, s));
@@ -575,18 +604,12 @@ int mg_step_host(mg_handle h, const float *act_host, float *obs_host, double *re
     if (term_obs_host && !tobs_a)
         MG_CUDA(h, cudaMemcpyAsync(term_obs_host, h->d_term_obs, N * MG_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (n_elem_host && !nel_a) MG_CUDA(h, cudaMemcpyAsync(n_elem_host, h->d_nel, N * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    MG_CUDA(h, cudaMemcpyAsync(h->h_cnt, h->P.counters, CNT_N * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     MG_CUDA(h, cudaStreamSynchronize(s));
-    // bytes that crossed PCIe towards the host: rewards, flags, element counts for every env; observation rows of the
-    // envs that changed (all rows without delta mode or through staging); terminal rows of finished envs (all rows
-    // through staging)
-    const int cur = h->h_cnt[CNT_CUR] & 1;
-    const int64_t row = sizeof(float) * MG_OBS_DIM;
-    d2h += (obs_a && !io.obs_full) ? (int64_t)(h->h_cnt[CNT_SET * cur + CNT_OBSERVE] + h->h_cnt[CNT_SET * cur + CNT_OBSERVE + 1] + h->h_cnt[CNT_SET * cur + CNT_OBSERVE + 2] +
-                                             h->h_cnt[CNT_SET * cur + CNT_OBSERVE + 3]) * row : (int64_t)N * row;
-    if (term_obs_host) d2h += tobs_a ? (int64_t)h->h_cnt[CNT_SET * cur + CNT_DONE] * row : (int64_t)N * row;
-    h->last_h2d = (int64_t)(N * 3 * sizeof(float));
-    h->last_d2h = d2h;
+    // what the byte accounting of this step needs (mg_last_host_bytes reads the step counters only when asked)
+    h->acct_valid = true;
+    h->acct_obs_rows_delta = obs_a && !io.obs_full;
+    h->acct_term_obs = term_obs_host ? (tobs_a ? 1 : 2) : 0;
+    h->acct_n_elem = n_elem_host != nullptr;
     return MG_OK;
 }
 
@@ -622,6 +645,21 @@ int mg_set_host_delta(mg_handle h, int enabled) { return mg_set_obs_delta(h, ena
 
 int mg_last_host_bytes(mg_handle h, int64_t *h2d, int64_t *d2h) {
     if (!h) return fail(h, MG_ERR_ARG, "mg_last_host_bytes: null handle");
+    if (h->acct_valid) {
+        // bytes that crossed PCIe in the last mg_step_host: the actions; rewards, flags, element counts for every env;
+        // observation rows of the envs that changed (all rows without delta mode or through staging); terminal rows of
+        // finished envs (all rows through staging).  The step counters are still those of that step.
+        MG_DEVICE(h);
+        MG_CUDA(h, cudaMemcpy(h->h_cnt, h->P.counters, CNT_N * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        const int64_t N = h->num_envs, row = sizeof(float) * MG_OBS_DIM;
+        const int32_t *c = h->h_cnt + CNT_SET * (h->h_cnt[CNT_CUR] & 1);
+        int64_t bytes = N * (sizeof(double) + 2) + (h->acct_n_elem ? N * (int64_t)sizeof(int32_t) : 0);
+        bytes += h->acct_obs_rows_delta ? (int64_t)(c[CNT_OBSERVE] + c[CNT_OBSERVE + 1] + c[CNT_OBSERVE + 2] + c[CNT_OBSERVE + 3] + c[CNT_RESET]) * row : N * row;
+        if (h->acct_term_obs) bytes += h->acct_term_obs == 1 ? (int64_t)c[CNT_DONE] * row : N * row;
+        h->last_h2d = N * 3 * (int64_t)sizeof(float);
+        h->last_d2h = bytes;
+        h->acct_valid = false;
+    }
     if (h2d) *h2d = h->last_h2d;
     if (d2h) *d2h = h->last_d2h;
     return MG_OK;
@@ -758,6 +796,46 @@ int mg_stats(mg_handle h, mg_episode_stats *out, int reset) {
 int mg_set_option(mg_handle h, const char *name, int value) {
     if (!h || !name) return fail(h, MG_ERR_ARG, "mg_set_option: null pointer");
     if (std::strcmp(name, "fuse_decide") == 0) { h->fuse_decide = value != 0; return MG_OK; }
+    if (std::strcmp(name, "reset_side") == 0) { h->reset_side = value != 0; return MG_OK; }
+    // resident one-warp blocks per SM of the item kernels (grid size; default = what fits, see configure_kernels)
+    if (std::strcmp(name, "update_blocks") == 0 && value > 0) { h->blocks_update = value; return MG_OK; }
+    if (std::strcmp(name, "observe_blocks") == 0 && value > 0) { h->blocks_observe = value; return MG_OK; }
+    if (std::strcmp(name, "reset_blocks") == 0 && value > 0) { h->blocks_reset = value; return MG_OK; }
+#ifdef MG_TRACE
+    // profiling variant: "trace" = capacity arms the item timeline; "trace_dump" writes it to $MESHGEN_TRACE_FILE
+    if (std::strcmp(name, "trace") == 0) {
+        MG_DEVICE(h);
+        MG_CUDA(h, cudaDeviceSynchronize());
+        TraceRec *buf = nullptr;
+        const unsigned cap = (unsigned)value, zero = 0;
+        MG_CUDA(h, cudaMalloc((void **)&buf, sizeof(TraceRec) * (size_t)cap));
+        MG_CUDA(h, cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf)));
+        MG_CUDA(h, cudaMemcpyToSymbol(g_trace_cap, &cap, sizeof(cap)));
+        MG_CUDA(h, cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(zero)));
+        return MG_OK;
+    }
+    if (std::strcmp(name, "trace_dump") == 0) {
+        MG_DEVICE(h);
+        MG_CUDA(h, cudaDeviceSynchronize());
+        TraceRec *buf = nullptr;
+        unsigned cap = 0, n = 0;
+        MG_CUDA(h, cudaMemcpyFromSymbol(&buf, g_trace, sizeof(buf)));
+        MG_CUDA(h, cudaMemcpyFromSymbol(&cap, g_trace_cap, sizeof(cap)));
+        MG_CUDA(h, cudaMemcpyFromSymbol(&n, g_trace_n, sizeof(n)));
+        if (n > cap) n = cap;
+        std::vector<TraceRec> host(n);
+        if (n) MG_CUDA(h, cudaMemcpy(host.data(), buf, sizeof(TraceRec) * n, cudaMemcpyDeviceToHost));
+        const char *path = std::getenv("MESHGEN_TRACE_FILE");
+        FILE *f = std::fopen(path ? path : "trace.bin", "wb");
+        if (!f) return fail(h, MG_ERR_ARG, "trace_dump: cannot open the output file");
+        std::fwrite(host.data(), sizeof(TraceRec), n, f);
+        std::fclose(f);
+        const TraceRec *null_buf = nullptr;
+        cudaMemcpyToSymbol(g_trace, &null_buf, sizeof(null_buf));
+        cudaFree(buf);
+        return MG_OK;
+    }
+#endif
     return fail(h, MG_ERR_ARG, std::string("mg_set_option: unknown option ") + name);
 }
 

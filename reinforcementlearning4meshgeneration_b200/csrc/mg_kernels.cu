@@ -32,6 +32,37 @@ namespace mg {
 constexpr int UNROLL_OBS = MG_UNROLL_OBS, UNROLL_BQ = MG_UNROLL_BQ, UNROLL_PIP = MG_UNROLL_PIP;   // tuning knobs (profiles/README.md)
 constexpr int QCAP = 128 + 256;  // per-warp scratch: 4x32 ints + 32x4 doubles (coarse polygon of the generator)
 
+// Item timeline of the warp-per-item kernels (profiling variant only, -DMG_TRACE; tests/trace_items.py): one record per
+// item = {kernel, kind, n, SM, start ns, end ns} appended to a device buffer armed with mg_set_option("trace", capacity).
+#ifdef MG_TRACE
+struct TraceRec { int kernel, kind, n, sm; unsigned long long t0, t1; };
+__device__ TraceRec *g_trace = nullptr;
+__device__ unsigned g_trace_cap = 0, g_trace_n = 0;
+__device__ __forceinline__ unsigned long long trace_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void trace_item(int kernel, int kind, int n, unsigned long long t0, int lane) {
+    if (lane == 0 && g_trace != nullptr) {
+        const unsigned i = atomicAdd(&g_trace_n, 1u);
+        if (i < g_trace_cap) {
+            unsigned sm;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+            TraceRec r; r.kernel = kernel; r.kind = kind; r.n = n; r.sm = (int)sm; r.t0 = t0; r.t1 = trace_now();
+            g_trace[i] = r;
+        }
+    }
+}
+#define MG_TRACE_T0 const unsigned long long trace_t0_ = trace_now();
+#define MG_TRACE_BLOCK trace_item(0, -1, (int)blockIdx.x, trace_now(), lane);
+#define MG_TRACE_ITEM(kernel, kind, n) trace_item(kernel, kind, n, trace_t0_, lane);
+#else
+#define MG_TRACE_T0
+#define MG_TRACE_BLOCK
+#define MG_TRACE_ITEM(kernel, kind, n)
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // per-warp view of the environment
 // ---------------------------------------------------------------------------------------------
@@ -206,8 +237,8 @@ __device__ __noinline__ int find_reference_index(const Warp w, const double *key
     int bs = 0x7fffffff, bj = -1;
 #pragma unroll 4
     for (int j = w.lane; j < w.n; j += 32) {
-        double k = key[j];
-        int s = stamp[j];
+        double k = __ldcg(key + j);
+        int s = __ldcg(stamp + j);
         if (k < bk || (k == bk && k != CUDART_INF && s < bs)) {
             bk = k;
             bs = s;
@@ -782,8 +813,8 @@ size_t smem_bytes(int cap, bool with_queue = true) { return (size_t)cap * 16 + (
 enum { W_N = 0, W_REF = 1, W_NEL = 2, W_FLAGS = 3, W_FAILED = 6, W_EP_LEN = 7, W_N0 = 38, W_NEXT_VID = 39, W_STAMP_CTR = 40 };
 enum { D_BASE = 2, D_EP_RETURN = 4, D_CUR_AREA = 5, D_ORIGINAL_AREA = 16, D_AREA_MIN = 17, D_AREA_CRIT = 18 };
 __device__ __forceinline__ void stash_records(const Params &P, int4 *stash, int env, int lane) {
-    if (lane < 8) stash[lane] = reinterpret_cast<const int4 *>(P.hot + env)[lane];
-    else if (lane < 12) stash[lane] = reinterpret_cast<const int4 *>(P.cold + env)[lane - 8];
+    if (lane < 8) stash[lane] = __ldcg(reinterpret_cast<const int4 *>(P.hot + env) + lane);
+    else if (lane < 12) stash[lane] = __ldcg(reinterpret_cast<const int4 *>(P.cold + env) + lane - 8);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1094,12 +1125,38 @@ __device__ __forceinline__ WorkItem fetch_item(const WorkItem *list, const int (
 constexpr int SCREEN_THREADS = 128;
 __global__ void __launch_bounds__(SCREEN_THREADS) mg_step_screen_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io) {
     __shared__ uint8_t s_copy[SCREEN_THREADS];     // bit 0: cached observation -> obs_out, bit 1: -> term_obs_out
+    // The block's 128 records (16 KB) come in with coalesced 16-byte loads, eight in flight per thread -- one DRAM round
+    // trip instead of two dependent ones (scalars, then the fan) -- and are read back from shared memory; chunk c of
+    // record r sits at r * 8 + (c ^ (r & 7)) so that neither the stores nor the per-thread reads conflict.
+    __shared__ int4 s_rec[SCREEN_THREADS * 8];
     const int env = blockIdx.x * SCREEN_THREADS + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool active = env < P.num_envs;
-    const int set = P.counters[CNT_STEP] & 1;
+    float a0 = 0, a1 = 0, a2 = 0;
+    int set;
+    {
+        const int4 *src = reinterpret_cast<const int4 *>(P.hot) + (size_t)blockIdx.x * SCREEN_THREADS * 8;
+        const int limit = (P.num_envs - blockIdx.x * SCREEN_THREADS) * 8;        // chunks of this block that exist
+        int4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int g = k * SCREEN_THREADS + threadIdx.x;
+            v[k] = g < limit ? src[g] : make_int4(0, 0, 0, 0);
+        }
+        // the action and the step parity are requested before the first use of the records
+        if (active) { a0 = io.act[(size_t)env * 3 + 0]; a1 = io.act[(size_t)env * 3 + 1]; a2 = io.act[(size_t)env * 3 + 2]; }
+        set = P.counters[CNT_STEP] & 1;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int g = k * SCREEN_THREADS + threadIdx.x, r = g >> 3, c = g & 7;
+            s_rec[r * 8 + (c ^ (r & 7))] = v[k];
+        }
+    }
+    (void)a2;
     if (env == 0) P.counters[CNT_CUR] = set;          // the set this step's lists use
     int *cnt = P.counters + CNT_SET * set;
+    __syncthreads();
+    auto rec_chunk = [&](int c) { return s_rec[threadIdx.x * 8 + (c ^ (threadIdx.x & 7))]; };
 
     // where the step goes: 0 = settled here, 1 = decide list, 2 = accept list
     int route = 0;
@@ -1109,8 +1166,7 @@ __global__ void __launch_bounds__(SCREEN_THREADS) mg_step_screen_kernel(const __
     double ep_return = 0;
     uint8_t copy_code = 0;
     if (active) {
-        const int4 *rec = reinterpret_cast<const int4 *>(P.hot + env);
-        const int4 c0 = rec[0], c1 = rec[1], c2 = rec[2];
+        const int4 c0 = rec_chunk(0), c1 = rec_chunk(1), c2 = rec_chunk(2);
         n = c0.x;
         const int ref_index = c0.y, flags = c0.w;
         n_elements = c0.z;
@@ -1118,7 +1174,6 @@ __global__ void __launch_bounds__(SCREEN_THREADS) mg_step_screen_kernel(const __
         int failed_num = c1.z;
         ep_len = c1.w;
         ep_return = __hiloint2double(c2.y, c2.x);
-        const float a0 = io.act[(size_t)env * 3 + 0], a1 = io.act[(size_t)env * 3 + 1], a2 = io.act[(size_t)env * 3 + 2];
         W.n = n;
         // An env without a reference point (empty candidate list, E:736-738 returns None) has no defined
         // continuation in the reference (its next step raises): it is reported truncated.
@@ -1135,9 +1190,10 @@ __global__ void __launch_bounds__(SCREEN_THREADS) mg_step_screen_kernel(const __
             else if (flags & (m1 ? HOT_PEND_M1 : HOT_PEND_P1)) { route = 1; W.kind = WORK_DECIDE_RULE; }
             else fail_penalty = true;
         } else {
-            const double2 *fan = reinterpret_cast<const double2 *>(rec) + 3;
-            const double2 f1 = fan[1], f2 = fan[2], f3 = fan[3];
-            const P2 ref = mk(f2.x, f2.y), right_p = mk(f1.x, f1.y), left_p = mk(f3.x, f3.y);
+            const int4 q1 = rec_chunk(4), q2 = rec_chunk(5), q3 = rec_chunk(6);          // fan[1], fan[2], fan[3]
+            const P2 ref = mk(__hiloint2double(q2.y, q2.x), __hiloint2double(q2.w, q2.z)),
+                     right_p = mk(__hiloint2double(q1.y, q1.x), __hiloint2double(q1.w, q1.z)),
+                     left_p = mk(__hiloint2double(q3.y, q3.x), __hiloint2double(q3.w, q3.z));
             const P2 newp = action_to_point(a1, a2, ref, right_p, base_length);
             // the new-vertex element (E:264-270) must pass Mesh.is_valid (E:319); if the candidate vertex coincides
             // with a boundary vertex the rule -1 element is used instead (E:258-262).  When neither can be accepted
@@ -1170,32 +1226,26 @@ __global__ void __launch_bounds__(SCREEN_THREADS) mg_step_screen_kernel(const __
             copy_code = (io.obs_full ? 1 : 0) | ((done && io.term_obs_out) ? 2 : 0);
         }
     }
-    // ---- work lists: one atomicAdd per warp, list and size bin --------------------------------
+    // ---- work lists: the lanes of a warp that feed the same (list, size bin) share one atomicAdd, and the atomics of the
+    // up to nine lists are issued together (one round trip to L2, not one per list) --------------------------------
     {
-        const int bin = size_bin(n, P.cap);
-#pragma unroll 1
-        for (int r = 1; r <= 2; r++) {
-            const unsigned any = __ballot_sync(FULL, route == r);
-            if (!any) continue;
-            WorkItem *list = r == 1 ? P.decide_list : P.accept_list;
-            int *ctr = cnt + (r == 1 ? CNT_DECIDE : CNT_ACCEPT);
-#pragma unroll 1
-            for (int b = 0; b < NBINS; b++) {
-                const unsigned m = __ballot_sync(FULL, route == r && bin == b);
-                if (!m) continue;
-                int base = 0;
-                if (lane == __ffs(m) - 1) base = atomicAdd(&ctr[b], __popc(m));
-                base = __shfl_sync(FULL, base, __ffs(m) - 1);
-                if (route == r && bin == b) list[(size_t)b * P.num_envs + base + __popc(m & ((1u << lane) - 1))] = W;
-            }
-        }
+        // envs whose episode ended in a step settled here are reset by mg_step_reset_kernel, which runs next to the
+        // update kernel (a reset is the longest item of a step and depends on nothing the other kernels produce)
         const bool to_reset = settled_done && P.auto_reset;
-        const unsigned r = __ballot_sync(FULL, to_reset);
-        if (r) {                                        // resets are the longest items: first bin
-            int base = 0;
-            if (lane == __ffs(r) - 1) base = atomicAdd(&cnt[CNT_OBSERVE], __popc(r));
-            base = __shfl_sync(FULL, base, __ffs(r) - 1);
-            if (to_reset) P.observe_list[base + __popc(r & ((1u << lane) - 1))] = make_item(env, 0, WORK_RESET, 0, 0, 0, 0.0, 0.0);
+        const int dest = route ? (route - 1) * NBINS + size_bin(n, P.cap) : (to_reset ? 2 * NBINS : -1);
+        const unsigned grp = __match_any_sync(FULL, dest);
+        const int leader = __ffs(grp) - 1;
+        int base = 0;
+        if (dest >= 0 && lane == leader) {
+            int *ctr = dest < NBINS ? cnt + CNT_DECIDE + dest : (dest < 2 * NBINS ? cnt + CNT_ACCEPT + dest - NBINS : cnt + CNT_RESET);
+            base = atomicAdd(ctr, __popc(grp));
+        }
+        base = __shfl_sync(FULL, base, leader);
+        const int slot = base + __popc(grp & ((1u << lane) - 1));
+        if (dest >= 0 && slot < P.num_envs) {
+            if (dest < NBINS) P.decide_list[(size_t)dest * P.num_envs + slot] = W;
+            else if (dest < 2 * NBINS) P.accept_list[(size_t)(dest - NBINS) * P.num_envs + slot] = W;
+            else P.reset_list[slot] = env;
         }
     }
     // ---- statistics: one set of atomics per warp --------------------------------------------
@@ -1248,17 +1298,26 @@ __global__ void __launch_bounds__(SCREEN_THREADS) mg_step_screen_kernel(const __
 
 // ---- the warp-per-item kernels ------------------------------------------------------------------
 // Item loop shared by them: the first item of a block is its block index, later ones come from a ticket counter (an
-// early finisher takes the next item; the ticket is requested at the start of the previous item, so its latency is
-// hidden).
+// early finisher takes the next item).  The ticket is requested shortly before the END of the current item
+// (MG_ITEM_TICKET): its latency hides behind the item's last stores, and an item is only bound to a block when that
+// block is about to be free.  (Requested at the start of an item, every second-wave item was bound at t = 0 to an
+// arbitrary block and waited for that block's first item, however long -- profiles/r2_trace_c3_before.txt.)
 #define MG_ITEM_LOOP_BEGIN(total, ticket)                                                   \
     int t_ = blockIdx.x;                                                                    \
-    if (t_ >= (total)) return;                                                              \
-    init_mbar(L.mbar, lane);                                                                \
+    MG_TRACE_BLOCK                                                                          \
+    if (t_ < (total)) init_mbar(L.mbar, lane);                                              \
     unsigned phase = 0;                                                                     \
+    int *const ticket_ = (ticket);                                                          \
     _Pragma("unroll 1") while (t_ < (total)) {                                              \
         int next_t_ = 0;                                                                    \
-        if (lane == 0) next_t_ = gridDim.x + atomicAdd((ticket), 1);
+        bool have_next_ = false;
+#define MG_ITEM_TICKET                                                                      \
+        if (!have_next_) {                                                                  \
+            if (lane == 0) next_t_ = gridDim.x + atomicAdd(ticket_, 1);                     \
+            have_next_ = true;                                                              \
+        }
 #define MG_ITEM_LOOP_END                          \
+        MG_ITEM_TICKET                            \
         t_ = __shfl_sync(FULL, next_t_, 0);       \
     }
 
@@ -1293,7 +1352,7 @@ __device__ __forceinline__ bool rule_quad_clear(const Warp w, int rule, int idx)
 // stash.  Returns true when an element is accepted (rule / new_vertex say which); a failed step is finished here
 // (nothing changed: cached observation, same tail as the screen kernel).
 __device__ __forceinline__ bool decide_item(const Params &P, const StepIO &io, int *cnt, const Warp &w, const WorkItem &W,
-                                            const Stash S, int &rule, bool &new_vertex) {
+                                            const Stash S, int &rule, bool &new_vertex, int *ticket, int &next_t) {
     const int lane = w.lane, env = W.env;
     const size_t off = (size_t)env * P.cap;
     const int idx = S.i(W_REF);
@@ -1331,6 +1390,7 @@ __device__ __forceinline__ bool decide_item(const Params &P, const StepIO &io, i
     if (flags_changed && lane == 0) P.hot[env].flags = flags;
     if (accepted) return true;
     // ---- failed step ----------------------------------------------------------------------------
+    if (lane == 0) next_t = gridDim.x + atomicAdd(ticket, 1);            // the block's next item (see MG_ITEM_TICKET)
     const int n_el = S.i(W_NEL);
     const double reward = n_el ? -1.0 / n_el : -1;                      // E:279 / E:357
     const int failed_num = S.i(W_FAILED) + 1;
@@ -1388,9 +1448,10 @@ __global__ void __launch_bounds__(32, MG_MINB_DECIDE) mg_step_decide_kernel(cons
         stage_wait(L.mbar, phase);
         phase ^= 1u;
         int rule; bool new_vertex;
-        if (decide_item(P, io, cnt, w, W, S, rule, new_vertex))
+        if (decide_item(P, io, cnt, w, W, S, rule, new_vertex, ticket_, next_t_))
             push_item(P.accept_list, cnt + CNT_ACCEPT, P, size_bin(W.n, P.cap),
                       make_item(W.env, W.n, WORK_APPLY, rule, new_vertex ? 1 : 0, 0, W.newx, W.newy), lane);
+        else have_next_ = true;
     MG_ITEM_LOOP_END
 }
 
@@ -1585,6 +1646,7 @@ __global__ void __launch_bounds__(32, MG_MINB_UPDATE) mg_step_update_kernel(cons
     if (fused) total += load_counts(cnt + CNT_DECIDE, P.num_envs, counts_d);
     const Stash S{L.stash};
     MG_ITEM_LOOP_BEGIN(total, &cnt[CNT_TICKET_UPDATE])
+        MG_TRACE_T0
         WorkItem W;
         {
             // bin b holds counts_a[b] accept items followed by counts_d[b] decide items
@@ -1633,12 +1695,14 @@ __global__ void __launch_bounds__(32, MG_MINB_UPDATE) mg_step_update_kernel(cons
         int rule = W.rule;
         bool new_vertex = W.flag != 0;
         if (W.kind != WORK_APPLY) {
-            if (!decide_item(P, io, cnt, w, W, S, rule, new_vertex)) {
+            if (!decide_item(P, io, cnt, w, W, S, rule, new_vertex, ticket_, next_t_)) {
+                MG_TRACE_ITEM(1, 10 + W.kind, n)
                 t_ = __shfl_sync(FULL, next_t_, 0);
                 continue;
             }
         }
         const ApplyOut A = apply_element<true>(P, w, S, env, n, idx, rule, new_vertex, mk(W.newx, W.newy), fan_vid);
+        MG_ITEM_TICKET
         const int nn = A.nn, n_elements = A.n_elements, next_vid0 = A.next_vid0;
         const double reward = A.reward, current_area = A.current_area;
         const bool done = A.done;
@@ -1671,7 +1735,10 @@ __global__ void __launch_bounds__(32, MG_MINB_UPDATE) mg_step_update_kernel(cons
             P.cold[env].next_vid = next_vid0 + (new_vertex ? 1 : 0);
             P.cold[env].stamp_ctr = S.i(W_STAMP_CTR) - 4;
         }
-        push_item(P.observe_list, cnt + CNT_OBSERVE, P, size_bin(nn, P.cap), make_item(env, nn, WORK_OBSERVE, 0, 0, done ? 1 : 0, 0.0, 0.0), lane);
+        // (a completed episode is followed by the env's in-place reset in the same observe item: the longest kind, first bin)
+        push_item(P.observe_list, cnt + CNT_OBSERVE, P, done && P.auto_reset ? 0 : size_bin(nn, P.cap),
+                  make_item(env, nn, WORK_OBSERVE, 0, 0, done ? 1 : 0, 0.0, 0.0), lane);
+        MG_TRACE_ITEM(1, W.kind, n)
     MG_ITEM_LOOP_END
 }
 
@@ -1690,6 +1757,63 @@ __device__ __noinline__ void reset_in_place(const Params &P, const StepIO &io, i
 #ifndef MG_MINB_OBSERVE
 #define MG_MINB_OBSERVE 20
 #endif
+// One observe / reset item; the env's records are (re)loaded here.
+__device__ __forceinline__ void observe_item(const Params &P, const StepIO &io, int *cnt, const SmemLayout &L, const WorkItem &W, unsigned &phase,
+                                             int *ticket, int &next_t, int grid, int lane) {
+    const Stash S{L.stash};
+    const int env = W.env;
+    Warp w;
+    w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = 0;
+    if (W.kind == WORK_RESET) {
+        reset_in_place(P, io, env, w);
+        if (lane == 0) next_t = grid + atomicAdd(ticket, 1);
+        return;
+    }
+    const size_t off = (size_t)env * P.cap;
+    __syncwarp();
+    stage_issue(L.ring, L.mbar, P.xy + off, W.n, lane);
+    stash_records(P, L.stash, env, lane);
+    __syncwarp();
+    w.n = W.n;
+    stage_wait(L.mbar, phase);
+    phase ^= 1u;
+    // ---- next state (E:361-386) -----------------------------------------------------
+    const int ref_index = find_reference_index(w, P.key + off, P.stamp + off);
+    float obs = 0.0f;
+    double base = S.d(D_BASE);
+    if (ref_index >= 0) {
+        const ObsOut R = compute_obs(w, P.sc_full, ref_index, S.d(D_CUR_AREA) / S.d(D_ORIGINAL_AREA));
+        obs = R.obs; base = R.base;
+    }
+    if (lane == 0) next_t = grid + atomicAdd(ticket, 1);      // the block's next item (see MG_ITEM_TICKET)
+    // An env without a reference point (empty candidate list, E:736-738) is reported truncated (sentinel)
+    const bool truncated = !W.done && ref_index < 0;
+    const bool done = W.done || truncated;
+    if (truncated && lane == 0) {
+        io.trunc_out[env] = 1;
+        StatsAcc *T = P.stats + (env & (STAT_SLOTS - 1));
+        atomicAdd(&cnt[CNT_DONE], 1);
+        atomicAdd(&T->episodes, 1ull);
+        atomicAdd(&T->truncated, 1ull);
+        atomicAdd(&T->elements, (unsigned long long)S.i(W_NEL));
+        atomicAdd(&T->sum_return, S.d(D_EP_RETURN));
+        atomicAdd(&T->sum_length, (double)S.i(W_EP_LEN));
+    }
+    if (lane < MG_OBS_DIM) {
+        if (io.term_obs_out && done) io.term_obs_out[(size_t)env * MG_OBS_DIM + lane] = obs;
+        P.obs_cache[(size_t)env * MG_OBS_DIM + lane] = obs;
+        io.obs_out[(size_t)env * MG_OBS_DIM + lane] = obs;
+    }
+    if (done && P.auto_reset) {
+        __syncwarp();
+        reset_in_place(P, io, env, w);
+    } else {
+        // the state changed: new memo (rule -1 / +1 verdicts, neighbour fan) and the rest of the record
+        const int flags = done ? 0 : memo_flags(w, ref_index);
+        store_hot(P.hot + env, w, ref_index, S.i(W_NEL), flags, base, 0, S.i(W_EP_LEN), S.d(D_EP_RETURN), S.d(D_CUR_AREA));
+    }
+}
+
 __global__ void __launch_bounds__(32, MG_MINB_OBSERVE) mg_step_observe_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
@@ -1704,58 +1828,32 @@ __global__ void __launch_bounds__(32, MG_MINB_OBSERVE) mg_step_observe_kernel(co
     }
     int counts[NBINS];
     const int total = load_counts(cnt + CNT_OBSERVE, P.num_envs, counts);
-    const Stash S{L.stash};
     MG_ITEM_LOOP_BEGIN(total, &cnt[CNT_TICKET_OBSERVE])
+        MG_TRACE_T0
         const WorkItem W = fetch_item(P.observe_list, counts, P.num_envs, t_);
-        const int env = W.env;
+        observe_item(P, io, cnt, L, W, phase, ticket_, next_t_, gridDim.x, lane);
+        have_next_ = true;
+        MG_TRACE_ITEM(2, W.kind, W.n)
+    MG_ITEM_LOOP_END
+}
+
+// ---- kernel 5: resets of the envs the screen kernel truncated ------------------------------------------------------
+// Runs on a side stream next to the update kernel: a reset in random-polygon mode (generator, candidate rebuild, first
+// observation) is the longest item of a step (~40 us), touches only its own env and needs nothing the update / observe
+// kernels produce.  (Inside the observe kernel the resets alone stretched that launch to ~52 us for ~30 us of work.)
+__global__ void __launch_bounds__(32, MG_MINB_OBSERVE) mg_step_reset_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    const SmemLayout L = carve(smem_raw, P.cap, true);
+    int *cnt = P.counters + CNT_SET * P.counters[CNT_CUR];
+    const int total = min(cnt[CNT_RESET], P.num_envs);
+    MG_ITEM_LOOP_BEGIN(total, &cnt[CNT_TICKET_RESET])
+        MG_TRACE_T0
+        const int env = P.reset_list[t_];
         Warp w;
         w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = 0;
-        if (W.kind == WORK_RESET) {
-            reset_in_place(P, io, env, w);
-        } else {
-            const size_t off = (size_t)env * P.cap;
-            __syncwarp();
-            stage_issue(L.ring, L.mbar, P.xy + off, W.n, lane);
-            stash_records(P, L.stash, env, lane);
-            __syncwarp();
-            w.n = W.n;
-            stage_wait(L.mbar, phase);
-            phase ^= 1u;
-            // ---- next state (E:361-386) -----------------------------------------------------
-            const int ref_index = find_reference_index(w, P.key + off, P.stamp + off);
-            float obs = 0.0f;
-            double base = S.d(D_BASE);
-            if (ref_index >= 0) {
-                const ObsOut R = compute_obs(w, P.sc_full, ref_index, S.d(D_CUR_AREA) / S.d(D_ORIGINAL_AREA));
-                obs = R.obs; base = R.base;
-            }
-            // An env without a reference point (empty candidate list, E:736-738) is reported truncated (sentinel)
-            const bool truncated = !W.done && ref_index < 0;
-            const bool done = W.done || truncated;
-            if (truncated && lane == 0) {
-                io.trunc_out[env] = 1;
-                StatsAcc *T = P.stats + (env & (STAT_SLOTS - 1));
-                atomicAdd(&cnt[CNT_DONE], 1);
-                atomicAdd(&T->episodes, 1ull);
-                atomicAdd(&T->truncated, 1ull);
-                atomicAdd(&T->elements, (unsigned long long)S.i(W_NEL));
-                atomicAdd(&T->sum_return, S.d(D_EP_RETURN));
-                atomicAdd(&T->sum_length, (double)S.i(W_EP_LEN));
-            }
-            if (lane < MG_OBS_DIM) {
-                if (io.term_obs_out && done) io.term_obs_out[(size_t)env * MG_OBS_DIM + lane] = obs;
-                P.obs_cache[(size_t)env * MG_OBS_DIM + lane] = obs;
-                io.obs_out[(size_t)env * MG_OBS_DIM + lane] = obs;
-            }
-            if (done && P.auto_reset) {
-                __syncwarp();
-                reset_in_place(P, io, env, w);
-            } else {
-                // the state changed: new memo (rule -1 / +1 verdicts, neighbour fan) and the rest of the record
-                const int flags = done ? 0 : memo_flags(w, ref_index);
-                store_hot(P.hot + env, w, ref_index, S.i(W_NEL), flags, base, 0, S.i(W_EP_LEN), S.d(D_EP_RETURN), S.d(D_CUR_AREA));
-            }
-        }
+        reset_in_place(P, io, env, w);
+        MG_TRACE_ITEM(3, WORK_RESET, 0)
     MG_ITEM_LOOP_END
 }
 

@@ -92,12 +92,12 @@ enum { WORK_DECIDE_NEW = 0, WORK_DECIDE_RULE = 1, WORK_APPLY = 2, WORK_OBSERVE =
 // Every work list has NBINS segments of num_envs records, binned by boundary size (largest first), so that the item
 // kernels hand out long items before short ones.
 constexpr int NBINS = 4;
-// counters[CNT_SET * set + ...]: sizes of the decide / accept / observe list bins of counter set `set`, the item tickets
-// of the warp-per-item kernels and the number of episodes that ended in the step; CNT_STEP = parity of the next
+// counters[CNT_SET * set + ...]: sizes of the decide / accept / observe list bins and of the reset list of counter set
+// `set`, the item tickets of the warp-per-item kernels and the number of episodes that ended in the step; CNT_STEP = parity of the next
 // step (the set its screen kernel will use); CNT_CUR = the set the current step uses.  Two sets alternate so that no
 // memset sits between the launches of a step and any sequence of steps can be captured in a CUDA graph.
 enum { CNT_DECIDE = 0, CNT_ACCEPT = 4, CNT_OBSERVE = 8, CNT_DONE = 12, CNT_TICKET_DECIDE = 13, CNT_TICKET_UPDATE = 14,
-       CNT_TICKET_OBSERVE = 15, CNT_SET = 16, CNT_STEP = 32, CNT_CUR = 33, CNT_N = 40 };
+       CNT_TICKET_OBSERVE = 15, CNT_RESET = 16, CNT_TICKET_RESET = 17, CNT_SET = 20, CNT_STEP = 40, CNT_CUR = 41, CNT_N = 48 };
 
 constexpr int ANGLE_TAB_N = 62833;      // round(2 pi, 4) = 6.2832
 
@@ -123,7 +123,8 @@ struct Params {
     // per-step work lists
     WorkItem *decide_list;   // [NBINS][num_envs]  screen -> decide
     WorkItem *accept_list;   // [NBINS][num_envs]  screen / decide -> update
-    WorkItem *observe_list;  // [NBINS][num_envs]  screen / decide (resets of truncated envs), update -> observe
+    WorkItem *observe_list;  // [NBINS][num_envs]  decide (resets of truncated envs), update -> observe
+    int32_t *reset_list;     // [num_envs]         screen -> reset (envs truncated by a step the screen kernel settled)
     int *counters;           // [CNT_N]
     // element log: quads as 4 vertex ids, coordinates of inserted vertices
     int32_t *elem;       // [num_envs][elem_cap][4]
