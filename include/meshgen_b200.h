@@ -251,8 +251,9 @@ int mg_snapshot_load(mg_handle h, const void *blob_dev, int64_t blob_bytes, void
  * share one launch -- a warp that accepts an element applies it with the boundary it has already staged; 0 = two
  * launches with smaller code images.  "reset_side" (default 1): the in-place resets of the envs a step truncated run
  * in their own kernel on a side stream next to the update kernel (0: in the caller's stream, before the observe
- * kernel).  "update_blocks" / "observe_blocks" / "reset_blocks": resident one-warp blocks per SM of those kernels
- * (default: what fits). */
+ * kernel).  "pdl" (default 1): the update and observe kernels are launched as programmatic dependents of their
+ * predecessor (their blocks are placed while it drains and wait for it with griddepcontrol.wait).  "update_blocks" /
+ * "observe_blocks" / "reset_blocks": resident one-warp blocks per SM of those kernels (default: what fits). */
 int mg_set_option(mg_handle h, const char *name, int value);
 
 /* Profiling aid (bench.py roofline.per_kernel): with enabled != 0 every mg_step / mg_step_host records CUDA events

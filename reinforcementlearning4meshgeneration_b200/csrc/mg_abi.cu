@@ -58,6 +58,7 @@ struct mg_env_s {
     int blocks_decide = 16, blocks_update = 16, blocks_observe = 16, blocks_reset = 16;
     bool fuse_decide = true;           // one launch for the decide and update work (mg_set_option "fuse_decide")
     bool reset_side = true;            // resets on the side stream, next to the update kernel (mg_set_option "reset_side")
+    bool pdl = true;                   // update / observe kernels as programmatic dependents of their predecessor (mg_set_option "pdl")
     std::string err;
 };
 
@@ -204,10 +205,22 @@ int launch_step(mg_handle h, const StepIO &io, cudaStream_t s) {
     }
     if (!h->fuse_decide) mg_step_decide_kernel<<<grid(h->blocks_decide), 32, h->smem_nq, s>>>(h->P, io);
     if (ev) cudaEventRecord(ev[2], s);
-    mg_step_update_kernel<<<grid(h->blocks_update), 32, h->smem_nq, s>>>(h->P, io, h->fuse_decide ? 1 : 0);
+    const bool pdl = h->pdl && !ev;
+    auto launch_dependent = [&](auto kernel, int blocks, size_t smem, auto... args) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3(32); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, kernel, args...);
+    };
+    if (pdl && h->fuse_decide) MG_CUDA(h, launch_dependent(mg_step_update_kernel, grid(h->blocks_update), h->smem_nq, h->P, io, 1));
+    else mg_step_update_kernel<<<grid(h->blocks_update), 32, h->smem_nq, s>>>(h->P, io, h->fuse_decide ? 1 : 0);
     if (ev) cudaEventRecord(ev[3], s);
     if (h->P.auto_reset != 0 && !side) mg_step_reset_kernel<<<grid(h->blocks_reset), 32, h->smem, s>>>(h->P, io);
-    mg_step_observe_kernel<<<grid(h->blocks_observe), 32, h->smem, s>>>(h->P, io);
+    if (pdl && (side || h->P.auto_reset == 0)) MG_CUDA(h, launch_dependent(mg_step_observe_kernel, grid(h->blocks_observe), h->smem, h->P, io));
+    else mg_step_observe_kernel<<<grid(h->blocks_observe), 32, h->smem, s>>>(h->P, io);
     if (side) MG_CUDA(h, cudaStreamWaitEvent(s, h->ev_join, 0));
     if (ev) { cudaEventRecord(ev[4], s); h->timing_steps++; }
     h->launches += (h->fuse_decide ? 3 : 4) + (h->P.auto_reset != 0 ? 1 : 0);
@@ -291,7 +304,7 @@ int mg_create(mg_handle *out, int device, int num_envs, int max_verts) {
     A(dalloc(&P.hot, (size_t)num_envs), "hot"); A(dalloc(&P.cold, (size_t)num_envs), "cold");
     A(dalloc(&P.stats, (size_t)STAT_SLOTS), "stats");
     A(dalloc(&P.obs_cache, (size_t)num_envs * MG_OBS_DIM), "obs");
-    A(dalloc(&P.decide_list, (size_t)NBINS * num_envs), "decide_list"); A(dalloc(&P.accept_list, (size_t)NBINS * num_envs), "accept_list");
+    A(dalloc(&P.decide_list, (size_t)DECIDE_SEGS * num_envs), "decide_list"); A(dalloc(&P.accept_list, (size_t)NBINS * num_envs), "accept_list");
     A(dalloc(&P.observe_list, (size_t)NBINS * num_envs), "observe_list"); A(dalloc(&P.counters, (size_t)CNT_N), "counters");
     A(dalloc(&P.reset_list, (size_t)num_envs), "reset_list");
     A(dalloc(&P.elem, (size_t)num_envs * P.elem_cap * 4), "elem"); A(dalloc(&P.ins_xy, (size_t)num_envs * P.ins_cap), "ins_xy");
@@ -386,7 +399,7 @@ struct SnapHeader {
     int64_t env_id_offset;
 };
 static_assert(sizeof(SnapHeader) <= SNAP_ALIGN, "snapshot header");
-constexpr int64_t SNAP_MAGIC = 0x4d4753324e415053ll, SNAP_VERSION = 3;
+constexpr int64_t SNAP_MAGIC = 0x4d4753324e415053ll, SNAP_VERSION = 4;
 SnapHeader snap_header(mg_handle h, int64_t total) {
     SnapHeader H{};
     H.magic = SNAP_MAGIC; H.version = SNAP_VERSION; H.total_bytes = total;
@@ -797,6 +810,7 @@ int mg_set_option(mg_handle h, const char *name, int value) {
     if (!h || !name) return fail(h, MG_ERR_ARG, "mg_set_option: null pointer");
     if (std::strcmp(name, "fuse_decide") == 0) { h->fuse_decide = value != 0; return MG_OK; }
     if (std::strcmp(name, "reset_side") == 0) { h->reset_side = value != 0; return MG_OK; }
+    if (std::strcmp(name, "pdl") == 0) { h->pdl = value != 0; return MG_OK; }
     // resident one-warp blocks per SM of the item kernels (grid size; default = what fits, see configure_kernels)
     if (std::strcmp(name, "update_blocks") == 0 && value > 0) { h->blocks_update = value; return MG_OK; }
     if (std::strcmp(name, "observe_blocks") == 0 && value > 0) { h->blocks_observe = value; return MG_OK; }

@@ -668,22 +668,23 @@ __device__ __forceinline__ bool intersects_boundary(const Warp w, const Quad Q, 
     const P2 c1a = r1 ? m[0] : m[1], c1b = r1 ? m[3] : m[0], c2a = c1b, c2b = r1 ? m[2] : m[3];
     const DistBound MD = dist_bound(max_dist);
     auto in_mesh = [&](int j) { return j == qi[0] || j == qi[1] || j == qi[2] || j == qi[3]; };
-#pragma unroll 2
+    // Compact code on purpose (one copy of the crossing test, no unrolling): the update kernel is bound by instruction
+    // fetch (profiles/r2e_*: stall_no_instruction 4.9 of 13 cycles per issue), and only the few vertices inside the
+    // distance cut ever reach the test.
+#pragma unroll 1
     for (int base = 0; base < n; base += 32) {
         int j = base + w.lane;
         bool hit = false;
         if (j < n && !in_mesh(j)) {
             P2 v = w.at(j);
             if (dist_less(ref, v, MD)) {
-                int jp = j == 0 ? n - 1 : j - 1, jn = j + 1 == n ? 0 : j + 1;
                 // any of (c1,prev) (c1,next) (c2,prev) (c2,next) crossing -> True (order irrelevant)
-                if (!in_mesh(jp)) {
-                    P2 q = w.at(jp);
-                    hit = is_cross(c1a, c1b, v, q) || is_cross(c2a, c2b, v, q);
-                }
-                if (!hit && !in_mesh(jn)) {
-                    P2 q = w.at(jn);
-                    hit = is_cross(c1a, c1b, v, q) || is_cross(c2a, c2b, v, q);
+#pragma unroll 1
+                for (int t = 0; t < 4 && !hit; t++) {
+                    const int jq = (t & 1) ? (j + 1 == n ? 0 : j + 1) : (j == 0 ? n - 1 : j - 1);
+                    if (in_mesh(jq)) continue;
+                    const P2 q = w.at(jq);
+                    hit = (t & 2) ? is_cross(c2a, c2b, v, q) : is_cross(c1a, c1b, v, q);
                 }
             }
         }
@@ -1112,13 +1113,14 @@ __device__ __forceinline__ WorkItem make_item(int env, int n, int kind, int rule
     W.kind = (int8_t)kind; W.rule = (int8_t)rule; W.flag = (int8_t)flag; W.done = (int8_t)done; W.pad = 0;
     return W;
 }
-// item t of a binned list (bins in order); counts[] = the list's NBINS counters, already clamped
-__device__ __forceinline__ WorkItem fetch_item(const WorkItem *list, const int (&counts)[NBINS], int num_envs, int t) {
-    int bin = 0;
+// item t of a segmented list (segments in order); counts[] = the list's segment counters, already clamped
+template <int NSEG>
+__device__ __forceinline__ WorkItem fetch_item(const WorkItem *list, const int (&counts)[NSEG], int num_envs, int t) {
+    int seg = 0;
 #pragma unroll
-    for (int b = 0; b < NBINS - 1; b++)
-        if (bin == b && t >= counts[b]) { t -= counts[b]; bin = b + 1; }
-    return list[(size_t)bin * num_envs + t];
+    for (int b = 0; b < NSEG - 1; b++)
+        if (seg == b && t >= counts[b]) { t -= counts[b]; seg = b + 1; }
+    return list[(size_t)seg * num_envs + t];
 }
 
 // ---- kernel 1: screen ------------------------------------------------------------------------
@@ -1132,6 +1134,7 @@ __global__ void __launch_bounds__(SCREEN_THREADS) mg_step_screen_kernel(const __
     const int env = blockIdx.x * SCREEN_THREADS + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool active = env < P.num_envs;
+    asm volatile("griddepcontrol.launch_dependents;");      // the update kernel may be placed while this grid runs (see "pdl")
     float a0 = 0, a1 = 0, a2 = 0;
     int set;
     {
@@ -1232,19 +1235,24 @@ __global__ void __launch_bounds__(SCREEN_THREADS) mg_step_screen_kernel(const __
         // envs whose episode ended in a step settled here are reset by mg_step_reset_kernel, which runs next to the
         // update kernel (a reset is the longest item of a step and depends on nothing the other kernels produce)
         const bool to_reset = settled_done && P.auto_reset;
-        const int dest = route ? (route - 1) * NBINS + size_bin(n, P.cap) : (to_reset ? 2 * NBINS : -1);
+        // destinations: decide list segments (new-vertex candidates 0..3, pending rule verdicts 4..7), accept list bins
+        // (8..11), reset list (12)
+        const int bin = size_bin(n, P.cap);
+        const int dest = route == 1 ? (W.kind == WORK_DECIDE_RULE ? NBINS : 0) + bin
+                                    : (route == 2 ? DECIDE_SEGS + bin : (to_reset ? DECIDE_SEGS + NBINS : -1));
         const unsigned grp = __match_any_sync(FULL, dest);
         const int leader = __ffs(grp) - 1;
         int base = 0;
         if (dest >= 0 && lane == leader) {
-            int *ctr = dest < NBINS ? cnt + CNT_DECIDE + dest : (dest < 2 * NBINS ? cnt + CNT_ACCEPT + dest - NBINS : cnt + CNT_RESET);
+            int *ctr = dest < DECIDE_SEGS ? cnt + CNT_DECIDE + dest
+                                          : (dest < DECIDE_SEGS + NBINS ? cnt + CNT_ACCEPT + dest - DECIDE_SEGS : cnt + CNT_RESET);
             base = atomicAdd(ctr, __popc(grp));
         }
         base = __shfl_sync(FULL, base, leader);
         const int slot = base + __popc(grp & ((1u << lane) - 1));
         if (dest >= 0 && slot < P.num_envs) {
-            if (dest < NBINS) P.decide_list[(size_t)dest * P.num_envs + slot] = W;
-            else if (dest < 2 * NBINS) P.accept_list[(size_t)(dest - NBINS) * P.num_envs + slot] = W;
+            if (dest < DECIDE_SEGS) P.decide_list[(size_t)dest * P.num_envs + slot] = W;
+            else if (dest < DECIDE_SEGS + NBINS) P.accept_list[(size_t)(dest - DECIDE_SEGS) * P.num_envs + slot] = W;
             else P.reset_list[slot] = env;
         }
     }
@@ -1297,23 +1305,27 @@ __global__ void __launch_bounds__(SCREEN_THREADS) mg_step_screen_kernel(const __
 }
 
 // ---- the warp-per-item kernels ------------------------------------------------------------------
-// Item loop shared by them: the first item of a block is its block index, later ones come from a ticket counter (an
-// early finisher takes the next item).  The ticket is requested shortly before the END of the current item
-// (MG_ITEM_TICKET): its latency hides behind the item's last stores, and an item is only bound to a block when that
-// block is about to be free.  (Requested at the start of an item, every second-wave item was bound at t = 0 to an
-// arbitrary block and waited for that block's first item, however long -- profiles/r2_trace_c3_before.txt.)
+// Item loop shared by them: every item comes from a ticket counter -- also a block's first one, so that an item never
+// waits for one particular block to become resident (blocks of the reset kernel on the side stream can hold slots when
+// a grid starts: a statically assigned first item then started tens of microseconds late).  The next ticket is
+// requested shortly before the END of the current item (MG_ITEM_TICKET): its latency hides behind the item's last
+// stores, and an item is only bound to a block when that block is about to be free.  (Requested at the start of an
+// item, every second-wave item was bound at t = 0 to an arbitrary block and waited for that block's first item, however
+// long -- profiles/r2_trace_c3_before.txt.)
 #define MG_ITEM_LOOP_BEGIN(total, ticket)                                                   \
-    int t_ = blockIdx.x;                                                                    \
+    int *const ticket_ = (ticket);                                                          \
+    int t_ = 0;                                                                             \
+    if (lane == 0) t_ = atomicAdd(ticket_, 1);                                              \
+    t_ = __shfl_sync(FULL, t_, 0);                                                          \
     MG_TRACE_BLOCK                                                                          \
     if (t_ < (total)) init_mbar(L.mbar, lane);                                              \
     unsigned phase = 0;                                                                     \
-    int *const ticket_ = (ticket);                                                          \
     _Pragma("unroll 1") while (t_ < (total)) {                                              \
         int next_t_ = 0;                                                                    \
         bool have_next_ = false;
 #define MG_ITEM_TICKET                                                                      \
         if (!have_next_) {                                                                  \
-            if (lane == 0) next_t_ = gridDim.x + atomicAdd(ticket_, 1);                     \
+            if (lane == 0) next_t_ = atomicAdd(ticket_, 1);                                 \
             have_next_ = true;                                                              \
         }
 #define MG_ITEM_LOOP_END                          \
@@ -1321,10 +1333,11 @@ __global__ void __launch_bounds__(SCREEN_THREADS) mg_step_screen_kernel(const __
         t_ = __shfl_sync(FULL, next_t_, 0);       \
     }
 
-__device__ __forceinline__ int load_counts(const int *ctr, int num_envs, int (&counts)[NBINS]) {
+template <int NSEG>
+__device__ __forceinline__ int load_counts(const int *ctr, int num_envs, int (&counts)[NSEG]) {
     int total = 0;
 #pragma unroll
-    for (int b = 0; b < NBINS; b++) { counts[b] = min(ctr[b], num_envs); total += counts[b]; }
+    for (int b = 0; b < NSEG; b++) { counts[b] = min(ctr[b], num_envs); total += counts[b]; }
     return total;
 }
 
@@ -1390,7 +1403,7 @@ __device__ __forceinline__ bool decide_item(const Params &P, const StepIO &io, i
     if (flags_changed && lane == 0) P.hot[env].flags = flags;
     if (accepted) return true;
     // ---- failed step ----------------------------------------------------------------------------
-    if (lane == 0) next_t = gridDim.x + atomicAdd(ticket, 1);            // the block's next item (see MG_ITEM_TICKET)
+    if (lane == 0) next_t = atomicAdd(ticket, 1);                        // the block's next item (see MG_ITEM_TICKET)
     const int n_el = S.i(W_NEL);
     const double reward = n_el ? -1.0 / n_el : -1;                      // E:279 / E:357
     const int failed_num = S.i(W_FAILED) + 1;
@@ -1434,7 +1447,7 @@ __global__ void __launch_bounds__(32, MG_MINB_DECIDE) mg_step_decide_kernel(cons
     const int lane = threadIdx.x;
     const SmemLayout L = carve(smem_raw, P.cap, false);
     int *cnt = P.counters + CNT_SET * P.counters[CNT_CUR];
-    int counts[NBINS];
+    int counts[DECIDE_SEGS];
     const int total = load_counts(cnt + CNT_DECIDE, P.num_envs, counts);
     const Stash S{L.stash};
     MG_ITEM_LOOP_BEGIN(total, &cnt[CNT_TICKET_DECIDE])
@@ -1634,34 +1647,29 @@ __device__ __forceinline__ ApplyOut apply_element(const Params &P, Warp &w, cons
 __global__ void __launch_bounds__(32, MG_MINB_UPDATE) mg_step_update_kernel(const __grid_constant__ Params P, const __grid_constant__ StepIO io, int fused) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
+    // Programmatic dependent launches (mg_set_option "pdl"): the blocks of a step kernel are placed while its predecessor
+    // is still running -- as blocks of that grid exit -- and wait here for it to complete, instead of being launched after
+    // it; both instructions are no-ops under a plain launch.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
     const SmemLayout L = carve(smem_raw, P.cap, false);
     int *cnt = P.counters + CNT_SET * P.counters[CNT_CUR];
     // fused mode: the decide list is processed here too (a warp that accepts an element applies it with the boundary it
     // has already staged); items are taken bin by bin, accepted elements before open decisions
-    int counts_a[NBINS], counts_d[NBINS];
+    // Items are served kind by kind -- new-vertex candidates (the longest: decision + update), pending rule verdicts,
+    // accepted rule elements -- and largest first within a kind: the warps that share an SM start on the same code.
+    int counts_a[NBINS], counts_d[DECIDE_SEGS];
     const int total_a = load_counts(cnt + CNT_ACCEPT, P.num_envs, counts_a);
-    int total = total_a;
+    int total_d = 0;
 #pragma unroll
-    for (int b = 0; b < NBINS; b++) counts_d[b] = 0;
-    if (fused) total += load_counts(cnt + CNT_DECIDE, P.num_envs, counts_d);
+    for (int b = 0; b < DECIDE_SEGS; b++) counts_d[b] = 0;
+    if (fused) total_d = load_counts(cnt + CNT_DECIDE, P.num_envs, counts_d);
+    const int total = total_d + total_a;
     const Stash S{L.stash};
     MG_ITEM_LOOP_BEGIN(total, &cnt[CNT_TICKET_UPDATE])
         MG_TRACE_T0
-        WorkItem W;
-        {
-            // bin b holds counts_a[b] accept items followed by counts_d[b] decide items
-            int t = t_, bin = 0;
-            bool from_decide = false;
-#pragma unroll
-            for (int b = 0; b < NBINS; b++) {
-                if (bin == b) {
-                    if (t < counts_a[b]) { from_decide = false; }
-                    else if (t < counts_a[b] + counts_d[b]) { t -= counts_a[b]; from_decide = true; }
-                    else if (b < NBINS - 1) { t -= counts_a[b] + counts_d[b]; bin = b + 1; }
-                }
-            }
-            W = (from_decide ? P.decide_list : P.accept_list)[(size_t)bin * P.num_envs + t];
-        }
+        const WorkItem W = t_ < total_d ? fetch_item(P.decide_list, counts_d, P.num_envs, t_)
+                                        : fetch_item(P.accept_list, counts_a, P.num_envs, t_ - total_d);
         const int env = W.env;
         const size_t off = (size_t)env * P.cap;
         __syncwarp();
@@ -1759,14 +1767,14 @@ __device__ __noinline__ void reset_in_place(const Params &P, const StepIO &io, i
 #endif
 // One observe / reset item; the env's records are (re)loaded here.
 __device__ __forceinline__ void observe_item(const Params &P, const StepIO &io, int *cnt, const SmemLayout &L, const WorkItem &W, unsigned &phase,
-                                             int *ticket, int &next_t, int grid, int lane) {
+                                             int *ticket, int &next_t, int lane) {
     const Stash S{L.stash};
     const int env = W.env;
     Warp w;
     w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = 0;
     if (W.kind == WORK_RESET) {
         reset_in_place(P, io, env, w);
-        if (lane == 0) next_t = grid + atomicAdd(ticket, 1);
+        if (lane == 0) next_t = atomicAdd(ticket, 1);
         return;
     }
     const size_t off = (size_t)env * P.cap;
@@ -1785,10 +1793,11 @@ __device__ __forceinline__ void observe_item(const Params &P, const StepIO &io, 
         const ObsOut R = compute_obs(w, P.sc_full, ref_index, S.d(D_CUR_AREA) / S.d(D_ORIGINAL_AREA));
         obs = R.obs; base = R.base;
     }
-    if (lane == 0) next_t = grid + atomicAdd(ticket, 1);      // the block's next item (see MG_ITEM_TICKET)
     // An env without a reference point (empty candidate list, E:736-738) is reported truncated (sentinel)
     const bool truncated = !W.done && ref_index < 0;
     const bool done = W.done || truncated;
+    const bool reset_follows = done && P.auto_reset;
+    if (!reset_follows && lane == 0) next_t = atomicAdd(ticket, 1);      // the block's next item (see MG_ITEM_TICKET)
     if (truncated && lane == 0) {
         io.trunc_out[env] = 1;
         StatsAcc *T = P.stats + (env & (STAT_SLOTS - 1));
@@ -1804,9 +1813,10 @@ __device__ __forceinline__ void observe_item(const Params &P, const StepIO &io, 
         P.obs_cache[(size_t)env * MG_OBS_DIM + lane] = obs;
         io.obs_out[(size_t)env * MG_OBS_DIM + lane] = obs;
     }
-    if (done && P.auto_reset) {
+    if (reset_follows) {
         __syncwarp();
         reset_in_place(P, io, env, w);
+        if (lane == 0) next_t = atomicAdd(ticket, 1);
     } else {
         // the state changed: new memo (rule -1 / +1 verdicts, neighbour fan) and the rest of the record
         const int flags = done ? 0 : memo_flags(w, ref_index);
@@ -1818,6 +1828,7 @@ __global__ void __launch_bounds__(32, MG_MINB_OBSERVE) mg_step_observe_kernel(co
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
     const SmemLayout L = carve(smem_raw, P.cap, true);
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // no-op unless launched as a programmatic dependent
     const int set = P.counters[CNT_CUR];                   // written by the screen kernel of this step
     int *cnt = P.counters + CNT_SET * set;
     if (blockIdx.x == 0 && lane == 0) {                    // the other counter set is idle during this step
@@ -1831,7 +1842,7 @@ __global__ void __launch_bounds__(32, MG_MINB_OBSERVE) mg_step_observe_kernel(co
     MG_ITEM_LOOP_BEGIN(total, &cnt[CNT_TICKET_OBSERVE])
         MG_TRACE_T0
         const WorkItem W = fetch_item(P.observe_list, counts, P.num_envs, t_);
-        observe_item(P, io, cnt, L, W, phase, ticket_, next_t_, gridDim.x, lane);
+        observe_item(P, io, cnt, L, W, phase, ticket_, next_t_, lane);
         have_next_ = true;
         MG_TRACE_ITEM(2, W.kind, W.n)
     MG_ITEM_LOOP_END

@@ -454,3 +454,65 @@ def test_move_facade_like_the_data_generation_scripts():
             env.reset()
             o.reset()
     env.close()
+
+
+def test_results_do_not_depend_on_the_tuning_options():
+    """mg_set_option only changes how a step is scheduled (side-stream resets, fused decision, grid sizes): random
+    polygons with auto-reset across episode boundaries must come out bit-identical under every setting."""
+    import torch
+    N, T = 2048, 260
+    kw = dict(random_polygons=dict(min_verts=32, max_verts=96), max_verts=96, seed=31, obs_delta=False)
+    settings = [dict(), dict(reset_side=0), dict(fuse_decide=0), dict(update_blocks=3, observe_blocks=2, reset_blocks=1),
+                dict(fuse_decide=0, reset_side=0), dict(pdl=0)]
+    ref = None
+    for opts in settings:
+        env = _mk(None, N, **kw)
+        for k, v in opts.items():
+            env.set_option(k, v)
+        env.reset()
+        got = []
+        for t in range(T):
+            r = env.step(env.sample_actions(5, t))
+            got.append([x.clone() for x in (r.obs, r.reward, r.terminated, r.truncated, r.terminal_obs, r.n_elements)])
+        torch.cuda.synchronize()
+        st = env.stats()
+        assert st["episodes"] > N // 2, "the run must cross episode boundaries"
+        if ref is None:
+            ref, ref_stats = got, st
+        else:
+            for t in range(T):
+                done = (ref[t][2] | ref[t][3]).bool()
+                for i, (a, b) in enumerate(zip(ref[t], got[t])):
+                    if i == 4:                       # terminal rows are defined where the episode ended
+                        a, b = a[done], b[done]
+                    assert torch.equal(a, b), (opts, t, i)
+            for k, v in st.items():              # the two float sums are accumulated with atomics (order-dependent)
+                if isinstance(v, float):
+                    assert abs(v - ref_stats[k]) <= 1e-9 * max(1.0, abs(v)), (opts, k)
+                else:
+                    assert v == ref_stats[k], (opts, k)
+        env.close()
+
+
+def test_host_step_reads_pinned_actions_in_place():
+    """mg_step_host with a pinned action buffer (read by the screen kernel over PCIe, no staging copy) against the
+    same call with a pageable one (cudaMemcpyAsync into the staging buffer)."""
+    import torch
+    doms, _ = load_domains()
+    N, T = 1024, 40
+    envs = [_mk([doms["boundary16"], doms["test1"]], N) for _ in range(2)]
+    for e in envs:
+        e.reset()
+    rng = np.random.default_rng(3)
+    pinned = torch.empty((N, 3), dtype=torch.float32).pin_memory()
+    for t in range(T):
+        a = rng.uniform(LOW_A, HIGH_A, size=(N, 3)).astype(np.float32)
+        pinned.copy_(torch.from_numpy(a))
+        r0 = envs[0].step_host(a)
+        r1 = envs[1].step_host(pinned)
+        for k in ("obs", "reward", "terminated", "truncated", "n_elements"):
+            assert np.array_equal(r0[k], r1[k]), (t, k)
+    h2d, d2h = envs[1].last_host_bytes()
+    assert h2d == N * 12 and d2h >= N * 10
+    for e in envs:
+        e.close()
