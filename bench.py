@@ -475,8 +475,9 @@ def run_gpu(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_meas, "d2h_bytes_per_step": d2h_meas, "steps": Ke,
                     "pcie_gbs_per_rank": (h2d_meas + d2h_meas) / (e2e_ms_max * 1e-3 / Ke) / 1e9, "numa_binding": numa,
-                    "note": "mg_step_host with pinned host buffers: H2D actions; rewards, flags, element counts, changed "
-                            "observation rows and terminal rows written by the step kernels into the caller's arrays; one sync"},
+                    "note": "mg_step_host with pinned host buffers: actions read over PCIe by the screen kernel (no staging copy); "
+                            "rewards, flags, element counts, changed observation rows and terminal rows written by the step "
+                            "kernels into the caller's arrays; one sync"},
             "gpu_launches": int(launches),
             "collective": {"op": "all_reduce(sum) of mg_episode_stats (10 x int64 + 2 x float64)", "backend": "nccl" if world > 1 else "none (1 rank: device-side sum only)",
                            "every_steps": STATS_INTERVAL, "inside_timed_loop": n_reduces},
@@ -491,7 +492,9 @@ def run_gpu(args):
                          "memo_alg_bytes_per_launch": memo_bytes,
                          "memo_frac": memo_bytes / kern_s_per_launch / 1e9 / peak,
                          "per_kernel": per_kernel,
-                         "per_kernel_note": f"CUDA events around each kernel inside mg_step, {ktimes['steps']} steps after the timed region"},
+                         "per_kernel_note": f"CUDA events around each kernel inside mg_step, {ktimes['steps']} steps after the timed region "
+                                            "(plain launches; decide = 0 when fused into the update launch; mg_step_reset_kernel "
+                                            "runs on a side stream next to the update / observe kernels and is not in this list)"},
             "episode_stats": {k: (float(v) if isinstance(v, float) else int(v)) for k, v in gstats.items()},
             "mean_boundary_n": gstats["sum_n"] / max(1, gstats["steps"]),
             "success_rate": gstats["successes"] / max(1, gstats["steps"]),

@@ -50,6 +50,46 @@ class Actor(nn.Module):
         return a, logp
 
 
+class SAC:
+    """Soft actor-critic learner with the reference's settings (twin critics, polyak targets, automatic entropy
+    coefficient with target entropy -|A|); ``update`` takes one batch of the device replay buffer."""
+
+    def __init__(self, dev, gamma=0.5, lr=3e-4, tau=0.005):
+        self.gamma, self.tau = gamma, tau
+        self.actor, self.q1, self.q2 = Actor().to(dev), mlp(21, 1).to(dev), mlp(21, 1).to(dev)
+        self.q1_t, self.q2_t = copy.deepcopy(self.q1), copy.deepcopy(self.q2)
+        self.log_alpha = torch.zeros(1, device=dev, requires_grad=True)
+        self.opt_a = torch.optim.Adam(self.actor.parameters(), lr=lr)
+        self.opt_q = torch.optim.Adam(list(self.q1.parameters()) + list(self.q2.parameters()), lr=lr)
+        self.opt_al = torch.optim.Adam([self.log_alpha], lr=lr)
+        self.target_entropy = -3.0
+        self.low = torch.from_numpy(ACTION_LOW.copy()).to(dev)
+        self.high = torch.from_numpy(ACTION_HIGH.copy()).to(dev)
+
+    def update(self, b):
+        """One gradient step on critics, actor and entropy coefficient; returns (critic loss, actor loss) tensors."""
+        a_unit = (b.actions - self.low) / (self.high - self.low) * 2 - 1
+        alpha = self.log_alpha.exp().detach()
+        with torch.no_grad():
+            na, nlogp = self.actor(b.next_observations)
+            nx = torch.cat([b.next_observations, na], 1)
+            target = b.rewards + (1 - b.dones) * self.gamma * (torch.min(self.q1_t(nx), self.q2_t(nx)) - alpha * nlogp)
+        x = torch.cat([b.observations, a_unit], 1)
+        loss_q = F.mse_loss(self.q1(x), target) + F.mse_loss(self.q2(x), target)
+        self.opt_q.zero_grad(set_to_none=True); loss_q.backward(); self.opt_q.step()
+        pa, plogp = self.actor(b.observations)
+        px = torch.cat([b.observations, pa], 1)
+        loss_a = (alpha * plogp - torch.min(self.q1(px), self.q2(px))).mean()
+        self.opt_a.zero_grad(set_to_none=True); loss_a.backward(); self.opt_a.step()
+        loss_al = -(self.log_alpha * (plogp.detach() + self.target_entropy).mean())
+        self.opt_al.zero_grad(set_to_none=True); loss_al.backward(); self.opt_al.step()
+        with torch.no_grad():
+            for net, tgt in ((self.q1, self.q1_t), (self.q2, self.q2_t)):
+                for p_, tp in zip(net.parameters(), tgt.parameters()):
+                    tp.lerp_(p_, self.tau)
+        return loss_q.detach(), loss_a.detach()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--domain", default=None, help="<npz>:<key> or a reference-style domain .json file")
@@ -77,15 +117,9 @@ def main():
         env = BatchedBoudaryEnv([load_domain(args.domain)], num_envs=args.envs, device=dev)
     low, high = torch.from_numpy(ACTION_LOW.copy()).to(dev), torch.from_numpy(ACTION_HIGH.copy()).to(dev)
     to_env = lambda a: (low + (a + 1) * 0.5 * (high - low)).contiguous()
-    to_unit = lambda a: (a - low) / (high - low) * 2 - 1
 
-    actor, q1, q2 = Actor().to(dev), mlp(21, 1).to(dev), mlp(21, 1).to(dev)
-    q1_t, q2_t = copy.deepcopy(q1), copy.deepcopy(q2)
-    log_alpha = torch.zeros(1, device=dev, requires_grad=True)
-    opt_a = torch.optim.Adam(actor.parameters(), lr=args.lr)
-    opt_q = torch.optim.Adam(list(q1.parameters()) + list(q2.parameters()), lr=args.lr)
-    opt_al = torch.optim.Adam([log_alpha], lr=args.lr)
-    target_entropy = -3.0
+    learner = SAC(dev, gamma=args.gamma, lr=args.lr, tau=args.tau)
+    actor = learner.actor
 
     buf = DeviceReplayBuffer(env, args.buffer_steps)
     obs = env.reset().clone()
@@ -102,33 +136,14 @@ def main():
         obs.copy_(r.obs)
         if len(buf) >= args.learning_starts:
             for _ in range(args.updates_per_step):
-                b = buf.sample(args.batch)
-                a_unit = to_unit(b.actions)
-                alpha = log_alpha.exp().detach()
-                with torch.no_grad():
-                    na, nlogp = actor(b.next_observations)
-                    nx = torch.cat([b.next_observations, na], 1)
-                    target = b.rewards + (1 - b.dones) * args.gamma * (torch.min(q1_t(nx), q2_t(nx)) - alpha * nlogp)
-                x = torch.cat([b.observations, a_unit], 1)
-                loss_q = F.mse_loss(q1(x), target) + F.mse_loss(q2(x), target)
-                opt_q.zero_grad(set_to_none=True); loss_q.backward(); opt_q.step()
-                pa, plogp = actor(b.observations)
-                px = torch.cat([b.observations, pa], 1)
-                loss_a = (alpha * plogp - torch.min(q1(px), q2(px))).mean()
-                opt_a.zero_grad(set_to_none=True); loss_a.backward(); opt_a.step()
-                loss_al = -(log_alpha * (plogp.detach() + target_entropy).mean())
-                opt_al.zero_grad(set_to_none=True); loss_al.backward(); opt_al.step()
-                with torch.no_grad():
-                    for net, tgt in ((q1, q1_t), (q2, q2_t)):
-                        for p_, tp in zip(net.parameters(), tgt.parameters()):
-                            tp.lerp_(p_, args.tau)
+                learner.update(buf.sample(args.batch))
                 n_updates += 1
         if (t + 1) % args.log_every == 0:
             s = env.stats(reset=True)            # the only host sync of the loop
             if s["episodes"]:
                 print(f"step {t+1}: episodes {s['episodes']} completed {s['completed']} mean return "
                       f"{s['sum_return']/s['episodes']:.3f} mean elements {s['elements']/s['episodes']:.1f} "
-                      f"success rate {s['successes']/max(1, s['steps']):.3f} updates {n_updates} alpha {log_alpha.exp().item():.3f}", flush=True)
+                      f"success rate {s['successes']/max(1, s['steps']):.3f} updates {n_updates} alpha {learner.log_alpha.exp().item():.3f}", flush=True)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     print(f"{args.envs} envs x {args.steps} steps in {dt:.1f} s: {args.envs*args.steps/dt:.3e} env-steps/s with SAC in the loop "

@@ -516,3 +516,45 @@ def test_host_step_reads_pinned_actions_in_place():
     assert h2d == N * 12 and d2h >= N * 10
     for e in envs:
         e.close()
+
+
+def test_sac_learner_on_the_device_replay_buffer():
+    """examples/sac_train.py: transitions of the batched env go through mg_replay_add into the device
+    replay ring and the SAC learner fits its critics on them -- a fixed buffer, 300 gradient steps: the TD loss must fall
+    and everything must stay finite; the policy then drives the env through the same tensors (no host copy)."""
+    import importlib.util
+    import os
+    import torch
+    spec = importlib.util.spec_from_file_location(
+        "sac_train", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "sac_train.py"))
+    sac = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sac)
+    from reinforcementlearning4meshgeneration_b200.replay import DeviceReplayBuffer
+    doms, _ = load_domains()
+    env = _mk([doms["boundary16"]], 1024)
+    torch.manual_seed(0)
+    learner = sac.SAC(env.device, gamma=0.5)
+    buf = DeviceReplayBuffer(env, 32)
+    obs = env.reset().clone()
+    for t in range(32):
+        act = env.sample_actions(11, t)
+        r = env.step(act)
+        buf.add(obs, act, r)
+        obs.copy_(r.obs)
+    assert len(buf) == 32 * 1024
+    losses = []
+    for _ in range(300):
+        lq, la = learner.update(buf.sample(512))
+        losses.append(float(lq))
+        assert torch.isfinite(lq) and torch.isfinite(la)
+    first, last = np.mean(losses[:20]), np.mean(losses[-20:])
+    assert last < 0.7 * first, (first, last)
+    low = torch.from_numpy(LOW_A).to(env.device)
+    high = torch.from_numpy(HIGH_A).to(env.device)
+    with torch.no_grad():
+        for _ in range(8):
+            a = learner.actor(obs)[0]
+            r = env.step((low + (a + 1) * 0.5 * (high - low)).contiguous())
+            obs.copy_(r.obs)
+    assert torch.isfinite(r.reward).all() and torch.isfinite(r.obs).all()
+    env.close()
