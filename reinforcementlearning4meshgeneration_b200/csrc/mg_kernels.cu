@@ -1,13 +1,13 @@
 // Batched BoudaryEnv reset/step for sm_100a.
 //
-// A step is two kernels (see the block comment above mg_step_screen_kernel): a screen over all envs, one thread per
-// env, that settles every step whose outcome follows from the env's 128-byte record (memoised rule -1 / +1
-// verdicts, Mesh.is_valid of the new-vertex quad from the neighbour fan), and a ring kernel, one warp per item,
-// for the steps that need the whole boundary.  There the active boundary (updated_boundary.vertices) is staged
-// once per item from HBM into a per-warp shared-memory ring with a single 1-D bulk async copy (cp.async.bulk +
-// mbarrier, UBLKCP in SASS); every O(n) predicate then strides the ring with 32 lanes (double2 loads) and is
-// resolved with ballots / shuffle reductions.  Angle classifications use the exact-safe filters of mg_math.cuh, so
-// atan2 only runs where the quantised value itself is needed (candidate keys, observation, element quality).
+// A step is a handful of kernels (see the block comment above mg_step_screen_kernel): a screen over all envs, one thread
+// per env, that settles every step whose outcome follows from the env's 128-byte record (memoised rule -1 / +1
+// verdicts, Mesh.is_valid of the new-vertex quad from the neighbour fan), and warp-per-item kernels for the steps that
+// need the whole boundary.  There the active boundary (updated_boundary.vertices) is staged once per item from HBM
+// into a per-warp shared-memory ring with a single 1-D bulk async copy (cp.async.bulk + mbarrier, UBLKCP in SASS);
+// every O(n) predicate then strides the ring with 32 lanes (double2 loads) and is resolved with ballots / shuffle
+// reductions.  Angle classifications use the exact-safe filters of mg_math.cuh, so atan2 only runs where the quantised
+// value itself is needed (candidate keys, observation, element quality).
 //
 // Citations: E = v2/src/mesh_rl/envs/boundary_env.py, M = v2/src/mesh_rl/mesh_core.py,
 // C = v2/src/mesh_rl/components_core.py, D = v2/src/mesh_rl/data_core.py (reference tree).
@@ -1011,7 +1011,7 @@ __global__ void __launch_bounds__(32) mg_reset_kernel(const __grid_constant__ Pa
 }
 
 // ---------------------------------------------------------------------------------------------
-// One environment transition (E:388-457) + VecEnv auto-reset, as four kernels with SMALL code images.
+// One environment transition (E:388-457) + VecEnv auto-reset, as a few kernels with SMALL, HOMOGENEOUS code paths.
 //
 //   1  mg_step_screen_kernel   all envs, ONE THREAD per env.  Reads the 128-byte EnvHot record and the action and
 //      settles every step whose outcome follows from them: a rule -1 / +1 action against the memoised verdict
@@ -1020,26 +1020,29 @@ __global__ void __launch_bounds__(32) mg_reset_kernel(const __grid_constant__ Pa
 //      leaves the state untouched and returns the cached observation (verified bit-identical), so
 //      these envs never touch their boundary ring: reward, flags, counters and the 32 changed bytes of the record
 //      are all that moves.  Under a uniform random policy ~91 % of the steps end here.
-//   The other three run ONE WARP per work item over compacted lists; the boundary is staged once per item into a
+//   The others run ONE WARP per work item over compacted lists; the boundary is staged once per item into a
 //   shared-memory ring with one cp.async.bulk:
-//   2  mg_step_decide_kernel   rule-0 candidates whose new vertex still needs the whole boundary (point-in-polygon
-//      M:74-128, find_same_point E:766-769, boundary intersection M:536-556) and rule -1 / +1 actions whose verdict
-//      is still pending (valid quad, intersection test not done yet: evaluated once per state, then memoised).
-//      Failed steps end here; accepted elements go to the next list.
+//   2  mg_step_decide_kernel   (only with the option fuse_decide = 0; by default this work is the first half of kernel 3)
+//      rule-0 candidates whose new vertex still needs the whole boundary (point-in-polygon M:74-128, find_same_point
+//      E:766-769, boundary intersection M:536-556) and rule -1 / +1 actions whose verdict is still pending (valid
+//      quad, intersection test not done yet: evaluated once per state, then memoised).  Failed steps end here.
 //   3  mg_step_update_kernel   accepted elements: element log, boundary update, candidate keys, area, quality,
 //      reward, termination (M:601-674, C:943-958, C:881-892, M:355-452, E:590-607, E:345-351).
 //   4  mg_step_observe_kernel  every env whose state changed: reference point (M:295-316), next observation
-//      (C:1192-1290), new memo; and the in-place resets of finished envs (template copy or fresh random polygon).
+//      (C:1192-1290), new memo; and the in-place resets of the envs that finished inside kernel 3.
+//   5  mg_step_reset_kernel    in-place resets (template copy or fresh random polygon) of the envs kernel 1 truncated,
+//      on a side stream next to kernels 3 / 4.
 //
-// Why four launches: a warp-per-item kernel is bound by instruction fetch as soon as its image outgrows the SM's
-// instruction cache -- every warp walks its own path through the image (profiles/r2a_*: one 248 KB ring kernel
-// spent 57 % of its issue slots in stall_no_instruction; round 1's 186 KB apply kernel 25 %).  Each image here is
-// well under 100 KB on its common path.  Kernels hand items over through 32-byte work records.
+// Why several launches and why the lists are sorted by item kind: a warp-per-item kernel is bound by instruction
+// fetch as soon as the warps of an SM are at unrelated places of a large image (profiles/README.md: one 248 KB ring
+// kernel spent 57 % of its stall samples in stall_no_instruction, round 1's 186 KB apply kernel 25 %, round 2's fused
+// decide + update kernel 38 % until its list was served kind by kind).  Kernels hand items over through 32-byte work
+// records.
 //
-// Work lists are appended with one atomicAdd per warp.  Two sets of counters alternate: the screen kernel of step s
-// uses set (CNT_STEP & 1) and records it in CNT_CUR; the later kernels read CNT_CUR, and the first thread of the
-// observe kernel clears the other (idle) set and advances CNT_STEP for the next step.  The parity lives in device
-// memory, so no memset sits between launches and any sequence of mg_step calls can be captured in a CUDA graph.
+// Work lists are appended with one atomicAdd per warp and list segment.  Two sets of counters alternate: the screen
+// kernel of step s uses set (CNT_STEP & 1) and records it in CNT_CUR; the later kernels read CNT_CUR, and the first
+// thread of the observe kernel clears the other (idle) set and advances CNT_STEP for the next step.  The parity lives in
+// device memory, so no memset sits between launches and any sequence of mg_step calls can be captured in a CUDA graph.
 // ---------------------------------------------------------------------------------------------
 struct StepIO {
     const float *act;
