@@ -62,9 +62,12 @@ typedef struct {
     double dbg[8];                   /* last successful step: b_reward, e_reward, area, penalty, ... */
     /* move() (E:459-594): not_valid_points as coordinates (the reference excludes candidates within 0.001 of one of
      * them, M:428-433), static point environments (area-ratio slot of the observation = 0, C:1209-1214) */
-    double *excl; int nexcl, capexcl;
+    double *excl; int *excl_id; int nexcl, capexcl;
+    int *last_excl_id; int nlast, caplast;   /* last_not_valid_points (E:103, E:570-578): vertex identities */
     int static_obs;
-    int needs_smoothing;             /* move(): every candidate is excluded -> the reference calls smooth_pave (not restated) */
+    int needs_smoothing;             /* move(): every candidate is excluded -> the reference calls smooth_pave (M:816-821) */
+    int smooth_enabled;              /* 0: stop there and report needs_smoothing (round-1/2 tests); 1: run smooth_pave */
+    int n_smoothings;
 } OEnv;
 
 /* ---------------------------------------------------------------- rounding ------------- */
@@ -481,6 +484,7 @@ void oracle_reset(OEnv *e) {
     e->failed_num = 0;
     e->ep_return = 0; e->ep_len = 0;
     e->nexcl = 0; e->static_obs = 0; e->needs_smoothing = 0;
+    e->nlast = 0;      /* last_not_valid_points survives reset() in the reference, but holds vertex objects of the old episode */
     find_next_state(e);
     estimate_area_range(e);
 }
@@ -509,7 +513,7 @@ OEnv *oracle_create(const double *xy, int n, double original_area) {
 }
 
 void oracle_destroy(OEnv *e) {
-    if (e) free(e->excl);
+    if (e) { free(e->excl); free(e->excl_id); free(e->last_excl_id); }
     if (!e) return;
     free_pool(e);
     free(e->v); free(e->B); free(e->xy0); free(e->cand_id); free(e->cand_key); free(e->elements);
@@ -879,12 +883,300 @@ static double py_round6(double x) {
     return r / 1e6;
 }
 
-static void excl_push(OEnv *e, double x, double y) {
+static void excl_push(OEnv *e, double x, double y, int id) {
     if (e->nexcl == e->capexcl) {
         e->capexcl = e->capexcl ? 2 * e->capexcl : 32;
         e->excl = (double *)realloc(e->excl, sizeof(double) * 2 * e->capexcl);
+        e->excl_id = (int *)realloc(e->excl_id, sizeof(int) * e->capexcl);
     }
-    e->excl[2 * e->nexcl] = x; e->excl[2 * e->nexcl + 1] = y; e->nexcl++;
+    e->excl[2 * e->nexcl] = x; e->excl[2 * e->nexcl + 1] = y; e->excl_id[e->nexcl] = id; e->nexcl++;
+}
+
+/* ---------------------------------------------------------------- smooth_pave ----------
+ * M:816-821 smooth_pave(self.boundary.vertices, self.updated_boundary.vertices, iteration=400):
+ *   smooth_current_boundary_3()                      re-position every inserted vertex of the front     (M:965-1060)
+ *   smooth_fixed_vertices(interior vertices, 400)    Gauss-Seidel averaging over Vertex.segments        (M:1284-1316)
+ *   find_reference_candidates(0)                     full candidate rebuild                              (M:259-287)
+ * Vertex identity is Python object identity (no __eq__): vertex ids here.  x ** 2 is libm pow (see dist2). */
+#define DEG(x) ((x) * (180.0 / PI))          /* math.degrees: x * (180 / pi) */
+#define RAD(x) ((x) * (PI / 180.0))          /* math.radians: x * (pi / 180) */
+static double sq(double x) { return pow(x, 2.0); }
+
+/* C:123-132 get_connected_vertices: partners in the order their Segment was assigned, without duplicates */
+static int connected_vertices(const OEnv *e, int a, int *out) {
+    const OVertex *v = &e->v[a];
+    int m = 0;
+    for (int k = 0; k < v->nadj; k++) {
+        int dup = 0;
+        for (int j = 0; j < m; j++) if (out[j] == v->adj[k]) { dup = 1; break; }
+        if (!dup && v->adj[k] != a) out[m++] = v->adj[k];
+    }
+    return m;
+}
+static int max_degree(const OEnv *e) {
+    int m = 0;
+    for (int i = 0; i < e->nv; i++) if (e->v[i].nadj > m) m = e->v[i].nadj;
+    return m;
+}
+
+/* M:1106-1127 clockwise_vertices(inner_v, vertices): selection sort by clockwise angle from the previous entry, then the
+ * common neighbour of consecutive entries (other than inner_v) is spliced in.  Returns the length of `fin`. */
+static int clockwise_vertices(const OEnv *e, int inner, int *vs, int k, int *fin, int *tmp_a, int *tmp_b) {
+    P2 c = VP(e, inner);
+    for (int i = 1; i < k; i++) {
+        double max_angle = -1;
+        int flag = i;
+        for (int j = i; j < k; j++) {
+            double ang = cw_angle(c, VP(e, vs[j]), VP(e, vs[i - 1]));
+            if (ang > max_angle) { max_angle = ang; flag = j; }
+        }
+        if (flag != i) { int t = vs[i]; vs[i] = vs[flag]; vs[flag] = t; }
+    }
+    int m = 0;
+    for (int i = 0; i < k; i++) {
+        int prev = vs[(i + k - 1) % k];
+        int na = connected_vertices(e, vs[i], tmp_a), nb = connected_vertices(e, prev, tmp_b);
+        int inter = -1;
+        for (int x = 0; x < na && inter < 0; x++) {
+            if (tmp_a[x] == inner) continue;
+            for (int y = 0; y < nb; y++) if (tmp_b[y] == tmp_a[x]) { inter = tmp_a[x]; break; }
+        }
+        fin[m++] = prev;
+        if (inter >= 0) fin[m++] = inter;
+    }
+    return m;
+}
+
+/* M:1095-1104 is_inside_boundary(original_v, vertex, boundary, left_v, right_v) */
+static int is_inside_boundary(const OEnv *e, P2 orig, P2 cand, const int *bd, int m, int left, int right) {
+    for (int i = 0; i < m; i++) {
+        int a = bd[i], b = bd[(i + m - 1) % m];
+        if ((left == a || left == b) && (right == a || right == b)) continue;
+        int s1 = cw_angle(cand, VP(e, a), VP(e, b)) < PI;
+        int s2 = cw_angle(orig, VP(e, a), VP(e, b)) < PI;
+        if (s1 != s2) return 0;
+    }
+    return 1;
+}
+
+/* the candidate position keeps the vertex on the same side of every edge of its one-ring (M:984-997 and its twins) */
+static int ring_test(const OEnv *e, int vid, P2 cand, int left, int right, int *w1, int *w2, int *w3, int *w4) {
+    int k = connected_vertices(e, vid, w1);
+    int m = clockwise_vertices(e, vid, w1, k, w2, w3, w4);
+    return is_inside_boundary(e, VP(e, vid), cand, w2, m, left, right);
+}
+
+/* the two intersections of the circle |p - (a, b)| = r with the line through (a, b)-offsets used by M:856-866 / M:876-891
+ * / M:921-934: x from the quadratic (M^2 + 1) x^2 - t x + c = 0 exactly as the reference writes it */
+static void quad_roots(double M, double N, double t, double c4, double *x1, double *x2) {
+    double den = 2 * (sq(M) + 1);
+    double disc = sqrt(fabs(sq(t) - 4 * (sq(M) + 1) * c4));
+    *x1 = (t + disc) / den;
+    *x2 = (t - disc) / den;
+}
+
+/* M:832-864 middle_vertex(vertex, left_v, right_v, target_angle) */
+static P2 middle_vertex(P2 vertex, P2 left, P2 right, double target_angle) {
+    P2 m = { (left.x + right.x) / 2, (left.y + right.y) / 2 };
+    double A = right.x - left.x, B = right.y - left.y;
+    double D = pdist(left, m) / tan(RAD(target_angle / 2));
+    double x1, x2, y1, y2;
+    if (B == 0) { x1 = m.x; x2 = m.x; y1 = m.y + D; y2 = m.y - D; }
+    else if (A == 0) { x1 = m.x + D; x2 = m.x - D; y1 = m.y; y2 = m.y; }
+    else {
+        double M = -A / B;
+        double N = A * m.x / B + m.y;
+        double t = -2 * M * N + 2 * m.x + 2 * M * m.y;
+        quad_roots(M, N, t, sq(N - m.y) + sq(m.x) - sq(D), &x1, &x2);
+        y1 = M * x1 + N; y2 = M * x2 + N;
+    }
+    P2 V1 = { x1, y1 }, V2 = { x2, y2 };
+    return pdist(V1, vertex) < pdist(V2, vertex) ? V1 : V2;
+}
+
+/* shared by side_vertex (M:866-893) and indention_vertex (M:908-935): the point at distance `dist` from (a, b) whose
+ * projection on (A, B) is W; *nan_out is set when the reference would raise (math.sqrt of a negative number) */
+static void circle_line(double a, double b, double A, double B, double W, double dist, P2 *V1, P2 *V2, int *nan_out) {
+    double x1, x2, y1, y2;
+    if (B == 0) {
+        double r = sq(dist) - sq(W / A);
+        if (r < 0) *nan_out = 1;
+        x1 = W / A + a; x2 = W / A + a;
+        y1 = b + sqrt(r); y2 = b - sqrt(r);
+    } else if (A == 0) {
+        double r = sq(dist) - sq(W / B);
+        if (r < 0) *nan_out = 1;
+        x1 = a + sqrt(r); x2 = a - sqrt(r);
+        y1 = W / B + b; y2 = W / B + b;
+    } else {
+        double M = -A / B;
+        double N = (W + A * a + B * b) / B;
+        double t = 2 * M * b - 2 * M * N + 2 * a;
+        quad_roots(M, N, t, sq(N - b) + sq(a) - sq(dist), &x1, &x2);
+        y1 = M * x1 + N; y2 = M * x2 + N;
+    }
+    V1->x = x1; V1->y = y1; V2->x = x2; V2->y = y2;
+}
+/* M:866-893 side_vertex(vertex, next_v, nn_v, angle, dist) */
+static P2 side_vertex(P2 vertex, P2 next, P2 nn, double angle, double dist, int *nan_out) {
+    P2 V1, V2;
+    double W = dist * pdist(next, nn) * cos(RAD(angle));
+    circle_line(next.x, next.y, nn.x - next.x, nn.y - next.y, W, dist, &V1, &V2, nan_out);
+    return pdist(V1, vertex) < pdist(V2, vertex) ? V1 : V2;
+}
+/* M:908-935 indention_vertex(vertex, left_v, right_v, angle, dist) */
+static P2 indention_vertex(P2 vertex, P2 left, P2 right, double angle, double dist, int *nan_out) {
+    P2 V1, V2;
+    double W = dist * pdist(vertex, left) * cos(RAD(angle));
+    circle_line(vertex.x, vertex.y, left.x - vertex.x, left.y - vertex.y, W, dist, &V1, &V2, nan_out);
+    return cw_angle(V1, left, right) < cw_angle(V2, left, right) ? V1 : V2;
+}
+
+/* M:937-963 find_side_vertex(vertex, _next_v, next_v, nn_v, v_angle) */
+static P2 find_side_vertex(OEnv *e, int vid, int _next, int next, int nn, double v_angle, int *w1, int *w2, int *w3, int *w4) {
+    P2 vertex = VP(e, vid);
+    double dist = (pdist(vertex, VP(e, _next)) + pdist(vertex, VP(e, next)) + pdist(VP(e, next), VP(e, nn))) / 3;
+    double target_angle = 45;
+    P2 n_v;
+    for (;;) {
+        int bad = 0;
+        n_v = side_vertex(vertex, VP(e, next), VP(e, nn), target_angle, dist, &bad);
+        if (bad) { e->crashed = 1; return vertex; }
+        if (target_angle <= v_angle) return vertex;              /* failed */
+        if (ring_test(e, vid, n_v, _next, next, w1, w2, w3, w4)) return n_v;
+        target_angle -= 5;
+    }
+}
+
+/* M:1062-1093 find_indention_vertex(vertex, v_angle) */
+static P2 find_indention_vertex(OEnv *e, int vid, double v_angle, int *w1, int *w2, int *w3, int *w4) {
+    int index = B_index(e, vid), n = e->n;
+    int left = e->B[(index + 1) % n], right = BI(e, index - 1);
+    P2 vertex = VP(e, vid), lp = VP(e, left), rp = VP(e, right);
+    double dist = (pdist(vertex, lp) + pdist(vertex, rp)) / 2;
+    /* C:396-413 get_closet_points(..., exclusion = [B[i-2], right, left, B[i+2]], S_T = dist): only whether it is empty
+     * matters; a vertex at distance exactly S_T counts (<=) */
+    int ex[4] = { BI(e, index - 2), right, left, e->B[(index + 2) % n] };
+    int any = 0;
+    for (int i = 0; i < n && !any; i++) {
+        int id = e->B[i];
+        if (id == vid || id == ex[0] || id == ex[1] || id == ex[2] || id == ex[3]) continue;
+        if (pdist(vertex, VP(e, id)) <= dist) any = 1;
+    }
+    /* M:1129-1138 find_closest_segments(updated_boundary, vertex, dist) */
+    for (int i = 0; i < n && !any; i++) {
+        int p1 = BI(e, i - 1), p2 = e->B[i];
+        if (p1 == vid || p2 == vid) continue;
+        P2 a = VP(e, p1), b = VP(e, p2);
+        double A = b.x - a.x, B = b.y - a.y;                      /* C:642-649 perpendicular_point */
+        double s = (A * vertex.x + B * vertex.y - B * a.y - A * a.x) / (sq(A) + sq(B));
+        P2 target = { a.x + s * A, a.y + s * B };
+        if (0 <= s && s <= 1 && pdist(vertex, target) <= dist) any = 1;
+    }
+    if (!any) return vertex;
+    int times = 4;
+    for (;;) {
+        int bad = 0;
+        P2 n_v = indention_vertex(vertex, lp, rp, (360 - v_angle) / 2, dist / times, &bad);
+        if (bad) { e->crashed = 1; return vertex; }
+        if (times >= 10) return vertex;                          /* failed */
+        if (ring_test(e, vid, n_v, left, right, w1, w2, w3, w4)) return n_v;
+        times += 1;
+    }
+}
+
+/* M:895-906 inner_vertex(vertex, angle) */
+static P2 inner_vertex(const OEnv *e, int vid, double angle) {
+    int index = B_index(e, vid), n = e->n;
+    P2 left = VP(e, e->B[(index + 1) % n]), right = VP(e, BI(e, index - 1)), vertex = VP(e, vid);
+    P2 m = { (left.x + right.x) / 2, (left.y + right.y) / 2 };
+    double d = pdist(m, right) * tan(RAD(angle));
+    double A = vertex.x - m.x, B = vertex.y - m.y;
+    double s = sqrt(sq(d) / (sq(A) + sq(B)));
+    P2 r = { m.x + s * A, m.y + s * B };
+    return r;
+}
+
+/* C:475-481 Boundary2D.compute_boundary_angle */
+static double boundary_angle_deg(const OEnv *e, int index) {
+    int n = e->n;
+    index = ((index % n) + n) % n;
+    return DEG(cw_angle(BP(e, index), VP(e, e->B[(index + 1) % n]), BP(e, index - 1)));
+}
+
+/* M:965-1060 smooth_current_boundary_3 */
+static void smooth_current_boundary_3(OEnv *e) {
+    int cap = max_degree(e) + 2;
+    int *w1 = (int *)malloc(sizeof(int) * cap), *w2 = (int *)malloc(sizeof(int) * 2 * cap), *w3 = (int *)malloc(sizeof(int) * cap),
+        *w4 = (int *)malloc(sizeof(int) * cap);
+    for (int i = 0; i < e->n && !e->crashed; i++) {
+        int n = e->n, vid = e->B[i];
+        if (vid < e->n0) continue;                                /* in self.original_vertices */
+        int left = e->B[(i + 1) % n], right = BI(e, i - 1);
+        double v_angle = DEG(cw_angle(VP(e, vid), VP(e, left), VP(e, right)));
+        if (v_angle <= 90) {
+            double target_angle = v_angle >= 45 ? v_angle : 45;
+            for (;;) {
+                P2 new_v = middle_vertex(VP(e, vid), VP(e, left), VP(e, right), target_angle);
+                if (target_angle >= 135) break;                   /* failed */
+                if (ring_test(e, vid, new_v, left, right, w1, w2, w3, w4)) { e->v[vid].x = new_v.x; e->v[vid].y = new_v.y; break; }
+                target_angle += 5;
+            }
+        } else if (v_angle <= 180) {
+            double left_angle = boundary_angle_deg(e, i + 1), right_angle = boundary_angle_deg(e, i - 1);
+            P2 n_v;
+            if (right_angle < 45) n_v = find_side_vertex(e, vid, left, right, BI(e, i - 2), right_angle, w1, w2, w3, w4);
+            else if (left_angle < 45) n_v = find_side_vertex(e, vid, right, left, e->B[(i + 2) % n], left_angle, w1, w2, w3, w4);
+            else n_v = find_indention_vertex(e, vid, v_angle, w1, w2, w3, w4);
+            e->v[vid].x = n_v.x; e->v[vid].y = n_v.y;
+        } else if (v_angle <= 270) {
+            P2 n_v = find_indention_vertex(e, vid, v_angle, w1, w2, w3, w4);
+            e->v[vid].x = n_v.x; e->v[vid].y = n_v.y;
+        } else {
+            P2 n_v = inner_vertex(e, vid, 45);
+            e->v[vid].x = n_v.x; e->v[vid].y = n_v.y;
+            n_v = find_indention_vertex(e, vid, v_angle, w1, w2, w3, w4);
+            e->v[vid].x = n_v.x; e->v[vid].y = n_v.y;
+        }
+    }
+    free(w1); free(w2); free(w3); free(w4);
+}
+
+/* M:1284-1316 smooth_fixed_vertices(vertices not on the front, in self.boundary.vertices order = id order, 400) */
+static void smooth_fixed_vertices(OEnv *e, int iteration) {
+    int cap = max_degree(e) + 2;
+    int *cv = (int *)malloc(sizeof(int) * cap);
+    double sum_coordinates = 0, diffs = 100;
+    int it = 0;
+    while (diffs > 0.001 && it < iteration) {
+        it++;
+        double new_sum = 0;
+        for (int vid = 0; vid < e->nv; vid++) {
+            if (in_B(e, vid) || vid < e->n0) continue;
+            double x = 0, y = 0;
+            int count = 0;
+            int k = connected_vertices(e, vid, cv);
+            for (int q = 0; q < k; q++) {
+                x += e->v[cv[q]].x + e->v[vid].x;
+                y += e->v[cv[q]].y + e->v[vid].y;
+                count++;
+            }
+            if (count == 0) continue;
+            e->v[vid].x = x / (2 * count);
+            e->v[vid].y = y / (2 * count);
+            new_sum += e->v[vid].x + e->v[vid].y;
+        }
+        diffs = fabs(new_sum - sum_coordinates);
+        sum_coordinates = new_sum;
+    }
+    free(cv);
+}
+
+static void smooth_pave(OEnv *e) {
+    smooth_current_boundary_3(e);
+    smooth_fixed_vertices(e, 400);
+    find_reference_candidates(e);
+    e->n_smoothings++;
 }
 
 /* E:459-594 move(new_point = (r, phi) polar in units of radius * base_length, type).  Returns through the pointers:
@@ -951,17 +1243,34 @@ void oracle_move(OEnv *e, const double *polar, double type, int *done_out, int *
         }
     }
     if (not_valid_element) {
-        excl_push(e, ref.x, ref.y);       /* `reference_point not in not_valid_points`: it cannot be selected twice */
+        excl_push(e, ref.x, ref.y, rid);  /* `reference_point not in not_valid_points`: it cannot be selected twice */
         find_next_state(e);
     } else e->nexcl = 0;
     int is_complete;
     if (e->n > 4) {
         is_complete = 0;
-        if (e->obs_none) { e->needs_smoothing = 1; done = 1; }
+        if (e->obs_none) {
+            e->needs_smoothing = 1;
+            if (!e->smooth_enabled) done = 1;                 /* the caller stops here */
+            else {                                            /* E:548-583 */
+                smooth_pave(e);
+                if (e->nlast > 0 && e->nexcl > 0 && e->last_excl_id[0] == e->excl_id[0] &&
+                    e->last_excl_id[e->nlast - 1] == e->excl_id[e->nexcl - 1] && e->nexcl == e->nlast)
+                    done = 1;
+                if (e->nexcl > e->caplast) { e->caplast = e->nexcl + 16; e->last_excl_id = (int *)realloc(e->last_excl_id, sizeof(int) * e->caplast); }
+                memcpy(e->last_excl_id, e->excl_id, sizeof(int) * e->nexcl);
+                e->nlast = e->nexcl;
+                e->nexcl = 0;
+                find_next_state(e);
+                if (e->obs_none) done = 1;
+            }
+        }
     } else is_complete = 1;
     *done_out = done; *complete_out = is_complete; *smooth_out = e->needs_smoothing;
 }
 int oracle_n_excluded(const OEnv *e) { return e->nexcl; }
+void oracle_set_smoothing(OEnv *e, int enabled) { e->smooth_enabled = enabled; }
+int oracle_n_smoothings(const OEnv *e) { return e->n_smoothings; }
 
 /* ---------------------------------------------------------------- accessors ------------ */
 

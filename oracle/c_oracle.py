@@ -49,6 +49,9 @@ def lib():
         L.oracle_move.argtypes = [vp, vp, f64, vp, vp, vp]
         L.oracle_n_excluded.restype = i32
         L.oracle_n_excluded.argtypes = [vp]
+        L.oracle_set_smoothing.argtypes = [vp, i32]
+        L.oracle_n_smoothings.restype = i32
+        L.oracle_n_smoothings.argtypes = [vp]
         L.oracle_rollout.argtypes = [vp, vp, i32] + [vp] * 9
         L.oracle_run_random.restype = C.c_long
         L.oracle_run_random.argtypes = [vp, C.c_uint64, C.c_long, vp, vp, vp]
@@ -110,9 +113,18 @@ class OracleEnv:
         obs = None if lib().oracle_obs_none(self._h) else self.obs()
         return obs, r.value, bool(te.value), bool(tr.value), {"is_complete": not tr.value}
 
+    def set_smoothing(self, enabled=True):
+        """move(): run the restated smooth_pave (M:816-821) where the reference does, instead of stopping there."""
+        lib().oracle_set_smoothing(self._h, 1 if enabled else 0)
+
+    @property
+    def n_smoothings(self):
+        return lib().oracle_n_smoothings(self._h)
+
     def move(self, new_point, type):
-        """E:459-594 move((r, phi), type) -> (obs | None, 0, done, {"is_complete": ...}, needs_smoothing).  When
-        needs_smoothing is set the reference would call smooth_pave (not restated): stop comparing there."""
+        """E:459-594 move((r, phi), type) -> (obs | None, 0, done, {"is_complete": ...}, needs_smoothing).
+        needs_smoothing: the reference called smooth_pave in this move (every candidate was excluded); without
+        set_smoothing() the oracle stops there (done)."""
         p = np.ascontiguousarray(np.asarray(new_point, dtype=np.float64))
         d, c, sm = C.c_int(), C.c_int(), C.c_int()
         lib().oracle_move(self._h, _p(p), float(type), C.byref(d), C.byref(c), C.byref(sm))
