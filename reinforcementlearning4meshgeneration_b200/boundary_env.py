@@ -223,9 +223,10 @@ class BoudaryEnv(_EnvBase):
 
     def move(self, new_point, type, lr_1=None, lr_2=None):
         """E:459-594 / rl/boundary_env.py:265-432: apply the geometric move ``new_point = (r, phi)`` with element type
-        ``type``; returns ``(next_state | None, 0, done, {"is_complete": bool})``.  Where the reference would smooth the
-        mesh (every candidate on the not-valid list -> smooth_pave with lr_1 / lr_2) the episode ends instead and the info
-        dict carries ``"needs_smoothing": True``."""
+        ``type``; returns ``(next_state | None, 0, done, {"is_complete": bool})``.  Where every candidate is on the
+        not-valid list the mesh is smoothed like in the reference (smooth_pave; lr_1 / lr_2 are unused there too) and the
+        episode goes on; if that is not possible (element log overflown) the episode ends and the info dict carries
+        ``"needs_smoothing": True``."""
         r = self._batched.move(np.asarray([[float(new_point[0]), float(new_point[1])]], np.float64), np.asarray([float(type)], np.float64))
         done, complete, exhausted = bool(r["done"][0]), bool(r["is_complete"][0]), bool(r["exhausted"][0])
         self._n_elements = int(r["n_elements"][0])

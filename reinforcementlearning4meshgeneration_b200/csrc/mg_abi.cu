@@ -26,6 +26,12 @@ struct mg_env_s {
     mg_episode_stats *d_stats_out = nullptr;
     double2 *sc_tab = nullptr;      // [2][ANGLE_TAB_N] host-libm {sin, cos} of the quantised angles and their halves
     double2 *excl = nullptr;        // [num_envs][cap] not-valid points of mg_move (allocated by its first call)
+    int32_t *excl_id = nullptr, *last_excl_id = nullptr;   // their vertex ids; last_not_valid_points (E:570-578)
+    bool smooth_pave = true;        // mg_move runs smooth_pave where the reference does (mg_set_option "smooth_pave")
+    unsigned char *smooth_scratch = nullptr;
+    size_t smooth_slots = 0;
+    int32_t *smooth_list = nullptr;   // [num_envs] device list of the envs to smooth
+    uint8_t *h_flags = nullptr;       // pinned [num_envs]
     // staging buffers for mg_step_host (used for every caller buffer that is not pinned)
     float *d_act = nullptr, *d_obs = nullptr, *d_term_obs = nullptr;
     double *d_rew = nullptr;
@@ -335,7 +341,8 @@ int mg_destroy(mg_handle h) {
     cudaFree(P.obs_cache); cudaFree(P.elem); cudaFree(P.ins_xy);
     cudaFree(P.decide_list); cudaFree(P.accept_list); cudaFree(P.observe_list); cudaFree(P.counters); cudaFree(P.reset_list);
     free_templates(h);
-    cudaFree(h->sc_tab); cudaFree(h->excl);
+    cudaFree(h->sc_tab); cudaFree(h->excl); cudaFree(h->excl_id); cudaFree(h->last_excl_id); cudaFree(h->smooth_scratch);
+    cudaFree(h->smooth_list); cudaFreeHost(h->h_flags);
     cudaFree(h->d_stats_out); cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_term_obs); cudaFree(h->d_rew);
     cudaFree(h->d_term); cudaFree(h->d_trunc); cudaFree(h->d_nel);
     cudaFreeHost(h->h_cnt);
@@ -634,16 +641,51 @@ int mg_move(mg_handle h, const double *polar_dev, const double *type_dev, float 
     MG_DEVICE(h);
     if (!h->excl) {
         MG_CUDA(h, dalloc(&h->excl, (size_t)h->num_envs * h->P.cap));
+        MG_CUDA(h, dalloc(&h->excl_id, (size_t)h->num_envs * h->P.cap));
+        MG_CUDA(h, dalloc(&h->last_excl_id, (size_t)h->num_envs * h->P.cap));
+        MG_CUDA(h, dalloc(&h->smooth_list, (size_t)h->num_envs));
+        MG_CUDA(h, cudaMallocHost((void **)&h->h_flags, (size_t)h->num_envs));
         MG_CUDA(h, cudaFuncSetAttribute(mg_move_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        MG_CUDA(h, cudaFuncSetAttribute(mg_smooth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     }
+    cudaStream_t s = (cudaStream_t)stream;
     MoveIO io;
     io.polar = polar_dev; io.type = type_dev; io.obs_out = obs_dev; io.done_out = done_dev; io.complete_out = complete_dev;
     io.exhausted_out = exhausted_dev; io.n_elem_out = n_elem_dev;
-    mg_move_kernel<<<h->num_envs, 32, h->smem, (cudaStream_t)stream>>>(h->P, io, h->excl);
+    mg_move_kernel<<<h->num_envs, 32, h->smem, s>>>(h->P, io, h->excl, h->excl_id);
     h->launches++;
     MG_CUDA(h, cudaGetLastError());
     h->obs_bound = obs_dev;              // every row was written
-    note_user_stream(h, (cudaStream_t)stream);
+    note_user_stream(h, s);
+    // E:548-583: the envs whose candidates are all excluded are smoothed and go on.  Needs the list of those envs on the
+    // host (one synchronisation per call: move() is the data-generation API, not a throughput path); domain mode only.
+    if (h->smooth_pave && !h->P.random_mode) {
+        const int N = h->num_envs;
+        MG_CUDA(h, cudaMemcpyAsync(h->h_flags, exhausted_dev, (size_t)N, cudaMemcpyDeviceToHost, s));
+        MG_CUDA(h, cudaStreamSynchronize(s));
+        std::vector<int32_t> list;
+        for (int e = 0; e < N; e++)
+            if (h->h_flags[e]) list.push_back(e);
+        if (!list.empty()) {
+            const size_t per = smooth_scratch_bytes(h->P.cap, h->P.ins_cap);
+            const size_t want = list.size() < 1024 ? list.size() : 1024;          // envs per launch
+            if (h->smooth_slots < want) {
+                cudaFree(h->smooth_scratch);
+                h->smooth_scratch = nullptr; h->smooth_slots = 0;
+                MG_CUDA(h, cudaMalloc((void **)&h->smooth_scratch, per * want));
+                h->smooth_slots = want;
+            }
+            MG_CUDA(h, cudaMemcpyAsync(h->smooth_list, list.data(), sizeof(int32_t) * list.size(), cudaMemcpyHostToDevice, s));
+            for (size_t first = 0; first < list.size(); first += h->smooth_slots) {
+                const size_t cnt = list.size() - first < h->smooth_slots ? list.size() - first : h->smooth_slots;
+                mg_smooth_kernel<<<(unsigned)cnt, 32, h->smem, s>>>(h->P, io, h->smooth_list + first, h->smooth_scratch, per, h->excl_id,
+                                                                    h->last_excl_id);
+                h->launches++;
+            }
+            MG_CUDA(h, cudaGetLastError());
+            MG_CUDA(h, cudaStreamSynchronize(s));            // `list` is a host object
+        }
+    }
     return MG_OK;
 }
 
@@ -811,6 +853,8 @@ int mg_set_option(mg_handle h, const char *name, int value) {
     if (std::strcmp(name, "fuse_decide") == 0) { h->fuse_decide = value != 0; return MG_OK; }
     if (std::strcmp(name, "reset_side") == 0) { h->reset_side = value != 0; return MG_OK; }
     if (std::strcmp(name, "pdl") == 0) { h->pdl = value != 0; return MG_OK; }
+    // not a tuning switch: 0 = mg_move stops where the reference would smooth (env reported done + exhausted)
+    if (std::strcmp(name, "smooth_pave") == 0) { h->smooth_pave = value != 0; return MG_OK; }
     // resident one-warp blocks per SM of the item kernels (grid size; default = what fits, see configure_kernels)
     if (std::strcmp(name, "update_blocks") == 0 && value > 0) { h->blocks_update = value; return MG_OK; }
     if (std::strcmp(name, "observe_blocks") == 0 && value > 0) { h->blocks_observe = value; return MG_OK; }

@@ -17,6 +17,7 @@
 
 #include "mg_math.cuh"
 #include "mg_state.cuh"
+#include "mg_smooth.cuh"
 
 namespace mg {
 
@@ -1880,7 +1881,7 @@ __global__ void __launch_bounds__(32, MG_MINB_OBSERVE) mg_step_reset_kernel(cons
 // of a listed point (M:310-314, M:428-433); point environments are static (area-ratio slot of the observation = 0,
 // C:1209-1214).  One warp per env, one launch: this is not a throughput path.
 // When every candidate is excluded the reference smooths the whole mesh (smooth_pave, general/mesh.py:790-1067) and
-// goes on; that is not built: the env reports done with `exhausted` set.
+// goes on: this kernel reports such an env as done with `exhausted` set, and mg_move then runs mg_smooth_kernel on it.
 // ---------------------------------------------------------------------------------------------
 // rint(x * 1e6) / 1e6 as CPython's round(x, 6) picks it (see py_rint4)
 __device__ __forceinline__ double py_round6(double x) {
@@ -1931,7 +1932,8 @@ struct MoveIO {
     int32_t *n_elem_out;
 };
 
-__global__ void __launch_bounds__(32) mg_move_kernel(const __grid_constant__ Params P, const __grid_constant__ MoveIO io, double2 *excl_all) {
+__global__ void __launch_bounds__(32) mg_move_kernel(const __grid_constant__ Params P, const __grid_constant__ MoveIO io, double2 *excl_all,
+                                                     int32_t *excl_id_all) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
     const int env = blockIdx.x;
@@ -2003,7 +2005,10 @@ __global__ void __launch_bounds__(32) mg_move_kernel(const __grid_constant__ Par
         next_vid += new_vertex ? 1 : 0;
         stamp_ctr -= 4;
     } else {
-        if (lane == 0 && nexcl < P.cap) excl[nexcl] = make_double2(ref.x, ref.y);       // E:538-540
+        if (lane == 0 && nexcl < P.cap) {                                               // E:538-540
+            excl[nexcl] = make_double2(ref.x, ref.y);
+            excl_id_all[off + nexcl] = P.vid[off + idx];                                // the vertex itself (E:570-576 compares identities)
+        }
         nexcl++;
     }
     __syncwarp();
@@ -2029,6 +2034,108 @@ __global__ void __launch_bounds__(32) mg_move_kernel(const __grid_constant__ Par
         P.cold[env].pad[0] = nexcl;
     }
     finish(obs, done, w.n <= 4, exhausted);
+}
+
+// The rest of move() for the envs mg_move_kernel reported as exhausted (E:548-583): smooth_pave (mg_smooth.cuh), the
+// last_not_valid_points rule, an empty not-valid list, the next state.  One warp per listed env; domain mode only (the
+// original polygon comes from the domain template).  An env this kernel cannot smooth (log overflow, a vertex with more
+// than SM_MAXDEG segments, a construction on which the reference raises) keeps its exhausted / done flags.
+__global__ void __launch_bounds__(32) mg_smooth_kernel(const __grid_constant__ Params P, const __grid_constant__ MoveIO io, const int32_t *env_list,
+                                                       unsigned char *scratch_all, size_t scratch_bytes, int32_t *excl_id_all,
+                                                       int32_t *last_id_all) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    const int env = env_list[blockIdx.x];
+    const SmemLayout L = carve(smem_raw, P.cap, true);
+    const Stash S{L.stash};
+    const size_t off = (size_t)env * P.cap;
+    stash_records(P, L.stash, env, lane);
+    __syncwarp();
+    const int n = S.i(W_N), n0 = S.i(W_N0), nv = S.i(W_NEXT_VID), n_elements = S.i(W_NEL);
+    const int domain = reinterpret_cast<const int32_t *>(L.stash)[41];     // EnvCold::domain
+    int nexcl = reinterpret_cast<const int32_t *>(L.stash)[43], nlast = reinterpret_cast<const int32_t *>(L.stash)[44];   // pad[0], pad[1]
+    int failed = 0;
+    if (lane == 0) {
+        SmoothScratch M;
+        const size_t V = (size_t)P.cap + P.ins_cap;
+        unsigned char *base = scratch_all + (size_t)blockIdx.x * scratch_bytes;
+        M.pool = reinterpret_cast<double2 *>(base);
+        M.deg = reinterpret_cast<int *>(base + V * 16);
+        M.adj = M.deg + V;
+        M.front = M.adj + V * SM_MAXDEG;
+        M.onfront = reinterpret_cast<uint8_t *>(M.front + P.cap);
+        M.n = n; M.n0 = n0; M.nv = nv; M.failed = false;
+        if (P.random_mode || nv - n0 > P.ins_cap || n_elements > P.elem_cap || P.elem == nullptr || P.ins_xy == nullptr || n < 5) M.failed = true;
+        if (!M.failed) {
+            // vertex pool: the episode's original polygon (never moved) + the inserted vertices at their current positions
+            for (int id = 0; id < n0; id++) M.pool[id] = P.t_xy[(size_t)domain * P.cap + id];
+            for (int id = n0; id < nv; id++) M.pool[id] = P.ins_xy[(size_t)env * P.ins_cap + id - n0];
+            for (int id = 0; id < nv; id++) { M.deg[id] = 0; M.onfront[id] = 0; }
+            // Segments in the reference's creation order: Boundary2D.deep_copy (C:221-228), then Mesh.connect_vertices of
+            // every element (C:840-845)
+            for (int i = 0; i < n0; i++) sm_connect(M, (i + n0 - 1) % n0, i);
+            for (int e = 0; e < n_elements && !M.failed; e++) {
+                const int32_t *q = P.elem + ((size_t)env * P.elem_cap + e) * 4;
+                for (int i = 0; i < 4; i++) {
+                    const int a = q[i], b = q[(i + 3) & 3];
+                    if (a < 0 || a >= nv || b < 0 || b >= nv) { M.failed = true; break; }
+                    if (!sm_has(M, a, b)) sm_connect(M, a, b);
+                }
+            }
+            for (int i = 0; i < n; i++) {
+                const int id = P.vid[off + i];
+                M.front[i] = id;
+                if (id < 0 || id >= nv) M.failed = true; else M.onfront[id] = 1;
+            }
+        }
+        if (!M.failed) sm_smooth_front(M);
+        if (!M.failed) sm_smooth_interior(M, 400);
+        if (!M.failed) {
+            for (int i = 0; i < n; i++) P.xy[off + i] = M.pool[M.front[i]];
+            for (int id = n0; id < nv; id++) P.ins_xy[(size_t)env * P.ins_cap + id - n0] = M.pool[id];
+        }
+        failed = M.failed ? 1 : 0;
+        __threadfence_block();
+    }
+    failed = __shfl_sync(FULL, failed, 0);
+    if (failed) return;                                     // exhausted / done stay set
+    // ---- find_reference_candidates(0), the last_not_valid_points rule, the next state (E:570-583) ----------------------
+    Warp w;
+    w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = n;
+    for (int j = lane; j < n; j += 32) w.ring[j] = P.xy[off + j];
+    __syncwarp();
+    rebuild_candidates(w, P.key + off, P.stamp + off);
+    __syncwarp();
+    __threadfence_block();
+    bool done = false;
+    const int32_t *cur = excl_id_all + off;
+    int32_t *last = last_id_all + off;
+    const int ne = nexcl < P.cap ? nexcl : P.cap, nl = nlast < P.cap ? nlast : P.cap;
+    if (nl > 0 && ne > 0 && last[0] == cur[0] && last[nl - 1] == cur[ne - 1] && nexcl == nlast) done = true;
+    __syncwarp();
+    for (int j = lane; j < ne; j += 32) last[j] = cur[j];
+    nlast = nexcl;
+    nexcl = 0;
+    const int ref_index = find_reference_index(w, P.key + off, P.stamp + off);
+    float obs = 0.0f, obs_cache = 0.0f;
+    double base = S.d(D_BASE);
+    if (ref_index >= 0) {
+        const ObsOut R = compute_obs(w, P.sc_full, ref_index, S.d(D_CUR_AREA) / S.d(D_ORIGINAL_AREA));
+        obs_cache = R.obs; base = R.base;
+        obs = lane == 1 ? 0.0f : R.obs;                      // static point environment
+    } else done = true;                                      // E:582-583
+    if (lane < MG_OBS_DIM) {
+        P.obs_cache[(size_t)env * MG_OBS_DIM + lane] = obs_cache;
+        io.obs_out[(size_t)env * MG_OBS_DIM + lane] = obs;
+    }
+    const int flags = done ? 0 : memo_flags(w, ref_index);
+    store_hot(P.hot + env, w, ref_index, n_elements, flags, base, S.i(W_FAILED), S.i(W_EP_LEN), S.d(D_EP_RETURN), S.d(D_CUR_AREA));
+    if (lane == 0) {
+        P.cold[env].stamp_ctr = 0;
+        P.cold[env].pad[0] = nexcl;
+        P.cold[env].pad[1] = nlast;
+        io.done_out[env] = done; io.complete_out[env] = 0; io.exhausted_out[env] = 0;
+    }
 }
 
 // Uniform actions in Box([-1,-1.5,0],[1,1.5,1.5]) -- the synthetic policy of the benchmarks.

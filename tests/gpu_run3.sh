@@ -1,1 +1,1 @@
-timeout 1500 bash tests/ab_variants.sh et ur8 etur8 2>&1 | tail -5
+timeout 900 python -m pytest tests/test_gpu_parity_r2.py -m gpu -x -q -k "move" 2>&1 | tail -30

@@ -390,7 +390,8 @@ def test_move_against_golden_trace_and_oracle(name):
     """BoudaryEnv.move() (E:459-594) on the CUDA env -- env 0 replays the golden trace recorded from the live
     reference, the other envs fresh action streams checked against the C oracle: observation (static point environment)
     bit-exact, done / is_complete / element count / boundary ids and coordinates / reference index exact, up to the step
-    where the reference would call smooth_pave (reported as `exhausted`; not built), after which the env is reset."""
+    where the reference would call smooth_pave (option smooth_pave = 0: reported as `exhausted`, the way these traces were
+    recorded), after which the env is reset.  The smoothing itself: test_move_with_smooth_pave_*."""
     import os
     import torch
     from helpers import GOLDEN
@@ -400,6 +401,7 @@ def test_move_against_golden_trace_and_oracle(name):
     T = min(len(tr["type"]), 600)
     N = 4
     env = _mk([tr["xy0"]], N, auto_reset=False)
+    env.set_option("smooth_pave", 0)
     env.reset()
     rng = np.random.default_rng(17)
     pol = np.stack([np.stack([rng.uniform(0.05, 0.5, T), rng.uniform(0.2, 2.9, T)], axis=1) for _ in range(N)], axis=1)   # [T, N, 2]
@@ -442,12 +444,13 @@ def test_move_facade_like_the_data_generation_scripts():
     env = BoudaryEnv(tr["xy0"])
     env.reset()
     o = OracleEnv(tr["xy0"], original_area=float(tr["original_area"]))
+    o.set_smoothing(True)
     rng = np.random.default_rng(4)
     for t in range(200):
         p, ty = [float(rng.uniform(0.05, 0.5)), float(rng.uniform(0.2, 2.9))], float(rng.choice([0.1, 0.5, 0.9], p=[0.15, 0.7, 0.15]))
         state, reward, done, info = env.move(p, round(ty, 2))
         oo, _, od, oinfo, osm = o.move(p, round(ty, 2))
-        assert reward == 0 and done == od and info["is_complete"] == oinfo["is_complete"] and info.get("needs_smoothing", False) == osm
+        assert reward == 0 and done == od and info["is_complete"] == oinfo["is_complete"] and not info.get("needs_smoothing", False)
         assert (state is None) == (oo is None) and (state is None or np.array_equal(state, oo))
         assert len(env.generated_meshes) == o.n_elements
         if done:
@@ -557,4 +560,77 @@ def test_sac_learner_on_the_device_replay_buffer():
             r = env.step((low + (a + 1) * 0.5 * (high - low)).contiguous())
             obs.copy_(r.obs)
     assert torch.isfinite(r.reward).all() and torch.isfinite(r.obs).all()
+    env.close()
+
+
+SMOOTH_TOL = 1e-9      # smoothed coordinates: device libm vs glibc (tan / cos / sqrt / atan2 of non-quantised arguments)
+
+
+def _check_move_state(env, e, oracle, where):
+    """front ids exact, front + interior coordinates within SMOOTH_TOL, element log exact"""
+    s = env.get_state(e)
+    ids, xy = oracle.boundary()
+    assert s["n"] == oracle.n and np.array_equal(s["ids"], ids), f"{where}: front ids differ"
+    assert np.max(np.abs(s["xy"] - xy)) <= SMOOTH_TOL, f"{where}: front coordinates differ by {np.max(np.abs(s['xy'] - xy)):.3e}"
+    quads, vxy, _ = env.get_elements(e)
+    ovx = oracle.vertex_xy()
+    assert len(quads) == oracle.n_elements and vxy.shape == ovx.shape, f"{where}: mesh sizes differ"
+    assert np.max(np.abs(vxy - ovx)) <= SMOOTH_TOL, f"{where}: vertex coordinates differ by {np.max(np.abs(vxy - ovx)):.3e}"
+
+
+@pytest.mark.parametrize("name", ["boundary0", "tool", "bird"])
+def test_move_with_smooth_pave_against_golden_trace_and_oracle(name):
+    """SURVEY 8f-4, second half: where every reference candidate is on the not-valid list the reference smooths the whole
+    mesh (smooth_pave, M:816-1140 / M:1284-1316) and goes on.  Env 0 replays the golden trace recorded from the live
+    reference WITH its smoothing (oracle/sweep_smooth_vs_reference.py --record), the other envs fresh move streams checked
+    against the C oracle (pinned on the same reference runs, bit-equal coordinates).  Contract: flags, element counts,
+    front ids, reference index and the 4-decimal observations exact; coordinates of every vertex within 1e-9."""
+    import os
+    import torch
+    from helpers import GOLDEN
+    from oracle.c_oracle import OracleEnv
+    z = np.load(os.path.join(GOLDEN, f"smooth_{name}.npz"))
+    tr = {k: z[k] for k in z.files}
+    T = len(tr["type"])
+    N = 6
+    env = _mk([tr["xy0"]], N, auto_reset=False, log_capacity=1024)
+    env.reset()
+    rng = np.random.default_rng(23)
+    pol = np.stack([np.stack([rng.uniform(0.05, 0.5, T), rng.uniform(0.2, 2.9, T)], axis=1) for _ in range(N)], axis=1)   # [T, N, 2]
+    typ = np.stack([rng.choice([0.1, 0.5, 0.9], size=T, p=[0.15, 0.7, 0.15]) for _ in range(N)], axis=1)
+    pol[:, 0], typ[:, 0] = tr["polar"][:T], tr["type"][:T]
+    oracles = [OracleEnv(tr["xy0"], original_area=float(tr["original_area"])) for _ in range(N)]
+    for o in oracles:
+        o.set_smoothing(True)
+    n_smooth = 0
+    for t in range(T):
+        r = env.move(pol[t], typ[t])
+        obs, done, comp, exh, nel = (r[k].cpu().numpy() for k in ("obs", "done", "is_complete", "exhausted", "n_elements"))
+        reset_mask = np.zeros(N, np.uint8)
+        for e in range(N):
+            oo, _, od, oinfo, osm = oracles[e].move(pol[t, e], typ[t, e])
+            where = f"{name} t={t} env={e} (smoothing {osm})"
+            assert not exh[e], f"{where}: the kernel could not smooth"
+            assert bool(done[e]) == od and bool(comp[e]) == oinfo["is_complete"], f"{where}: flags differ"
+            assert np.array_equal(obs[e], np.zeros(18, np.float32) if oo is None else oo), f"{where}: observation differs"
+            assert int(nel[e]) == oracles[e].n_elements
+            n_smooth += osm
+            if e == 0:
+                assert bool(tr["smooth"][t]) == osm and bool(tr["done"][t]) == od and int(tr["n_elements"][t]) == int(nel[0])
+                assert np.array_equal(obs[0], tr["obs"][t])
+                nv = int(tr["n_vertices"][t])
+                _, vxy, _ = env.get_elements(0)
+                assert vxy.shape[0] == nv and np.max(np.abs(vxy - tr["vertex_xy"][t, :nv])) <= SMOOTH_TOL, f"{where}: golden vertex coordinates"
+                s0 = env.get_state(0)
+                assert s0["ids"].tolist() == tr["boundary_ids"][t, :s0["n"]].tolist() and s0["n"] == int(tr["n_boundary"][t])
+            if osm or od or t % 5 == 0:
+                _check_move_state(env, e, oracles[e], where)
+                if oo is not None:
+                    assert env.get_state(e)["ref_index"] == oracles[e].ref_index
+            if od:
+                reset_mask[e] = 1
+                oracles[e].reset()
+        if reset_mask.any():
+            env.reset(torch.from_numpy(reset_mask))
+    assert n_smooth >= 5
     env.close()
