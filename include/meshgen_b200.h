@@ -146,14 +146,17 @@ int mg_step(mg_handle h, const float *act_dev, float *obs_dev, double *rew_dev, 
  *   obs_dev       out num_envs*18 float32 next observation of a STATIC point environment (area-ratio slot 0, C:1209-1214);
  *                                         zeros where the reference returns None
  *   done_dev / complete_dev out uint8     done and info["is_complete"] as the reference returns them (reward is always 0)
- *   exhausted_dev out uint8               every reference candidate is on the not-valid list: the reference would smooth the
- *                                         whole mesh here (smooth_pave, general/mesh.py:790-1067) and go on; that is NOT built,
- *                                         the env reports done.  Reset it before the next move.
+ *   exhausted_dev out uint8               every reference candidate was on the not-valid list and the mesh could NOT be
+ *                                         smoothed (see below): the env reports done.  Reset it before the next move.
  *   n_elem_dev    out num_envs int32      len(generated_meshes) (may be NULL)
  * A failed move puts the reference point on the env's not-valid list (cleared by the next accepted element or by
  * mg_reset), and the next reference point is the first candidate not within 0.001 of a listed point (M:310-314,
  * M:428-433).  mg_step does not look at that list (in the reference, step() after failed move()s would): reset between
- * the two APIs.  Entering with n <= 5 raises in the reference (unbound is_complete); here: done, complete iff n <= 4. */
+ * the two APIs.  Entering with n <= 5 raises in the reference (unbound is_complete); here: done, complete iff n <= 4.
+ * When every candidate is on the list the reference smooths the whole mesh (smooth_pave, general/mesh.py:790-1067,
+ * 1258-1288) and goes on (E:548-583): so does mg_move (domain mode), on the envs the move kernel reports -- it reads their
+ * flags, i.e. synchronises `stream` once per call.  Smoothed coordinates agree with the reference to <= 1e-9 (device libm
+ * vs glibc), every discrete outcome exactly.  mg_set_option("smooth_pave", 0) turns it off. */
 int mg_move(mg_handle h, const double *polar_dev, const double *type_dev, float *obs_dev, uint8_t *done_dev, uint8_t *complete_dev,
             uint8_t *exhausted_dev, int32_t *n_elem_dev, void *stream);
 
@@ -247,7 +250,8 @@ int64_t mg_snapshot_bytes(mg_handle h);
 int mg_snapshot_save(mg_handle h, void *blob_dev, void *stream);
 int mg_snapshot_load(mg_handle h, const void *blob_dev, int64_t blob_bytes, void *stream);
 
-/* Tuning switches (results never depend on them).  "fuse_decide" (default 1): the decide and update work of a step
+/* Switches.  "smooth_pave" (default 1) is behaviour: 0 = mg_move stops where the reference would smooth.  The others are
+ * tuning switches (results never depend on them).  "fuse_decide" (default 1): the decide and update work of a step
  * share one launch -- a warp that accepts an element applies it with the boundary it has already staged; 0 = two
  * launches with smaller code images.  "reset_side" (default 1): the in-place resets of the envs a step truncated run
  * in their own kernel on a side stream next to the update kernel (0: in the caller's stream, before the observe

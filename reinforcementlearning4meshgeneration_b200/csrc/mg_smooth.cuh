@@ -12,7 +12,7 @@
 //
 // Tolerance contract: tan / cos / sqrt / atan2 of non-quantised arguments come from the device
 // libm here and from glibc in the reference, and the reference's x ** 2 (libm pow) is x * x here: smoothed coordinates
-// agree to <= 1e-9 (observed ~1e-15); every discrete outcome (which construction a vertex gets, accepted or not,
+// agree to <= 1e-9 (observed <= 8.2e-13 over 589 smoothings); every discrete outcome (which construction a vertex gets, accepted or not,
 // iteration counts, done flags, element counts, next reference point) is compared exactly, as are the 4-decimal
 // observations that follow.
 #pragma once

@@ -634,3 +634,46 @@ def test_move_with_smooth_pave_against_golden_trace_and_oracle(name):
             env.reset(torch.from_numpy(reset_mask))
     assert n_smooth >= 5
     env.close()
+
+
+def test_move_with_smooth_pave_on_more_domains_and_coordinate_agreement():
+    """Differential run of move() + smooth_pave over six more reference domains (8 envs x 250 moves each, fresh streams)
+    against the oracle; also reports how far the smoothed coordinates are from the reference's (device libm vs glibc)."""
+    import torch
+    from oracle.c_oracle import OracleEnv
+    doms, areas = load_domains()
+    rng = np.random.default_rng(41)
+    worst, n_smooth = 0.0, 0
+    for name in ["star", "half_wheel", "dolphine3", "easy1_1", "boundary16", "test1"]:
+        xy = doms[name]
+        N, T = 8, 250
+        env = _mk([xy], N, auto_reset=False, log_capacity=2048)
+        env.reset()
+        oracles = [OracleEnv(xy, original_area=float(areas[name])) for _ in range(N)]
+        for o in oracles:
+            o.set_smoothing(True)
+        for t in range(T):
+            pol = np.stack([rng.uniform(0.05, 0.5, N), rng.uniform(0.2, 2.9, N)], axis=1)
+            typ = rng.choice([0.1, 0.5, 0.9], size=N, p=[0.15, 0.7, 0.15])
+            r = env.move(pol, typ)
+            obs, done, comp, exh, nel = (r[k].cpu().numpy() for k in ("obs", "done", "is_complete", "exhausted", "n_elements"))
+            reset_mask = np.zeros(N, np.uint8)
+            for e in range(N):
+                oo, _, od, oinfo, osm = oracles[e].move(pol[e], typ[e])
+                where = f"{name} t={t} env={e} (smoothing {osm})"
+                assert not exh[e] and bool(done[e]) == od and bool(comp[e]) == oinfo["is_complete"], f"{where}: flags differ"
+                assert np.array_equal(obs[e], np.zeros(18, np.float32) if oo is None else oo), f"{where}: observation differs"
+                assert int(nel[e]) == oracles[e].n_elements
+                if osm:
+                    n_smooth += 1
+                    _check_move_state(env, e, oracles[e], where)
+                    _, vxy, _ = env.get_elements(e)
+                    worst = max(worst, float(np.max(np.abs(vxy - oracles[e].vertex_xy()))))
+                if od:
+                    reset_mask[e] = 1
+                    oracles[e].reset()
+            if reset_mask.any():
+                env.reset(torch.from_numpy(reset_mask))
+        env.close()
+    print(f"smooth_pave: {n_smooth} smoothings, largest coordinate deviation from the oracle {worst:.3e}")
+    assert n_smooth >= 20 and worst <= SMOOTH_TOL
