@@ -154,7 +154,7 @@ int mg_step(mg_handle h, const float *act_dev, float *obs_dev, double *rew_dev, 
  * M:428-433).  mg_step does not look at that list (in the reference, step() after failed move()s would): reset between
  * the two APIs.  Entering with n <= 5 raises in the reference (unbound is_complete); here: done, complete iff n <= 4.
  * When every candidate is on the list the reference smooths the whole mesh (smooth_pave, general/mesh.py:790-1067,
- * 1258-1288) and goes on (E:548-583): so does mg_move (domain mode), on the envs the move kernel reports -- it reads their
+ * 1258-1288) and goes on (E:548-583): so does mg_move, on the envs the move kernel reports -- it reads their
  * flags, i.e. synchronises `stream` once per call.  Smoothed coordinates agree with the reference to <= 1e-9 (device libm
  * vs glibc), every discrete outcome exactly.  mg_set_option("smooth_pave", 0) turns it off. */
 int mg_move(mg_handle h, const double *polar_dev, const double *type_dev, float *obs_dev, uint8_t *done_dev, uint8_t *complete_dev,

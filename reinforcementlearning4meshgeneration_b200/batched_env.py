@@ -176,9 +176,8 @@ class BatchedBoudaryEnv:
         """``BoudaryEnv.move`` (E:459-594) for every env: ``polar`` float64 [N,2] = (r, phi), ``type`` float64 [N].
         Returns device tensors: obs (static point environment), done, is_complete, exhausted, n_elements.  Reward is always
         0.  Where every reference candidate is on the not-valid list the mesh is smoothed and the episode goes on like in
-        the reference (smooth_pave, M:816-821; domain mode; one host synchronisation per call); ``exhausted`` marks an env
-        that needed it and could not get it (random-polygon mode, ``set_option("smooth_pave", 0)``, an overflown element
-        log): such an env is reported done."""
+        the reference (smooth_pave, M:816-821; one host synchronisation per call); ``exhausted`` marks an env
+        that needed it and could not get it (``set_option("smooth_pave", 0)``, an overflown element log): such an env is reported done."""
         polar = torch.as_tensor(polar, dtype=torch.float64).to(self.device).contiguous().reshape(self.num_envs, 2)
         type = torch.as_tensor(type, dtype=torch.float64).to(self.device).contiguous().reshape(self.num_envs)
         if not hasattr(self, "_move_flags"):

@@ -658,8 +658,8 @@ int mg_move(mg_handle h, const double *polar_dev, const double *type_dev, float 
     h->obs_bound = obs_dev;              // every row was written
     note_user_stream(h, s);
     // E:548-583: the envs whose candidates are all excluded are smoothed and go on.  Needs the list of those envs on the
-    // host (one synchronisation per call: move() is the data-generation API, not a throughput path); domain mode only.
-    if (h->smooth_pave && !h->P.random_mode) {
+    // host (one synchronisation per call: move() is the data-generation API, not a throughput path).
+    if (h->smooth_pave) {
         const int N = h->num_envs;
         MG_CUDA(h, cudaMemcpyAsync(h->h_flags, exhausted_dev, (size_t)N, cudaMemcpyDeviceToHost, s));
         MG_CUDA(h, cudaStreamSynchronize(s));

@@ -2037,8 +2037,7 @@ __global__ void __launch_bounds__(32) mg_move_kernel(const __grid_constant__ Par
 }
 
 // The rest of move() for the envs mg_move_kernel reported as exhausted (E:548-583): smooth_pave (mg_smooth.cuh), the
-// last_not_valid_points rule, an empty not-valid list, the next state.  One warp per listed env; domain mode only (the
-// original polygon comes from the domain template).  An env this kernel cannot smooth (log overflow, a vertex with more
+// last_not_valid_points rule, an empty not-valid list, the next state.  One warp per listed env.  An env this kernel cannot smooth (log overflow, a vertex with more
 // than SM_MAXDEG segments, a construction on which the reference raises) keeps its exhausted / done flags.
 __global__ void __launch_bounds__(32) mg_smooth_kernel(const __grid_constant__ Params P, const __grid_constant__ MoveIO io, const int32_t *env_list,
                                                        unsigned char *scratch_all, size_t scratch_bytes, int32_t *excl_id_all,
@@ -2055,6 +2054,15 @@ __global__ void __launch_bounds__(32) mg_smooth_kernel(const __grid_constant__ P
     const int domain = reinterpret_cast<const int32_t *>(L.stash)[41];     // EnvCold::domain
     int nexcl = reinterpret_cast<const int32_t *>(L.stash)[43], nlast = reinterpret_cast<const int32_t *>(L.stash)[44];   // pad[0], pad[1]
     int failed = 0;
+    // random-polygon mode: the episode's original polygon is not stored -- regenerate it from the generator's counter
+    // (as mg_get_elements does) into the warp's ring; lane 0 copies it into the vertex pool below
+    int n_gen = n0;
+    if (P.random_mode) {
+        Warp g;
+        g.ring = L.ring; g.queue = L.queue; g.lane = lane; g.n = 0;
+        n_gen = generate_polygon(P, g, P.env_id_offset + env, reinterpret_cast<const int32_t *>(L.stash)[42]);   // EnvCold::episode
+        __syncwarp();
+    }
     if (lane == 0) {
         SmoothScratch M;
         const size_t V = (size_t)P.cap + P.ins_cap;
@@ -2065,10 +2073,10 @@ __global__ void __launch_bounds__(32) mg_smooth_kernel(const __grid_constant__ P
         M.front = M.adj + V * SM_MAXDEG;
         M.onfront = reinterpret_cast<uint8_t *>(M.front + P.cap);
         M.n = n; M.n0 = n0; M.nv = nv; M.failed = false;
-        if (P.random_mode || nv - n0 > P.ins_cap || n_elements > P.elem_cap || P.elem == nullptr || P.ins_xy == nullptr || n < 5) M.failed = true;
+        if (n_gen != n0 || nv - n0 > P.ins_cap || n_elements > P.elem_cap || P.elem == nullptr || P.ins_xy == nullptr || n < 5) M.failed = true;
         if (!M.failed) {
             // vertex pool: the episode's original polygon (never moved) + the inserted vertices at their current positions
-            for (int id = 0; id < n0; id++) M.pool[id] = P.t_xy[(size_t)domain * P.cap + id];
+            for (int id = 0; id < n0; id++) M.pool[id] = P.random_mode ? L.ring[id] : P.t_xy[(size_t)domain * P.cap + id];
             for (int id = n0; id < nv; id++) M.pool[id] = P.ins_xy[(size_t)env * P.ins_cap + id - n0];
             for (int id = 0; id < nv; id++) { M.deg[id] = 0; M.onfront[id] = 0; }
             // Segments in the reference's creation order: Boundary2D.deep_copy (C:221-228), then Mesh.connect_vertices of

@@ -677,3 +677,41 @@ def test_move_with_smooth_pave_on_more_domains_and_coordinate_agreement():
         env.close()
     print(f"smooth_pave: {n_smooth} smoothings, largest coordinate deviation from the oracle {worst:.3e}")
     assert n_smooth >= 20 and worst <= SMOOTH_TOL
+
+
+def test_move_with_smooth_pave_on_random_polygons():
+    """move() + smooth_pave in random-polygon mode: the original polygon of an episode is not stored there, the smoothing
+    kernel regenerates it from the generator's counter.  Polygons read back from the device, replayed through the oracle."""
+    import torch
+    from oracle.c_oracle import OracleEnv
+    N, T = 8, 220
+    env = _mk(None, N, random_polygons=dict(min_verts=32, max_verts=96), max_verts=96, seed=77, auto_reset=False, log_capacity=1024)
+    env.reset()
+    polys = [env.debug_polygon(e) for e in range(N)]
+    oracles = [OracleEnv(p["xy"], original_area=p["original_area"]) for p in polys]
+    for o in oracles:
+        o.set_smoothing(True)
+    rng = np.random.default_rng(5)
+    n_smooth = 0
+    for t in range(T):
+        pol = np.stack([rng.uniform(0.05, 0.5, N), rng.uniform(0.2, 2.9, N)], axis=1)
+        typ = rng.choice([0.1, 0.5, 0.9], size=N, p=[0.15, 0.7, 0.15])
+        r = env.move(pol, typ)
+        obs, done, comp, exh, nel = (r[k].cpu().numpy() for k in ("obs", "done", "is_complete", "exhausted", "n_elements"))
+        reset_mask = np.zeros(N, np.uint8)
+        for e in range(N):
+            oo, _, od, oinfo, osm = oracles[e].move(pol[e], typ[e])
+            where = f"random polygon t={t} env={e} (smoothing {osm})"
+            assert not exh[e] and bool(done[e]) == od and bool(comp[e]) == oinfo["is_complete"], f"{where}: flags differ"
+            assert np.array_equal(obs[e], np.zeros(18, np.float32) if oo is None else oo), f"{where}: observation differs"
+            assert int(nel[e]) == oracles[e].n_elements
+            if osm:
+                n_smooth += 1
+                _check_move_state(env, e, oracles[e], where)
+            if od:
+                reset_mask[e] = 1
+                oracles[e].reset()
+        if reset_mask.any():
+            env.reset(torch.from_numpy(reset_mask))
+    assert n_smooth >= 3
+    env.close()
