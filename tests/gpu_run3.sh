@@ -1,1 +1,1 @@
-timeout 900 python -m pytest tests -m gpu -x -q -k "move" 2>&1 | tail -12
+timeout 1500 bash tests/ab_variants.sh af af 2>&1 | tail -4
