@@ -245,7 +245,8 @@ int mg_replay_add(mg_handle h, int64_t capacity_steps, int64_t slot, float *buf_
  * mg_snapshot_bytes(h) bytes of DEVICE memory owned by the caller; copies are enqueued on `stream`.  A blob can be
  * loaded into any handle created with the same num_envs / max_verts and the same domains or generator settings; the header of the blob
  * records num_envs, max_verts, mode, log capacities, domain count, generator seed and env id offset, and
- * mg_snapshot_load rejects a blob that disagrees with the handle or is shorter than mg_snapshot_bytes. */
+ * mg_snapshot_load rejects a blob that disagrees with the handle or is shorter than mg_snapshot_bytes.  The not-valid
+ * lists of mg_move are not part of a snapshot (take it at an episode boundary or after an accepted move). */
 int64_t mg_snapshot_bytes(mg_handle h);
 int mg_snapshot_save(mg_handle h, void *blob_dev, void *stream);
 int mg_snapshot_load(mg_handle h, const void *blob_dev, int64_t blob_bytes, void *stream);
