@@ -1,15 +1,17 @@
 /*
  * TEST INFRASTRUCTURE ONLY.  CPU restatement (plain C, scalar, sequential) of the reference
- * BoudaryEnv reset/step path.  It exists so that the CUDA product path can be checked on a
+ * BoudaryEnv reset / step / move path, smooth_pave included.  It exists so that the CUDA product path can be checked on a
  * machine where the Python reference is absent (the GPU box), and as the "port" CPU baseline
  * of bench.py.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
  * reference legs may load this library; the product package never does.
  *
  * Parity pin: this file is validated bit-for-bit (obs, flags, element counts, boundary vertex
  * ids + coordinates, candidate list; rewards exactly equal) against the *live* reference env
- * (v2/src/mesh_rl/envs/boundary_env.py) by tests/test_oracle_vs_reference.py whenever
- * /root/reference is present, and against the golden traces in tests/golden/ (recorded from the
- * reference by oracle/record_golden.py) everywhere else.  The reference ships no golden vectors
+ * (v2/src/mesh_rl/envs/boundary_env.py) by tests/test_oracle_vs_live_reference_cpu.py and the live halves of
+ * tests/test_oracle_move_cpu.py whenever /root/reference is present (and by oracle/sweep_vs_reference.py,
+ * sweep_move_vs_reference.py, sweep_smooth_vs_reference.py run by hand), and against the golden traces in
+ * tests/golden/ (recorded from the reference by oracle/record_golden.py and the sweep scripts' --record)
+ * everywhere else.  The reference ships no golden vectors
  * of its own for this path.
  *
  * It deliberately keeps the reference's *data-structure semantics* (Python list with index 0,
