@@ -1864,6 +1864,7 @@ __global__ void __launch_bounds__(32, MG_MINB_OBSERVE) mg_step_reset_kernel(cons
     const int total = min(cnt[CNT_RESET], P.num_envs);
     MG_ITEM_LOOP_BEGIN(total, &cnt[CNT_TICKET_RESET])
         MG_TRACE_T0
+        (void)phase;                                   // no ring is staged here
         const int env = P.reset_list[t_];
         Warp w;
         w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = 0;
