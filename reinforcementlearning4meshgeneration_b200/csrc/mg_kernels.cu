@@ -1323,7 +1323,7 @@ __global__ void __launch_bounds__(SCREEN_THREADS) mg_step_screen_kernel(const __
     t_ = __shfl_sync(FULL, t_, 0);                                                          \
     MG_TRACE_BLOCK                                                                          \
     if (t_ < (total)) init_mbar(L.mbar, lane);                                              \
-    unsigned phase = 0;                                                                     \
+    [[maybe_unused]] unsigned phase = 0;                                                    \
     _Pragma("unroll 1") while (t_ < (total)) {                                              \
         int next_t_ = 0;                                                                    \
         bool have_next_ = false;
@@ -1864,7 +1864,6 @@ __global__ void __launch_bounds__(32, MG_MINB_OBSERVE) mg_step_reset_kernel(cons
     const int total = min(cnt[CNT_RESET], P.num_envs);
     MG_ITEM_LOOP_BEGIN(total, &cnt[CNT_TICKET_RESET])
         MG_TRACE_T0
-        (void)phase;                                   // no ring is staged here
         const int env = P.reset_list[t_];
         Warp w;
         w.ring = L.ring; w.queue = L.queue; w.lane = lane; w.n = 0;
