@@ -175,7 +175,10 @@ int mg_step_host(mg_handle h, const float *act_host, float *obs_host, double *re
  * observation, so with enabled != 0 mg_step / mg_step_host write only the observation rows that changed (accepted
  * element or reset) when they are handed the SAME obs buffer as the previous call (or the preceding mg_reset) --
  * the caller promises not to modify that buffer in between.  A different pointer, mg_reset without an obs buffer or
- * mg_snapshot_load fall back to one full write.  Off by default.  mg_set_host_delta is the round-1 name. */
+ * mg_snapshot_load fall back to one full write.  Off by default.  mg_set_host_delta is the round-1 name.
+ * mg_step_host extends the same promise to PINNED reward / flag / element-count arrays: a value crosses PCIe only where it
+ * differs from what the caller's array already holds (a failed step mostly repeats the env's previous reward, flags and
+ * count), so do not modify those arrays between calls either -- read them, or copy them. */
 int mg_set_obs_delta(mg_handle h, int enabled);
 int mg_set_host_delta(mg_handle h, int enabled);
 

@@ -191,8 +191,9 @@ class BatchedBoudaryEnv:
     def step_host(self, actions: np.ndarray, out: Optional[dict] = None) -> dict:
         """Same transition through host (numpy / pinned) buffers: H2D + step + D2H + sync inside the
         library (mg_step_host) -- the path a numpy-facing caller such as SB3 pays.  With pinned ``out`` buffers
-        (torch ``.pin_memory()``) the GPU writes the results straight into them (only the observation rows that
-        changed when ``obs_delta`` is on: keep passing the same, unmodified ``out['obs']``)."""
+        (torch ``.pin_memory()``) the GPU writes the results straight into them -- with ``obs_delta`` on only the
+        observation rows, rewards, flags and element counts that differ from what the buffers already hold: keep passing
+        the same ``out`` buffers and do not modify them in place."""
         is_t = isinstance(actions, torch.Tensor)
         if is_t:
             if actions.dtype != torch.float32 or not actions.is_contiguous() or actions.device.type != "cpu":

@@ -45,6 +45,8 @@ struct mg_env_s {
     // observation (written in full by mg_reset or by the previous mg_step with the same pointer)
     bool obs_delta = false;
     const float *obs_bound = nullptr;
+    const void *res_bound[4] = {nullptr, nullptr, nullptr, nullptr};   // result delta: the caller arrays the shadows mirror
+    bool acct_res_delta = false;
     int64_t last_h2d = 0, last_d2h = 0;
     bool acct_valid = false, acct_obs_rows_delta = false, acct_n_elem = false;
     int acct_term_obs = 0;             // 0 none, 1 pinned (finished rows only), 2 staged (all rows)
@@ -574,6 +576,7 @@ int mg_step(mg_handle h, const float *act_dev, float *obs_dev, double *rew_dev, 
     StepIO io;
     io.act = act_dev; io.obs_out = obs_dev; io.rew_out = rew_dev; io.term_out = term_dev; io.trunc_out = trunc_dev;
     io.term_obs_out = term_obs_dev; io.n_elem_out = n_elem_dev;
+    io.rew_sh = nullptr; io.term_sh = nullptr; io.trunc_sh = nullptr; io.nel_sh = nullptr; io.res_full = 1;
     io.obs_full = (h->obs_delta && h->obs_bound == obs_dev) ? 0 : 1;
     const int rc = launch_step(h, io, (cudaStream_t)stream);
     if (rc != MG_OK) return rc;
@@ -614,9 +617,20 @@ int mg_step_host(mg_handle h, const float *act_host, float *obs_host, double *re
     io.term_obs_out = term_obs_host ? (tobs_a ? tobs_a : h->d_term_obs) : nullptr;
     io.n_elem_out = n_elem_host ? (nel_a ? nel_a : h->d_nel) : nullptr;
     io.obs_full = (h->obs_delta && h->obs_bound == io.obs_out) ? 0 : 1;
+    // Result delta: with pinned reward / flag / count arrays in delta mode the kernels write a value over PCIe only where it
+    // differs from what the caller's array already holds (the handle's staging buffers keep a device copy of that).
+    io.rew_sh = nullptr; io.term_sh = nullptr; io.trunc_sh = nullptr; io.nel_sh = nullptr; io.res_full = 1;
+    const bool res_delta = h->obs_delta && rew_a && term_a && trunc_a && (!n_elem_host || nel_a);
+    if (res_delta) {
+        io.rew_sh = h->d_rew; io.term_sh = h->d_term; io.trunc_sh = h->d_trunc; io.nel_sh = n_elem_host ? h->d_nel : nullptr;
+        io.res_full = (h->res_bound[0] == rew_a && h->res_bound[1] == term_a && h->res_bound[2] == trunc_a && h->res_bound[3] == nel_a) ? 0 : 1;
+    }
     const int rc = launch_step(h, io, s);
     if (rc != MG_OK) return rc;
     h->obs_bound = io.obs_out;
+    h->res_bound[0] = res_delta ? rew_a : nullptr; h->res_bound[1] = res_delta ? term_a : nullptr;
+    h->res_bound[2] = res_delta ? trunc_a : nullptr; h->res_bound[3] = res_delta ? nel_a : nullptr;
+    h->acct_res_delta = res_delta && !io.res_full;
     if (!obs_a) MG_CUDA(h, cudaMemcpyAsync(obs_host, h->d_obs, N * MG_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (!rew_a) MG_CUDA(h, cudaMemcpyAsync(rew_host, h->d_rew, N * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (!term_a) MG_CUDA(h, cudaMemcpyAsync(term_host, h->d_term, N, cudaMemcpyDeviceToHost, s));
@@ -693,6 +707,7 @@ int mg_set_obs_delta(mg_handle h, int enabled) {
     if (!h) return fail(h, MG_ERR_ARG, "mg_set_obs_delta: null handle");
     h->obs_delta = enabled != 0;
     h->obs_bound = nullptr;
+    for (auto &b : h->res_bound) b = nullptr;
     return MG_OK;
 }
 
@@ -708,7 +723,8 @@ int mg_last_host_bytes(mg_handle h, int64_t *h2d, int64_t *d2h) {
         MG_CUDA(h, cudaMemcpy(h->h_cnt, h->P.counters, CNT_N * sizeof(int32_t), cudaMemcpyDeviceToHost));
         const int64_t N = h->num_envs, row = sizeof(float) * MG_OBS_DIM;
         const int32_t *c = h->h_cnt + CNT_SET * (h->h_cnt[CNT_CUR] & 1);
-        int64_t bytes = N * (sizeof(double) + 2) + (h->acct_n_elem ? N * (int64_t)sizeof(int32_t) : 0);
+        int64_t bytes = h->acct_res_delta ? (int64_t)c[CNT_RESBYTES]
+                                          : N * (int64_t)(sizeof(double) + 2) + (h->acct_n_elem ? N * (int64_t)sizeof(int32_t) : 0);
         bytes += h->acct_obs_rows_delta ? (int64_t)(c[CNT_OBSERVE] + c[CNT_OBSERVE + 1] + c[CNT_OBSERVE + 2] + c[CNT_OBSERVE + 3] + c[CNT_RESET]) * row : N * row;
         if (h->acct_term_obs) bytes += h->acct_term_obs == 1 ? (int64_t)c[CNT_DONE] * row : N * row;
         h->last_h2d = N * 3 * (int64_t)sizeof(float);

@@ -1055,7 +1055,39 @@ struct StepIO {
     int32_t *n_elem_out;
     int obs_full;     // 1: every row of obs_out is written.  0: obs_out still holds the previous step's observations
                       // (same unmodified buffer, mg_set_obs_delta): only the rows that change are written
+    // Result delta (mg_step_host with pinned result buffers in delta mode): device-resident copies of what the caller's
+    // reward / flag / element-count arrays hold.  A value is written to the caller's array -- a posted PCIe write --
+    // only when it differs from that copy (a failed step mostly repeats the env's previous reward, flags and count:
+    // ~85 % of the result writes of a step); res_full = 1 writes everything once (new buffers).  All nullptr otherwise.
+    double *rew_sh;
+    uint8_t *term_sh, *trunc_sh;
+    int32_t *nel_sh;
+    int res_full;
 };
+
+// reward, flags and element count of one env to the caller's arrays (see StepIO::rew_sh); returns the bytes written in
+// delta mode (0 otherwise: every env's 10 or 14 bytes are then accounted on the host)
+__device__ __forceinline__ int emit_results(const StepIO &io, int env, double reward, bool term, bool trunc, int n_elements) {
+    if (io.rew_sh == nullptr) {
+        io.rew_out[env] = reward;
+        io.term_out[env] = term;
+        io.trunc_out[env] = trunc;
+        if (io.n_elem_out) io.n_elem_out[env] = n_elements;
+        return 0;
+    }
+    const bool full = io.res_full != 0;
+    const double r0 = io.rew_sh[env];
+    const uint8_t t0 = io.term_sh[env], u0 = io.trunc_sh[env];
+    int bytes = 0;
+    if (full || __double_as_longlong(r0) != __double_as_longlong(reward)) { io.rew_out[env] = reward; io.rew_sh[env] = reward; bytes += 8; }
+    if (full || t0 != (uint8_t)term) { io.term_out[env] = term; io.term_sh[env] = term; bytes += 1; }
+    if (full || u0 != (uint8_t)trunc) { io.trunc_out[env] = trunc; io.trunc_sh[env] = trunc; bytes += 1; }
+    if (io.n_elem_out) {
+        const int32_t n0 = io.nel_sh[env];
+        if (full || n0 != n_elements) { io.n_elem_out[env] = n_elements; io.nel_sh[env] = n_elements; bytes += 4; }
+    }
+    return bytes;
+}
 
 // |x * 1e4 - (k + 0.5)| < tol for some integer k: np_round4(x) could flip under a perturbation of x
 __device__ __forceinline__ bool near_round4_tie(double x, double tol) {
@@ -1172,6 +1204,7 @@ __global__ void __launch_bounds__(SCREEN_THREADS) mg_step_screen_kernel(const __
     int n = 0, n_elements = 0, ep_len = 0;
     double ep_return = 0;
     uint8_t copy_code = 0;
+    int res_bytes = 0;
     if (active) {
         const int4 c0 = rec_chunk(0), c1 = rec_chunk(1), c2 = rec_chunk(2);
         n = c0.x;
@@ -1223,10 +1256,7 @@ __global__ void __launch_bounds__(SCREEN_THREADS) mg_step_screen_kernel(const __
             ep_return += reward;
             ep_len++;
             settled_done = done;
-            io.rew_out[env] = reward;
-            io.term_out[env] = term_flag;
-            io.trunc_out[env] = trunc_flag;
-            if (io.n_elem_out) io.n_elem_out[env] = n_elements;
+            res_bytes = emit_results(io, env, reward, term_flag, trunc_flag, n_elements);
             int4 *dst = reinterpret_cast<int4 *>(P.hot + env);
             dst[1] = make_int4(c1.x, c1.y, failed_num, ep_len);
             dst[2] = make_int4(__double2loint(ep_return), __double2hiint(ep_return), c2.z, c2.w);
@@ -1268,6 +1298,10 @@ __global__ void __launch_bounds__(SCREEN_THREADS) mg_step_screen_kernel(const __
         StatsAcc *T = P.stats + ((blockIdx.x * (SCREEN_THREADS / 32) + (threadIdx.x >> 5)) & (STAT_SLOTS - 1));
         const unsigned rm = __ballot_sync(FULL, route != 0);
         const unsigned ring_n = __reduce_add_sync(FULL, route != 0 ? (unsigned)n : 0u);
+        if (io.rew_sh != nullptr) {
+            const int wb = __reduce_add_sync(FULL, res_bytes);
+            if (lane == 0 && wb) atomicAdd(&cnt[CNT_RESBYTES], wb);
+        }
         if (lane == 0 && steps) {
             atomicAdd(&T->steps, (unsigned long long)steps);
             atomicAdd(&T->sum_n, (unsigned long long)sum_n);
@@ -1415,10 +1449,8 @@ __device__ __forceinline__ bool decide_item(const Params &P, const StepIO &io, i
     const double ep_return = S.d(D_EP_RETURN) + reward;
     const int ep_len = S.i(W_EP_LEN) + 1;
     if (lane == 0) {
-        io.rew_out[env] = reward;
-        io.term_out[env] = 0;
-        io.trunc_out[env] = done;
-        if (io.n_elem_out) io.n_elem_out[env] = n_el;
+        const int wb = emit_results(io, env, reward, false, done, n_el);
+        if (wb) atomicAdd(&cnt[CNT_RESBYTES], wb);
         int4 *dst = reinterpret_cast<int4 *>(P.hot + env);
         const int4 c1 = S.p[1], c2 = S.p[2];
         dst[1] = make_int4(c1.x, c1.y, failed_num, ep_len);
@@ -1733,10 +1765,8 @@ __global__ void __launch_bounds__(32, MG_MINB_UPDATE) mg_step_update_kernel(cons
                 atomicAdd(&T->sum_return, ep_return);
                 atomicAdd(&T->sum_length, (double)ep_len);
             }
-            io.rew_out[env] = reward;
-            io.term_out[env] = done;
-            io.trunc_out[env] = 0;
-            if (io.n_elem_out) io.n_elem_out[env] = n_elements;
+            const int wb = emit_results(io, env, reward, done, false, n_elements);
+            if (wb) atomicAdd(&cnt[CNT_RESBYTES], wb);
             // the part of the records this kernel owns (reference index, base length, flags and fan follow in observe)
             int4 *dst = reinterpret_cast<int4 *>(P.hot + env);
             const int4 c1 = S.p[1];
@@ -1804,6 +1834,7 @@ __device__ __forceinline__ void observe_item(const Params &P, const StepIO &io, 
     if (!reset_follows && lane == 0) next_t = atomicAdd(ticket, 1);      // the block's next item (see MG_ITEM_TICKET)
     if (truncated && lane == 0) {
         io.trunc_out[env] = 1;
+        if (io.trunc_sh) { io.trunc_sh[env] = 1; atomicAdd(&cnt[CNT_RESBYTES], 1); }
         StatsAcc *T = P.stats + (env & (STAT_SLOTS - 1));
         atomicAdd(&cnt[CNT_DONE], 1);
         atomicAdd(&T->episodes, 1ull);

@@ -101,7 +101,8 @@ constexpr int DECIDE_SEGS = 2 * NBINS;
 // alternate so that no memset sits between the launches of a step and any sequence of steps can be captured in a CUDA
 // graph.
 enum { CNT_DECIDE = 0, CNT_ACCEPT = 8, CNT_OBSERVE = 12, CNT_DONE = 16, CNT_TICKET_DECIDE = 17, CNT_TICKET_UPDATE = 18,
-       CNT_TICKET_OBSERVE = 19, CNT_RESET = 20, CNT_TICKET_RESET = 21, CNT_SET = 24, CNT_STEP = 48, CNT_CUR = 49, CNT_N = 56 };
+       CNT_TICKET_OBSERVE = 19, CNT_RESET = 20, CNT_TICKET_RESET = 21, CNT_RESBYTES = 22 /* result bytes written in delta mode */,
+       CNT_SET = 24, CNT_STEP = 48, CNT_CUR = 49, CNT_N = 56 };
 
 constexpr int ANGLE_TAB_N = 62833;      // round(2 pi, 4) = 6.2832
 
