@@ -41,6 +41,7 @@ ENVS_PER_GPU = {"c3": 65536, "c4": 131072, "c2": 4096, "c1": 4096}
 GEN = dict(min_verts=64, max_verts=512)
 SEED = 2026
 STATS_INTERVAL = 64
+GRAPH_STEPS = 4          # steps per CUDA-graph launch in the timed loop (divides STATS_INTERVAL)
 WORKLOAD_TEXT = {
     "c3": "c3: random star polygons 64..512 vertices, in-kernel auto-reset",
     "c4": "c4: random star polygons 64..512 vertices, in-kernel auto-reset, 131072 envs per GPU",
@@ -336,42 +337,86 @@ def run_gpu(args):
     for _ in range(args.burn_in):
         env.step(env.sample_actions(SEED, step_idx))
         step_idx += 1
-    for _ in range(args.warmup):
-        env.step(env.sample_actions(SEED, step_idx))
-        step_idx += 1
+    # The launches of a step (policy kernel + the kernels of mg_step) are replayed from CUDA graphs -- GRAPH_STEPS steps
+    # per launch, single steps for the remainder -- when the state is larger than L2 (no flush between steps): mg_step
+    # keeps no step state on the host, and the policy's step index lives in device memory (mg_sample_actions_seq).
+    use_graph = not need_flush and not args.no_graph
+    K = args.steps
+    graphs, launches_per_step = {}, 0
+    if use_graph:
+        step_ctr = torch.tensor([step_idx, 0], dtype=torch.int64, device=dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                        # (torch's capture recipe: first use of the path on a side stream)
+            env.step(env.sample_actions(SEED, step_ctr))
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        for n in (1, GRAPH_STEPS):
+            g = torch.cuda.CUDAGraph()
+            l0 = env.launch_count
+            with torch.cuda.graph(g):
+                for _ in range(n):
+                    env.step(env.sample_actions(SEED, step_ctr))
+            launches_per_step = (env.launch_count - l0) // n
+            graphs[n] = g
+
+    def run_steps(k0, k1, record=None):
+        """Steps k0..k1-1 of a loop; returns the statistics all-reduces it enqueued (every STATS_INTERVAL steps)."""
+        nonlocal step_idx
+        reduces, k = 0, k0
+        while k < k1:
+            if use_graph:
+                n = GRAPH_STEPS if (k1 - k >= GRAPH_STEPS and k % STATS_INTERVAL + GRAPH_STEPS <= STATS_INTERVAL) else 1
+                graphs[n].replay()
+            else:
+                n = 1
+                if need_flush:
+                    flush_buf.fill_(k & 0xFF)               # evict the env state from L2 (not timed)
+                record[k][0].record()
+                a = env.sample_actions(SEED, step_idx)
+                record[k][1].record()
+                env.step(a)
+            k += n
+            step_idx += n
+            if k % STATS_INTERVAL == 0:                     # SURVEY 8d C4: the job's one collective, inside the timed loop
+                allreduce_stats_device(env.stats_async(stats_dev))
+                reduces += 1
+            if not use_graph:
+                record[k - 1][2].record()
+        return reduces
+
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(max(K, args.warmup))]
+    run_steps(0, args.warmup, ev)
     if world > 1:                                            # warm the collective up (communicator set-up is not a step)
         allreduce_stats_device(env.stats_async(stats_dev))
     env.stats(reset=True)
     launches0 = env.launch_count
 
-    K = args.steps
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(K)]
-    n_reduces = 0
     barrier()
     t_wall0 = time.perf_counter()
-    for k in range(K):
-        if need_flush:
-            flush_buf.fill_(k & 0xFF)                       # evict the env state from L2 (not timed)
-        ev[k][0].record()
-        a = env.sample_actions(SEED, step_idx)
-        ev[k][1].record()
-        env.step(a)
-        if (k + 1) % STATS_INTERVAL == 0:                   # the job's one collective, inside the timed loop
-            allreduce_stats_device(env.stats_async(stats_dev))
-            n_reduces += 1
-        ev[k][2].record()
-        step_idx += 1
+    if use_graph:
+        ev[0][0].record()
+    n_reduces = run_steps(0, K, ev)
+    if use_graph:
+        ev[0][2].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    if need_flush:
-        total_ms = sum(e[0].elapsed_time(e[2]) for e in ev)
+    if use_graph:
+        total_ms = ev[0][0].elapsed_time(ev[0][2])
+        kern_ms = total_ms                                   # (includes the policy kernel: no events inside a graph)
+        launches = K * launches_per_step + n_reduces           # + mg_stats_kernel per reduce
+        step_idx = int(step_ctr[0].item())
     else:
-        total_ms = ev[0][0].elapsed_time(ev[-1][2])
-    kern_ms = sum(e[1].elapsed_time(e[2]) for e in ev)      # mg_step (+ the statistics reduce on its steps) only
+        if need_flush:
+            total_ms = sum(e[0].elapsed_time(e[2]) for e in ev[:K])
+        else:
+            total_ms = ev[0][0].elapsed_time(ev[K - 1][2])
+        kern_ms = sum(e[1].elapsed_time(e[2]) for e in ev[:K])   # mg_step (+ the statistics reduce on its steps) only
+        launches = env.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
-    launches = env.launch_count - launches0
     stats = env.stats(reset=True)
+    graphs.clear()
 
     # ---- per-kernel device times (CUDA events inside mg_step, a separate short pass on the same steady state) ----
     env.set_kernel_timing(True)
@@ -479,6 +524,10 @@ def run_gpu(args):
                             "rewards, flags, element counts, changed observation rows and terminal rows written by the step "
                             "kernels into the caller's arrays; one sync"},
             "gpu_launches": int(launches),
+            "launch_mode": ({"cuda_graph": True, "steps_per_graph": GRAPH_STEPS, "kernels_per_step": launches_per_step,
+                             "note": "policy kernel + the kernels of mg_step replayed from CUDA graphs (mg_step keeps no host state; "
+                                     "the policy's step index lives in device memory); --no-graph launches them one by one"}
+                            if use_graph else {"cuda_graph": False}),
             "collective": {"op": "all_reduce(sum) of mg_episode_stats (10 x int64 + 2 x float64)", "backend": "nccl" if world > 1 else "none (1 rank: device-side sum only)",
                            "every_steps": STATS_INTERVAL, "inside_timed_loop": n_reduces},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -547,6 +596,7 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's BASELINE size)")
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every step kernel eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-python-reference", action="store_true", help="skip the Python reference even when its tree is importable")
     ap.add_argument("--python-ref-seconds", type=float, default=10.0)
     ap.add_argument("--burn-in", type=int, default=1500, help="untimed setup steps that de-synchronise the episodes")

@@ -189,6 +189,10 @@ int mg_last_host_bytes(mg_handle h, int64_t *h2d, int64_t *d2h);
 /* Uniform actions in the action box (E:78-80) from the handle's Philox stream -- the synthetic
  * policy used by the benchmarks.  act_dev: out num_envs*3 float32. */
 int mg_sample_actions(mg_handle h, uint64_t seed, uint64_t step_index, float *act_dev, void *stream);
+/* The same with the step index in device memory: step_counter_dev[0] = the index this launch uses, advanced by one when
+ * the launch is done (step_counter_dev[1] is scratch, zero it once), so that policy + mg_step can be captured in a CUDA
+ * graph once and replayed -- every replay draws the next step's actions. */
+int mg_sample_actions_seq(mg_handle h, uint64_t seed, uint64_t *step_counter_dev, float *act_dev, void *stream);
 
 /* Parity/debug read-back of env `env` (synchronises). */
 int mg_get_state(mg_handle h, int env, mg_state_view *view);

@@ -21,7 +21,7 @@ NVCC_FLAGS = [
 
 SYMBOLS = [
     "mg_create", "mg_set_domains", "mg_set_random", "mg_set_auto_reset", "mg_reset", "mg_step", "mg_move", "mg_step_host",
-    "mg_set_obs_delta", "mg_set_host_delta", "mg_last_host_bytes", "mg_sample_actions", "mg_get_state", "mg_get_elements", "mg_debug_polygon",
+    "mg_set_obs_delta", "mg_set_host_delta", "mg_last_host_bytes", "mg_sample_actions", "mg_sample_actions_seq", "mg_get_state", "mg_get_elements", "mg_debug_polygon",
     "mg_stats", "mg_stats_async", "mg_set_log_capacity", "mg_log_capacity", "mg_replay_add", "mg_snapshot_bytes",
     "mg_snapshot_save", "mg_snapshot_load", "mg_set_option", "mg_set_kernel_timing", "mg_kernel_times", "mg_num_envs", "mg_max_verts",
     "mg_launch_count", "mg_destroy", "mg_last_error", "mg_version",
@@ -90,6 +90,7 @@ def load():
     L.mg_set_host_delta.argtypes = [vp, i32]
     L.mg_last_host_bytes.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.mg_sample_actions.argtypes = [vp, u64, u64, vp, vp]
+    L.mg_sample_actions_seq.argtypes = [vp, u64, vp, vp, vp]
     L.mg_get_state.argtypes = [vp, i32, C.POINTER(StateView)]
     L.mg_get_elements.argtypes = [vp, i32, vp, i32, C.POINTER(C.c_int32), vp, i32, C.POINTER(C.c_int32)]
     L.mg_debug_polygon.argtypes = [vp, i32, i32, vp, i32, C.POINTER(C.c_int32), C.POINTER(C.c_double), vp, C.POINTER(C.c_int32),

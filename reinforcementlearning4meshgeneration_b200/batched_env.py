@@ -244,11 +244,18 @@ class BatchedBoudaryEnv:
         check(self._L.mg_last_host_bytes(self._h, C.byref(h2d), C.byref(d2h)), self._h, "mg_last_host_bytes")
         return h2d.value, d2h.value
 
-    def sample_actions(self, seed: int, step_index: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Uniform actions in the action box from the library's Philox stream (synthetic policy)."""
+    def sample_actions(self, seed: int, step_index, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Uniform actions in the action box from the library's Philox stream (synthetic policy).  ``step_index``: an
+        int, or a device tensor of two int64 -- [0] the step index, advanced by the launch itself, [1] scratch (zero) --
+        for loops that are captured in a CUDA graph (mg_sample_actions_seq)."""
         out = self._act if out is None else out
-        check(self._L.mg_sample_actions(self._h, int(seed), int(step_index), C.c_void_p(out.data_ptr()), self._stream()),
-              self._h, "mg_sample_actions")
+        if isinstance(step_index, torch.Tensor):
+            assert step_index.dtype == torch.int64 and step_index.numel() >= 2 and step_index.device == self.device
+            check(self._L.mg_sample_actions_seq(self._h, int(seed), C.c_void_p(step_index.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                self._stream()), self._h, "mg_sample_actions_seq")
+        else:
+            check(self._L.mg_sample_actions(self._h, int(seed), int(step_index), C.c_void_p(out.data_ptr()), self._stream()),
+                  self._h, "mg_sample_actions")
         return out
 
     # ------------------------------------------------------------------

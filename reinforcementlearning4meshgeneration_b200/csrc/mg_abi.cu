@@ -740,7 +740,17 @@ int mg_sample_actions(mg_handle h, uint64_t seed, uint64_t step_index, float *ac
     if (!h || !act_dev) return fail(h, MG_ERR_ARG, "mg_sample_actions: null pointer");
     MG_DEVICE(h);
     mg_sample_actions_kernel<<<(h->num_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->num_envs, seed, step_index,
-                                                                                         h->P.env_id_offset, act_dev);
+                                                                                         h->P.env_id_offset, act_dev, nullptr);
+    h->launches++;
+    MG_CUDA(h, cudaGetLastError());
+    return MG_OK;
+}
+
+int mg_sample_actions_seq(mg_handle h, uint64_t seed, uint64_t *step_counter_dev, float *act_dev, void *stream) {
+    if (!h || !act_dev || !step_counter_dev) return fail(h, MG_ERR_ARG, "mg_sample_actions_seq: null pointer");
+    MG_DEVICE(h);
+    mg_sample_actions_kernel<<<(h->num_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        h->num_envs, seed, 0, h->P.env_id_offset, act_dev, reinterpret_cast<unsigned long long *>(step_counter_dev));
     h->launches++;
     MG_CUDA(h, cudaGetLastError());
     return MG_OK;

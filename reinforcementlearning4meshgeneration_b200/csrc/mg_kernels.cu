@@ -2178,8 +2178,22 @@ __global__ void __launch_bounds__(32) mg_smooth_kernel(const __grid_constant__ P
 }
 
 // Uniform actions in Box([-1,-1.5,0],[1,1.5,1.5]) -- the synthetic policy of the benchmarks.
-__global__ void mg_sample_actions_kernel(int num_envs, uint64_t seed, uint64_t step, int64_t env_id_offset, float *act) {
+// step_ctr != nullptr: the step index is step_ctr[0] in device memory and the last block to finish advances it
+// (step_ctr[1] counts the blocks that are done), so that the launch can be replayed from a CUDA graph.
+__global__ void mg_sample_actions_kernel(int num_envs, uint64_t seed, uint64_t step, int64_t env_id_offset, float *act,
+                                         unsigned long long *step_ctr) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (step_ctr) {
+        step = *reinterpret_cast<volatile unsigned long long *>(step_ctr);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(step_ctr + 1, 1ull) == gridDim.x - 1) {
+                step_ctr[1] = 0;
+                step_ctr[0] = step + 1;
+            }
+        }
+    }
     if (e >= num_envs) return;
     unsigned long long g = (unsigned long long)(env_id_offset + e);
     uint4 r = philox4x32(make_uint4((unsigned)step, (unsigned)(step >> 32), (unsigned)g, (unsigned)(g >> 32)),

@@ -715,3 +715,57 @@ def test_move_with_smooth_pave_on_random_polygons():
             env.reset(torch.from_numpy(reset_mask))
     assert n_smooth >= 3
     env.close()
+
+
+def test_synthetic_policy_with_a_device_side_step_index_replays_from_a_graph():
+    """mg_sample_actions_seq (the step index lives in device memory and is advanced by the launch itself): a loop of
+    policy + env step captured once and replayed -- what bench.py times -- draws the same actions and produces the
+    same rollout (observations, rewards, statistics) as eager launches with the step index passed from the host."""
+    import torch
+    N, T, G = 2048, 60, 4
+    gen = dict(min_coarse=5, max_coarse=10, min_verts=16, max_verts=48)
+    eager = _mk(None, N, random_polygons=gen, seed=5)
+    eager.reset()
+    exp_a, exp_obs, exp_rew = [], [], []
+    for t in range(T):
+        a = eager.sample_actions(77, 100 + t)
+        exp_a.append(a.clone())
+        r = eager.step(a)
+        exp_obs.append(r.obs.clone()); exp_rew.append(r.reward.clone())
+    exp_stats = eager.stats()
+    env = _mk(None, N, random_polygons=gen, seed=5)
+    env.reset()
+    ctr = torch.tensor([100, 0], dtype=torch.int64, device=env.device)
+    a_log = torch.zeros((G, N, 3), device=env.device)
+    obs_log = torch.zeros((G, N, 18), device=env.device)
+    rew_log = torch.zeros((G, N), dtype=torch.float64, device=env.device)
+    snap = env.snapshot()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        env.step(env.sample_actions(77, ctr))                    # first use outside the capture, then rewind
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    assert ctr.tolist() == [101, 0]
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for k in range(G):
+            a = env.sample_actions(77, ctr)
+            a_log[k].copy_(a)
+            r = env.step(a)
+            obs_log[k].copy_(r.obs); rew_log[k].copy_(r.reward)
+    env.restore(snap)
+    env.stats(reset=True)
+    ctr.copy_(torch.tensor([100, 0]))
+    for rep in range(T // G):
+        g.replay()
+        for k in range(G):
+            t = rep * G + k
+            assert torch.equal(a_log[k], exp_a[t]), f"actions differ at step {t}"
+            assert torch.equal(obs_log[k], exp_obs[t]), f"obs differ at step {t}"
+            assert torch.equal(rew_log[k], exp_rew[t]), f"reward differs at step {t}"
+    assert ctr.tolist() == [100 + T, 0]
+    got = env.stats()
+    for k, v in exp_stats.items():                # (the two float sums are accumulated with atomics: order-dependent rounding)
+        assert got[k] == v if isinstance(v, int) else abs(got[k] - v) <= 1e-9 * max(1.0, abs(v)), k
+    assert got["successes"] > 0
