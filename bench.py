@@ -443,7 +443,7 @@ def run_gpu(args):
     host_actions = [torch.from_numpy(rng.uniform(lo, hi, size=(N, 3)).astype(np.float32)).pin_memory() for _ in range(4)]
     out = {k: v for k, v in pinned.items() if k != "act"}
     reward_view = out["reward"].numpy()                       # host view the caller reads its results through
-    for k in range(3):
+    for k in range(12):                                       # (mg_step_host builds a graph per action buffer on its second use)
         env.step_host(host_actions[k % 4], out)
     barrier()
     t0 = time.perf_counter()

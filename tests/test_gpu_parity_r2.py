@@ -769,3 +769,45 @@ def test_synthetic_policy_with_a_device_side_step_index_replays_from_a_graph():
     for k, v in exp_stats.items():                # (the two float sums are accumulated with atomics: order-dependent rounding)
         assert got[k] == v if isinstance(v, int) else abs(got[k] - v) <= 1e-9 * max(1.0, abs(v)), k
     assert got["successes"] > 0
+
+
+def test_host_steps_replayed_from_cached_graphs_equal_plain_launches():
+    """mg_step_host replays the launches of a step from a CUDA graph once it has seen the same buffers twice
+    (mg_set_option "host_graph"): rotating pinned action buffers, persistent pinned result buffers in delta mode,
+    random polygons with auto-reset, a partial reset and an option change in the middle -- every result array equals
+    the one of an env that launches its kernels one by one."""
+    import torch
+    N, T = 4096, 90
+    gen = dict(min_coarse=5, max_coarse=10, min_verts=16, max_verts=48)
+    envs = [_mk(None, N, random_polygons=gen, seed=11) for _ in range(2)]
+    envs[1].set_option("host_graph", 0)
+    rng = np.random.default_rng(4)
+    acts = [torch.empty((N, 3), dtype=torch.float32).pin_memory() for _ in range(3)]
+    outs = []
+    for e in envs:
+        e.reset()
+        outs.append(dict(obs=torch.zeros((N, 18), dtype=torch.float32).pin_memory(), reward=torch.zeros(N, dtype=torch.float64).pin_memory(),
+                         terminated=torch.zeros(N, dtype=torch.uint8).pin_memory(), truncated=torch.zeros(N, dtype=torch.uint8).pin_memory(),
+                         terminal_obs=torch.zeros((N, 18), dtype=torch.float32).pin_memory(),
+                         n_elements=torch.zeros(N, dtype=torch.int32).pin_memory()))
+    launches0 = [e.launch_count for e in envs]
+    for t in range(T):
+        a = acts[t % 3]
+        a.copy_(torch.from_numpy(rng.uniform(LOW_A, HIGH_A, size=(N, 3)).astype(np.float32)))
+        if t == 40:                                  # state changes behind the graphs' back: partial reset on the caller's stream
+            mask = torch.zeros(N, dtype=torch.bool, device=envs[0].device)
+            mask[::7] = True
+            for e in envs:
+                e.reset(mask)
+        if t == 60:                                  # a different launch configuration: new graphs
+            for e in envs:
+                e.set_option("pdl", 0)
+        for e, o in zip(envs, outs):
+            e.step_host(a, o)
+        for k in ("obs", "reward", "terminated", "truncated", "n_elements"):
+            assert torch.equal(outs[0][k], outs[1][k]), (t, k)
+    assert envs[0].launch_count - launches0[0] == envs[1].launch_count - launches0[1]
+    s0, s1 = envs[0].stats(), envs[1].stats()
+    assert all(s0[k] == s1[k] for k in s0 if isinstance(s0[k], int)) and s0["steps"] == N * T and s0["episodes"] > 0
+    for e in envs:
+        e.close()
