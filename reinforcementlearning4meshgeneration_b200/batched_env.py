@@ -86,6 +86,7 @@ class BatchedBoudaryEnv:
         self.num_envs = int(num_envs)
         self._h = C.c_void_p()
         self.random_mode = random_polygons is not None
+        self._host_args = {}
         if self.random_mode:
             cfg = dict(ctr_x=250.0, ctr_y=250.0, ave_radius=100.0, irregularity=0.55, spikeyness=0.7,
                        min_coarse=8, max_coarse=24, min_verts=64, max_verts=512)
@@ -194,25 +195,40 @@ class BatchedBoudaryEnv:
         (torch ``.pin_memory()``) the GPU writes the results straight into them -- with ``obs_delta`` on only the
         observation rows, rewards, flags and element counts that differ from what the buffers already hold: keep passing
         the same ``out`` buffers and do not modify them in place."""
-        is_t = isinstance(actions, torch.Tensor)
-        if is_t:
-            if actions.dtype != torch.float32 or not actions.is_contiguous() or actions.device.type != "cpu":
-                raise ValueError("actions tensor must be a contiguous float32 CPU tensor (pinned for the fastest path)")
+        # The marshalled pointers of (action tensor, result buffers) are kept for callers that keep passing the same
+        # objects -- ~6 us of ctypes conversions per call otherwise; entries hold the objects, so an id cannot be recycled.
+        ent = self._host_args.get(id(actions)) if out is not None else None
+        if ent is not None and ent[0] is actions and ent[1] is out and tuple(map(id, out.values())) == ent[2] \
+                and actions.data_ptr() == ent[3][0].value:
+            args = ent[3]
         else:
-            a = np.ascontiguousarray(actions, dtype=np.float32)
-        N = self.num_envs
-        if out is None:
-            out = dict(obs=np.empty((N, OBS_DIM), np.float32), reward=np.empty(N, np.float64),
-                       terminated=np.empty(N, np.uint8), truncated=np.empty(N, np.uint8),
-                       terminal_obs=np.empty((N, OBS_DIM), np.float32), n_elements=np.empty(N, np.int32))
+            is_t = isinstance(actions, torch.Tensor)
+            if is_t:
+                if actions.dtype != torch.float32 or not actions.is_contiguous() or actions.device.type != "cpu":
+                    raise ValueError("actions tensor must be a contiguous float32 CPU tensor (pinned for the fastest path)")
+            else:
+                a = np.ascontiguousarray(actions, dtype=np.float32)
+            N = self.num_envs
+            if out is None:
+                out = dict(obs=np.empty((N, OBS_DIM), np.float32), reward=np.empty(N, np.float64),
+                           terminated=np.empty(N, np.uint8), truncated=np.empty(N, np.uint8),
+                           terminal_obs=np.empty((N, OBS_DIM), np.float32), n_elements=np.empty(N, np.int32))
+                cacheable = False
+            else:
+                cacheable = is_t and all(isinstance(v, torch.Tensor) for v in out.values())
 
-        def ptr(x):
-            return C.c_void_p(x.data_ptr()) if isinstance(x, torch.Tensor) else C.c_void_p(x.ctypes.data)
+            def ptr(x):
+                return C.c_void_p(x.data_ptr()) if isinstance(x, torch.Tensor) else C.c_void_p(x.ctypes.data)
 
-        aptr = ptr(actions) if is_t else C.c_void_p(a.ctypes.data)
-        check(self._L.mg_step_host(self._h, aptr, ptr(out["obs"]), ptr(out["reward"]), ptr(out["terminated"]),
-                                   ptr(out["truncated"]), ptr(out["terminal_obs"]), ptr(out["n_elements"])),
-              self._h, "mg_step_host")
+            args = (ptr(actions) if is_t else C.c_void_p(a.ctypes.data), ptr(out["obs"]), ptr(out["reward"]), ptr(out["terminated"]),
+                    ptr(out["truncated"]), ptr(out["terminal_obs"]), ptr(out["n_elements"]))
+            if cacheable:
+                if len(self._host_args) >= 16:
+                    self._host_args.clear()
+                self._host_args[id(actions)] = (actions, out, tuple(map(id, out.values())), args, tuple(out.values()))
+        rc = self._L.mg_step_host(self._h, *args)
+        if rc != 0:
+            check(rc, self._h, "mg_step_host")
         return out
 
     def snapshot(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
