@@ -49,28 +49,37 @@ class Actor(torch.nn.Module):
         return (self.low + (a + 1) * 0.5 * (self.high - self.low)).contiguous()
 
 
+def capture_step(env, actor, stochastic=True):
+    """One CUDA graph of policy forward + env step (mg_step keeps no host state: capturable).  The env state is
+    the same before and after the call."""
+    snap = env.snapshot()                                    # the warm-up below must not advance the rollout
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            env.step(actor(env.obs, stochastic))
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    env.restore(snap)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        act = actor(env.obs, stochastic)                     # env.obs is the env's persistent output buffer
+        env.step(act)
+    env.restore(snap)
+    torch.cuda.synchronize()
+    return g, act
+
+
 def rollout(env, actor, steps, graph=False, stochastic=True, stats_every=64, record=None):
-    """``steps`` transitions of ``env`` under ``actor``; with ``graph`` the policy forward and the env step (four
-    kernels, no host state: capturable) are replayed from one CUDA graph.  ``record`` (optional list) receives a clone
-    of (action, obs, reward, terminated | truncated) per step.  Returns the all-reduced device statistics tensor."""
+    """``steps`` transitions of ``env`` under ``actor``; ``graph``: True (capture here) or a (graph, action buffer) pair
+    from ``capture_step`` -- the policy forward and the env step are then replayed from one CUDA graph.  ``record``
+    (optional list) receives a clone of (action, obs, reward, terminated | truncated) per step.  Returns the all-reduced
+    device statistics tensor."""
     from reinforcementlearning4meshgeneration_b200.distributed import allreduce_stats_device
     obs = env.obs
     g = None
     if graph:
-        snap = env.snapshot()                                # the warm-up below must not advance the rollout
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(3):
-                env.step(actor(env.obs, stochastic))
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        env.restore(snap)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            act = actor(env.obs, stochastic)                 # env.obs is the env's persistent output buffer
-            env.step(act)
-        env.restore(snap)
+        g, act = capture_step(env, actor, stochastic) if graph is True else graph
     stats = None
     for t in range(steps):
         if g is not None:
@@ -113,13 +122,16 @@ def main():
     if rank == 0:
         sampler.start()
     rollout(env, actor, args.warmup, graph=False, stats_every=args.stats_every)
+    graph = capture_step(env, actor) if args.graph else False      # set-up, not a step: outside the timed region
+    if args.graph:
+        rollout(env, actor, 8, graph=graph, stats_every=args.stats_every)
     env.stats(reset=True)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    stats = rollout(env, actor, args.steps, graph=args.graph, stats_every=args.stats_every)
+    stats = rollout(env, actor, args.steps, graph=graph, stats_every=args.stats_every)
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
