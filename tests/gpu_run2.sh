@@ -1,16 +1,13 @@
+# 2-GPU check of the bench (driver-style launch) and of the config-5 rollout
 set -x
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
-for w in c3 c4 c2 c1; do
-  timeout 600 python bench.py --workload $w --steps 400 --warmup 10 > gpurun_out/r2c_bench_$w.json 2> gpurun_out/r2c_bench_$w.err
-done
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29502 bench.py --gpus 2 --steps 400 --warmup 10 > gpurun_out/r2_bench_c3_n2.json 2> gpurun_out/r2_bench_c3_n2.err
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29503 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/r2_bench_c3_n2_driverlike.json 2> gpurun_out/r2_bench_c3_n2_driverlike.err
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29504 bench.py --gpus 2 --impl reference --steps 2 --warmup 1 > gpurun_out/r2_bench_ref_n2.json 2> gpurun_out/r2_bench_ref_n2.err
 python - <<'PY'
 import json
-for w in ('c3','c4','c2','c1'):
+for f in ('r2_bench_c3_n2', 'r2_bench_c3_n2_driverlike', 'r2_bench_ref_n2'):
     try:
-        d=json.load(open(f'gpurun_out/r2c_bench_{w}.json'))
-        print(w,'value %.4g ms/step %.4f e2e %.4g frac %.3f memo_frac %.3f'%(d['value'],d['ms_per_step'],d['e2e']['value'],d['roofline']['frac'],d['roofline']['memo_frac']), [ round(k['ms']*1e3,1) for k in d['roofline']['per_kernel']], 'cpu', d['cpu_baseline'] and '%.3g'%d['cpu_baseline']['value'])
-    except Exception as ex: print(w,'failed',ex)
+        d=json.loads(open(f'gpurun_out/{f}.json').read().strip().splitlines()[-1])
+        print(f,'value %.4g ms/step %.4f'%(d['value'],d['ms_per_step']), 'e2e %.4g'%d['e2e']['value'] if 'e2e' in d else '', d.get('collective',{}).get('inside_timed_loop'), d.get('gpu_launches'), d.get('clocks'))
+    except Exception as ex: print(f,'failed',ex); print(open(f'gpurun_out/{f}.err').read()[-1500:])
 PY
-timeout 600 python examples/sac_rollout.py --envs 65536 --steps 300 --graph > gpurun_out/r2c_c5_n1.json 2> gpurun_out/r2c_c5_n1.err; cat gpurun_out/r2c_c5_n1.json | cut -c1-300
-timeout 600 python examples/sac_rollout.py --envs 65536 --steps 300 > gpurun_out/r2c_c5_n1_eager.json 2> gpurun_out/r2c_c5_n1_eager.err; cat gpurun_out/r2c_c5_n1_eager.json | cut -c1-200
-timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2c_bench_ref.json 2> gpurun_out/r2c_bench_ref.err; cut -c1-400 gpurun_out/r2c_bench_ref.json
