@@ -343,6 +343,7 @@ def run_gpu(args):
     use_graph = not need_flush and not args.no_graph
     K = args.steps
     graphs, launches_per_step = {}, 0
+    graph_note = None
     if use_graph:
         step_ctr = torch.tensor([step_idx, 0], dtype=torch.int64, device=dev)
         side = torch.cuda.Stream(dev)
@@ -351,14 +352,21 @@ def run_gpu(args):
             env.step(env.sample_actions(SEED, step_ctr))
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        for n in (1, GRAPH_STEPS):
-            g = torch.cuda.CUDAGraph()
-            l0 = env.launch_count
-            with torch.cuda.graph(g):
-                for _ in range(n):
-                    env.step(env.sample_actions(SEED, step_ctr))
-            launches_per_step = (env.launch_count - l0) // n
-            graphs[n] = g
+        try:
+            for n in (1, GRAPH_STEPS):
+                g = torch.cuda.CUDAGraph()
+                l0 = env.launch_count
+                with torch.cuda.graph(g):
+                    for _ in range(n):
+                        env.step(env.sample_actions(SEED, step_ctr))
+                launches_per_step = (env.launch_count - l0) // n
+                graphs[n] = g
+        except Exception as ex:                              # no capture on this box: the same steps, launched one by one
+            graph_note = f"graph capture failed ({type(ex).__name__}: {str(ex)[:120]}); eager launches"
+            graphs.clear()
+            use_graph = False
+            torch.cuda.synchronize(dev)
+            step_idx = int(step_ctr[0].item())
 
     def run_steps(k0, k1, record=None):
         """Steps k0..k1-1 of a loop; returns the statistics all-reduces it enqueued (every STATS_INTERVAL steps)."""
@@ -527,13 +535,16 @@ def run_gpu(args):
             "launch_mode": ({"cuda_graph": True, "steps_per_graph": GRAPH_STEPS, "kernels_per_step": launches_per_step,
                              "note": "policy kernel + the kernels of mg_step replayed from CUDA graphs (mg_step keeps no host state; "
                                      "the policy's step index lives in device memory); --no-graph launches them one by one"}
-                            if use_graph else {"cuda_graph": False}),
+                            if use_graph else {"cuda_graph": False, "note": graph_note}),
             "collective": {"op": "all_reduce(sum) of mg_episode_stats (10 x int64 + 2 x float64)", "backend": "nccl" if world > 1 else "none (1 rank: device-side sum only)",
                            "every_steps": STATS_INTERVAL, "inside_timed_loop": n_reduces},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "kernel": max(per_kernel, key=lambda k: k["ms"])["name"],
                          "kernel_ms_per_launch": kern_ms_max / K,
+                         "kernel_ms_note": ("CUDA events around the whole graph-replayed loop / steps: one mg_step (its four kernels, the "
+                                            "reset kernel beside two of them) + the 2-us policy kernel -- no events inside a graph"
+                                            if use_graph else "CUDA events around every mg_step call of the timed loop"),
                          "alg_bytes_per_launch": alg_bytes_per_launch_per_gpu,
                          "model": "SURVEY 8d: sum(28 n + 14 n s + 226) per env-step, i.e. every env's boundary crossing HBM once per "
                                   "step.  The kernels memoise the state-only predicates, so ~93 % of the steps never read their "
