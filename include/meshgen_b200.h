@@ -170,6 +170,14 @@ int mg_move(mg_handle h, const double *polar_dev, const double *type_dev, float 
  * finished, and returns after its own work has finished. */
 int mg_step_host(mg_handle h, const float *act_host, float *obs_host, double *rew_host,
                  uint8_t *term_host, uint8_t *trunc_host, float *term_obs_host, int32_t *n_elem_host);
+/* The two halves of mg_step_host: _begin enqueues the step on the handle's private stream and returns, _end waits for
+ * it (the result arrays are defined after _end).  For callers that split their envs over two handles (SB3's VecEnv
+ * step_async / step_wait, rl/baselines/dummy_vec_env.py:38-58, is the same split): while one half runs on the GPU the
+ * host reads the other half's results, runs its policy and enqueues its next step, so the host's latency and the PCIe
+ * transfers of one half hide behind the other half's kernels.  One step per handle in flight. */
+int mg_step_host_begin(mg_handle h, const float *act_host, float *obs_host, double *rew_host,
+                       uint8_t *term_host, uint8_t *trunc_host, float *term_obs_host, int32_t *n_elem_host);
+int mg_step_host_end(mg_handle h);
 
 /* Observation delta.  A failed step leaves the env untouched and the reference itself returns a bit-identical
  * observation, so with enabled != 0 mg_step / mg_step_host write only the observation rows that changed (accepted

@@ -20,7 +20,7 @@ NVCC_FLAGS = [
 ]
 
 SYMBOLS = [
-    "mg_create", "mg_set_domains", "mg_set_random", "mg_set_auto_reset", "mg_reset", "mg_step", "mg_move", "mg_step_host",
+    "mg_create", "mg_set_domains", "mg_set_random", "mg_set_auto_reset", "mg_reset", "mg_step", "mg_move", "mg_step_host", "mg_step_host_begin", "mg_step_host_end",
     "mg_set_obs_delta", "mg_set_host_delta", "mg_last_host_bytes", "mg_sample_actions", "mg_sample_actions_seq", "mg_get_state", "mg_get_elements", "mg_debug_polygon",
     "mg_stats", "mg_stats_async", "mg_set_log_capacity", "mg_log_capacity", "mg_replay_add", "mg_snapshot_bytes",
     "mg_snapshot_save", "mg_snapshot_load", "mg_set_option", "mg_set_kernel_timing", "mg_kernel_times", "mg_num_envs", "mg_max_verts",
@@ -86,6 +86,8 @@ def load():
     L.mg_step.argtypes = [vp] + [vp] * 7 + [vp]
     L.mg_move.argtypes = [vp] + [vp] * 7 + [vp]
     L.mg_step_host.argtypes = [vp] + [vp] * 7
+    L.mg_step_host_begin.argtypes = [vp] + [vp] * 7
+    L.mg_step_host_end.argtypes = [vp]
     L.mg_set_obs_delta.argtypes = [vp, i32]
     L.mg_set_host_delta.argtypes = [vp, i32]
     L.mg_last_host_bytes.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]

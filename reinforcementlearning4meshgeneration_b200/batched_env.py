@@ -189,7 +189,7 @@ class BatchedBoudaryEnv:
                               C.c_void_p(self.n_elements.data_ptr()), self._stream()), self._h, "mg_move")
         return dict(obs=self.obs, done=f[0], is_complete=f[1], exhausted=f[2], n_elements=self.n_elements)
 
-    def step_host(self, actions: np.ndarray, out: Optional[dict] = None) -> dict:
+    def step_host(self, actions: np.ndarray, out: Optional[dict] = None, _begin_only: bool = False) -> dict:
         """Same transition through host (numpy / pinned) buffers: H2D + step + D2H + sync inside the
         library (mg_step_host) -- the path a numpy-facing caller such as SB3 pays.  With pinned ``out`` buffers
         (torch ``.pin_memory()``) the GPU writes the results straight into them -- with ``obs_delta`` on only the
@@ -226,10 +226,21 @@ class BatchedBoudaryEnv:
                 if len(self._host_args) >= 16:
                     self._host_args.clear()
                 self._host_args[id(actions)] = (actions, out, tuple(map(id, out.values())), args, tuple(out.values()))
-        rc = self._L.mg_step_host(self._h, *args)
+        rc = (self._L.mg_step_host_begin if _begin_only else self._L.mg_step_host)(self._h, *args)
         if rc != 0:
             check(rc, self._h, "mg_step_host")
         return out
+
+    def step_host_begin(self, actions, out: dict) -> dict:
+        """First half of ``step_host``: enqueue the step and return; ``out`` is defined after ``step_host_end``.  With the
+        envs split over two ``BatchedBoudaryEnv`` objects the host works on one half (results, policy, next launch) while
+        the other half runs on the GPU -- the step_async / step_wait split of SB3's VecEnv (mg_step_host_begin / _end)."""
+        return self.step_host(actions, out, _begin_only=True)
+
+    def step_host_end(self) -> None:
+        rc = self._L.mg_step_host_end(self._h)
+        if rc != 0:
+            check(rc, self._h, "mg_step_host_end")
 
     def snapshot(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Complete env state as one uint8 device tensor (mg_snapshot_save); ``.cpu()`` it to persist."""

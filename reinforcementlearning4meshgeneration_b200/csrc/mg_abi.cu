@@ -70,6 +70,7 @@ struct mg_env_s {
     // mg_step_host replays the launches of a step from a CUDA graph (mg_set_option "host_graph"): one graph per distinct
     // (buffers, parameters, options) combination, instantiated the second time the combination is seen
     bool host_graph = true;
+    bool host_step_pending = false;    // between mg_step_host_begin and mg_step_host_end
     struct StepGraph {
         StepIO io;
         Params P;
@@ -636,6 +637,7 @@ int mg_reset(mg_handle h, const uint8_t *mask_dev, float *obs_dev, void *stream)
     if (!h) return fail(h, MG_ERR_ARG, "mg_reset: null handle");
     if (!h->ready) return fail(h, MG_ERR_STATE, "mg_reset: call mg_set_domains or mg_set_random first");
     if (mask_dev && !h->was_reset) return fail(h, MG_ERR_STATE, "mg_reset: the first reset must cover all envs (mask = NULL)");
+    if (h->host_step_pending) return fail(h, MG_ERR_STATE, "mg_reset: a host step is in flight (mg_step_host_end first)");
     MG_DEVICE(h);
     mg_reset_kernel<<<h->num_envs, 32, h->smem, (cudaStream_t)stream>>>(h->P, mask_dev, obs_dev);
     h->launches++;
@@ -650,6 +652,7 @@ int mg_step(mg_handle h, const float *act_dev, float *obs_dev, double *rew_dev, 
             float *term_obs_dev, int32_t *n_elem_dev, void *stream) {
     if (!h || !act_dev || !obs_dev || !rew_dev || !term_dev || !trunc_dev) return fail(h, MG_ERR_ARG, "mg_step: null pointer");
     if (!h->was_reset) return fail(h, MG_ERR_STATE, "mg_step: call mg_reset first");
+    if (h->host_step_pending) return fail(h, MG_ERR_STATE, "mg_step: a host step is in flight (mg_step_host_end first)");
     MG_DEVICE(h);
     StepIO io;
     io.act = act_dev; io.obs_out = obs_dev; io.rew_out = rew_dev; io.term_out = term_dev; io.trunc_out = trunc_dev;
@@ -665,8 +668,25 @@ int mg_step(mg_handle h, const float *act_dev, float *obs_dev, double *rew_dev, 
 
 int mg_step_host(mg_handle h, const float *act_host, float *obs_host, double *rew_host, uint8_t *term_host,
                  uint8_t *trunc_host, float *term_obs_host, int32_t *n_elem_host) {
+    const int rc = mg_step_host_begin(h, act_host, obs_host, rew_host, term_host, trunc_host, term_obs_host, n_elem_host);
+    return rc != MG_OK ? rc : mg_step_host_end(h);
+}
+
+int mg_step_host_end(mg_handle h) {
+    if (!h) return fail(h, MG_ERR_ARG, "mg_step_host_end: null handle");
+    if (!h->host_step_pending) return fail(h, MG_ERR_STATE, "mg_step_host_end: no mg_step_host_begin in flight");
+    MG_DEVICE(h);
+    h->host_step_pending = false;
+    MG_CUDA(h, cudaStreamSynchronize(h->host_stream));
+    h->acct_valid = true;      // (mg_last_host_bytes reads the step counters only when asked)
+    return MG_OK;
+}
+
+int mg_step_host_begin(mg_handle h, const float *act_host, float *obs_host, double *rew_host, uint8_t *term_host,
+                       uint8_t *trunc_host, float *term_obs_host, int32_t *n_elem_host) {
     if (!h || !act_host || !obs_host || !rew_host || !term_host || !trunc_host) return fail(h, MG_ERR_ARG, "mg_step_host: null pointer");
     if (!h->was_reset) return fail(h, MG_ERR_STATE, "mg_step_host: call mg_reset first");
+    if (h->host_step_pending) return fail(h, MG_ERR_STATE, "mg_step_host_begin: the previous host step has not been ended");
     MG_DEVICE(h);
     const size_t N = h->num_envs;
     cudaStream_t s = h->host_stream;
@@ -717,9 +737,9 @@ int mg_step_host(mg_handle h, const float *act_host, float *obs_host, double *re
     if (term_obs_host && !tobs_a)
         MG_CUDA(h, cudaMemcpyAsync(term_obs_host, h->d_term_obs, N * MG_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (n_elem_host && !nel_a) MG_CUDA(h, cudaMemcpyAsync(n_elem_host, h->d_nel, N * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    MG_CUDA(h, cudaStreamSynchronize(s));
-    // what the byte accounting of this step needs (mg_last_host_bytes reads the step counters only when asked)
-    h->acct_valid = true;
+    // what the byte accounting of this step needs
+    h->host_step_pending = true;
+    h->acct_valid = false;
     h->acct_obs_rows_delta = obs_a && !io.obs_full;
     h->acct_term_obs = term_obs_host ? (tobs_a ? 1 : 2) : 0;
     h->acct_n_elem = n_elem_host != nullptr;

@@ -124,11 +124,20 @@ class _VecEnvCore:
         return obs.cpu().numpy().copy()
 
     def step_async(self, actions) -> None:
+        # the step is enqueued here (mg_step_host_begin) and runs on the GPU while the caller goes on; step_wait joins it
         self._actions = np.asarray(actions, dtype=np.float32).reshape(self.num_envs, ACT_DIM)
+        self._act.copy_(torch.from_numpy(self._actions))
+        self._in_flight = hasattr(self._b, "step_host_begin")
+        if self._in_flight:
+            self._b.step_host_begin(self._act, self._out)
 
     def step_wait(self):
-        self._act.copy_(torch.from_numpy(self._actions))
-        o = self._b.step_host(self._act, self._out)
+        if getattr(self, "_in_flight", False):
+            self._b.step_host_end()
+            self._in_flight = False
+            o = self._out
+        else:
+            o = self._b.step_host(self._act, self._out)
         obs = o["obs"].numpy().copy()
         rew64 = o["reward"].numpy()
         term = o["terminated"].numpy().astype(bool)

@@ -811,3 +811,46 @@ def test_host_steps_replayed_from_cached_graphs_equal_plain_launches():
     assert all(s0[k] == s1[k] for k in s0 if isinstance(s0[k], int)) and s0["steps"] == N * T and s0["episodes"] > 0
     for e in envs:
         e.close()
+
+
+def test_host_step_begin_end_halves_equal_one_env():
+    """mg_step_host_begin / _end: two handles that hold the two halves of the envs (env_id_offset keeps the generator's
+    counters), their host steps interleaved -- begin A, begin B, end A, ... -- give the rows a single handle gives; a
+    second begin without end, and a device step while a host step is in flight, are refused."""
+    import torch
+    from reinforcementlearning4meshgeneration_b200._lib import MeshgenError
+    N, T = 2048, 50
+    gen = dict(min_coarse=5, max_coarse=10, min_verts=16, max_verts=48)
+    full = _mk(None, N, random_polygons=gen, seed=9)
+    parts = [_mk(None, N // 2, random_polygons=gen, seed=9, env_id_offset=p * (N // 2)) for p in range(2)]
+
+    def outs(n):
+        return dict(obs=torch.zeros((n, 18), dtype=torch.float32).pin_memory(), reward=torch.zeros(n, dtype=torch.float64).pin_memory(),
+                    terminated=torch.zeros(n, dtype=torch.uint8).pin_memory(), truncated=torch.zeros(n, dtype=torch.uint8).pin_memory(),
+                    terminal_obs=torch.zeros((n, 18), dtype=torch.float32).pin_memory(), n_elements=torch.zeros(n, dtype=torch.int32).pin_memory())
+    for e in [full] + parts:
+        e.reset()
+    o_full, o_parts = outs(N), [outs(N // 2) for _ in range(2)]
+    rng = np.random.default_rng(12)
+    a_full = torch.empty((N, 3), dtype=torch.float32).pin_memory()
+    a_parts = [torch.empty((N // 2, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
+    for t in range(T):
+        a = torch.from_numpy(rng.uniform(LOW_A, HIGH_A, size=(N, 3)).astype(np.float32))
+        a_full.copy_(a)
+        full.step_host(a_full, o_full)
+        for p in range(2):
+            a_parts[p].copy_(a[p * (N // 2):(p + 1) * (N // 2)])
+            parts[p].step_host_begin(a_parts[p], o_parts[p])
+        if t == 3:
+            with pytest.raises(MeshgenError):
+                parts[0].step_host_begin(a_parts[0], o_parts[0])
+            with pytest.raises(MeshgenError):
+                parts[0].step(torch.zeros((N // 2, 3), device=parts[0].device))
+        for p in range(2):
+            parts[p].step_host_end()
+        for k in ("obs", "reward", "terminated", "truncated", "n_elements"):
+            assert torch.equal(torch.cat([o_parts[0][k], o_parts[1][k]]), o_full[k]), (t, k)
+    with pytest.raises(MeshgenError):
+        parts[0].step_host_end()
+    for e in [full] + parts:
+        e.close()
