@@ -143,6 +143,8 @@ class BatchedBoudaryEnv:
         if getattr(self, "_h", None) is not None and self._h.value:
             self._L.mg_destroy(self._h)
             self._h = C.c_void_p()
+        if getattr(self, "_host_args", None):
+            self._host_args.clear()                # (the entries hold the caller's buffers)
 
     def __del__(self):
         try:
