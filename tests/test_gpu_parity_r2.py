@@ -347,6 +347,22 @@ def test_current_device_is_left_alone():
     assert torch.cuda.current_device() == 0
     x = torch.zeros(4, device="cuda")
     assert x.device.index == 0
+    # host steps on the other device: plain launches, then the cached graph (captured and replayed on cuda:1)
+    ref = _mk([doms["star"]], 4, device="cuda:0")
+    ref.reset()
+    ref.step(ref.sample_actions(0, 0))
+    a = torch.zeros((4, 3), dtype=torch.float32).pin_memory()
+    rng = np.random.default_rng(2)
+    outs = [dict(obs=torch.zeros((4, 18)).pin_memory(), reward=torch.zeros(4, dtype=torch.float64).pin_memory(),
+                 terminated=torch.zeros(4, dtype=torch.uint8).pin_memory(), truncated=torch.zeros(4, dtype=torch.uint8).pin_memory(),
+                 terminal_obs=torch.zeros((4, 18)).pin_memory(), n_elements=torch.zeros(4, dtype=torch.int32).pin_memory()) for _ in range(2)]
+    for t in range(8):
+        a.copy_(torch.from_numpy(rng.uniform(LOW_A, HIGH_A, size=(4, 3)).astype(np.float32)))
+        env.step_host(a, outs[0])
+        ref.step_host(a, outs[1])
+        assert torch.cuda.current_device() == 0
+        for k in ("obs", "reward", "terminated", "truncated", "n_elements"):
+            assert torch.equal(outs[0][k], outs[1][k]), (t, k)
 
 
 def test_graph_captured_policy_and_env_rollout_equals_eager():
