@@ -174,7 +174,9 @@ int mg_step_host(mg_handle h, const float *act_host, float *obs_host, double *re
  * it (the result arrays are defined after _end).  For callers that split their envs over two handles (SB3's VecEnv
  * step_async / step_wait, rl/baselines/dummy_vec_env.py:38-58, is the same split): while one half runs on the GPU the
  * host reads the other half's results, runs its policy and enqueues its next step, so the host's latency and the PCIe
- * transfers of one half hide behind the other half's kernels.  One step per handle in flight. */
+ * transfers of one half hide behind the other half's kernels.  One step per handle in flight: until _end, a second
+ * _begin and the calls that touch the env state (mg_reset, mg_step, mg_move, mg_snapshot_*) are refused with
+ * MG_ERR_STATE. */
 int mg_step_host_begin(mg_handle h, const float *act_host, float *obs_host, double *rew_host,
                        uint8_t *term_host, uint8_t *trunc_host, float *term_obs_host, int32_t *n_elem_host);
 int mg_step_host_end(mg_handle h);

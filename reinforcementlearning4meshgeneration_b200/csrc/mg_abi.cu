@@ -508,6 +508,7 @@ int64_t mg_snapshot_bytes(mg_handle h) {
 int mg_snapshot_save(mg_handle h, void *blob_dev, void *stream) {
     if (!h || !blob_dev) return fail(h, MG_ERR_ARG, "mg_snapshot_save: null pointer");
     if (!h->was_reset) return fail(h, MG_ERR_STATE, "mg_snapshot_save: call mg_reset first");
+    if (h->host_step_pending) return fail(h, MG_ERR_STATE, "mg_snapshot_save: a host step is in flight (mg_step_host_end first)");
     MG_DEVICE(h);
     cudaStream_t s = (cudaStream_t)stream;
     const SnapHeader hdr = snap_header(h, mg_snapshot_bytes(h));
@@ -526,6 +527,7 @@ int mg_snapshot_load(mg_handle h, const void *blob_dev, int64_t blob_bytes, void
     if (!h || !blob_dev) return fail(h, MG_ERR_ARG, "mg_snapshot_load: null pointer");
     if (!h->ready) return fail(h, MG_ERR_STATE, "mg_snapshot_load: configure domains or the generator first");
     if (blob_bytes < (int64_t)SNAP_ALIGN) return fail(h, MG_ERR_ARG, "mg_snapshot_load: blob shorter than its header");
+    if (h->host_step_pending) return fail(h, MG_ERR_STATE, "mg_snapshot_load: a host step is in flight (mg_step_host_end first)");
     MG_DEVICE(h);
     cudaStream_t s = (cudaStream_t)stream;
     SnapHeader got{};
@@ -751,6 +753,7 @@ int mg_move(mg_handle h, const double *polar_dev, const double *type_dev, float 
     if (!h || !polar_dev || !type_dev || !obs_dev || !done_dev || !complete_dev || !exhausted_dev)
         return fail(h, MG_ERR_ARG, "mg_move: null pointer");
     if (!h->was_reset) return fail(h, MG_ERR_STATE, "mg_move: call mg_reset first");
+    if (h->host_step_pending) return fail(h, MG_ERR_STATE, "mg_move: a host step is in flight (mg_step_host_end first)");
     MG_DEVICE(h);
     if (!h->excl) {
         MG_CUDA(h, dalloc(&h->excl, (size_t)h->num_envs * h->P.cap));
