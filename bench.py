@@ -11,6 +11,10 @@ Workloads (BASELINE.json configs):
   c4          : the same with 131072 envs per GPU (1 M envs on 8 GPUs)
   c2          : paper domains d1/d2/d3 (120/196/272 vertices), 4096 envs per GPU
   c1          : BoudaryEnv(boundary()), 30 vertices, 4096 envs per GPU
+Launches: the step's kernels are replayed from CUDA graphs (c3 / c4: four steps per graph launch; c2 / c1, which flush
+L2 between timed steps: the whole timed loop as one graph with external event-record nodes around every step);
+`--no-graph` launches every kernel eagerly.  Timed on the device with CUDA events either way (`launch_mode` in the line).
+`e2e` = the same step through mg_step_host with pinned host buffers, one call and one synchronisation per step.
 Multi-GPU: launched by torchrun, one rank per GPU, envs sharded by global env id (weak scaling); the only
 collective is the all-reduce of the 12-element episode-statistics vector, enqueued every 64 steps inside the
 timed loop (NCCL, no host synchronisation).
