@@ -499,16 +499,19 @@ def run_gpu(args):
         n_elements=torch.empty(N, dtype=torch.int32).pin_memory())
     rng = np.random.default_rng(rank)
     lo, hi = np.array([-1, -1.5, 0], np.float32), np.array([1, 1.5, 1.5], np.float32)
-    # the policy's output of every step sits in pinned host memory (four rotating action buffers)
-    host_actions = [torch.from_numpy(rng.uniform(lo, hi, size=(N, 3)).astype(np.float32)).pin_memory() for _ in range(4)]
+    # The policy's output of every step sits in pinned host memory: a pool of pre-drawn action buffers, one per timed step
+    # (at most 64), so that no env sees the same action twice within the window -- a failed action repeated on an unchanged
+    # state fails again, and with a short cycle most envs would run into the 100-failures truncation inside the window.
+    n_act = max(4, min(Ke, 64))
+    host_actions = [torch.from_numpy(rng.uniform(lo, hi, size=(N, 3)).astype(np.float32)).pin_memory() for _ in range(n_act)]
     out = {k: v for k, v in pinned.items() if k != "act"}
     reward_view = out["reward"].numpy()                       # host view the caller reads its results through
-    for k in range(12):                                       # (mg_step_host builds a graph per action buffer on its second use)
-        env.step_host(host_actions[k % 4], out)
+    for k in range(2 * n_act + 4):                            # (mg_step_host builds a graph per action buffer on its second use)
+        env.step_host(host_actions[k % n_act], out)
     barrier()
     t0 = time.perf_counter()
     for k in range(Ke):
-        env.step_host(host_actions[k % 4], out)               # H2D of this step's actions is inside mg_step_host
+        env.step_host(host_actions[k % n_act], out)           # H2D of this step's actions is inside mg_step_host
         _ = float(reward_view[0])                             # the caller reads the result on the host
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0

@@ -225,7 +225,7 @@ class BatchedBoudaryEnv:
             args = (ptr(actions) if is_t else C.c_void_p(a.ctypes.data), ptr(out["obs"]), ptr(out["reward"]), ptr(out["terminated"]),
                     ptr(out["truncated"]), ptr(out["terminal_obs"]), ptr(out["n_elements"]))
             if cacheable:
-                if len(self._host_args) >= 16:
+                if len(self._host_args) >= 128:
                     self._host_args.clear()
                 self._host_args[id(actions)] = (actions, out, tuple(map(id, out.values())), args, tuple(out.values()))
         rc = (self._L.mg_step_host_begin if _begin_only else self._L.mg_step_host)(self._h, *args)

@@ -264,7 +264,7 @@ void drop_step_graphs(mg_handle h) {
 // cache is bounded.
 int launch_step_cached(mg_handle h, const StepIO &io, cudaStream_t s) {
     if (!h->host_graph || h->timing) return launch_step(h, io, s);
-    constexpr size_t MAX_GRAPHS = 16;
+    constexpr size_t MAX_GRAPHS = 96;
     const int opts[8] = {h->fuse_decide, h->reset_side, h->pdl, h->blocks_decide, h->blocks_update, h->blocks_observe, h->blocks_reset, 0};
     mg_env_s::StepGraph *hit = nullptr;
     for (auto &g : h->step_graphs)
