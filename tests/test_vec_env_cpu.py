@@ -71,3 +71,43 @@ def test_vecenv_surface_and_infos():
     assert env.seed(5) == [5, 6, 7]
     env.close()
     assert env._b.closed
+
+
+class FakeBatchedAsync(FakeBatched):
+    """The same backend with the begin / end split of mg_step_host: the results only appear at step_host_end."""
+
+    def __init__(self, n):
+        super().__init__(n)
+        self.calls = []
+        self._pending = None
+
+    def step_host(self, act, out):
+        raise AssertionError("the adapter must use the begin / end pair when the backend has one")
+
+    def step_host_begin(self, act, out):
+        assert self._pending is None
+        self.calls.append("begin")
+        self._pending = (act.clone(), out)
+
+    def step_host_end(self):
+        self.calls.append("end")
+        act, out = self._pending
+        self._pending = None
+        FakeBatched.step_host(self, act, out)
+
+
+def test_step_async_enqueues_and_step_wait_joins():
+    """VecEnv.step_async / step_wait (rl/baselines/dummy_vec_env.py:38-58) map onto step_host_begin / step_host_end: the
+    step is in flight between the two calls, and the results are the ones of the plain backend."""
+    plain, split = SB3VecEnv(FakeBatched(3)), SB3VecEnv(FakeBatchedAsync(3))
+    plain.reset(); split.reset()
+    for t in range(8):
+        a = np.full((3, 3), 0.1 * t, np.float32)
+        split.step_async(a)
+        assert split._b.calls[-1] == "begin" and split._b._pending is not None
+        got = split.step_wait()
+        assert split._b.calls[-1] == "end" and split._b._pending is None
+        exp = plain.step(a)
+        assert np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1]) and np.array_equal(got[2], exp[2])
+        assert [sorted(i) for i in got[3]] == [sorted(i) for i in exp[3]]
+    assert split._b.calls == ["begin", "end"] * 8
