@@ -584,6 +584,7 @@ int mg_set_domains(mg_handle h, const double *xy_host, const int32_t *offsets_ho
     }
     MG_CUDA(h, cudaDeviceSynchronize());
     h->ready = false; h->was_reset = false;          // a failure below leaves the handle unconfigured, not half configured
+    drop_step_graphs(h);                             // (they were captured with the old templates)
     free_templates(h);
     MG_CUDA(h, dalloc(&h->t_xy, (size_t)n_domains * cap));
     MG_CUDA(h, dalloc(&h->t_key, (size_t)n_domains * cap));
@@ -631,6 +632,7 @@ int mg_set_random(mg_handle h, uint64_t seed, const mg_polygen_cfg *cfg, int64_t
     MG_CUDA(h, cudaMemset(h->P.hot, 0, sizeof(EnvHot) * h->num_envs));
     MG_CUDA(h, cudaMemset(h->P.cold, 0, sizeof(EnvCold) * h->num_envs));
     h->P.random_mode = 1; h->P.seed = seed; h->P.gen = c; h->P.env_id_offset = env_id_offset;
+    drop_step_graphs(h);
     h->ready = true; h->was_reset = false;
     return MG_OK;
 }
@@ -939,6 +941,7 @@ int mg_set_log_capacity(mg_handle h, int max_elements_per_env, int max_inserted_
     MG_DEVICE(h);
     MG_CUDA(h, cudaDeviceSynchronize());
     Params &P = h->P;
+    drop_step_graphs(h);                             // (they were captured with the old logs)
     cudaFree(P.elem); cudaFree(P.ins_xy);
     P.elem = nullptr; P.ins_xy = nullptr;
     h->was_reset = false;            // logs were discarded: the caller resets before stepping again
